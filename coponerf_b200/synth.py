@@ -1,0 +1,171 @@
+"""Seeded synthetic inputs and weights for the render path.
+
+Everything is drawn from numpy's PCG64 so the same seed yields the same
+bytes in this container, on the GPU box and inside the golden-vector script.
+Shapes follow the reference dataloader's output dict
+(data/realestate10k_dataio.py:442-451) and the render-path parameters of
+models/CoPoNeRF.py:71-104 / models/lightfield.py:87-116.
+"""
+import math
+
+import numpy as np
+import torch
+
+# name -> shape of every parameter the per-ray stage reads (models/CoPoNeRF.py:71-104).
+RENDER_PARAM_SHAPES = {
+    "query_encode_latent.weight": (832, 835, 1, 1),
+    "query_encode_latent.bias": (832,),
+    "query_encode_latent_2.weight": (416, 832, 1, 1),
+    "query_encode_latent_2.bias": (416,),
+    "latent_value.weight": (416, 832, 1, 1),
+    "latent_value.bias": (416,),
+    "key_map.weight": (128, 832, 1, 1),
+    "key_map.bias": (128,),
+    "key_map_2.weight": (128, 128, 1, 1),
+    "key_map_2.bias": (128,),
+    "query_embed.weight": (128, 16, 1, 1),
+    "query_embed.bias": (128,),
+    "query_embed_2.weight": (128, 128, 1, 1),
+    "query_embed_2.bias": (128,),
+    "query_repeat_embed.weight": (128, 144, 1, 1),
+    "query_repeat_embed.bias": (128,),
+    "query_repeat_embed_2.weight": (128, 128, 1, 1),
+    "query_repeat_embed_2.bias": (128,),
+    "encode_latent.weight": (128, 416, 1),
+    "encode_latent.bias": (128,),
+    "phi.lin_in.weight": (128, 18),
+    "phi.lin_in.bias": (128,),
+    "phi.lin_z.0.weight": (128, 832),
+    "phi.lin_z.0.bias": (128,),
+    "phi.lin_z.1.weight": (128, 832),
+    "phi.lin_z.1.bias": (128,),
+    "phi.lin_z.2.weight": (128, 832),
+    "phi.lin_z.2.bias": (128,),
+    "phi.blocks.0.fc_0.weight": (128, 128),
+    "phi.blocks.0.fc_0.bias": (128,),
+    "phi.blocks.0.fc_1.weight": (128, 128),
+    "phi.blocks.0.fc_1.bias": (128,),
+    "phi.blocks.1.fc_0.weight": (128, 128),
+    "phi.blocks.1.fc_0.bias": (128,),
+    "phi.blocks.1.fc_1.weight": (128, 128),
+    "phi.blocks.1.fc_1.bias": (128,),
+    "phi.blocks.2.fc_0.weight": (128, 128),
+    "phi.blocks.2.fc_0.bias": (128,),
+    "phi.blocks.2.fc_1.weight": (128, 128),
+    "phi.blocks.2.fc_1.bias": (128,),
+    "phi.lin_out.weight": (3, 128),
+    "phi.lin_out.bias": (3,),
+}
+
+# Layers whose gain is raised so the 128-way softmax is peaked rather than
+# uniform; a uniform softmax makes the exported argmax (at_wt_max) a coin toss.
+_GAIN = {"key_map_2.weight": 6.0, "query_embed_2.weight": 6.0, "query_repeat_embed_2.weight": 6.0}
+
+
+def render_state_dict(seed=0):
+    """Render-path weights, U(-g/sqrt(fan_in), g/sqrt(fan_in)); biases U(-0.1, 0.1).
+
+    The reference zero-initialises phi.blocks.*.fc_1 and every phi bias
+    (models/lightfield.py:35-38,88-93); they are randomised here so the whole
+    decoder is exercised (SURVEY.md section 8(c) pitfall i).
+    """
+    rng = np.random.default_rng(1000 + seed)
+    sd = {}
+    for name, shape in RENDER_PARAM_SHAPES.items():
+        if name.endswith(".bias"):
+            a = rng.uniform(-0.1, 0.1, size=shape)
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            bound = _GAIN.get(name, 1.7) / math.sqrt(fan_in)
+            a = rng.uniform(-bound, bound, size=shape)
+        sd[name] = torch.from_numpy(a.astype(np.float32))
+    return sd
+
+
+def _pose(tx, yaw, ty=0.0, tz=0.0):
+    c, s = math.cos(yaw), math.sin(yaw)
+    m = np.eye(4, dtype=np.float64)
+    m[0, 0], m[0, 2], m[2, 0], m[2, 2] = c, s, -s, c
+    m[:3, 3] = (tx, ty, tz)
+    return m.astype(np.float32)
+
+
+POSE_SETS = {
+    # every target ray has a valid epipolar segment in both context views
+    "frontal": dict(ctx=((-0.15, 0.05), (0.15, -0.05)), qry=(0.0, 0.0)),
+    # 54 % valid in both / 9 % in one / 37 % in none
+    "oblique": dict(ctx=((-0.15, 0.05), (0.15, -0.05)), qry=(0.6, 0.4)),
+    "mild": dict(ctx=((-0.15, 0.05), (0.15, -0.05)), qry=(0.3, 0.25)),
+}
+
+
+def smooth_image(rng, H, W):
+    """Sum of 8 random sinusoids per channel, in [-1, 1]."""
+    yy, xx = np.meshgrid(np.linspace(0, 1, H), np.linspace(0, 1, W), indexing="ij")
+    img = np.zeros((H, W, 3), dtype=np.float64)
+    for c in range(3):
+        for _ in range(8):
+            fx, fy = rng.uniform(-6, 6, size=2)
+            ph = rng.uniform(0, 2 * math.pi)
+            img[..., c] += rng.uniform(0.2, 1.0) * np.sin(2 * math.pi * (fx * xx + fy * yy) + ph)
+    img /= np.abs(img).max()
+    return img.astype(np.float32)
+
+
+def make_input(H=256, W=256, n_rays=None, seed=1, pose_set="frontal", batch=1, focal=0.9):
+    """The dict CoPoNeRF.forward() takes (models/CoPoNeRF.py:208-216)."""
+    rng = np.random.default_rng(2000 + seed)
+    ps = POSE_SETS[pose_set]
+    K = np.eye(4, dtype=np.float32)
+    K[0, 0] = K[1, 1] = focal * W
+    K[0, 2], K[1, 2] = W / 2, H / 2
+    ctx_c2w = np.stack([_pose(*ps["ctx"][0]), _pose(*ps["ctx"][1])])[None].repeat(batch, 0)
+    qry_c2w = _pose(*ps["qry"])[None, None].repeat(batch, 0)
+    rgb = np.stack([np.stack([smooth_image(rng, H, W) for _ in range(2)]) for _ in range(batch)])
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    uv_full = np.stack([xs.reshape(-1), ys.reshape(-1)], -1).astype(np.float32)
+    if n_rays is None or n_rays >= H * W:
+        uv = np.broadcast_to(uv_full, (batch, 1, H * W, 2)).copy()
+    else:
+        uv = np.stack([uv_full[rng.permutation(H * W)[:n_rays]] for _ in range(batch)])[:, None]
+    N = uv.shape[2]
+    t = torch.from_numpy
+    return {
+        "context": {
+            "rgb": t(rgb),
+            "cam2world": t(ctx_c2w.copy()),
+            "intrinsics": t(K[None, None].repeat(batch, 0).repeat(2, 1)),
+        },
+        "query": {
+            "uv": t(uv),
+            "cam2world": t(qry_c2w.copy()),
+            "intrinsics": t(K[None, None].repeat(batch, 0)),
+            "rgb": t(rng.uniform(-1, 1, size=(batch, 1, N, 3)).astype(np.float32)),
+        },
+    }
+
+
+def make_features(H=256, W=256, seed=1, batch=1):
+    """Stand-ins for get_z()'s outputs at any resolution.
+
+    Returns (z list of 4 maps, rel_pose (B,4,4), flow tuple of 4).
+    """
+    rng = np.random.default_rng(3000 + seed)
+    n = 2 * batch
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    z = [
+        f32(rng.standard_normal((n, 256, H // 16, W // 16))),
+        f32(rng.standard_normal((n, 256, H // 8, W // 8))),
+        f32(rng.standard_normal((n, 256, H // 4, W // 4))),
+        f32(rng.standard_normal((n, 64, H, W))),
+    ]
+    fh, fw = H // 4, W // 4
+    flow = (
+        f32(rng.standard_normal((batch, 2, fh, fw)) * 2),
+        f32(rng.standard_normal((batch, 2, fh, fw)) * 2),
+        f32(rng.uniform(-1, 1, size=(batch, 2, fh, fw))),
+        f32(rng.uniform(-1, 1, size=(batch, 2, fh, fw))),
+    )
+    # estimated context-1 -> context-2 pose: close to the true one, not equal to it
+    rel = np.stack([_pose(0.3, -0.1, 0.01 * b, -0.02) for b in range(batch)])
+    return z, f32(rel), flow
