@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Rendered rays/s of the CoPoNeRF render path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): one RealEstate10K-shape 256x256 stereo pair, all 65 536 target rays,
+S = 64 samples per epipolar line; at N > 1 one such pair per rank (configs[2]: pairs shard across ranks,
+one NCCL gather of the final pixels to rank 0, weak scaling). A "step" renders the whole image(s):
+per-pair setup + every ray through CoPoNeRF.forward(z=..., rel_pose=..., flow=...). The image encoder /
+cost aggregation that produce z are not part of the timed path yet (scope).
+
+`value`  : inputs resident in HBM, timed on the device with CUDA events, L2 flushed between steps.
+`e2e`    : the same through the drop-in forward() with HOST inputs: pinned host -> device copies of the
+           feature maps / poses / uv and the device -> host read of rgb (+ the reference's pixel_val.cpu())
+           are inside the timed region.
+`--impl reference`: the CPU oracle port of the reference path (oracle/render_oracle.py, torch CPU, all host
+           threads) on a bounded sample of the same workload; rank 0 only.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H = W = 256
+S = 64
+N_RAYS = H * W
+FLOP_PER_RAY = 667.9e6                    # reference formulation, S = 64
+DOMINANT_MACS_PER_ROW = 835 * 832         # query_encode_latent, one encoder row
+CPU_SAMPLE_RAYS = 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chunk-rays", type=int, default=2048)
+    ap.add_argument("--simt", action="store_true", help="fp32 CUDA-core GEMMs only (cross-check path)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(seed):
+    from coponerf_b200 import synth
+    inp = synth.make_input(H, W, None, seed=seed, pose_set="frontal")
+    z, rel_pose, flow = synth.make_features(H, W, seed=seed)
+    return inp, z, rel_pose, flow
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "measured (bf16 dense, sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md sustained)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.path = f"/tmp/cpn_clocks_{os.getpid()}.csv"
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, reasons = [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                out["sm_max_mhz"] = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def run_reference(args, rank):
+    """The reference arm: CPU oracle port on a bounded sample of the workload, all host threads."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import render_oracle
+    from coponerf_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inp, z, rel_pose, flow = workload(10)
+    sd = synth.render_state_dict(0)
+    sub = {"context": inp["context"], "query": dict(inp["query"])}
+    idx = torch.arange(0, N_RAYS, N_RAYS // CPU_SAMPLE_RAYS)[:CPU_SAMPLE_RAYS]
+    sub["query"]["uv"] = inp["query"]["uv"][:, :, idx].contiguous()
+    sub["query"]["rgb"] = inp["query"]["rgb"][:, :, idx].contiguous()
+
+    def step():
+        return render_oracle.render_forward(sd, sub, z, rel_pose, flow, H, W, S, True, chunk=512)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = CPU_SAMPLE_RAYS * args.steps / dt
+    sample = f"{CPU_SAMPLE_RAYS} evenly strided rays of the 65536-ray image per step (chunks of 512), torch CPU fp32"
+    line = {
+        "impl": "reference", "metric": "rendered rays/sec at 256x256 stereo", "value": v, "unit": "rays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "256x256 stereo pair, 65536 rays, S=64 (render half: forward with z given)",
+                   "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from coponerf_b200 import _lib, synth
+    from coponerf_b200.model import CoPoNeRF
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    model = CoPoNeRF(n_view=2, npoints=S, chunk_rays=args.chunk_rays)
+    model.load_state_dict(synth.render_state_dict(0), strict=False)
+    model = model.to(dev).eval()
+    model.H, model.W = H, W
+    eng = model.engine()
+    eng.flags = _lib.FLAG_SIMT_ONLY if args.simt else 0
+    lib = _lib.load()
+
+    # ---- this rank's pair: host (pinned) and device copies
+    inp_h, z_h, rel_h, flow_h = workload(10 + rank)
+    pin = lambda t: t.contiguous().pin_memory()
+    host = {
+        "context": {k: pin(v) for k, v in inp_h["context"].items()},
+        "query": {k: pin(v) for k, v in inp_h["query"].items() if k != "rgb"},
+    }
+    z_host = [pin(t) for t in z_h]
+    flow_host = tuple(pin(t) for t in flow_h)
+    rel_host = pin(rel_h)
+    todev = lambda t: t.to(dev, non_blocking=True)
+    inp_d = {"context": {k: todev(v) for k, v in host["context"].items()},
+             "query": {k: todev(v) for k, v in host["query"].items()}}
+    z_d = [todev(t) for t in z_host]
+    flow_d = tuple(todev(t) for t in flow_host)
+    rel_d = todev(rel_host)
+    uv_d = inp_d["query"]["uv"].reshape(1, N_RAYS, 2)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    gather_buf = [torch.empty((1, 1, N_RAYS, 3), device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    state = {}
+
+    def device_step():
+        # feature re-layout included every step (the cache would hide it): new pair state each image
+        eng._feat_cache.clear()
+        st = eng.prepare_pair(inp_d, z_d, rel_d, flow_d, H, W, True)
+        o = eng.render_rays(st, uv_d, S)
+        if world > 1:
+            dist.gather(o["rgb"], gather_buf, dst=0)
+        state["out"] = o
+        return o
+
+    rgb_pinned = torch.empty((1, 1, N_RAYS, 3)).pin_memory()
+
+    def e2e_step():
+        eng._feat_cache.clear()
+        inp = {"context": {k: todev(v) for k, v in host["context"].items()},
+               "query": {k: todev(v) for k, v in host["query"].items()}}
+        z = [todev(t) for t in z_host]
+        fl = tuple(todev(t) for t in flow_host)
+        out = model(inp, z=z, rel_pose=todev(rel_host), val=True, flow=fl)
+        if world > 1:
+            dist.gather(out["rgb"], gather_buf, dst=0)
+        rgb_pinned.copy_(out["rgb"], non_blocking=True)
+        return out
+
+    h2d = sum(t.numel() * t.element_size() for d in host.values() for t in d.values())
+    h2d += sum(t.numel() * t.element_size() for t in z_host) + sum(t.numel() * t.element_size() for t in flow_host)
+    h2d += rel_host.numel() * 4
+    d2h = N_RAYS * 3 * 4 + 2 * N_RAYS * S * 2 * 4    # rgb + the reference's out['pixel_val'].cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        barrier()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    chunks = (N_RAYS + args.chunk_rays - 1) // args.chunk_rays
+    # warm up first so the profiling session only sees the timed launches
+    for _ in range(args.warmup):
+        device_step()
+    torch.cuda.synchronize()
+    _lib.check(lib.cpn_prof_begin(chunks * args.steps), "cpn_prof_begin")
+    ms_dev = timed(device_step, args.steps, 0)
+    dom_ms, dom_n = ctypes.c_float(0), ctypes.c_int(0)
+    _lib.check(lib.cpn_prof_end(ctypes.byref(dom_ms), ctypes.byref(dom_n)), "cpn_prof_end")
+    launches = args.steps * (eng.last_launch_count + 6)   # + 4 feature re-layouts, pair_setup, pair_prologue
+    ms_e2e = timed(e2e_step, args.steps, 2)
+    clk = clocks.stop() if clocks else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_rays = world * N_RAYS * args.steps
+    value = total_rays / (ms_dev * 1e-3)
+    e2e_value = total_rays / (ms_e2e * 1e-3)
+    peak, peak_src = peaks()
+    rows_per_launch = 2 * 2 * S * min(args.chunk_rays, N_RAYS)       # encoder rows: 2 branches x 2 views x S per ray
+    flop_per_launch = 2.0 * DOMINANT_MACS_PER_ROW * rows_per_launch
+    achieved = flop_per_launch * dom_n.value / (dom_ms.value * 1e-3) / 1e12 if dom_ms.value > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("simt" if args.simt else "tc")
+    line = {
+        "metric": "rendered rays/sec at 256x256 stereo", "value": value, "unit": "rays/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "256x256 stereo pair, 65536 rays, S=64 (render half: forward with z given)",
+                   "pairs_per_gpu": 1, "chunk_rays": args.chunk_rays, "l2": "flushed between timed steps (256 MB write)",
+                   "gemm_path": "simt-fp32" if args.simt else "tcgen05 split-fp16 (3 MMA) + simt-fp32 small layers",
+                   "parallelism": f"pairs sharded over {world} GPU(s), one NCCL gather of rgb" if world > 1 else "1 GPU"},
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "query_encode_latent GEMM (835->832, ReLU)", "achieved": achieved,
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "launches": dom_n.value,
+                     "avg_launch_ms": dom_ms.value / max(dom_n.value, 1),
+                     "share_of_step": dom_ms.value / ms_dev if world == 1 else None,
+                     "flop_per_launch": flop_per_launch,
+                     "whole_path_tflops": value * FLOP_PER_RAY / 1e12 / world},
+        "clocks": clk,
+    }
+
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import render_oracle
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        idx = torch.arange(0, N_RAYS, N_RAYS // CPU_SAMPLE_RAYS)[:CPU_SAMPLE_RAYS]
+        sub = {"context": inp_h["context"], "query": dict(inp_h["query"])}
+        sub["query"]["uv"] = inp_h["query"]["uv"][:, :, idx].contiguous()
+        sub["query"]["rgb"] = inp_h["query"]["rgb"][:, :, idx].contiguous()
+        sd = synth.render_state_dict(0)
+        run = lambda: render_oracle.render_forward(sd, sub, z_h, rel_h, flow_h, H, W, S, True, chunk=512)
+        run()
+        t0 = time.perf_counter()
+        ref = run()
+        t1 = time.perf_counter()
+        ref = run()
+        t2 = time.perf_counter()
+        dt = min(t1 - t0, t2 - t1)
+        sample = f"{CPU_SAMPLE_RAYS} evenly strided rays of the same image (chunks of 512), best of 2"
+        line["cpu_baseline"] = {"value": CPU_SAMPLE_RAYS / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+                                "sample": sample}
+        got = state["out"]["rgb"][0, 0].cpu()[idx]
+        want = ref["rgb"][0, 0]
+        err = float((got - want).abs().max() / want.abs().max())
+        mse = float(((got.clamp(-1, 1) - want.clamp(-1, 1)) ** 2).mean())
+        import math
+        line["parity"] = {"rgb_max_rel_err_vs_oracle": err,
+                          "psnr_vs_oracle_db": (-10 * math.log10(mse)) if mse > 0 else None,
+                          "rays_checked": CPU_SAMPLE_RAYS}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,103 @@
+"""ctypes binding of libcoponerf_b200.so (the C-ABI declared in include/coponerf_b200.h).
+
+There is no fallback: if the library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcoponerf_b200.so")
+
+N_LEVELS = 4
+FEAT_DIM = 832
+LATENT = 416
+HIDDEN = 128
+PAIR_CONSTS_FLOATS = 320
+FLAG_SIMT_ONLY = 1
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+
+
+class RenderArgs(ctypes.Structure):
+    """cpn_render_args (include/coponerf_b200.h)."""
+    _fields_ = [
+        ("B", ctypes.c_int32), ("N", ctypes.c_int32), ("S", ctypes.c_int32),
+        ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("flow_h", ctypes.c_int32),
+        ("chunk_rays", ctypes.c_int32), ("flags", ctypes.c_int32),
+        ("feat", ctypes.c_void_p * N_LEVELS),
+        ("feat_h", ctypes.c_int32 * N_LEVELS), ("feat_w", ctypes.c_int32 * N_LEVELS),
+        ("feat_c", ctypes.c_int32 * N_LEVELS),
+        ("pair_consts", ctypes.c_void_p), ("uv", ctypes.c_void_p), ("interval", ctypes.c_void_p),
+        ("weights", ctypes.c_void_p), ("up_flow2", ctypes.c_void_p), ("mask_padded2", ctypes.c_void_p),
+        ("rgb", ctypes.c_void_p), ("valid_mask", ctypes.c_void_p), ("depth_ray", ctypes.c_void_p),
+        ("at_wt", ctypes.c_void_p), ("at_wt_max", ctypes.c_void_p), ("pixel_val", ctypes.c_void_p),
+        ("coords", ctypes.c_void_p), ("T_to_C1_pts", ctypes.c_void_p), ("T_to_C2_pts", ctypes.c_void_p),
+        ("C2_pts_to_C1", ctypes.c_void_p), ("mask_c2", ctypes.c_void_p),
+        ("matchability_cycle_mask", ctypes.c_void_p),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+    ]
+
+
+# symbol -> (restype, argtypes); every entry point include/coponerf_b200.h declares
+SIGNATURES = {
+    "cpn_version": (ctypes.c_int, []),
+    "cpn_last_error": (ctypes.c_char_p, []),
+    "cpn_sizeof_render_args": (ctypes.c_size_t, []),
+    "cpn_prof_begin": (ctypes.c_int, [ctypes.c_int]),
+    "cpn_prof_end": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
+    "cpn_packed_weights_bytes": (ctypes.c_size_t, []),
+    "cpn_raw_weights_floats": (ctypes.c_size_t, []),
+    "cpn_n_weight_tensors": (ctypes.c_int, []),
+    "cpn_weight_name": (ctypes.c_char_p, [ctypes.c_int]),
+    "cpn_weight_numel": (ctypes.c_size_t, [ctypes.c_int]),
+    "cpn_pack_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "cpn_pack_features": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_void_p]),
+    "cpn_pair_setup": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_void_p]),
+    "cpn_pair_prologue": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 +
+                          [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "cpn_render_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "cpn_render_rays": (ctypes.c_int, [ctypes.POINTER(RenderArgs), ctypes.c_void_p]),
+    "cpn_render_launch_count": (ctypes.c_int, [ctypes.POINTER(RenderArgs)]),
+    "cpn_gemm_simt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p]),
+    "cpn_gemm_tc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+class CpnError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CpnError(f"{LIB_PATH} is missing: run `python -m coponerf_b200.build` (or __graft_entry__.build()); "
+                       "there is no CPU or PyTorch fallback for the render path")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.cpn_sizeof_render_args() != ctypes.sizeof(RenderArgs):
+        raise CpnError("cpn_render_args layout mismatch between _lib.py and the built library: rebuild")
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().cpn_last_error()
+        raise CpnError(f"{what} failed with status {status}: {msg.decode() if msg else ''}")
+
+
+def weight_names():
+    lib = load()
+    return [lib.cpn_weight_name(i).decode() for i in range(lib.cpn_n_weight_tensors())]

@@ -1,0 +1,107 @@
+// Internal declarations shared by the coponerf_b200 kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/coponerf_b200.h"
+
+#define CPN_KA 848  // 835 encoder inputs padded to a multiple of 16 (zero columns)
+
+// ---- packed fp32 weight blob (offsets in floats) -------------------------------------------
+// Every matrix is stored transposed, [K][N], so consecutive threads read consecutive outputs.
+namespace pw {
+constexpr size_t W1T = 0;                        // [848][832]  query_encode_latent (rows >= 835 are zero)
+constexpr size_t B1 = W1T + 848 * 832;           // [832]
+constexpr size_t W2T = B1 + 832;                 // [832][416]  query_encode_latent_2
+constexpr size_t B2 = W2T + 832 * 416;           // [416]
+constexpr size_t WVT = B2 + 416;                 // [832][416]  latent_value
+constexpr size_t BV = WVT + 832 * 416;           // [416]
+constexpr size_t WKT = BV + 416;                 // [832][128]  key_map
+constexpr size_t BK = WKT + 832 * 128;           // [128]
+constexpr size_t WK2T = BK + 128;                // [128][128]  key_map_2
+constexpr size_t BK2 = WK2T + 128 * 128;
+constexpr size_t WQT = BK2 + 128;                // [16][128]   query_embed
+constexpr size_t BQ = WQT + 16 * 128;
+constexpr size_t WQ2T = BQ + 128;                // [128][128]  query_embed_2
+constexpr size_t BQ2 = WQ2T + 128 * 128;
+constexpr size_t WQRA_T = BQ2 + 128;             // [128][128]  query_repeat_embed, z_embed input channels
+constexpr size_t WQRB_T = WQRA_T + 128 * 128;    // [16][128]   query_repeat_embed, local_coords input channels
+constexpr size_t BQR = WQRB_T + 16 * 128;
+constexpr size_t WQR2T = BQR + 128;              // [128][128]  query_repeat_embed_2
+constexpr size_t BQR2 = WQR2T + 128 * 128;
+constexpr size_t WET = BQR2 + 128;               // [416][128]  encode_latent
+constexpr size_t BE = WET + 416 * 128;
+constexpr size_t PHI_INT = BE + 128;             // [18][128]   phi.lin_in
+constexpr size_t PHI_BIN = PHI_INT + 18 * 128;
+constexpr size_t PHI_ZT = PHI_BIN + 128;         // 3 x [832][128] phi.lin_z.i
+constexpr size_t PHI_BZ = PHI_ZT + 3 * 832 * 128;  // 3 x [128]
+constexpr size_t PHI_F0T = PHI_BZ + 3 * 128;     // 3 x [128][128] phi.blocks.i.fc_0
+constexpr size_t PHI_B0 = PHI_F0T + 3 * 128 * 128;
+constexpr size_t PHI_F1T = PHI_B0 + 3 * 128;     // 3 x [128][128] phi.blocks.i.fc_1
+constexpr size_t PHI_B1 = PHI_F1T + 3 * 128 * 128;
+constexpr size_t PHI_OUT = PHI_B1 + 3 * 128;     // [3][128]    phi.lin_out (not transposed)
+constexpr size_t PHI_BOUT = PHI_OUT + 3 * 128;   // [3] (+1 pad)
+constexpr size_t FP32_END = PHI_BOUT + 4;
+}  // namespace pw
+
+// ---- per-pair constants (floats), written by cpn_pair_setup ---------------------------------
+namespace pc {
+constexpr int Q_C2W = 0;        // [2][16] query cam2world expressed in each context frame
+constexpr int KQ = 32;          // [16]    query intrinsics
+constexpr int KC = 48;          // [2][16] context intrinsics
+constexpr int KN = 80;          // [2][9]  context intrinsics, rows 0-1 divided by H
+constexpr int IDEN = 98;        // [2][16] inv(c2w_v) @ c2w_v
+constexpr int T_OWN = 130;      // [2][16] sample point -> its own view's frame
+constexpr int T_OTHER = 162;    // [2][16] sample point -> the other view's frame
+constexpr int INV_QC2W = 194;   // [16]    inverse(query cam2world)
+constexpr int INV_KQ3 = 210;    // [9]     inverse(query K[:3,:3])
+constexpr int REL_FLIP = 219;   // [16] outputs rel_pose_flip, gt_rel_pose, gt_rel_pose_flip
+constexpr int GT_REL = 235;
+constexpr int GT_REL_FLIP = 251;
+constexpr int END = 267;
+static_assert(END <= CPN_PAIR_CONSTS_FLOATS, "pair consts overflow");
+}  // namespace pc
+
+// ---- per-row scratch written by the sample kernel ---------------------------------------------
+// row = ((b * N_chunk + n) * 2 + v) * S + s : the 2S rows of a ray are contiguous.
+#define CPN_ROWAUX 8  // grid_prim.xy, grid_sec.xy, clamp(pt).xyz, pad
+
+void cpn_set_error(const char* fmt, ...);
+#define CPN_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      cpn_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CPN_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+#define CPN_CHECK_LAUNCH(name)                                                            \
+  do {                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      cpn_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));            \
+      return CPN_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+// launchers implemented across the .cu files (all asynchronous on `st`)
+int launch_ray_setup(const cpn_render_args& a, int ray0, int nr, float* seg, cudaStream_t st);
+int launch_sample(const cpn_render_args& a, int ray0, int nr, const float* seg, float* rowaux, float* local16,
+                  float* A, cudaStream_t st);
+int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowaux, float* A, cudaStream_t st);
+int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias, const float* rowbias,
+                     int rows_per_bias, float* C, int ldc, int M, int N, int K, int relu, cudaStream_t st);
+int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, const float* qemb, const float* value,
+                 const float* rowaux, float* r1, float* wp, cudaStream_t st);
+int launch_attn2(const cpn_render_args& a, int nr, const float* q2, const float* qemb, const float* value,
+                 const float* r1, float* z, cudaStream_t st);
+int launch_phi(const cpn_render_args& a, int ray0, int nr, const float* z, const float* seg, cudaStream_t st);
+int launch_ray_epilogue(const cpn_render_args& a, int ray0, int nr, const float* wp, cudaStream_t st);
+
+// tensor-core path (gemm_tc.cu)
+size_t cpn_packed_fp32_floats();
+size_t cpn_tc_weights_bytes();
+int cpn_pack_tc_weights(const float* raw, void* dst, cudaStream_t st);
+// layer: 0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value, 3 key_map
+int launch_gemm_tc(const void* packed, int layer, const float* A, int lda, float* C, int ldc, int M, int relu,
+                   cudaStream_t st);

@@ -1,0 +1,114 @@
+// Epipolar-line feature gather: F.grid_sample(bilinear, align_corners=False) of the four
+// channels-last feature maps, primary ('border' padding, models/CoPoNeRF.py:312) and secondary
+// ('zeros' padding at the reprojected coordinates, models/CoPoNeRF.py:370).
+#include "cpn_common.cuh"
+
+namespace {
+
+struct Taps {
+  int off[4];   // element offset of each tap's channel vector inside one image of the level (or -1)
+  float w[4];   // bilinear weights in PyTorch's nw, ne, sw, se order
+};
+
+// grid_sampler_compute_source_index + bilinear weights (ATen/native/GridSampler.h)
+__device__ __forceinline__ Taps make_taps(float gx, float gy, int h, int w, int C, bool border) {
+  float ix = ((gx + 1.f) * (float)w - 1.f) / 2.f;
+  float iy = ((gy + 1.f) * (float)h - 1.f) / 2.f;
+  if (border) {
+    ix = fminf((float)(w - 1), fmaxf(ix, 0.f));
+    iy = fminf((float)(h - 1), fmaxf(iy, 0.f));
+  }
+  float x0 = floorf(ix), y0 = floorf(iy);
+  float x1 = x0 + 1.f, y1 = y0 + 1.f;
+  Taps t;
+  t.w[0] = (x1 - ix) * (y1 - iy);
+  t.w[1] = (ix - x0) * (y1 - iy);
+  t.w[2] = (x1 - ix) * (iy - y0);
+  t.w[3] = (ix - x0) * (iy - y0);
+  float xs[4] = {x0, x1, x0, x1}, ys[4] = {y0, y0, y1, y1};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    bool in = xs[k] >= 0.f && xs[k] <= (float)(w - 1) && ys[k] >= 0.f && ys[k] <= (float)(h - 1);
+    t.off[k] = in ? ((int)ys[k] * w + (int)xs[k]) * C : -1;
+  }
+  return t;
+}
+
+// One warp per (row, branch). Row = ((b*nr + n)*2 + v)*S + s; branch 0 reads view v at the sample
+// position, branch 1 reads view 1-v at the reprojected position.
+__global__ void __launch_bounds__(256) gather_kernel(cpn_render_args a, int nr, const float* __restrict__ rowaux,
+                                                     float* __restrict__ A) {
+  long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  long long nrows = (long long)a.B * nr * 2 * a.S;
+  if (wid >= nrows * 2) return;
+  long long row = wid >> 1;
+  int branch = (int)(wid & 1);
+  int v = (int)((row / a.S) & 1);
+  int b = (int)(row / ((long long)2 * a.S * nr));
+  int img = b * 2 + (branch ? 1 - v : v);
+  const float* ra = rowaux + (size_t)row * CPN_ROWAUX;
+  float gx = ra[branch * 2 + 0], gy = ra[branch * 2 + 1];
+  float* out = A + (size_t)wid * CPN_KA;
+  int col = 0;
+#pragma unroll
+  for (int l = 0; l < CPN_N_LEVELS; ++l) {
+    int h = a.feat_h[l], w = a.feat_w[l], C = a.feat_c[l];
+    Taps t = make_taps(gx, gy, h, w, C, branch == 0);
+    const float* base = a.feat[l] + (size_t)img * h * w * C;
+    for (int c = lane * 4; c < C; c += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (t.off[k] >= 0) {
+          float4 f = __ldg(reinterpret_cast<const float4*>(base + t.off[k] + c));
+          acc.x += f.x * t.w[k];
+          acc.y += f.y * t.w[k];
+          acc.z += f.z * t.w[k];
+          acc.w += f.w * t.w[k];
+        }
+      }
+      *reinterpret_cast<float4*>(out + col + c) = acc;
+    }
+    col += C;
+  }
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+  __shared__ float tile[32][33];
+  int img = blockIdx.z;
+  int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* s = src + (size_t)img * C * HW;
+  float* d = dst + (size_t)img * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) tile[i][threadIdx.x] = s[(size_t)c * HW + p];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int p = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && p < HW) d[(size_t)p * C + c] = tile[threadIdx.x][i];
+  }
+}
+
+}  // namespace
+
+int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowaux, float* A, cudaStream_t st) {
+  (void)ray0;
+  long long warps = (long long)a.B * nr * 2 * a.S * 2;
+  long long blocks = (warps * 32 + 255) / 256;
+  gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, nr, rowaux, A);
+  CPN_CHECK_LAUNCH("gather_kernel");
+  return CPN_OK;
+}
+
+extern "C" int cpn_pack_features(const float* nchw, float* nhwc, int n_img, int C, int h, int w, void* stream) {
+  if (!nchw || !nhwc || n_img <= 0 || C <= 0 || h <= 0 || w <= 0 || (C % 4) != 0) {
+    cpn_set_error("cpn_pack_features: bad argument (C must be a multiple of 4)");
+    return CPN_ERR_ARG;
+  }
+  dim3 grid((h * w + 31) / 32, (C + 31) / 32, n_img), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(nchw, nhwc, C, h * w);
+  CPN_CHECK_LAUNCH("nchw_to_nhwc_kernel");
+  return CPN_OK;
+}

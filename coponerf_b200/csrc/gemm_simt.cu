@@ -1,0 +1,140 @@
+// fp32 CUDA-core GEMM for the 1x1-conv layers whose K or N is too small for the tensor-core path
+// (query_embed 16->128, the 128->128 second layers, encode_latent) and as the bring-up / cross-check
+// path for the large layers:  C[M,N] = act(A[M,K] * Wt[K,N] + bias[N] + rowbias[m / rows_per_bias, N]).
+//
+// Replaces the nn.Conv2d(kernel 1) calls of models/CoPoNeRF.py:387-408,446,467-473.
+// The k-loop order is fixed and independent of the tile a row lands in, so a ray's result does not
+// depend on the chunk or rank that renders it.
+#include "cpn_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, NT = 256;
+
+__global__ void __launch_bounds__(NT, 2)
+gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Wt, const float* __restrict__ bias,
+                 const float* __restrict__ rowbias, int rows_per_bias, float* __restrict__ C, int ldc, int M, int N,
+                 int K, int relu) {
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // A loader: thread -> (row, 8 consecutive k)
+  const int a_row = tid & (BM - 1), a_k = (tid >> 7) * 8;
+  const bool a_ok = (m0 + a_row) < M;
+  const float* a_ptr = A + (size_t)(m0 + a_row) * lda + a_k;
+  // B loader: thread -> (k, float4 column), two k rows
+  const int b_k = tid >> 5, b_n = (tid & 31) * 4;
+  const bool b_ok = (n0 + b_n) < N;
+  const float* b_ptr = Wt + (size_t)b_k * N + n0 + b_n;
+
+  float4 ra[2], rb[2];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      int k = k0 + a_k + j * 4;
+      ra[j] = (a_ok && k < K) ? *reinterpret_cast<const float4*>(a_ptr + k0 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      int kb = k0 + b_k + j * 8;
+      rb[j] = (b_ok && kb < K) ? *reinterpret_cast<const float4*>(b_ptr + (size_t)(k0 + j * 8) * N)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      As[buf][a_k + j * 4 + 0][a_row] = ra[j].x;
+      As[buf][a_k + j * 4 + 1][a_row] = ra[j].y;
+      As[buf][a_k + j * 4 + 2][a_row] = ra[j].z;
+      As[buf][a_k + j * 4 + 3][a_row] = ra[j].w;
+      *reinterpret_cast<float4*>(&Bs[buf][b_k + j * 8][b_n]) = rb[j];
+    }
+  };
+
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each an 8 x 8 micro-tile split in 4 + 4
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    const bool more = (k0 + BK) < K;
+    if (more) load_tiles(k0 + BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+    const float* rbp = rowbias ? rowbias + (size_t)(m / rows_per_bias) * N : nullptr;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int n = n0 + h * 64 + tx * 4;
+      if (n >= N) continue;
+      float4 v = make_float4(acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]);
+      if (bias) {
+        float4 bb = *reinterpret_cast<const float4*>(bias + n);
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+      }
+      if (rbp) {
+        float4 bb = *reinterpret_cast<const float4*>(rbp + n);
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+      }
+      if (relu) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      }
+      *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) = v;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias, const float* rowbias,
+                     int rows_per_bias, float* C, int ldc, int M, int N, int K, int relu, cudaStream_t st) {
+  if (M <= 0) return CPN_OK;
+  if ((K & 3) || (N & 3) || (lda & 3) || (ldc & 3)) {
+    cpn_set_error("gemm_simt: K, N, lda and ldc must be multiples of 4 (K=%d N=%d lda=%d ldc=%d)", K, N, lda, ldc);
+    return CPN_ERR_ARG;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  if (grid.y > 65535) {
+    cpn_set_error("gemm_simt: M=%d too large for one launch", M);
+    return CPN_ERR_ARG;
+  }
+  gemm_simt_kernel<<<grid, NT, 0, st>>>(A, lda, wt, bias, rowbias, rows_per_bias > 0 ? rows_per_bias : 1, C, ldc, M, N,
+                                        K, relu);
+  CPN_CHECK_LAUNCH("gemm_simt_kernel");
+  return CPN_OK;
+}
+
+extern "C" int cpn_gemm_simt(const float* A, int lda, const float* wt, const float* bias, float* C, int ldc, int M,
+                             int N, int K, int relu, void* stream) {
+  if (!A || !wt || !C) {
+    cpn_set_error("cpn_gemm_simt: null pointer");
+    return CPN_ERR_ARG;
+  }
+  return launch_gemm_simt(A, lda, wt, bias, nullptr, 1, C, ldc, M, N, K, relu, (cudaStream_t)stream);
+}

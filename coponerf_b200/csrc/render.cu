@@ -1,0 +1,221 @@
+// cpn_render_rays: the per-ray stage of CoPoNeRF.forward() (models/CoPoNeRF.py:246-566) as one
+// asynchronous sequence of kernels per chunk of rays. Also the library's error string and version.
+#include <stdarg.h>
+#include <string.h>
+#include "cpn_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void cpn_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* cpn_last_error(void) { return g_err; }
+extern "C" int cpn_version(void) { return 100; }
+extern "C" size_t cpn_sizeof_render_args(void) { return sizeof(cpn_render_args); }
+
+// ---- optional device timing of the dominant kernel (bench.py's roofline) -------------------
+// Off unless cpn_prof_begin() was called; events are recorded on the caller's stream around every
+// launch of the query_encode_latent GEMM. Not thread-safe: one profiling session per process.
+static cudaEvent_t* g_prof_ev = nullptr;
+static int g_prof_cap = 0, g_prof_n = 0;
+
+extern "C" int cpn_prof_begin(int max_launches) {
+  if (g_prof_ev || max_launches <= 0) {
+    cpn_set_error("cpn_prof_begin: session already open or bad capacity");
+    return CPN_ERR_ARG;
+  }
+  g_prof_ev = new cudaEvent_t[2 * (size_t)max_launches];
+  for (int i = 0; i < 2 * max_launches; ++i) CPN_CHECK_CUDA(cudaEventCreate(&g_prof_ev[i]));
+  g_prof_cap = max_launches;
+  g_prof_n = 0;
+  return CPN_OK;
+}
+
+// Waits for the recorded events, returns the summed duration and the number of launches, closes the session.
+extern "C" int cpn_prof_end(float* total_ms, int* launches) {
+  if (!g_prof_ev) {
+    cpn_set_error("cpn_prof_end: no session");
+    return CPN_ERR_ARG;
+  }
+  float tot = 0.f;
+  for (int i = 0; i < g_prof_n; ++i) {
+    float ms = 0.f;
+    CPN_CHECK_CUDA(cudaEventSynchronize(g_prof_ev[2 * i + 1]));
+    CPN_CHECK_CUDA(cudaEventElapsedTime(&ms, g_prof_ev[2 * i], g_prof_ev[2 * i + 1]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = g_prof_n;
+  for (int i = 0; i < 2 * g_prof_cap; ++i) cudaEventDestroy(g_prof_ev[i]);
+  delete[] g_prof_ev;
+  g_prof_ev = nullptr;
+  g_prof_cap = g_prof_n = 0;
+  return CPN_OK;
+}
+
+namespace {
+
+struct ProfScope {  // records an event pair around the enclosed launches when a session is open
+  cudaStream_t st;
+  bool on;
+  explicit ProfScope(cudaStream_t s) : st(s), on(g_prof_ev && g_prof_n < g_prof_cap) {
+    if (on) cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], st);
+      ++g_prof_n;
+    }
+  }
+};
+
+// Workspace carve-up for one chunk of `nr` rays of each of B pairs (R = B * nr * 2 * S sample rows).
+struct Workspace {
+  float *seg, *rowaux, *local16, *A, *H1, *E, *V, *K1, *Kk, *Q1, *Qe, *r1, *wp, *zemb, *rbias, *z;
+  size_t bytes;
+};
+
+Workspace carve(void* base, int B, int nr, int S) {
+  Workspace w;
+  size_t rays = (size_t)B * nr, R = rays * 2 * S;
+  size_t off = 0;
+  auto take = [&](size_t floats) {
+    float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+    off += (floats * sizeof(float) + 255) / 256 * 256;
+    return p;
+  };
+  w.seg = take(rays * 2 * 6);
+  w.rowaux = take(R * CPN_ROWAUX);
+  w.local16 = take(R * 16);
+  w.A = take(R * 2 * CPN_KA);
+  w.H1 = take(R * 2 * CPN_FEAT_DIM);
+  w.E = take(R * CPN_FEAT_DIM);
+  w.V = take(R * CPN_LATENT);
+  w.K1 = take(R * CPN_HIDDEN);
+  w.Kk = take(R * CPN_HIDDEN);
+  w.Q1 = take(R * CPN_HIDDEN);
+  w.Qe = take(R * CPN_HIDDEN);
+  w.r1 = take(rays * CPN_LATENT);
+  w.wp = take(rays * 4);
+  w.zemb = take(rays * CPN_HIDDEN);
+  w.rbias = take(rays * CPN_HIDDEN);
+  w.z = take(rays * CPN_LATENT);
+  w.bytes = off;
+  return w;
+}
+
+int check_args(const cpn_render_args* a) {
+  if (!a) {
+    cpn_set_error("cpn_render_rays: null args");
+    return CPN_ERR_ARG;
+  }
+  if (a->B <= 0 || a->N < 0 || a->H <= 0 || a->W <= 0 || a->chunk_rays <= 0 || a->flow_h <= 0) {
+    cpn_set_error("cpn_render_rays: bad sizes B=%d N=%d H=%d W=%d chunk_rays=%d flow_h=%d", a->B, a->N, a->H, a->W,
+                  a->chunk_rays, a->flow_h);
+    return CPN_ERR_ARG;
+  }
+  if (a->S <= 0 || a->S > 128 || ((2 * a->S) % 32) != 0) {
+    cpn_set_error("cpn_render_rays: S=%d unsupported (2*S must be a multiple of 32, S <= 128)", a->S);
+    return CPN_ERR_ARG;
+  }
+  int csum = 0;
+  for (int l = 0; l < CPN_N_LEVELS; ++l) {
+    if (!a->feat[l] || a->feat_h[l] <= 0 || a->feat_w[l] <= 0 || a->feat_c[l] <= 0 || (a->feat_c[l] & 3)) {
+      cpn_set_error("cpn_render_rays: bad feature level %d", l);
+      return CPN_ERR_ARG;
+    }
+    csum += a->feat_c[l];
+  }
+  if (csum != CPN_FEAT_DIM) {
+    cpn_set_error("cpn_render_rays: feature channels sum to %d, expected %d", csum, CPN_FEAT_DIM);
+    return CPN_ERR_ARG;
+  }
+  const void* ptrs[] = {a->pair_consts, a->uv, a->interval, a->weights, a->up_flow2, a->mask_padded2, a->rgb,
+                        a->valid_mask, a->depth_ray, a->at_wt, a->at_wt_max, a->pixel_val, a->coords, a->T_to_C1_pts,
+                        a->T_to_C2_pts, a->C2_pts_to_C1, a->mask_c2, a->matchability_cycle_mask, a->workspace};
+  for (const void* p : ptrs)
+    if (!p) {
+      cpn_set_error("cpn_render_rays: null pointer in args");
+      return CPN_ERR_ARG;
+    }
+  return CPN_OK;
+}
+
+#define CPN_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != CPN_OK) return _s; \
+  } while (0)
+
+// Encoder GEMMs: tensor-core path when the packed blob carries the split-fp16 tiles and the
+// caller did not ask for the fp32 CUDA-core cross-check path (args.reserved bit 0).
+int dense(const cpn_render_args& a, int tc_layer, const float* A, int lda, size_t wt, size_t bias, float* C, int ldc,
+          int M, int N, int K, int relu, cudaStream_t st) {
+  const float* W = reinterpret_cast<const float*>(a.weights);
+  if (tc_layer >= 0 && !(a.flags & CPN_FLAG_SIMT_ONLY) && cpn_tc_weights_bytes() > 0) return launch_gemm_tc(a.weights, tc_layer, A, lda, C, ldc, M, relu, st);
+  return launch_gemm_simt(A, lda, W + wt, W + bias, nullptr, 1, C, ldc, M, N, K, relu, st);
+}
+
+}  // namespace
+
+extern "C" size_t cpn_render_workspace_bytes(int B, int chunk_rays, int S) {
+  if (B <= 0 || chunk_rays <= 0 || S <= 0) return 0;
+  return carve(nullptr, B, chunk_rays, S).bytes;
+}
+
+extern "C" int cpn_render_launch_count(const cpn_render_args* a) {
+  if (!a || a->chunk_rays <= 0) return 0;
+  int chunks = (a->N + a->chunk_rays - 1) / a->chunk_rays;
+  return chunks * 18;
+}
+
+extern "C" int cpn_render_rays(const cpn_render_args* args, void* stream) {
+  CPN_TRY(check_args(args));
+  const cpn_render_args& a = *args;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a.N == 0) return CPN_OK;
+  int chunk = a.chunk_rays < a.N ? a.chunk_rays : a.N;
+  Workspace w = carve(a.workspace, a.B, chunk, a.S);
+  if (w.bytes > a.workspace_bytes) {
+    cpn_set_error("cpn_render_rays: workspace of %zu bytes needed, %zu given", w.bytes, a.workspace_bytes);
+    return CPN_ERR_WORKSPACE;
+  }
+  const float* W = reinterpret_cast<const float*>(a.weights);
+  for (int ray0 = 0; ray0 < a.N; ray0 += chunk) {
+    int nr = (a.N - ray0) < chunk ? (a.N - ray0) : chunk;
+    int rays = a.B * nr;
+    int R = rays * 2 * a.S;
+    CPN_TRY(launch_ray_setup(a, ray0, nr, w.seg, st));
+    CPN_TRY(launch_sample(a, ray0, nr, w.seg, w.rowaux, w.local16, w.A, st));
+    CPN_TRY(launch_gather(a, ray0, nr, w.rowaux, w.A, st));
+    // per-sample encoder, CoPoNeRF.py:387-397: (835 -> 832 ReLU -> 416) for the primary and the secondary row
+    {
+      ProfScope prof(st);
+      CPN_TRY(dense(a, 0, w.A, CPN_KA, pw::W1T, pw::B1, w.H1, CPN_FEAT_DIM, 2 * R, CPN_FEAT_DIM, CPN_KA, 1, st));
+    }
+    CPN_TRY(dense(a, 1, w.H1, CPN_FEAT_DIM, pw::W2T, pw::B2, w.E, CPN_LATENT, 2 * R, CPN_LATENT, CPN_FEAT_DIM, 0, st));
+    // value and key, CoPoNeRF.py:404-408 (E is (R, 832): [enc(primary) | enc(secondary)])
+    CPN_TRY(dense(a, 2, w.E, CPN_FEAT_DIM, pw::WVT, pw::BV, w.V, CPN_LATENT, R, CPN_LATENT, CPN_FEAT_DIM, 0, st));
+    CPN_TRY(dense(a, 3, w.E, CPN_FEAT_DIM, pw::WKT, pw::BK, w.K1, CPN_HIDDEN, R, CPN_HIDDEN, CPN_FEAT_DIM, 1, st));
+    CPN_TRY(dense(a, -1, w.K1, CPN_HIDDEN, pw::WK2T, pw::BK2, w.Kk, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
+    // coordinate embedding, CoPoNeRF.py:446
+    CPN_TRY(dense(a, -1, w.local16, 16, pw::WQT, pw::BQ, w.Q1, CPN_HIDDEN, R, CPN_HIDDEN, 16, 1, st));
+    CPN_TRY(dense(a, -1, w.Q1, CPN_HIDDEN, pw::WQ2T, pw::BQ2, w.Qe, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
+    CPN_TRY(launch_attn1(a, ray0, nr, w.Kk, w.Qe, w.V, w.rowaux, w.r1, w.wp, st));
+    // round 2, CoPoNeRF.py:467-473: query_repeat_embed(cat(encode_latent(R1), local_coords)); the z_embed
+    // channels are the same for every sample of a ray, so they enter as a per-ray bias.
+    CPN_TRY(dense(a, -1, w.r1, CPN_LATENT, pw::WET, pw::BE, w.zemb, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_LATENT, 0, st));
+    CPN_TRY(dense(a, -1, w.zemb, CPN_HIDDEN, pw::WQRA_T, pw::BQR, w.rbias, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_HIDDEN, 0, st));
+    CPN_TRY(launch_gemm_simt(w.local16, 16, W + pw::WQRB_T, nullptr, w.rbias, 2 * a.S, w.K1, CPN_HIDDEN, R, CPN_HIDDEN,
+                             16, 1, st));
+    CPN_TRY(dense(a, -1, w.K1, CPN_HIDDEN, pw::WQR2T, pw::BQR2, w.Kk, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
+    CPN_TRY(launch_attn2(a, nr, w.Kk, w.Qe, w.V, w.r1, w.z, st));
+    CPN_TRY(launch_phi(a, ray0, nr, w.z, w.seg, st));
+    CPN_TRY(launch_ray_epilogue(a, ray0, nr, w.wp, st));
+  }
+  return CPN_OK;
+}

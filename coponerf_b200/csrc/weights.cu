@@ -1,0 +1,114 @@
+// One-time repack of the render-path state_dict tensors into the kernel layouts (cpn_common.cuh, namespace pw).
+// Replaces the nn.Module parameter storage of models/CoPoNeRF.py:71-104 and models/lightfield.py:87-116.
+#include "cpn_common.cuh"
+
+namespace {
+
+struct WTensor {
+  const char* name;  // state_dict key
+  int out, in;       // weight (out, in[,1,1]); bias: (out, 1)
+};
+
+// Order of the raw blob handed to cpn_pack_weights.
+const WTensor kTensors[] = {
+    {"query_encode_latent.weight", 832, 835},   {"query_encode_latent.bias", 832, 1},
+    {"query_encode_latent_2.weight", 416, 832}, {"query_encode_latent_2.bias", 416, 1},
+    {"latent_value.weight", 416, 832},          {"latent_value.bias", 416, 1},
+    {"key_map.weight", 128, 832},               {"key_map.bias", 128, 1},
+    {"key_map_2.weight", 128, 128},             {"key_map_2.bias", 128, 1},
+    {"query_embed.weight", 128, 16},            {"query_embed.bias", 128, 1},
+    {"query_embed_2.weight", 128, 128},         {"query_embed_2.bias", 128, 1},
+    {"query_repeat_embed.weight", 128, 144},    {"query_repeat_embed.bias", 128, 1},
+    {"query_repeat_embed_2.weight", 128, 128},  {"query_repeat_embed_2.bias", 128, 1},
+    {"encode_latent.weight", 128, 416},         {"encode_latent.bias", 128, 1},
+    {"phi.lin_in.weight", 128, 18},             {"phi.lin_in.bias", 128, 1},
+    {"phi.lin_z.0.weight", 128, 832},           {"phi.lin_z.0.bias", 128, 1},
+    {"phi.lin_z.1.weight", 128, 832},           {"phi.lin_z.1.bias", 128, 1},
+    {"phi.lin_z.2.weight", 128, 832},           {"phi.lin_z.2.bias", 128, 1},
+    {"phi.blocks.0.fc_0.weight", 128, 128},     {"phi.blocks.0.fc_0.bias", 128, 1},
+    {"phi.blocks.0.fc_1.weight", 128, 128},     {"phi.blocks.0.fc_1.bias", 128, 1},
+    {"phi.blocks.1.fc_0.weight", 128, 128},     {"phi.blocks.1.fc_0.bias", 128, 1},
+    {"phi.blocks.1.fc_1.weight", 128, 128},     {"phi.blocks.1.fc_1.bias", 128, 1},
+    {"phi.blocks.2.fc_0.weight", 128, 128},     {"phi.blocks.2.fc_0.bias", 128, 1},
+    {"phi.blocks.2.fc_1.weight", 128, 128},     {"phi.blocks.2.fc_1.bias", 128, 1},
+    {"phi.lin_out.weight", 3, 128},             {"phi.lin_out.bias", 3, 1},
+};
+constexpr int kNumTensors = sizeof(kTensors) / sizeof(kTensors[0]);
+
+size_t tensor_offset(int i) {
+  size_t off = 0;
+  for (int j = 0; j < i; ++j) off += (size_t)kTensors[j].out * kTensors[j].in;
+  return off;
+}
+
+// dst[k * N + n] = (k < K) ? src[n * src_ld + col0 + k] : 0    for k in [0, Kpad), n in [0, N)
+__global__ void transpose_pack_kernel(const float* __restrict__ src, int src_ld, int col0, int K, int Kpad, int N,
+                                      float* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Kpad * N) return;
+  int k = i / N, n = i % N;
+  dst[i] = (k < K) ? src[(size_t)n * src_ld + col0 + k] : 0.f;
+}
+
+struct Job {
+  int tensor, col0, K, Kpad;  // K == 0: plain copy of the whole tensor
+  size_t dst;
+};
+
+}  // namespace
+
+extern "C" int cpn_n_weight_tensors(void) { return kNumTensors; }
+extern "C" const char* cpn_weight_name(int i) { return (i >= 0 && i < kNumTensors) ? kTensors[i].name : nullptr; }
+extern "C" size_t cpn_weight_numel(int i) {
+  return (i >= 0 && i < kNumTensors) ? (size_t)kTensors[i].out * kTensors[i].in : 0;
+}
+extern "C" size_t cpn_raw_weights_floats(void) { return tensor_offset(kNumTensors); }
+extern "C" size_t cpn_packed_weights_bytes(void) { return cpn_packed_fp32_floats() * sizeof(float) + cpn_tc_weights_bytes(); }
+
+size_t cpn_packed_fp32_floats() { return (pw::FP32_END + 63) / 64 * 64; }
+
+extern "C" int cpn_pack_weights(const float* src, void* dst_v, void* stream) {
+  if (!src || !dst_v) {
+    cpn_set_error("cpn_pack_weights: null pointer");
+    return CPN_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* dst = reinterpret_cast<float*>(dst_v);
+  const Job jobs[] = {
+      {0, 0, 835, CPN_KA, pw::W1T},   {1, 0, 0, 0, pw::B1},
+      {2, 0, 832, 832, pw::W2T},      {3, 0, 0, 0, pw::B2},
+      {4, 0, 832, 832, pw::WVT},      {5, 0, 0, 0, pw::BV},
+      {6, 0, 832, 832, pw::WKT},      {7, 0, 0, 0, pw::BK},
+      {8, 0, 128, 128, pw::WK2T},     {9, 0, 0, 0, pw::BK2},
+      {10, 0, 16, 16, pw::WQT},       {11, 0, 0, 0, pw::BQ},
+      {12, 0, 128, 128, pw::WQ2T},    {13, 0, 0, 0, pw::BQ2},
+      {14, 0, 128, 128, pw::WQRA_T},  {14, 128, 16, 16, pw::WQRB_T},
+      {15, 0, 0, 0, pw::BQR},
+      {16, 0, 128, 128, pw::WQR2T},   {17, 0, 0, 0, pw::BQR2},
+      {18, 0, 416, 416, pw::WET},     {19, 0, 0, 0, pw::BE},
+      {20, 0, 18, 18, pw::PHI_INT},   {21, 0, 0, 0, pw::PHI_BIN},
+      {22, 0, 832, 832, pw::PHI_ZT},  {23, 0, 0, 0, pw::PHI_BZ},
+      {24, 0, 832, 832, pw::PHI_ZT + 832 * 128},      {25, 0, 0, 0, pw::PHI_BZ + 128},
+      {26, 0, 832, 832, pw::PHI_ZT + 2 * 832 * 128},  {27, 0, 0, 0, pw::PHI_BZ + 256},
+      {28, 0, 128, 128, pw::PHI_F0T},                 {29, 0, 0, 0, pw::PHI_B0},
+      {30, 0, 128, 128, pw::PHI_F1T},                 {31, 0, 0, 0, pw::PHI_B1},
+      {32, 0, 128, 128, pw::PHI_F0T + 128 * 128},     {33, 0, 0, 0, pw::PHI_B0 + 128},
+      {34, 0, 128, 128, pw::PHI_F1T + 128 * 128},     {35, 0, 0, 0, pw::PHI_B1 + 128},
+      {36, 0, 128, 128, pw::PHI_F0T + 2 * 128 * 128}, {37, 0, 0, 0, pw::PHI_B0 + 256},
+      {38, 0, 128, 128, pw::PHI_F1T + 2 * 128 * 128}, {39, 0, 0, 0, pw::PHI_B1 + 256},
+      {40, 0, 0, 0, pw::PHI_OUT},                     {41, 0, 0, 0, pw::PHI_BOUT},
+  };
+  CPN_CHECK_CUDA(cudaMemsetAsync(dst, 0, cpn_packed_fp32_floats() * sizeof(float), st));
+  for (const Job& j : jobs) {
+    const WTensor& t = kTensors[j.tensor];
+    const float* s = src + tensor_offset(j.tensor);
+    if (j.K == 0) {
+      CPN_CHECK_CUDA(cudaMemcpyAsync(dst + j.dst, s, (size_t)t.out * t.in * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+      int total = j.Kpad * t.out;
+      transpose_pack_kernel<<<(total + 255) / 256, 256, 0, st>>>(s, t.in, j.col0, j.K, j.Kpad, t.out, dst + j.dst);
+      CPN_CHECK_LAUNCH("transpose_pack_kernel");
+    }
+  }
+  return cpn_pack_tc_weights(src, reinterpret_cast<char*>(dst_v) + cpn_packed_fp32_floats() * sizeof(float), st);
+}

@@ -1,0 +1,143 @@
+/*
+ * coponerf_b200 -- C-ABI of the B200-native CoPoNeRF render path.
+ *
+ * The reference (cvlab-kaist/CoPoNeRF) is pure Python over PyTorch and has no FFI of its
+ * own; the "interface each entry point replaces" is therefore the Python call site in
+ * models/CoPoNeRF.py that the host-side mirror (coponerf_b200/model.py) routes here.
+ * Citations are relative to the reference root.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a caller-owned, contiguous buffer (fp32 unless
+ *     the name says otherwise); the library allocates nothing and keeps no global state;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*): no host
+ *     sync, no host copies;
+ *   - return value: 0 on success, a negative cpn_status otherwise; cpn_last_error()
+ *     returns a per-thread message.
+ */
+#ifndef COPONERF_B200_H
+#define COPONERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  CPN_OK = 0,
+  CPN_ERR_ARG = -1,        /* bad shape / null pointer / unsupported size */
+  CPN_ERR_WORKSPACE = -2,  /* workspace too small */
+  CPN_ERR_CUDA = -3        /* a CUDA runtime call or launch failed */
+} cpn_status;
+
+#define CPN_N_LEVELS 4      /* feature maps per view: 3 refined ResNet levels + conv_map */
+#define CPN_FEAT_DIM 832    /* 256*3 + 64, models/CoPoNeRF.py:68 */
+#define CPN_LATENT 416      /* latent_dim // 2, models/CoPoNeRF.py:74 */
+#define CPN_HIDDEN 128      /* hidden_dim, models/CoPoNeRF.py:78 */
+#define CPN_PAIR_CONSTS_FLOATS 320
+#define CPN_FLAG_SIMT_ONLY 1  /* run the big 1x1 convs on the fp32 CUDA-core GEMM (cross-check path) */
+
+int cpn_version(void);
+const char* cpn_last_error(void);
+size_t cpn_sizeof_render_args(void);   /* ABI check for FFI bindings */
+
+/* ---- one-time weight repack ------------------------------------------------------------
+ * Replaces: nn.Module parameter storage of the render-path layers
+ * (models/CoPoNeRF.py:71-104, models/lightfield.py:87-116). `src` holds the fp32
+ * state_dict tensors back to back in the order of cpn_weight_names(); `dst` receives the
+ * kernel layouts (transposed fp32 copies and split-bf16 tensor-core tiles). */
+size_t cpn_packed_weights_bytes(void);
+size_t cpn_raw_weights_floats(void);
+int cpn_n_weight_tensors(void);
+const char* cpn_weight_name(int i);    /* state_dict key */
+size_t cpn_weight_numel(int i);
+int cpn_pack_weights(const float* src, void* dst, void* stream);
+
+/* ---- per-pair setup ----------------------------------------------------------------------
+ * cpn_pack_features: NCHW (2B, C, h, w) -> channels-last (2B, h, w, C), one call per level.
+ * Replaces the implicit layout F.grid_sample reads (models/CoPoNeRF.py:312,370). */
+int cpn_pack_features(const float* nchw, float* nhwc, int n_img, int C, int h, int w, void* stream);
+
+/* cpn_pair_setup: relative poses and intrinsics used by every ray of a pair.
+ * Replaces models/CoPoNeRF.py:239-244,259-261,325-332,572-575.
+ *   ctx_c2w (B,2,4,4) ctx_K (B,2,4,4) qry_c2w (B,4,4) qry_K (B,4,4) rel_pose (B,4,4)
+ *   consts  (B, CPN_PAIR_CONSTS_FLOATS)  out */
+int cpn_pair_setup(const float* ctx_c2w, const float* ctx_K, const float* qry_c2w, const float* qry_K,
+                   const float* rel_pose, int B, int H, int val, float* consts, void* stream);
+
+/* cpn_pair_prologue: flow upsampling and the cycle-consistency mask.
+ * Replaces models/CoPoNeRF.py:230-236 (+ the F.interpolate of utils.flow2kps, utils.py:55).
+ *   flow0, flow1 (B,2,fh,fw)  ->  up_flow2 (B,2,256,256) UNSCALED bilinear upsample of flow1,
+ *   mask_padded2 (B,256,256) uint8.  rgb_w = context rgb.shape[-2]. */
+int cpn_pair_prologue(const float* flow0, const float* flow1, int B, int fh, int fw, int rgb_w,
+                      float* up_flow2, uint8_t* mask_padded2, void* stream);
+
+/* ---- the per-ray hot path ---------------------------------------------------------------
+ * Replaces the body of CoPoNeRF.forward() from models/CoPoNeRF.py:246 to :566:
+ * plucker rays, project_rays (models/epipolar.py:175-253), sample positions, primary and
+ * secondary bilinear gathers, fp64 triangulation (utils_training/geometry.py:98-162), the
+ * per-sample encoder, two rounds of 2S-way softmax attention, phi (models/lightfield.py:
+ * 131-167) and the auxiliary depth / correspondence outputs. */
+typedef struct {
+  int32_t B;          /* stereo pairs */
+  int32_t N;          /* target rays per pair */
+  int32_t S;          /* samples per epipolar line (npoints); 2*S must be a multiple of 32, S <= 128 */
+  int32_t H, W;       /* context image size (model.H, model.W) */
+  int32_t flow_h;     /* height of flow[1] (for flow2kps' scale 256/flow_h) */
+  int32_t chunk_rays; /* rays processed per internal pass (workspace is sized from it) */
+  int32_t flags;      /* CPN_FLAG_* */
+  /* inputs */
+  const float* feat[CPN_N_LEVELS];   /* channels-last maps (2B, h_l, w_l, C_l) */
+  int32_t feat_h[CPN_N_LEVELS], feat_w[CPN_N_LEVELS], feat_c[CPN_N_LEVELS];
+  const float* pair_consts;          /* (B, CPN_PAIR_CONSTS_FLOATS) from cpn_pair_setup */
+  const float* uv;                   /* (B, N, 2) pixel (x, y) */
+  const float* interval;             /* (S) = linspace(0, 1, S) */
+  const void* weights;               /* from cpn_pack_weights */
+  const float* up_flow2;             /* (B,2,256,256) from cpn_pair_prologue */
+  const uint8_t* mask_padded2;       /* (B,256,256) */
+  /* outputs (shapes as in the reference's out_dict) */
+  float* rgb;            /* (B, N, 3) */
+  float* valid_mask;     /* (B, N) */
+  float* depth_ray;      /* (B, N) */
+  float* at_wt;          /* (2B, N, S) round-1 attention weights */
+  int64_t* at_wt_max;    /* (2B, N) */
+  float* pixel_val;      /* (2B, N, S, 2) */
+  float* coords;         /* (2B, N, 9) */
+  float* T_to_C1_pts;    /* (B, N, 2) */
+  float* T_to_C2_pts;    /* (B, N, 2) */
+  float* C2_pts_to_C1;   /* (B, N, 2) */
+  uint8_t* mask_c2;      /* (B, N) */
+  uint8_t* matchability_cycle_mask; /* (B, N) */
+  void* workspace;
+  size_t workspace_bytes;
+} cpn_render_args;
+
+size_t cpn_render_workspace_bytes(int B, int chunk_rays, int S);
+int cpn_render_rays(const cpn_render_args* args, void* stream);
+/* number of kernels one cpn_render_rays call launches (for bench.py's gpu_launches) */
+int cpn_render_launch_count(const cpn_render_args* args);
+
+/* ---- device timing of the dominant kernel (the query_encode_latent GEMM), for roofline reports.
+ * Between cpn_prof_begin and cpn_prof_end every launch of that kernel by cpn_render_rays is bracketed
+ * by CUDA events on the caller's stream. cpn_prof_end waits for them and returns the summed duration.
+ * One session per process at a time; not for production use. */
+int cpn_prof_begin(int max_launches);
+int cpn_prof_end(float* total_ms, int* launches);
+
+/* ---- building blocks exported for unit tests ------------------------------------------
+ * C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]); fp32 row-major, lda/ldc in floats.
+ * `wt` is W transposed to [K,N] (fp32, as produced by cpn_pack_weights for SIMT layers). */
+int cpn_gemm_simt(const float* A, int lda, const float* wt, const float* bias, float* C, int ldc,
+                  int M, int N, int K, int relu, void* stream);
+
+/* Tensor-core GEMM of one packed layer (0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value,
+ * 3 key_map): C[M, N_layer] = act(A[M, K_layer] * W^T + b), operands split into fp16 hi/lo pairs and
+ * accumulated in fp32 on tcgen05 (3 MMAs per product). `packed` is the blob from cpn_pack_weights. */
+int cpn_gemm_tc(const void* packed, int layer, const float* A, int lda, float* C, int ldc, int M, int relu,
+                void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COPONERF_B200_H */

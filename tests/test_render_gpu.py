@@ -1,0 +1,139 @@
+"""Parity of the sm_100a render path (through the C-ABI, via the drop-in forward()) against
+(1) the committed outputs of the unmodified reference (tests/golden/*.npz) and (2) the CPU oracle,
+plus the size-independent properties: chunk / shard invariance and ray independence, bit-exact."""
+import ctypes
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cases import GOLDEN_DIR, GPU_TOL, check_against, rel_err, run_cuda, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "render_*.npz")))
+EXACT_KEYS = ("rgb", "valid_mask", "depth_ray", "at_wt", "at_wt_max", "pixel_val", "coords", "T_to_C1_pts",
+              "T_to_C2_pts", "C2_pts_to_C1", "mask_c2", "matchability_cycle_mask")
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_matches_reference_golden(case):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, case + ".npz")))
+    H, W, n_rays, S, seed, val = [int(v) for v in g["meta"]]
+    out = run_cuda(H, W, n_rays, S, seed, val)
+    check_against(out, g, case)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_simt_cross_check_path_matches_reference_golden(case):
+    """The fp32 CUDA-core GEMM path (CPN_FLAG_SIMT_ONLY) is held to the same gates."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, case + ".npz")))
+    H, W, n_rays, S, seed, val = [int(v) for v in g["meta"]]
+    out = run_cuda(H, W, n_rays, S, seed, val, flags=1)
+    check_against(out, g, case + "/simt")
+
+
+def test_matches_oracle_batch2_ragged():
+    """Two pairs, a ray count that is not a multiple of any tile, oblique pose (invalid rays present)."""
+    args = dict(H=64, W=64, n_rays=333, S=64, seed=2, val=True, batch=2)
+    ref = run_oracle(**args)
+    out = run_cuda(chunk_rays=100, **args)
+    check_against(out, ref, "batch2")
+    v = ref["valid_mask"].numpy()
+    assert 0.05 < v.mean() < 0.95  # the degenerate-ray paths are exercised
+
+
+def test_chunk_invariance_bit_exact():
+    """A ray's outputs do not depend on the chunk it is rendered in."""
+    args = dict(H=64, W=64, n_rays=512, S=64, seed=2, val=True)
+    a = run_cuda(chunk_rays=2048, **args)
+    b = run_cuda(chunk_rays=96, **args)
+    for k in EXACT_KEYS:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_ray_shard_invariance_bit_exact():
+    """Rendering a slice of the rays alone (what a rank does) equals the slice of the full render."""
+    args = dict(H=64, W=64, n_rays=512, S=64, seed=1, val=True)
+    full = run_cuda(**args)
+    lo, hi = 130, 389
+    part = run_cuda(ray_slice=slice(lo, hi), **args)
+    cat_dim = {"pixel_val": 1, "at_wt": 1, "at_wt_max": 1, "coords": 1, "mask_c2": 1, "matchability_cycle_mask": 1,
+               "rgb": 2}
+    for k in EXACT_KEYS:
+        d = cat_dim.get(k, 1)
+        assert torch.equal(part[k], full[k].narrow(d, lo, hi - lo)), k
+
+
+def test_full_resolution_properties():
+    """BASELINE config 2 size (256x256, all 65 536 rays): properties that need no oracle run."""
+    out = run_cuda(256, 256, None, 64, seed=4, val=True, chunk_rays=2048)
+    n = 65536
+    assert out["rgb"].shape == (1, 1, n, 3) and out["at_wt"].shape == (2, n, 64)
+    assert torch.isfinite(out["rgb"]).all()
+    w = out["at_wt"].view(1, 2, n, 64)
+    assert torch.allclose(w.sum(dim=(1, 3)), torch.ones(1, n), atol=1e-5)   # joint softmax over 2 x S
+    inval = out["valid_mask"][0, :, 0] == 0
+    assert (out["rgb"][0, 0][inval] == 1).all()                            # white where no epipolar segment
+    assert out["at_wt_max"].min() >= 0 and out["at_wt_max"].max() < 64
+    assert out["depth_ray"].min() >= 0 and out["depth_ray"].max() <= 10
+    # the committed golden is a 384-ray subset of this very case: same uv order is not guaranteed, so compare
+    # through a second full render in a different chunking instead (bit-exact)
+    again = run_cuda(256, 256, None, 64, seed=4, val=True, chunk_rays=1000)
+    for k in ("rgb", "at_wt_max", "pixel_val", "mask_c2"):
+        assert torch.equal(out[k], again[k]), k
+
+
+def test_empty_ray_set():
+    out = run_cuda(64, 64, 16, 64, seed=1, val=True, ray_slice=slice(0, 0))
+    assert out["rgb"].shape == (1, 1, 0, 3) and out["at_wt"].shape == (2, 0, 64)
+
+
+def test_bad_arguments_fail_loudly():
+    from coponerf_b200 import _lib
+    with pytest.raises(_lib.CpnError):
+        run_cuda(64, 64, 16, 40, seed=1, val=True)   # 2*S not a multiple of 32
+    lib = _lib.load()
+    assert lib.cpn_render_rays(None, None) != 0
+    assert b"null" in lib.cpn_last_error()
+
+
+def test_gemm_simt_against_torch_fp32():
+    from coponerf_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(0)
+    for (M, N, K, relu) in [(300, 832, 848, 1), (257, 416, 832, 0), (1000, 128, 16, 1), (64, 128, 416, 0)]:
+        A = torch.randn(M, K, device="cuda")
+        Wm = torch.randn(N, K, device="cuda") / K ** 0.5
+        bias = torch.randn(N, device="cuda")
+        C = torch.empty(M, N, device="cuda")
+        wt = Wm.t().contiguous()
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(lib.cpn_gemm_simt(p(A), K, p(wt), p(bias), p(C), N, M, N, K, relu, st), "cpn_gemm_simt")
+        ref = torch.nn.functional.linear(A.double(), Wm.double(), bias.double())
+        if relu:
+            ref = ref.relu()
+        assert rel_err(C.cpu().numpy(), ref.cpu().numpy()) < 2e-6, (M, N, K)
+
+
+def test_pair_prologue_against_oracle():
+    from oracle import render_oracle
+    from coponerf_b200 import synth
+    from cases import cuda_model, to_device
+    inp = synth.make_input(64, 64, 8, seed=3, pose_set="oblique", batch=2)
+    z, rel, flow = synth.make_features(64, 64, seed=3, batch=2)
+    flow = tuple(f * 2 for f in flow)  # large enough flows to hit both branches of the masks
+    up2, mask = render_oracle.pair_prologue(flow, inp["context"]["rgb"].shape[-2])
+    m = cuda_model()
+    dev = torch.device("cuda:0")
+    st = m.engine().prepare_pair(to_device(inp, dev), to_device(z, dev), rel.to(dev), to_device(flow, dev), 64, 64, True)
+    torch.cuda.synchronize()
+    scale = 256 / inp["context"]["rgb"].shape[-2]
+    assert rel_err((st.up_flow2 * scale).cpu().numpy(), up2.numpy()) < 1e-6
+    got = st.mask_padded2.cpu().bool()
+    # a mask bit may differ only where the cycle error sits on the threshold
+    assert (got != mask).float().mean() < 1e-3
+    assert 0.02 < mask.float().mean() < 0.98
