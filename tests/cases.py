@@ -41,11 +41,40 @@ def to_device(obj, dev):
     return obj
 
 
-def run_oracle(H, W, n_rays, S, seed, val, chunk=None, pose=None, batch=1):
+SENS_KEYS = ("rgb", "at_wt", "depth_ray", "T_to_C1_pts", "T_to_C2_pts", "C2_pts_to_C1")
+SENS_FACTOR = 8.0      # four 1-ulp perturbation samples understate the worst case by a few x (measured: <= 4)
+SENS_FLOOR = 1e-6      # rays whose reference output moves less than this (relative) get the plain gate
+
+
+def per_ray(d, key):
+    """max |delta| per ray, reduced like tests/golden/make_goldens.py:sensitivity."""
+    d = np.abs(np.asarray(d, dtype=np.float64))
+    if key == "rgb":
+        return d.max(axis=-1)[:, 0]
+    if key == "at_wt":
+        return d.max(axis=-1)
+    return d.reshape(d.shape[0], d.shape[1], -1).max(axis=-1)
+
+
+def run_oracle(H, W, n_rays, S, seed, val, chunk=None, pose=None, batch=1, with_sens=False):
     from oracle import render_oracle
     inp, z, rel_pose, flow = make_case(H, W, n_rays, seed, pose, batch)
     sd = synth.render_state_dict(0)
-    return render_oracle.render_forward(sd, inp, z, rel_pose, flow, H, W, S, bool(val), chunk=chunk)
+    base = render_oracle.render_forward(sd, inp, z, rel_pose, flow, H, W, S, bool(val), chunk=chunk)
+    if with_sens:   # the same 1-ulp pose perturbation the golden generator applies to the reference
+        import copy
+        g = torch.Generator().manual_seed(1234)
+        for _ in range(4):
+            pin = copy.deepcopy(inp)
+            for grp in ("context", "query"):
+                t = pin[grp]["cam2world"]
+                pin[grp]["cam2world"] = t * (1 + 6e-8 * torch.randn(t.shape, generator=g))
+            rp = rel_pose * (1 + 6e-8 * torch.randn(rel_pose.shape, generator=g))
+            out = render_oracle.render_forward(sd, pin, z, rp, flow, H, W, S, bool(val), chunk=chunk)
+            for k in SENS_KEYS:
+                d = per_ray(out[k].numpy() - base[k].numpy(), k)
+                base[k + "_sens"] = np.maximum(base.get(k + "_sens", 0), d)
+    return base
 
 
 _MODELS = {}
@@ -78,13 +107,31 @@ def run_cuda(H, W, n_rays, S, seed, val, chunk_rays=2048, pose=None, batch=1, fl
 
 
 def check_against(out, ref, tag, tol=GPU_TOL):
-    """Float outputs within `tol`; integer / boolean outputs exact up to float-noise ties."""
+    """Float outputs within `tol` (relative to max|ref|); integer / boolean outputs exact up to float-noise ties.
+
+    The reference is ill-conditioned on a minority of rays: triangulating near-parallel rays amplifies
+    one-ulp differences of the fp32 pose arithmetic by up to 1e4 (measured per ray on
+    the reference itself by the golden generator, `<key>_sens`). When `ref` carries that measurement the gate
+    of a ray is tol + SENS_FACTOR * max(0, sens - floor): the plain gate wherever the reference is stable.
+    """
     get = lambda d, k: np.asarray(d[k].numpy() if isinstance(d[k], torch.Tensor) else d[k])
     for k, t in tol.items():
         a, b = get(out, k), get(ref, k)
         assert a.shape == b.shape, (tag, k, a.shape, b.shape)
-        e = rel_err(a, b)
-        assert e <= t, f"{tag}:{k} rel err {e:.3e} > {t}"
+        scale = max(float(np.abs(b).max()), 1e-30) if b.size else 1.0
+        if k + "_sens" in ref and b.size:
+            sens = np.asarray(ref[k + "_sens"], dtype=np.float64)
+            err = per_ray(a.astype(np.float64) - b.astype(np.float64), k)
+            allowed = t * scale + SENS_FACTOR * np.maximum(0.0, sens - SENS_FLOOR * scale)
+            bad = err > allowed
+            assert not bad.any(), (f"{tag}:{k} {int(bad.sum())} rays over the gate; worst err/scale "
+                                   f"{(err / scale).max():.3e}, worst excess {(err - allowed).max() / scale:.3e}")
+            if k == "rgb":   # the plain gate must cover most of the image, or the case is a poor test
+                stable = sens <= SENS_FLOOR * scale
+                assert stable.mean() > 0.4, f"{tag}: only {stable.mean():.2f} of the rays are well-conditioned"
+        else:
+            e = rel_err(a, b)
+            assert e <= t, f"{tag}:{k} rel err {e:.3e} > {t}"
     # argmax of the round-1 weights: may differ only where the top two reference weights tie within noise
     am, gm, w = get(out, "at_wt_max"), get(ref, "at_wt_max"), get(ref, "at_wt")
     assert am.shape == gm.shape and am.dtype == gm.dtype, (tag, am.shape, gm.shape, am.dtype, gm.dtype)

@@ -38,7 +38,7 @@ def test_simt_cross_check_path_matches_reference_golden(case):
 def test_matches_oracle_batch2_ragged():
     """Two pairs, a ray count that is not a multiple of any tile, oblique pose (invalid rays present)."""
     args = dict(H=64, W=64, n_rays=333, S=64, seed=2, val=True, batch=2)
-    ref = run_oracle(**args)
+    ref = run_oracle(with_sens=True, **args)
     out = run_cuda(chunk_rays=100, **args)
     check_against(out, ref, "batch2")
     v = ref["valid_mask"].numpy()
