@@ -137,3 +137,32 @@ def test_pair_prologue_against_oracle():
     # a mask bit may differ only where the cycle error sits on the threshold
     assert (got != mask).float().mean() < 1e-3
     assert 0.02 < mask.float().mean() < 0.98
+
+
+@pytest.mark.parametrize("layer,name,relu", [(0, "query_encode_latent", 1), (1, "query_encode_latent_2", 0),
+                                             (2, "latent_value", 0), (3, "key_map", 1)])
+def test_gemm_tc_against_torch_fp64(layer, name, relu):
+    """tcgen05 split-fp16 GEMM of one packed layer vs fp64: error must sit at fp32 level, far below TF32's 5e-4."""
+    from coponerf_b200 import _lib, synth
+    from cases import cuda_model
+    lib = _lib.load()
+    eng = cuda_model().engine()
+    sd = synth.render_state_dict(0)
+    Wm = sd[name + ".weight"].reshape(sd[name + ".weight"].shape[0], -1).cuda()
+    bias = sd[name + ".bias"].cuda()
+    N, K = Wm.shape
+    lda = 848 if K == 835 else K
+    torch.manual_seed(layer)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for M in (1, 128, 300, 1000):
+        A = torch.zeros(M, lda, device="cuda")
+        A[:, :K] = torch.randn(M, K, device="cuda") * 3
+        C = torch.full((M, N), float("nan"), device="cuda")
+        _lib.check(lib.cpn_gemm_tc(p(eng.weights), layer, p(A), lda, p(C), N, M, relu, st), "cpn_gemm_tc")
+        ref = torch.nn.functional.linear(A[:, :K].double(), Wm.double(), bias.double())
+        if relu:
+            ref = ref.relu()
+        e = rel_err(C.cpu().numpy(), ref.cpu().numpy())
+        print(f"gemm_tc {name} M={M}: rel err {e:.2e}")
+        assert e < 1e-5, (name, M, e)
