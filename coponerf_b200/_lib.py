@@ -14,6 +14,9 @@ LATENT = 416
 HIDDEN = 128
 PAIR_CONSTS_FLOATS = 320
 FLAG_SIMT_ONLY = 1
+TC_A_IMAGE = 1
+TC_OUT_IMAGE = 2
+ACT_CHUNK_BYTES = 16384
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
 
@@ -63,7 +66,8 @@ SIGNATURES = {
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_void_p]),
     "cpn_gemm_tc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
-                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_void_p]),
 }
 
 _lib = None

@@ -66,6 +66,12 @@ static_assert(END <= CPN_PAIR_CONSTS_FLOATS, "pair consts overflow");
 // row = ((b * N_chunk + n) * 2 + v) * S + s : the 2S rows of a ray are contiguous.
 #define CPN_ROWAUX 8  // grid_prim.xy, grid_sec.xy, clamp(pt).xyz, pad
 
+// Row of the encoder-input matrix A for (sample row, branch): tiles of 128 sample rows, the 128 primary rows of
+// a tile followed by its 128 secondary rows, so that one 128-row GEMM tile is one (tile, branch).
+__host__ __device__ __forceinline__ size_t enc_row(size_t row, int branch) {
+  return (row >> 7) * 256 + (size_t)branch * 128 + (row & 127);
+}
+
 void cpn_set_error(const char* fmt, ...);
 #define CPN_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \
@@ -89,8 +95,10 @@ int launch_ray_setup(const cpn_render_args& a, int ray0, int nr, float* seg, cud
 int launch_sample(const cpn_render_args& a, int ray0, int nr, const float* seg, float* rowaux, float* local16,
                   float* A, cudaStream_t st);
 int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowaux, float* A, cudaStream_t st);
+// remap256: output row m goes to row (m / 256) * 128 + m % 128 at column offset ((m / 128) & 1) * N (undoes enc_row)
 int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias, const float* rowbias,
-                     int rows_per_bias, float* C, int ldc, int M, int N, int K, int relu, cudaStream_t st);
+                     int rows_per_bias, float* C, int ldc, int M, int N, int K, int relu, cudaStream_t st,
+                     int remap256 = 0);
 int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, const float* qemb, const float* value,
                  const float* rowaux, float* r1, float* wp, cudaStream_t st);
 int launch_attn2(const cpn_render_args& a, int nr, const float* q2, const float* qemb, const float* value,
@@ -99,9 +107,16 @@ int launch_phi(const cpn_render_args& a, int ray0, int nr, const float* z, const
 int launch_ray_epilogue(const cpn_render_args& a, int ray0, int nr, const float* wp, cudaStream_t st);
 
 // tensor-core path (gemm_tc.cu)
+// "Operand image" of an activation matrix [rows x K]: tiles of 128 rows; per tile and 32-wide k-chunk one
+// 16 KB block [hi | lo] x [4 groups of 8 k][128 rows][8 fp16] -- exactly what the MMA reads from shared memory
+// (K-major, no swizzle), so a consumer stages it with one bulk copy. Block index = tile * (K / 32) + k-chunk.
+constexpr int ACT_BK = 32;
+constexpr int ACT_CHUNK_BYTES = 2 * (ACT_BK / 8) * 128 * 16;
+constexpr int CPN_TC_LAYERS = 7;
 size_t cpn_packed_fp32_floats();
 size_t cpn_tc_weights_bytes();
 int cpn_pack_tc_weights(const float* raw, void* dst, cudaStream_t st);
-// layer: 0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value, 3 key_map
-int launch_gemm_tc(const void* packed, int layer, const float* A, int lda, float* C, int ldc, int M, int relu,
-                   cudaStream_t st);
+// layer: 0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value, 3 key_map, 4 key_map_2,
+//        5 query_embed_2, 6 query_repeat_embed_2.  mode: CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE.
+int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,
+                   int out_div, int out_kchunks, cudaStream_t st);

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) gather_kernel(cpn_render_args a, int nr, 
   int img = b * 2 + (branch ? 1 - v : v);
   const float* ra = rowaux + (size_t)row * CPN_ROWAUX;
   float gx = ra[branch * 2 + 0], gy = ra[branch * 2 + 1];
-  float* out = A + (size_t)wid * CPN_KA;
+  float* out = A + enc_row((size_t)row, branch) * CPN_KA;
   int col = 0;
 #pragma unroll
   for (int l = 0; l < CPN_N_LEVELS; ++l) {

@@ -1,18 +1,25 @@
-// Tensor-core GEMM for the four large 1x1 convolutions of the per-sample encoder
-// (models/CoPoNeRF.py:387-408): query_encode_latent, query_encode_latent_2, latent_value, key_map.
+// Tensor-core GEMM for the 1x1 convolutions of the per-sample encoder and attention MLPs
+// (models/CoPoNeRF.py:387-408,446,473): C[M, N] = act(A[M, K] * W^T + b).
 //
 // fp32 parity on fp16 tensor cores: every operand is split x = hi + lo into two fp16 values (error 2^-22 |x|)
 // and the product is accumulated in fp32 as  hi*hi + hi*lo + lo*hi  (three tcgen05.mma per k-step; the dropped
 // lo*lo term is 2^-22 relative). Weights are pre-split, pre-scaled by a per-layer power of two (so the lo halves
 // stay out of the fp16 subnormal range) and pre-tiled into the exact shared-memory image the MMA reads, so a
-// plain bulk copy (TMA engine, one instruction per stage) moves them. The activation operand is fp32 in global
-// memory: producer warps load it coalesced, split it and write the K-major core-matrix layout themselves.
+// plain bulk copy (TMA engine, one instruction per stage) moves them.
 //
-// CTA = one 128-row x NT-column output tile. 6 warps:
-//   warp 0   lane 0: bulk-copies the weight tile of each k-chunk into the stage ring
+// The activation operand comes in one of two forms:
+//   fp32 row-major      producer warps load it coalesced, split it and write the K-major core-matrix layout;
+//   "operand image"     already split and tiled by the epilogue of the layer that produced it (ACT_* in
+//                       cpn_common.cuh): the TMA warp bulk-copies 16 KB per 128-row tile and k-chunk, no
+//                       conversion work at all.
+// and the output is written either as fp32 row-major or as the operand image of the next layer.
+//
+// CTA = 256 rows (two UMMA M=128 sub-tiles sharing every weight stage: halves the L2 -> SM weight traffic per
+// flop) x one NT-column tile; the two accumulators sit in TMEM columns [0, NT) and [256, 256 + NT). 10 warps:
+//   warp 0   lane 0: bulk-copies weight tiles (and activation images) into the stage ring
 //   warp 1   allocates TMEM; lane 0 issues the MMAs and commits stage-free / accumulator-ready barriers
-//   warp 2-5 produce the A operand (fp32 -> hi/lo fp16, K-major, no swizzle), then run the epilogue
-//            (TMEM -> registers -> scale, bias, ReLU -> global)
+//   warp 2-9 fp32-A mode: produce the A operand (32 rows per warp, two k-chunks of loads in flight), then
+//            the epilogue: TMEM -> registers -> scale, bias, ReLU -> global (fp32 or hi/lo image)
 #include "cpn_common.cuh"
 #include "tc_common.cuh"
 
@@ -20,38 +27,47 @@ namespace {
 
 using namespace tc;
 
-constexpr int BM = 128;            // rows per CTA (UMMA M)
-constexpr int BK = 32;             // k per stage: 2 MMA k-steps of 16
-constexpr int STAGES = 4;
+constexpr int BM = 256;            // rows per CTA: 2 sub-tiles of UMMA M = 128
+constexpr int BK = ACT_BK;         // k per stage (32): 2 MMA k-steps of 16
+constexpr int STAGES = 3;
 constexpr int NT_MAX = 208;        // widest N tile (832 = 4 x 208, 416 = 2 x 208)
-constexpr int A_LBO = BM * 16 + 32;             // bytes between 8-wide k-chunks of A (+32: conflict-free STS.128)
-constexpr int A_HALF = (BK / 8) * A_LBO;        // hi (or lo) half of one A stage
+constexpr int A_LBO = 128 * 16;                 // bytes between 8-wide k-chunks of a 128-row A sub-tile
+constexpr int A_HALF = (BK / 8) * A_LBO;        // hi (or lo) half of one sub-tile stage = 8 KB
+constexpr int A_SUB = 2 * A_HALF;               // one sub-tile stage = ACT_CHUNK_BYTES
 constexpr int W_STAGE_MAX = 2 * (BK / 8) * NT_MAX * 16;
-constexpr int STAGE_BYTES = 2 * A_HALF + W_STAGE_MAX;
+constexpr int STAGE_BYTES = 2 * A_SUB + W_STAGE_MAX;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;
-constexpr int TMEM_COLS = 256;
-constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int NUM_THREADS = 320;
+static_assert(A_SUB == ACT_CHUNK_BYTES, "operand image chunk must equal one A sub-tile stage");
 
 struct TcLayer {
-  int tensor;      // index into the raw state_dict blob (weights.cu order)
   int out, in;     // weight shape
   int kpad;        // K padded to a multiple of BK (zero weights beyond `in`)
   int nt;          // N tile
+  size_t raw;      // offset of the weight in the raw state_dict blob (floats)
   size_t bias;     // offset of the fp32 bias in the packed fp32 section
 };
-// raw blob offsets (floats) of the four weights, see weights.cu kTensors
+// raw blob offsets (floats), see weights.cu kTensors
 constexpr size_t RAW_W1 = 0;
 constexpr size_t RAW_W2 = RAW_W1 + 832 * 835 + 832;
 constexpr size_t RAW_WV = RAW_W2 + 416 * 832 + 416;
 constexpr size_t RAW_WK = RAW_WV + 416 * 832 + 416;
-const TcLayer kLayers[4] = {
-    {0, 832, 835, 864, 208, pw::B1},
-    {2, 416, 832, 832, 208, pw::B2},
-    {4, 416, 832, 832, 208, pw::BV},
-    {6, 128, 832, 832, 128, pw::BK},
+constexpr size_t RAW_WK2 = RAW_WK + 128 * 832 + 128;
+constexpr size_t RAW_WQ = RAW_WK2 + 128 * 128 + 128;
+constexpr size_t RAW_WQ2 = RAW_WQ + 128 * 16 + 128;
+constexpr size_t RAW_WQR = RAW_WQ2 + 128 * 128 + 128;
+constexpr size_t RAW_WQR2 = RAW_WQR + 128 * 144 + 128;
+const TcLayer kLayers[CPN_TC_LAYERS] = {
+    {832, 835, 864, 208, RAW_W1, pw::B1},      // 0 query_encode_latent
+    {416, 832, 832, 208, RAW_W2, pw::B2},      // 1 query_encode_latent_2
+    {416, 832, 832, 208, RAW_WV, pw::BV},      // 2 latent_value
+    {128, 832, 832, 128, RAW_WK, pw::BK},      // 3 key_map
+    {128, 128, 128, 128, RAW_WK2, pw::BK2},    // 4 key_map_2
+    {128, 128, 128, 128, RAW_WQ2, pw::BQ2},    // 5 query_embed_2
+    {128, 128, 128, 128, RAW_WQR2, pw::BQR2},  // 6 query_repeat_embed_2
 };
-const size_t kRawOff[4] = {RAW_W1, RAW_W2, RAW_WV, RAW_WK};
-constexpr size_t TC_HEADER_BYTES = 256;   // [0..3] 1/scale per layer, [4..7] scale, [8..11] absmax bits
+constexpr size_t TC_HEADER_BYTES = 256;   // floats [0..7] 1/scale per layer, [8..15] scale, uints [16..23] absmax bits
 
 size_t layer_bytes(int l) { return (size_t)kLayers[l].out * kLayers[l].kpad * 4; }  // hi + lo fp16
 size_t layer_offset(int l) {
@@ -86,7 +102,7 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, int out, int in, int
   float scale = layer_scale(*absmax);
   if (i == 0) {
     header[layer] = 1.f / scale;
-    header[4 + layer] = scale;
+    header[8 + layer] = scale;
   }
   if (i >= total) return;
   int k = (int)(i % kpad), n = (int)(i / kpad);
@@ -104,10 +120,12 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, int out, int in, int
 
 // ---------------------------------------------------------------------------------------------- the GEMM
 struct GemmArgs {
-  const float* A;
+  const void* A;                 // fp32 row-major (lda) or operand image
   int lda, kreal, M;
-  float* C;
+  void* C;                       // fp32 row-major (ldc) or operand image
   int ldc, N, relu;
+  int out_div;                   // image output: source tile t lands in image tile t / out_div at k offset (t % out_div) * N
+  int out_kchunks;               // k-chunks per tile of the output image
   const unsigned char* wtiles;   // this layer's tiles
   const float* bias;
   const float* inv_scale;        // header[layer]
@@ -115,6 +133,7 @@ struct GemmArgs {
   uint32_t idesc;
 };
 
+template <bool A_IMAGE, bool OUT_IMAGE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bars[3 * STAGES + 1];
@@ -126,10 +145,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
                  accum = smem_u32(&bars[3 * STAGES]);
   const int NT = g.NT;
   const uint32_t w_half = (uint32_t)(BK / 8) * NT * 16;      // bytes of the hi (or lo) part of a weight tile
+  const bool sub1_valid = (m0 + 128) < g.M;                  // does the second 128-row sub-tile hold any row?
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_a + 8 * s, 128);
+      mbar_init(full_a + 8 * s, 256);
       mbar_init(full_w + 8 * s, 1);
       mbar_init(empty + 8 * s, 1);
     }
@@ -144,13 +164,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
 
   if (warp == 0) {
     if (lane == 0) {
-      const unsigned char* src = g.wtiles + (size_t)n_tile * g.kchunks * 2 * w_half;
+      const unsigned char* wsrc = g.wtiles + (size_t)n_tile * g.kchunks * 2 * w_half;
+      const unsigned char* asrc = reinterpret_cast<const unsigned char*>(g.A);
+      const size_t tile0 = (size_t)(m0 / 128);
       for (int i = 0; i < g.kchunks; ++i) {
         int s = i % STAGES;
         uint32_t u = i / STAGES;
         mbar_wait(empty + 8 * s, (u & 1) ^ 1);
-        mbar_arrive_expect_tx(full_w + 8 * s, 2 * w_half);
-        bulk_g2s(smem0 + s * STAGE_BYTES + 2 * A_HALF, src + (size_t)i * 2 * w_half, 2 * w_half, full_w + 8 * s);
+        uint32_t stage = smem0 + s * STAGE_BYTES;
+        uint32_t bytes = 2 * w_half + (A_IMAGE ? (sub1_valid ? 2 : 1) * A_SUB : 0);
+        mbar_arrive_expect_tx(full_w + 8 * s, bytes);
+        bulk_g2s(stage + 2 * A_SUB, wsrc + (size_t)i * 2 * w_half, 2 * w_half, full_w + 8 * s);
+        if (A_IMAGE) {
+          bulk_g2s(stage, asrc + (tile0 * g.kchunks + i) * ACT_CHUNK_BYTES, A_SUB, full_w + 8 * s);
+          if (sub1_valid)
+            bulk_g2s(stage + A_SUB, asrc + ((tile0 + 1) * g.kchunks + i) * ACT_CHUNK_BYTES, A_SUB, full_w + 8 * s);
+        }
       }
     }
   } else if (warp == 1) {
@@ -158,78 +187,132 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
       for (int i = 0; i < g.kchunks; ++i) {
         int s = i % STAGES;
         uint32_t u = i / STAGES;
-        mbar_wait(full_a + 8 * s, u & 1);
+        if (!A_IMAGE) mbar_wait(full_a + 8 * s, u & 1);
         mbar_wait(full_w + 8 * s, u & 1);
         tcgen05_fence_after();
-        uint32_t a_hi = smem0 + s * STAGE_BYTES, a_lo = a_hi + A_HALF;
-        uint32_t b_hi = a_hi + 2 * A_HALF, b_lo = b_hi + w_half;
+        uint32_t stage = smem0 + s * STAGE_BYTES;
+        uint32_t b_hi = stage + 2 * A_SUB, b_lo = b_hi + w_half;
 #pragma unroll
-        for (int j = 0; j < BK / 16; ++j) {
-          uint64_t da_hi = make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128);
-          uint64_t da_lo = make_desc(a_lo + j * 2 * A_LBO, A_LBO, 128);
-          uint64_t db_hi = make_desc(b_hi + j * 2 * NT * 16, NT * 16, 128);
-          uint64_t db_lo = make_desc(b_lo + j * 2 * NT * 16, NT * 16, 128);
-          mma_f16_ss(tmem, da_hi, db_hi, g.idesc, (i | j) != 0);
-          mma_f16_ss(tmem, da_hi, db_lo, g.idesc, 1);
-          mma_f16_ss(tmem, da_lo, db_hi, g.idesc, 1);
+        for (int sub = 0; sub < 2; ++sub) {
+          if (sub == 1 && !sub1_valid) break;
+          uint32_t a_hi = stage + sub * A_SUB, a_lo = a_hi + A_HALF;
+          uint32_t d = tmem + sub * 256;
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j) {
+            uint64_t da_hi = make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128);
+            uint64_t da_lo = make_desc(a_lo + j * 2 * A_LBO, A_LBO, 128);
+            uint64_t db_hi = make_desc(b_hi + j * 2 * NT * 16, NT * 16, 128);
+            uint64_t db_lo = make_desc(b_lo + j * 2 * NT * 16, NT * 16, 128);
+            mma_f16_ss(d, da_hi, db_hi, g.idesc, (i | j) != 0);
+            mma_f16_ss(d, da_hi, db_lo, g.idesc, 1);
+            mma_f16_ss(d, da_lo, db_hi, g.idesc, 1);
+          }
         }
         mma_commit(empty + 8 * s);   // the stage is free once these MMAs have read it
       }
       mma_commit(accum);
     }
   } else {
-    // ---- A producer: 4 warps, each covers 32 rows of the tile in 4 passes of 8 rows x 32 k
-    const int wq = warp - 2;
-    const int r_in = lane >> 2, c = lane & 3;
-    for (int i = 0; i < g.kchunks; ++i) {
-      int s = i % STAGES;
-      uint32_t u = i / STAGES;
-      const int k = i * BK + c * 8;
-      float4 v[4][2];
+    const int pwarp = warp - 2;               // 0..7: rows [32 * pwarp, 32 * pwarp + 32) of the CTA tile
+    if (!A_IMAGE) {
+      // ---- A producer. lane -> (k-chunk c = lane / 8, row r_in = lane % 8): 8 consecutive lanes store 128
+      // contiguous bytes. Loads of chunks i + 1 and i + 2 are in flight while chunk i is converted.
+      const float* Ag = reinterpret_cast<const float*>(g.A);
+      const int r_in = lane & 7, c = lane >> 3;
+      const int sub = pwarp >> 2, rbase = (pwarp & 3) * 32;
+      float4 buf[3][4][2];
+      auto load_chunk = [&](int i, float4 (&v)[4][2]) {
+        const int k = i * BK + c * 8;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        int row = m0 + wq * 32 + it * 8 + r_in;
-        if (row < g.M && k < g.kreal) {
-          const float4* p = reinterpret_cast<const float4*>(g.A + (size_t)row * g.lda + k);
-          v[it][0] = __ldg(p);
-          v[it][1] = __ldg(p + 1);
-        } else {
-          v[it][0] = v[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int it = 0; it < 4; ++it) {
+          int row = m0 + pwarp * 32 + it * 8 + r_in;
+          if (row < g.M && k < g.kreal) {
+            const float4* p = reinterpret_cast<const float4*>(Ag + (size_t)row * g.lda + k);
+            v[it][0] = __ldg(p);
+            v[it][1] = __ldg(p + 1);
+          } else {
+            v[it][0] = v[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
-      }
-      mbar_wait(empty + 8 * s, (u & 1) ^ 1);
-      unsigned char* a_hi = smem + s * STAGE_BYTES;
+      };
+      auto store_chunk = [&](int i, float4 (&v)[4][2]) {
+        int s = i % STAGES;
+        uint32_t u = i / STAGES;
+        mbar_wait(empty + 8 * s, (u & 1) ^ 1);
+        unsigned char* a_hi = smem + s * STAGE_BYTES + sub * A_SUB;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        int r = wq * 32 + it * 8 + r_in;
-        uint4 hi, lo;
-        split8(v[it][0], v[it][1], hi, lo);
-        *reinterpret_cast<uint4*>(a_hi + c * A_LBO + r * 16) = hi;
-        *reinterpret_cast<uint4*>(a_hi + A_HALF + c * A_LBO + r * 16) = lo;
+        for (int it = 0; it < 4; ++it) {
+          int r = rbase + it * 8 + r_in;
+          uint4 hi, lo;
+          split8(v[it][0], v[it][1], hi, lo);
+          *reinterpret_cast<uint4*>(a_hi + c * A_LBO + r * 16) = hi;
+          *reinterpret_cast<uint4*>(a_hi + A_HALF + c * A_LBO + r * 16) = lo;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(full_a + 8 * s);
+      };
+      if (0 < g.kchunks) load_chunk(0, buf[0]);
+      if (1 < g.kchunks) load_chunk(1, buf[1]);
+      int i = 0;
+      for (; i + 2 < g.kchunks; i += 3) {   // rotate three register buffers without copies
+        load_chunk(i + 2, buf[2]);
+        store_chunk(i, buf[0]);
+        if (i + 3 < g.kchunks) load_chunk(i + 3, buf[0]);
+        store_chunk(i + 1, buf[1]);
+        if (i + 4 < g.kchunks) load_chunk(i + 4, buf[1]);
+        store_chunk(i + 2, buf[2]);
       }
-      fence_proxy_async_smem();
-      mbar_arrive(full_a + 8 * s);
+      if (i < g.kchunks) store_chunk(i, buf[0]);
+      if (i + 1 < g.kchunks) store_chunk(i + 1, buf[1]);
     }
-    // ---- epilogue: warp w may touch TMEM lanes 32 * (w % 4) .. + 31
-    mbar_wait(accum, 0);
-    tcgen05_fence_after();
-    const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    const float inv = *g.inv_scale;
-    const int n0 = n_tile * NT;
-    for (int c0 = 0; c0 < NT; c0 += 16) {
-      float v[16];
-      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
-      if (row < g.M) {
-        float* out = g.C + (size_t)row * g.ldc + n0 + c0;
+    // ---- epilogue: warp w may touch TMEM lanes 32 * (w % 4) .. + 31; warps 2-5 drain sub-tile 0, 6-9 sub-tile 1
+    const int esub = pwarp >> 2, q = warp & 3;
+    if (esub == 0 || sub1_valid) {
+      mbar_wait(accum, 0);
+      tcgen05_fence_after();
+      const int rloc = q * 32 + lane;                  // row inside the 128-row sub-tile
+      const int row = m0 + esub * 128 + rloc;
+      const float inv = *g.inv_scale;
+      const int n0 = n_tile * NT;
+      const uint32_t tsrc = tmem + esub * 256 + ((uint32_t)(q * 32) << 16);
+      unsigned char* img = nullptr;   // this thread's row inside the output image tile
+      int kbase = 0;                  // k of the next layer that column n0 of this tile maps to
+      if (OUT_IMAGE) {
+        int t = m0 / 128 + esub;
+        img = reinterpret_cast<unsigned char*>(g.C) + (size_t)(t / g.out_div) * g.out_kchunks * ACT_CHUNK_BYTES + rloc * 16;
+        kbase = (t % g.out_div) * g.N + n0;
+      }
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        float v[16];
+        tmem_ld16(tsrc + c0, v);
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           float4 b = *reinterpret_cast<const float4*>(g.bias + n0 + c0 + j);
-          float4 o = make_float4(v[j] * inv + b.x, v[j + 1] * inv + b.y, v[j + 2] * inv + b.z, v[j + 3] * inv + b.w);
-          if (g.relu) {
-            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+          v[j] = v[j] * inv + b.x;
+          v[j + 1] = v[j + 1] * inv + b.y;
+          v[j + 2] = v[j + 2] * inv + b.z;
+          v[j + 3] = v[j + 3] * inv + b.w;
+        }
+        if (g.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (OUT_IMAGE) {
+          // 16 consecutive k of the next layer = two 8-wide k-chunks; lanes are consecutive rows -> 512 B runs
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            int k = kbase + c0 + h * 8;
+            unsigned char* p = img + (size_t)(k / BK) * ACT_CHUNK_BYTES + ((k % BK) / 8) * A_LBO;
+            uint4 hi, lo;
+            split8(make_float4(v[h * 8], v[h * 8 + 1], v[h * 8 + 2], v[h * 8 + 3]),
+                   make_float4(v[h * 8 + 4], v[h * 8 + 5], v[h * 8 + 6], v[h * 8 + 7]), hi, lo);
+            *reinterpret_cast<uint4*>(p) = hi;
+            *reinterpret_cast<uint4*>(p + A_HALF) = lo;
           }
-          *reinterpret_cast<float4*>(out + j) = o;
+        } else if (row < g.M) {
+          float* out = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       }
     }
@@ -241,59 +324,68 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
 
 }  // namespace
 
-size_t cpn_tc_weights_bytes() { return layer_offset(4); }
+size_t cpn_tc_weights_bytes() { return layer_offset(CPN_TC_LAYERS); }
 
 int cpn_pack_tc_weights(const float* raw, void* dst_v, cudaStream_t st) {
   unsigned char* dst = reinterpret_cast<unsigned char*>(dst_v);
   float* header = reinterpret_cast<float*>(dst);
-  unsigned int* absmax = reinterpret_cast<unsigned int*>(dst) + 8;
+  unsigned int* absmax = reinterpret_cast<unsigned int*>(dst) + 16;
   CPN_CHECK_CUDA(cudaMemsetAsync(dst, 0, cpn_tc_weights_bytes(), st));
-  for (int l = 0; l < 4; ++l) {
+  for (int l = 0; l < CPN_TC_LAYERS; ++l) {
     const TcLayer& L = kLayers[l];
     size_t n = (size_t)L.out * L.in;
-    absmax_kernel<<<64, 256, 0, st>>>(raw + kRawOff[l], n, absmax + l);
+    absmax_kernel<<<64, 256, 0, st>>>(raw + L.raw, n, absmax + l);
     CPN_CHECK_LAUNCH("absmax_kernel");
     size_t total = (size_t)L.out * L.kpad;
-    pack_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(raw + kRawOff[l], L.out, L.in, L.kpad, L.nt, absmax + l,
+    pack_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(raw + L.raw, L.out, L.in, L.kpad, L.nt, absmax + l,
                                                                     reinterpret_cast<__half*>(dst + layer_offset(l)), header, l);
     CPN_CHECK_LAUNCH("pack_tc_kernel");
   }
   return CPN_OK;
 }
 
-int launch_gemm_tc(const void* packed, int layer, const float* A, int lda, float* C, int ldc, int M, int relu,
-                   cudaStream_t st) {
-  if (!packed || !A || !C || layer < 0 || layer > 3 || M < 0 || (lda & 3) || (ldc & 3)) {
-    cpn_set_error("gemm_tc: bad argument (layer=%d M=%d lda=%d ldc=%d)", layer, M, lda, ldc);
+int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,
+                   int out_div, int out_kchunks, cudaStream_t st) {
+  const bool a_img = mode & CPN_TC_A_IMAGE, o_img = mode & CPN_TC_OUT_IMAGE;
+  if (!packed || !A || !C || layer < 0 || layer >= CPN_TC_LAYERS || M < 0 || (!a_img && (lda & 3)) || (!o_img && (ldc & 3)) ||
+      (o_img && (out_div < 1 || out_kchunks < 1))) {
+    cpn_set_error("gemm_tc: bad argument (layer=%d M=%d lda=%d ldc=%d mode=%d)", layer, M, lda, ldc, mode);
     return CPN_ERR_ARG;
   }
   if (M == 0) return CPN_OK;
-  CPN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const TcLayer& L = kLayers[layer];
   const unsigned char* tcw = reinterpret_cast<const unsigned char*>(packed) + cpn_packed_fp32_floats() * sizeof(float);
   GemmArgs g;
   g.A = A;
   g.lda = lda;
-  g.kreal = L.in < lda ? ((L.in + 7) / 8 * 8) : lda;   // columns of A that exist (the zero pad of 835 -> 848 is read)
-  if (g.kreal > lda) g.kreal = lda;
+  g.kreal = (L.in + 7) / 8 * 8;   // columns of A that exist (835 -> 840: the zero pad up to lda = 848 is read)
+  if (!a_img && g.kreal > lda) {
+    cpn_set_error("gemm_tc: lda=%d smaller than the layer's K=%d rounded up to 8", lda, L.in);
+    return CPN_ERR_ARG;
+  }
   g.M = M;
   g.C = C;
   g.ldc = ldc;
   g.N = L.out;
   g.relu = relu;
+  g.out_div = out_div;
+  g.out_kchunks = out_kchunks;
   g.wtiles = tcw + layer_offset(layer);
   g.bias = reinterpret_cast<const float*>(packed) + L.bias;
   g.inv_scale = reinterpret_cast<const float*>(tcw) + layer;
   g.kchunks = L.kpad / BK;
   g.NT = L.nt;
-  g.idesc = make_idesc_f16(BM, L.nt);
+  g.idesc = make_idesc_f16(128, L.nt);
   dim3 grid(L.out / L.nt, (M + BM - 1) / BM);
-  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(g);
+  auto kern = a_img ? (o_img ? gemm_tc_kernel<true, true> : gemm_tc_kernel<true, false>)
+                    : (o_img ? gemm_tc_kernel<false, true> : gemm_tc_kernel<false, false>);
+  CPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(g);
   CPN_CHECK_LAUNCH("gemm_tc_kernel");
   return CPN_OK;
 }
 
-extern "C" int cpn_gemm_tc(const void* packed, int layer, const float* A, int lda, float* C, int ldc, int M, int relu,
-                           void* stream) {
-  return launch_gemm_tc(packed, layer, A, lda, C, ldc, M, relu, (cudaStream_t)stream);
+extern "C" int cpn_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu,
+                           int mode, int out_div, int out_kchunks, void* stream) {
+  return launch_gemm_tc(packed, layer, A, lda, C, ldc, M, relu, mode, out_div, out_kchunks, (cudaStream_t)stream);
 }

@@ -378,8 +378,8 @@ __global__ void sample_kernel(cpn_render_args a, int ray0, int nr, const float* 
   ra[7] = 0.f;
 
   // tanh point codes go straight into the encoder input rows (columns 832..834, zero padding after)
-  float* Ap = A + ((size_t)row * 2 + 0) * CPN_KA + CPN_FEAT_DIM;
-  float* As = A + ((size_t)row * 2 + 1) * CPN_KA + CPN_FEAT_DIM;
+  float* Ap = A + enc_row((size_t)row, 0) * CPN_KA + CPN_FEAT_DIM;
+  float* As = A + enc_row((size_t)row, 1) * CPN_KA + CPN_FEAT_DIM;
   for (int i = 0; i < 3; ++i) {
     Ap[i] = tanhf(nan_to_num(own[i]) / 5.f);
     As[i] = tanhf(nan_to_num(oth[i]) / 5.f);

@@ -81,7 +81,7 @@ struct Workspace {
 
 Workspace carve(void* base, int B, int nr, int S) {
   Workspace w;
-  size_t rays = (size_t)B * nr, R = rays * 2 * S;
+  size_t rays = (size_t)B * nr, R = (rays * 2 * S + 127) / 128 * 128;   // whole 128-row tiles
   size_t off = 0;
   auto take = [&](size_t floats) {
     float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
@@ -151,13 +151,13 @@ int check_args(const cpn_render_args* a) {
     if (_s != CPN_OK) return _s; \
   } while (0)
 
-// Encoder GEMMs: tensor-core path when the packed blob carries the split-fp16 tiles and the
-// caller did not ask for the fp32 CUDA-core cross-check path (args.reserved bit 0).
-int dense(const cpn_render_args& a, int tc_layer, const float* A, int lda, size_t wt, size_t bias, float* C, int ldc,
-          int M, int N, int K, int relu, cudaStream_t st) {
+bool use_tc(const cpn_render_args& a) { return !(a.flags & CPN_FLAG_SIMT_ONLY); }
+
+// fp32 CUDA-core layer: C = act(A * Wt + bias)
+int dense_simt(const cpn_render_args& a, const float* A, int lda, size_t wt, size_t bias, float* C, int ldc, int M, int N,
+               int K, int relu, cudaStream_t st, int remap256 = 0) {
   const float* W = reinterpret_cast<const float*>(a.weights);
-  if (tc_layer >= 0 && !(a.flags & CPN_FLAG_SIMT_ONLY) && cpn_tc_weights_bytes() > 0) return launch_gemm_tc(a.weights, tc_layer, A, lda, C, ldc, M, relu, st);
-  return launch_gemm_simt(A, lda, W + wt, W + bias, nullptr, 1, C, ldc, M, N, K, relu, st);
+  return launch_gemm_simt(A, lda, W + wt, W + bias, nullptr, 1, C, ldc, M, N, K, relu, st, remap256);
 }
 
 }  // namespace
@@ -192,27 +192,47 @@ extern "C" int cpn_render_rays(const cpn_render_args* args, void* stream) {
     CPN_TRY(launch_ray_setup(a, ray0, nr, w.seg, st));
     CPN_TRY(launch_sample(a, ray0, nr, w.seg, w.rowaux, w.local16, w.A, st));
     CPN_TRY(launch_gather(a, ray0, nr, w.rowaux, w.A, st));
-    // per-sample encoder, CoPoNeRF.py:387-397: (835 -> 832 ReLU -> 416) for the primary and the secondary row
-    {
-      ProfScope prof(st);
-      CPN_TRY(dense(a, 0, w.A, CPN_KA, pw::W1T, pw::B1, w.H1, CPN_FEAT_DIM, 2 * R, CPN_FEAT_DIM, CPN_KA, 1, st));
+    const int Rp = (R + 127) / 128 * 128;
+    const int KC832 = CPN_FEAT_DIM / ACT_BK, KC128 = CPN_HIDDEN / ACT_BK;
+    if (use_tc(a)) {
+      // per-sample encoder, CoPoNeRF.py:387-397: (835 -> 832 ReLU -> 416) for the primary and the secondary rows.
+      // Activations travel between the tensor-core layers as fp16 hi/lo operand images (cpn_common.cuh).
+      {
+        ProfScope prof(st);
+        CPN_TRY(launch_gemm_tc(a.weights, 0, w.A, CPN_KA, w.H1, 0, 2 * Rp, 1, CPN_TC_OUT_IMAGE, 1, KC832, st));
+      }
+      // the (tile, primary) and (tile, secondary) results land side by side: E image rows = sample rows, K = 832
+      CPN_TRY(launch_gemm_tc(a.weights, 1, w.H1, 0, w.E, 0, 2 * Rp, 0, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE, 2, KC832, st));
+      // value and key, CoPoNeRF.py:404-408
+      CPN_TRY(launch_gemm_tc(a.weights, 2, w.E, 0, w.V, CPN_LATENT, R, 0, CPN_TC_A_IMAGE, 1, 1, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 3, w.E, 0, w.K1, 0, R, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE, 1, KC128, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 4, w.K1, 0, w.Kk, CPN_HIDDEN, R, 0, CPN_TC_A_IMAGE, 1, 1, st));
+      // coordinate embedding, CoPoNeRF.py:446
+      CPN_TRY(dense_simt(a, w.local16, 16, pw::WQT, pw::BQ, w.Q1, CPN_HIDDEN, R, CPN_HIDDEN, 16, 1, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 5, w.Q1, CPN_HIDDEN, w.Qe, CPN_HIDDEN, R, 0, 0, 1, 1, st));
+    } else {
+      {
+        ProfScope prof(st);
+        CPN_TRY(dense_simt(a, w.A, CPN_KA, pw::W1T, pw::B1, w.H1, CPN_FEAT_DIM, 2 * Rp, CPN_FEAT_DIM, CPN_KA, 1, st));
+      }
+      CPN_TRY(dense_simt(a, w.H1, CPN_FEAT_DIM, pw::W2T, pw::B2, w.E, CPN_FEAT_DIM, 2 * Rp, CPN_LATENT, CPN_FEAT_DIM, 0, st, 1));
+      CPN_TRY(dense_simt(a, w.E, CPN_FEAT_DIM, pw::WVT, pw::BV, w.V, CPN_LATENT, R, CPN_LATENT, CPN_FEAT_DIM, 0, st));
+      CPN_TRY(dense_simt(a, w.E, CPN_FEAT_DIM, pw::WKT, pw::BK, w.K1, CPN_HIDDEN, R, CPN_HIDDEN, CPN_FEAT_DIM, 1, st));
+      CPN_TRY(dense_simt(a, w.K1, CPN_HIDDEN, pw::WK2T, pw::BK2, w.Kk, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
+      CPN_TRY(dense_simt(a, w.local16, 16, pw::WQT, pw::BQ, w.Q1, CPN_HIDDEN, R, CPN_HIDDEN, 16, 1, st));
+      CPN_TRY(dense_simt(a, w.Q1, CPN_HIDDEN, pw::WQ2T, pw::BQ2, w.Qe, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
     }
-    CPN_TRY(dense(a, 1, w.H1, CPN_FEAT_DIM, pw::W2T, pw::B2, w.E, CPN_LATENT, 2 * R, CPN_LATENT, CPN_FEAT_DIM, 0, st));
-    // value and key, CoPoNeRF.py:404-408 (E is (R, 832): [enc(primary) | enc(secondary)])
-    CPN_TRY(dense(a, 2, w.E, CPN_FEAT_DIM, pw::WVT, pw::BV, w.V, CPN_LATENT, R, CPN_LATENT, CPN_FEAT_DIM, 0, st));
-    CPN_TRY(dense(a, 3, w.E, CPN_FEAT_DIM, pw::WKT, pw::BK, w.K1, CPN_HIDDEN, R, CPN_HIDDEN, CPN_FEAT_DIM, 1, st));
-    CPN_TRY(dense(a, -1, w.K1, CPN_HIDDEN, pw::WK2T, pw::BK2, w.Kk, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
-    // coordinate embedding, CoPoNeRF.py:446
-    CPN_TRY(dense(a, -1, w.local16, 16, pw::WQT, pw::BQ, w.Q1, CPN_HIDDEN, R, CPN_HIDDEN, 16, 1, st));
-    CPN_TRY(dense(a, -1, w.Q1, CPN_HIDDEN, pw::WQ2T, pw::BQ2, w.Qe, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
     CPN_TRY(launch_attn1(a, ray0, nr, w.Kk, w.Qe, w.V, w.rowaux, w.r1, w.wp, st));
     // round 2, CoPoNeRF.py:467-473: query_repeat_embed(cat(encode_latent(R1), local_coords)); the z_embed
     // channels are the same for every sample of a ray, so they enter as a per-ray bias.
-    CPN_TRY(dense(a, -1, w.r1, CPN_LATENT, pw::WET, pw::BE, w.zemb, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_LATENT, 0, st));
-    CPN_TRY(dense(a, -1, w.zemb, CPN_HIDDEN, pw::WQRA_T, pw::BQR, w.rbias, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_HIDDEN, 0, st));
+    CPN_TRY(dense_simt(a, w.r1, CPN_LATENT, pw::WET, pw::BE, w.zemb, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_LATENT, 0, st));
+    CPN_TRY(dense_simt(a, w.zemb, CPN_HIDDEN, pw::WQRA_T, pw::BQR, w.rbias, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_HIDDEN, 0, st));
     CPN_TRY(launch_gemm_simt(w.local16, 16, W + pw::WQRB_T, nullptr, w.rbias, 2 * a.S, w.K1, CPN_HIDDEN, R, CPN_HIDDEN,
                              16, 1, st));
-    CPN_TRY(dense(a, -1, w.K1, CPN_HIDDEN, pw::WQR2T, pw::BQR2, w.Kk, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
+    if (use_tc(a))
+      CPN_TRY(launch_gemm_tc(a.weights, 6, w.K1, CPN_HIDDEN, w.Kk, CPN_HIDDEN, R, 0, 0, 1, 1, st));
+    else
+      CPN_TRY(dense_simt(a, w.K1, CPN_HIDDEN, pw::WQR2T, pw::BQR2, w.Kk, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
     CPN_TRY(launch_attn2(a, nr, w.Kk, w.Qe, w.V, w.r1, w.z, st));
     CPN_TRY(launch_phi(a, ray0, nr, w.z, w.seg, st));
     CPN_TRY(launch_ray_epilogue(a, ray0, nr, w.wp, st));

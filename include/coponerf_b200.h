@@ -132,10 +132,16 @@ int cpn_gemm_simt(const float* A, int lda, const float* wt, const float* bias, f
                   int M, int N, int K, int relu, void* stream);
 
 /* Tensor-core GEMM of one packed layer (0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value,
- * 3 key_map): C[M, N_layer] = act(A[M, K_layer] * W^T + b), operands split into fp16 hi/lo pairs and
- * accumulated in fp32 on tcgen05 (3 MMAs per product). `packed` is the blob from cpn_pack_weights. */
-int cpn_gemm_tc(const void* packed, int layer, const float* A, int lda, float* C, int ldc, int M, int relu,
-                void* stream);
+ * 3 key_map, 4 key_map_2, 5 query_embed_2, 6 query_repeat_embed_2): C[M, N_layer] = act(A[M, K_layer] * W^T + b),
+ * operands split into fp16 hi/lo pairs and accumulated in fp32 on tcgen05 (3 MMAs per product).
+ * `packed` is the blob from cpn_pack_weights. mode bit CPN_TC_A_IMAGE: A is an "operand image" (128-row tiles,
+ * per 32-wide k-chunk a 16 KB block [hi|lo][4][128][8] of fp16) instead of fp32 row-major; CPN_TC_OUT_IMAGE: C is
+ * written as such an image with `out_kchunks` k-chunks per tile, source tile t landing in image tile t / out_div at
+ * k offset (t % out_div) * N_layer (how the two branches of a sample row are concatenated). */
+#define CPN_TC_A_IMAGE 1
+#define CPN_TC_OUT_IMAGE 2
+int cpn_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,
+                int out_div, int out_kchunks, void* stream);
 
 #ifdef __cplusplus
 }

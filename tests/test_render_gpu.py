@@ -139,30 +139,76 @@ def test_pair_prologue_against_oracle():
     assert 0.02 < mask.float().mean() < 0.98
 
 
-@pytest.mark.parametrize("layer,name,relu", [(0, "query_encode_latent", 1), (1, "query_encode_latent_2", 0),
-                                             (2, "latent_value", 0), (3, "key_map", 1)])
-def test_gemm_tc_against_torch_fp64(layer, name, relu):
-    """tcgen05 split-fp16 GEMM of one packed layer vs fp64: error must sit at fp32 level, far below TF32's 5e-4."""
+TC_LAYERS = [(0, "query_encode_latent", 1), (1, "query_encode_latent_2", 0), (2, "latent_value", 0), (3, "key_map", 1),
+             (4, "key_map_2", 0), (5, "query_embed_2", 0), (6, "query_repeat_embed_2", 0)]
+
+
+def _tc_setup(name):
     from coponerf_b200 import _lib, synth
     from cases import cuda_model
     lib = _lib.load()
     eng = cuda_model().engine()
     sd = synth.render_state_dict(0)
     Wm = sd[name + ".weight"].reshape(sd[name + ".weight"].shape[0], -1).cuda()
-    bias = sd[name + ".bias"].cuda()
+    return lib, eng, Wm, sd[name + ".bias"].cuda()
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _st():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("layer,name,relu", TC_LAYERS)
+def test_gemm_tc_against_torch_fp64(layer, name, relu):
+    """tcgen05 split-fp16 GEMM of one packed layer vs fp64: error must sit at fp32 level, far below TF32's 5e-4."""
+    from coponerf_b200 import _lib
+    lib, eng, Wm, bias = _tc_setup(name)
     N, K = Wm.shape
     lda = 848 if K == 835 else K
     torch.manual_seed(layer)
-    p = lambda t: ctypes.c_void_p(t.data_ptr())
-    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     for M in (1, 128, 300, 1000):
         A = torch.zeros(M, lda, device="cuda")
         A[:, :K] = torch.randn(M, K, device="cuda") * 3
         C = torch.full((M, N), float("nan"), device="cuda")
-        _lib.check(lib.cpn_gemm_tc(p(eng.weights), layer, p(A), lda, p(C), N, M, relu, st), "cpn_gemm_tc")
+        _lib.check(lib.cpn_gemm_tc(_p(eng.weights), layer, _p(A), lda, _p(C), N, M, relu, 0, 1, 1, _st()), "cpn_gemm_tc")
         ref = torch.nn.functional.linear(A[:, :K].double(), Wm.double(), bias.double())
         if relu:
             ref = ref.relu()
         e = rel_err(C.cpu().numpy(), ref.cpu().numpy())
         print(f"gemm_tc {name} M={M}: rel err {e:.2e}")
         assert e < 1e-5, (name, M, e)
+
+
+def test_gemm_tc_operand_image_chain():
+    """fp32 -> [GEMM1] -> hi/lo operand image -> [GEMM2, two branches side by side] -> image -> [latent_value] -> fp32,
+    the way cpn_render_rays chains the encoder layers, against fp64."""
+    from coponerf_b200 import _lib
+    lib, eng, W1, b1 = _tc_setup("query_encode_latent")
+    _, _, W2, b2 = _tc_setup("query_encode_latent_2")
+    _, _, WV, bV = _tc_setup("latent_value")
+    torch.manual_seed(7)
+    R = 300                                   # sample rows; 3 tiles of 128 with a ragged tail
+    Rp = (R + 127) // 128 * 128
+    x = torch.randn(2, R, 835, device="cuda")  # [branch][row]
+    A = torch.zeros(2 * Rp, 848, device="cuda")
+    rows = torch.arange(R, device="cuda")
+    for br in range(2):
+        A[(rows // 128) * 256 + br * 128 + rows % 128, :835] = x[br]
+    chunk = _lib.ACT_CHUNK_BYTES
+    H1 = torch.empty(2 * Rp // 128 * 26 * chunk, dtype=torch.uint8, device="cuda")
+    E = torch.empty(Rp // 128 * 26 * chunk, dtype=torch.uint8, device="cuda")
+    V = torch.full((R, 416), float("nan"), device="cuda")
+    w = _p(eng.weights)
+    _lib.check(lib.cpn_gemm_tc(w, 0, _p(A), 848, _p(H1), 0, 2 * Rp, 1, _lib.TC_OUT_IMAGE, 1, 26, _st()), "gemm1")
+    _lib.check(lib.cpn_gemm_tc(w, 1, _p(H1), 0, _p(E), 0, 2 * Rp, 0, _lib.TC_A_IMAGE | _lib.TC_OUT_IMAGE, 2, 26, _st()), "gemm2")
+    _lib.check(lib.cpn_gemm_tc(w, 2, _p(E), 0, _p(V), 416, R, 0, _lib.TC_A_IMAGE, 1, 1, _st()), "gemmV")
+    lin = torch.nn.functional.linear
+    h = lin(x.double(), W1.double(), b1.double()).relu()
+    e = lin(h, W2.double(), b2.double())                      # (2, R, 416)
+    ref = lin(torch.cat((e[0], e[1]), dim=-1), WV.double(), bV.double())
+    err = rel_err(V.cpu().numpy(), ref.cpu().numpy())
+    print(f"gemm_tc chain: rel err {err:.2e}")
+    assert err < 2e-5, err
