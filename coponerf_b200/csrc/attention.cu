@@ -126,7 +126,7 @@ __global__ void attn2_kernel(cpn_render_args a, int nr, const float* __restrict_
 // phi. One CTA of 128 threads renders PHI_RAYS rays; thread j owns hidden channel j.
 // Input of lin_z is cat(z, z) (both views carry the same latent, models/CoPoNeRF.py:545-552), coords18 is
 // [plucker6 + origin3] of view 0 then view 1.
-constexpr int PHI_RAYS = 16;
+constexpr int PHI_RAYS = 4;   // small tiles: the grid (rays / 4 CTAs) hides the serial k-loops' latency
 
 __device__ __forceinline__ void phi_dense128(const float* __restrict__ wT, const float* __restrict__ bias,
                                              float (*in)[CPN_HIDDEN], float* out, int j, bool relu_in) {
@@ -134,6 +134,7 @@ __device__ __forceinline__ void phi_dense128(const float* __restrict__ wT, const
   float bj = bias[j];
 #pragma unroll
   for (int r = 0; r < PHI_RAYS; ++r) out[r] = bj;
+#pragma unroll 8
   for (int k = 0; k < CPN_HIDDEN; ++k) {
     float wv = __ldg(wT + k * CPN_HIDDEN + j);
 #pragma unroll
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(128) phi_kernel(cpn_render_args a, int ray0, i
     float bj = W[pw::PHI_BZ + blk * CPN_HIDDEN + j];
 #pragma unroll
     for (int r = 0; r < PHI_RAYS; ++r) tmp[r] = bj;
+#pragma unroll 8
     for (int k = 0; k < 2 * CPN_LATENT; ++k) {
       float wv = __ldg(wz + (size_t)k * CPN_HIDDEN + j);
       int kk = k < CPN_LATENT ? k : k - CPN_LATENT;

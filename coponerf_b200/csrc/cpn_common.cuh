@@ -5,7 +5,8 @@
 #include <stdio.h>
 #include "../../include/coponerf_b200.h"
 
-#define CPN_KA 848  // 835 encoder inputs padded to a multiple of 16 (zero columns)
+#define CPN_KA 848      // 835 encoder inputs padded to a multiple of 16 (zero columns), fp32 row form
+#define CPN_KA_IMG 864  // ... padded to a multiple of 32, operand-image form (27 k-chunks)
 
 // ---- packed fp32 weight blob (offsets in floats) -------------------------------------------
 // Every matrix is stored transposed, [K][N], so consecutive threads read consecutive outputs.
@@ -72,6 +73,12 @@ __host__ __device__ __forceinline__ size_t enc_row(size_t row, int branch) {
   return (row >> 7) * 256 + (size_t)branch * 128 + (row & 127);
 }
 
+// Byte offset of the 16-byte group holding k .. k+7 (k % 8 == 0) of row r (0..127) in image tile t of an
+// operand image with `kchunks` 32-wide k-chunks per tile; the lo half sits 8192 bytes further.
+__host__ __device__ __forceinline__ size_t act_img_off(size_t t, int kchunks, int k, int r) {
+  return (t * kchunks + (k >> 5)) * 16384 + (size_t)((k & 31) >> 3) * 2048 + (size_t)r * 16;
+}
+
 void cpn_set_error(const char* fmt, ...);
 #define CPN_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \
@@ -92,9 +99,10 @@ void cpn_set_error(const char* fmt, ...);
 
 // launchers implemented across the .cu files (all asynchronous on `st`)
 int launch_ray_setup(const cpn_render_args& a, int ray0, int nr, float* seg, cudaStream_t st);
+// a_image: write the encoder input as the fp16 hi/lo operand image (K = CPN_KA_IMG) instead of fp32 rows of CPN_KA
 int launch_sample(const cpn_render_args& a, int ray0, int nr, const float* seg, float* rowaux, float* local16,
-                  float* A, cudaStream_t st);
-int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowaux, float* A, cudaStream_t st);
+                  float* A, int a_image, cudaStream_t st);
+int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowaux, float* A, int a_image, cudaStream_t st);
 // remap256: output row m goes to row (m / 256) * 128 + m % 128 at column offset ((m / 128) & 1) * N (undoes enc_row)
 int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias, const float* rowbias,
                      int rows_per_bias, float* C, int ldc, int M, int N, int K, int relu, cudaStream_t st,

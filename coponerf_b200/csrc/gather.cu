@@ -2,6 +2,7 @@
 // channels-last feature maps, primary ('border' padding, models/CoPoNeRF.py:312) and secondary
 // ('zeros' padding at the reprojected coordinates, models/CoPoNeRF.py:370).
 #include "cpn_common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -36,6 +37,7 @@ __device__ __forceinline__ Taps make_taps(float gx, float gy, int h, int w, int 
 
 // One warp per (row, branch). Row = ((b*nr + n)*2 + v)*S + s; branch 0 reads view v at the sample
 // position, branch 1 reads view 1-v at the reprojected position.
+template <bool IMAGE>
 __global__ void __launch_bounds__(256) gather_kernel(cpn_render_args a, int nr, const float* __restrict__ rowaux,
                                                      float* __restrict__ A) {
   long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -50,6 +52,10 @@ __global__ void __launch_bounds__(256) gather_kernel(cpn_render_args a, int nr, 
   const float* ra = rowaux + (size_t)row * CPN_ROWAUX;
   float gx = ra[branch * 2 + 0], gy = ra[branch * 2 + 1];
   float* out = A + enc_row((size_t)row, branch) * CPN_KA;
+  // image form: tile (row / 128, branch), row r inside it; lane l owns channels 4l .. 4l+3 of every 128-channel group
+  unsigned char* aimg = reinterpret_cast<unsigned char*>(A);
+  const size_t tile = (size_t)(row >> 7) * 2 + branch;
+  const int r = (int)(row & 127);
   int col = 0;
 #pragma unroll
   for (int l = 0; l < CPN_N_LEVELS; ++l) {
@@ -68,7 +74,17 @@ __global__ void __launch_bounds__(256) gather_kernel(cpn_render_args a, int nr, 
           acc.w += f.w * t.w[k];
         }
       }
-      *reinterpret_cast<float4*>(out + col + c) = acc;
+      if (IMAGE) {
+        uint2 hi, lo;
+        tc::split2(acc.x, acc.y, hi.x, lo.x);
+        tc::split2(acc.z, acc.w, hi.y, lo.y);
+        int k = col + c;
+        unsigned char* p = aimg + act_img_off(tile, CPN_KA_IMG / ACT_BK, k & ~7, r) + (k & 7) * 2;
+        *reinterpret_cast<uint2*>(p) = hi;
+        *reinterpret_cast<uint2*>(p + 8192) = lo;
+      } else {
+        *reinterpret_cast<float4*>(out + col + c) = acc;
+      }
     }
     col += C;
   }
@@ -93,11 +109,14 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __rest
 
 }  // namespace
 
-int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowaux, float* A, cudaStream_t st) {
+int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowaux, float* A, int a_image, cudaStream_t st) {
   (void)ray0;
   long long warps = (long long)a.B * nr * 2 * a.S * 2;
   long long blocks = (warps * 32 + 255) / 256;
-  gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, nr, rowaux, A);
+  if (a_image)
+    gather_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(a, nr, rowaux, A);
+  else
+    gather_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(a, nr, rowaux, A);
   CPN_CHECK_LAUNCH("gather_kernel");
   return CPN_OK;
 }

@@ -3,6 +3,7 @@
 // (and fp64 for the triangulation), so no contraction into FMAs here.
 #include <math.h>
 #include "cpn_common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -300,7 +301,7 @@ __device__ __forceinline__ void transform_point(const float* T, const float* p, 
 // (fp64 closest point), :336-367 (reprojection into the other view), :384-394 (tanh point codes),
 // :411-445 (local_coords).
 __global__ void sample_kernel(cpn_render_args a, int ray0, int nr, const float* __restrict__ seg,
-                              float* __restrict__ rowaux, float* __restrict__ local16, float* __restrict__ A) {
+                              float* __restrict__ rowaux, float* __restrict__ local16, float* __restrict__ A, int a_image) {
   long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long nrows = (long long)a.B * nr * 2 * a.S;
   if (row >= nrows) return;
@@ -378,15 +379,40 @@ __global__ void sample_kernel(cpn_render_args a, int ray0, int nr, const float* 
   ra[7] = 0.f;
 
   // tanh point codes go straight into the encoder input rows (columns 832..834, zero padding after)
-  float* Ap = A + enc_row((size_t)row, 0) * CPN_KA + CPN_FEAT_DIM;
-  float* As = A + enc_row((size_t)row, 1) * CPN_KA + CPN_FEAT_DIM;
+  float tp[3], ts[3];
   for (int i = 0; i < 3; ++i) {
-    Ap[i] = tanhf(nan_to_num(own[i]) / 5.f);
-    As[i] = tanhf(nan_to_num(oth[i]) / 5.f);
+    tp[i] = tanhf(nan_to_num(own[i]) / 5.f);
+    ts[i] = tanhf(nan_to_num(oth[i]) / 5.f);
   }
-  for (int i = 3; i < CPN_KA - CPN_FEAT_DIM; ++i) {
-    Ap[i] = 0.f;
-    As[i] = 0.f;
+  if (a_image) {
+    // operand image: k-chunk 26 holds k = 832..863; group 0 = the three codes + five zeros, groups 1-3 zeros
+    unsigned char* img = reinterpret_cast<unsigned char*>(A);
+    const int r = (int)(row & 127);
+    for (int br = 0; br < 2; ++br) {
+      const float* t3 = br ? ts : tp;
+      unsigned char* p = img + act_img_off((size_t)(row >> 7) * 2 + br, CPN_KA_IMG / ACT_BK, CPN_FEAT_DIM, r);
+      uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+      tc::split2(t3[0], t3[1], hi.x, lo.x);
+      tc::split2(t3[2], 0.f, hi.y, lo.y);
+      *reinterpret_cast<uint4*>(p) = hi;
+      *reinterpret_cast<uint4*>(p + 8192) = lo;
+      const uint4 zero = make_uint4(0, 0, 0, 0);
+      for (int gq = 1; gq < 4; ++gq) {
+        *reinterpret_cast<uint4*>(p + gq * 2048) = zero;
+        *reinterpret_cast<uint4*>(p + gq * 2048 + 8192) = zero;
+      }
+    }
+  } else {
+    float* Ap = A + enc_row((size_t)row, 0) * CPN_KA + CPN_FEAT_DIM;
+    float* As = A + enc_row((size_t)row, 1) * CPN_KA + CPN_FEAT_DIM;
+    for (int i = 0; i < 3; ++i) {
+      Ap[i] = tp[i];
+      As[i] = ts[i];
+    }
+    for (int i = 3; i < CPN_KA - CPN_FEAT_DIM; ++i) {
+      Ap[i] = 0.f;
+      As[i] = 0.f;
+    }
   }
 
   // local_coords (CoPoNeRF.py:411-445): [cam ray dir, 0 0 0, query ray dir, tanh(d / {1,10,100,1000}), query origin]
@@ -472,9 +498,9 @@ int launch_ray_setup(const cpn_render_args& a, int ray0, int nr, float* seg, cud
 }
 
 int launch_sample(const cpn_render_args& a, int ray0, int nr, const float* seg, float* rowaux, float* local16,
-                  float* A, cudaStream_t st) {
+                  float* A, int a_image, cudaStream_t st) {
   long long rows = (long long)a.B * nr * 2 * a.S;
-  sample_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(a, ray0, nr, seg, rowaux, local16, A);
+  sample_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(a, ray0, nr, seg, rowaux, local16, A, a_image);
   CPN_CHECK_LAUNCH("sample_kernel");
   return CPN_OK;
 }

@@ -91,7 +91,7 @@ Workspace carve(void* base, int B, int nr, int S) {
   w.seg = take(rays * 2 * 6);
   w.rowaux = take(R * CPN_ROWAUX);
   w.local16 = take(R * 16);
-  w.A = take(R * 2 * CPN_KA);
+  w.A = take(R * 2 * CPN_KA_IMG);   // fp32 rows of CPN_KA, or the operand image with K = CPN_KA_IMG
   w.H1 = take(R * 2 * CPN_FEAT_DIM);
   w.E = take(R * CPN_FEAT_DIM);
   w.V = take(R * CPN_LATENT);
@@ -190,8 +190,8 @@ extern "C" int cpn_render_rays(const cpn_render_args* args, void* stream) {
     int rays = a.B * nr;
     int R = rays * 2 * a.S;
     CPN_TRY(launch_ray_setup(a, ray0, nr, w.seg, st));
-    CPN_TRY(launch_sample(a, ray0, nr, w.seg, w.rowaux, w.local16, w.A, st));
-    CPN_TRY(launch_gather(a, ray0, nr, w.rowaux, w.A, st));
+    CPN_TRY(launch_sample(a, ray0, nr, w.seg, w.rowaux, w.local16, w.A, use_tc(a), st));
+    CPN_TRY(launch_gather(a, ray0, nr, w.rowaux, w.A, use_tc(a), st));
     const int Rp = (R + 127) / 128 * 128;
     const int KC832 = CPN_FEAT_DIM / ACT_BK, KC128 = CPN_HIDDEN / ACT_BK;
     if (use_tc(a)) {
@@ -199,7 +199,7 @@ extern "C" int cpn_render_rays(const cpn_render_args* args, void* stream) {
       // Activations travel between the tensor-core layers as fp16 hi/lo operand images (cpn_common.cuh).
       {
         ProfScope prof(st);
-        CPN_TRY(launch_gemm_tc(a.weights, 0, w.A, CPN_KA, w.H1, 0, 2 * Rp, 1, CPN_TC_OUT_IMAGE, 1, KC832, st));
+        CPN_TRY(launch_gemm_tc(a.weights, 0, w.A, 0, w.H1, 0, 2 * Rp, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE, 1, KC832, st));
       }
       // the (tile, primary) and (tile, secondary) results land side by side: E image rows = sample rows, K = 832
       CPN_TRY(launch_gemm_tc(a.weights, 1, w.H1, 0, w.E, 0, 2 * Rp, 0, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE, 2, KC832, st));
