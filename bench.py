@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk-rays", type=int, default=2048)
+    ap.add_argument("--lanes", type=int, default=3, help="chunks in flight on internal streams")
     ap.add_argument("--simt", action="store_true", help="fp32 CUDA-core GEMMs only (cross-check path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -176,7 +177,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    model = CoPoNeRF(n_view=2, npoints=S, chunk_rays=args.chunk_rays)
+    model = CoPoNeRF(n_view=2, npoints=S, chunk_rays=args.chunk_rays, lanes=args.lanes)
     model.load_state_dict(synth.render_state_dict(0), strict=False)
     model = model.to(dev).eval()
     model.H, model.W = H, W
@@ -294,7 +295,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "256x256 stereo pair, 65536 rays, S=64 (render half: forward with z given)",
-                   "pairs_per_gpu": 1, "chunk_rays": args.chunk_rays, "l2": "flushed between timed steps (256 MB write)",
+                   "pairs_per_gpu": 1, "chunk_rays": args.chunk_rays, "lanes": args.lanes, "l2": "flushed between timed steps (256 MB write)",
                    "gemm_path": "simt-fp32" if args.simt else "tcgen05 split-fp16 (3 MMA) + simt-fp32 small layers",
                    "parallelism": f"pairs sharded over {world} GPU(s), one NCCL gather of rgb" if world > 1 else "1 GPU"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -27,6 +27,7 @@ class RenderArgs(ctypes.Structure):
         ("B", ctypes.c_int32), ("N", ctypes.c_int32), ("S", ctypes.c_int32),
         ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("flow_h", ctypes.c_int32),
         ("chunk_rays", ctypes.c_int32), ("flags", ctypes.c_int32),
+        ("lanes", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("feat", ctypes.c_void_p * N_LEVELS),
         ("feat_h", ctypes.c_int32 * N_LEVELS), ("feat_w", ctypes.c_int32 * N_LEVELS),
         ("feat_c", ctypes.c_int32 * N_LEVELS),
@@ -59,7 +60,7 @@ SIGNATURES = {
     "cpn_pair_setup": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_void_p]),
     "cpn_pair_prologue": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 +
                           [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
-    "cpn_render_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "cpn_render_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5),
     "cpn_render_rays": (ctypes.c_int, [ctypes.POINTER(RenderArgs), ctypes.c_void_p]),
     "cpn_render_launch_count": (ctypes.c_int, [ctypes.POINTER(RenderArgs)]),
     "cpn_gemm_simt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

@@ -25,12 +25,23 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float warp_row_logits(const float* __restrict__ x, const float* __restrict__ y, size_t row0,
                                                  int warp, int lane) {
   float mine = 0.f;
-  for (int r = 0; r < 32; ++r) {
-    size_t row = row0 + warp * 32 + r;
-    float4 a = __ldg(reinterpret_cast<const float4*>(x + row * CPN_HIDDEN) + lane);
-    float4 b = __ldg(reinterpret_cast<const float4*>(y + row * CPN_HIDDEN) + lane);
-    float d = warp_sum(a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w);
-    if (lane == r) mine = d;
+  for (int r0 = 0; r0 < 32; r0 += 4) {   // four rows in flight: 8 independent 512-byte loads, interleaved reductions
+    float d[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      size_t row = row0 + warp * 32 + r0 + i;
+      float4 a = __ldg(reinterpret_cast<const float4*>(x + row * CPN_HIDDEN) + lane);
+      float4 b = __ldg(reinterpret_cast<const float4*>(y + row * CPN_HIDDEN) + lane);
+      d[i] = ((a.x * b.x + a.y * b.y) + a.z * b.z) + a.w * b.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d[i] += __shfl_xor_sync(0xffffffffu, d[i], o);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (lane == r0 + i) mine = d[i];
   }
   return mine / 11.31f;
 }
@@ -86,7 +97,9 @@ __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* _
   for (int c = t; c < CPN_LATENT; c += S2) {
     const float* vp = value + row0 * CPN_LATENT + c;
     float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 8
     for (int s = 0; s < S; ++s) acc0 += vp[(size_t)s * CPN_LATENT] * w[s];
+#pragma unroll 8
     for (int s = 0; s < S; ++s) acc1 += vp[(size_t)(S + s) * CPN_LATENT] * w[S + s];
     r1[(size_t)ray * CPN_LATENT + c] = acc0 + acc1;
   }
@@ -101,8 +114,9 @@ __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* _
 }
 
 // Round 2. z = sum_v (sum_s w2 * V + R1) = R2 + 2 R1.
-__global__ void attn2_kernel(cpn_render_args a, int nr, const float* __restrict__ q2, const float* __restrict__ qemb,
-                             const float* __restrict__ value, const float* __restrict__ r1, float* __restrict__ z) {
+__global__ void attn2_kernel(cpn_render_args a, int ray0, int nr, const float* __restrict__ q2,
+                             const float* __restrict__ qemb, const float* __restrict__ value,
+                             const float* __restrict__ r1, float* __restrict__ z_all) {
   extern __shared__ float sm[];
   const int S = a.S, S2 = 2 * S;
   float* w = sm;
@@ -116,118 +130,123 @@ __global__ void attn2_kernel(cpn_render_args a, int nr, const float* __restrict_
   for (int c = t; c < CPN_LATENT; c += S2) {
     const float* vp = value + row0 * CPN_LATENT + c;
     float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 8
     for (int s = 0; s < S; ++s) acc0 += vp[(size_t)s * CPN_LATENT] * w[s];
+#pragma unroll 8
     for (int s = 0; s < S; ++s) acc1 += vp[(size_t)(S + s) * CPN_LATENT] * w[S + s];
     float r = r1[(size_t)ray * CPN_LATENT + c];
-    z[(size_t)ray * CPN_LATENT + c] = (acc0 + r) + (acc1 + r);
+    const int b = ray / nr, n = ray0 + ray % nr;
+    z_all[((size_t)b * a.N + n) * CPN_LATENT + c] = (acc0 + r) + (acc1 + r);
   }
 }
 
-// phi. One CTA of 128 threads renders PHI_RAYS rays; thread j owns hidden channel j.
+// phi. One CTA of 128 threads renders PHI_RAYS = 16 rays. Thread (cq = t % 32, rg = t / 32) owns a 4-channel x
+// 4-ray register tile: per k one coalesced float4 of weights and one broadcast float4 of inputs feed 16 FMAs.
 // Input of lin_z is cat(z, z) (both views carry the same latent, models/CoPoNeRF.py:545-552), coords18 is
 // [plucker6 + origin3] of view 0 then view 1.
-constexpr int PHI_RAYS = 4;   // small tiles: the grid (rays / 4 CTAs) hides the serial k-loops' latency
+constexpr int PHI_RAYS = 16;
 
-__device__ __forceinline__ void phi_dense128(const float* __restrict__ wT, const float* __restrict__ bias,
-                                             float (*in)[CPN_HIDDEN], float* out, int j, bool relu_in) {
-  // out[r] = bias[j] + sum_k act(in[r][k]) * wT[k][j]
-  float bj = bias[j];
-#pragma unroll
-  for (int r = 0; r < PHI_RAYS; ++r) out[r] = bj;
-#pragma unroll 8
-  for (int k = 0; k < CPN_HIDDEN; ++k) {
-    float wv = __ldg(wT + k * CPN_HIDDEN + j);
-#pragma unroll
-    for (int r = 0; r < PHI_RAYS; ++r) {
-      float x = in[r][k];
-      if (relu_in) x = fmaxf(x, 0.f);
-      out[r] = fmaf(x, wv, out[r]);
+// acc[c][r] += sum_k act(in[k][rg*4 + r]) * (wT[k][cq*4 + c] (+ wT2[k][cq*4 + c]))
+template <bool RELU_IN, bool TWO>
+__device__ __forceinline__ void phi_dense(const float* __restrict__ wT, const float* __restrict__ wT2, int K,
+                                          const float (*in)[PHI_RAYS], int cq, int rg, float (&acc)[4][4]) {
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    float4 w = __ldg(reinterpret_cast<const float4*>(wT + (size_t)k * CPN_HIDDEN) + cq);
+    if (TWO) {
+      float4 w2 = __ldg(reinterpret_cast<const float4*>(wT2 + (size_t)k * CPN_HIDDEN) + cq);
+      w.x += w2.x; w.y += w2.y; w.z += w2.z; w.w += w2.w;
     }
+    float4 x = *reinterpret_cast<const float4*>(&in[k][rg * 4]);
+    if (RELU_IN) {
+      x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+    }
+    const float wv[4] = {w.x, w.y, w.z, w.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[c][r] = fmaf(wv[c], xv[r], acc[c][r]);
   }
 }
 
-__global__ void __launch_bounds__(128) phi_kernel(cpn_render_args a, int ray0, int nr, const float* __restrict__ z,
-                                                  const float* __restrict__ seg, float* __restrict__ rgb_raw) {
-  __shared__ float zs[PHI_RAYS][CPN_LATENT];
-  __shared__ float xs[PHI_RAYS][CPN_HIDDEN];
-  __shared__ float hs[PHI_RAYS][CPN_HIDDEN];
-  __shared__ float cs[PHI_RAYS][20];
+__device__ __forceinline__ void phi_set_bias(const float* __restrict__ bias, int cq, float (&acc)[4][4]) {
+  float4 b = __ldg(reinterpret_cast<const float4*>(bias) + cq);
+  const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[c][r] = bv[c];
+}
+
+__global__ void __launch_bounds__(128) phi_kernel(cpn_render_args a, const float* __restrict__ z) {
+  __shared__ __align__(16) float zt[CPN_LATENT][PHI_RAYS];   // transposed inputs: [k][ray]
+  __shared__ __align__(16) float xt[CPN_HIDDEN][PHI_RAYS];
+  __shared__ __align__(16) float ht[CPN_HIDDEN][PHI_RAYS];
+  __shared__ __align__(16) float ct[20][PHI_RAYS];
   const float* W = reinterpret_cast<const float*>(a.weights);
-  const int j = threadIdx.x;
-  const int total = a.B * nr;
+  const int t = threadIdx.x, cq = t & 31, rg = t >> 5;
+  const int total = a.B * a.N;   // ray index = b * N + n
   const int base = blockIdx.x * PHI_RAYS;
-  for (int i = j; i < PHI_RAYS * CPN_LATENT; i += 128) {
+  for (int i = t; i < PHI_RAYS * CPN_LATENT; i += 128) {
     int r = i / CPN_LATENT, c = i % CPN_LATENT;
-    zs[r][c] = (base + r < total) ? z[(size_t)(base + r) * CPN_LATENT + c] : 0.f;
+    zt[c][r] = (base + r < total) ? z[(size_t)(base + r) * CPN_LATENT + c] : 0.f;
   }
-  for (int i = j; i < PHI_RAYS * 18; i += 128) {
+  for (int i = t; i < PHI_RAYS * 18; i += 128) {
     int r = i / 18, c = i % 18, v = c / 9, cc = c % 9;
     float val = 0.f;
     if (base + r < total) {
-      int b = (base + r) / nr, n = ray0 + (base + r) % nr;
+      int b = (base + r) / a.N, n = (base + r) % a.N;
       val = a.coords[(((size_t)(b * 2 + v)) * a.N + n) * 9 + cc];
     }
-    cs[r][c] = val;
+    ct[c][r] = val;
   }
   __syncthreads();
-  float x[PHI_RAYS], tmp[PHI_RAYS];
-  {  // lin_in
-    float bj = W[pw::PHI_BIN + j];
-#pragma unroll
-    for (int r = 0; r < PHI_RAYS; ++r) x[r] = bj;
-    for (int k = 0; k < 18; ++k) {
-      float wv = W[pw::PHI_INT + k * CPN_HIDDEN + j];
-#pragma unroll
-      for (int r = 0; r < PHI_RAYS; ++r) x[r] = fmaf(cs[r][k], wv, x[r]);
-    }
-  }
+  float x[4][4], tmp[4][4];
+  phi_set_bias(W + pw::PHI_BIN, cq, x);
+  phi_dense<false, false>(W + pw::PHI_INT, nullptr, 18, ct, cq, rg, x);
   for (int blk = 0; blk < 3; ++blk) {
-    // x += lin_z[blk](cat(z, z))
+    // x += lin_z[blk](cat(z, z)): both halves of the weight see the same z
     const float* wz = W + pw::PHI_ZT + (size_t)blk * 2 * CPN_LATENT * CPN_HIDDEN;
-    float bj = W[pw::PHI_BZ + blk * CPN_HIDDEN + j];
+    phi_set_bias(W + pw::PHI_BZ + blk * CPN_HIDDEN, cq, tmp);
+    phi_dense<false, true>(wz, wz + (size_t)CPN_LATENT * CPN_HIDDEN, CPN_LATENT, zt, cq, rg, tmp);
 #pragma unroll
-    for (int r = 0; r < PHI_RAYS; ++r) tmp[r] = bj;
-#pragma unroll 8
-    for (int k = 0; k < 2 * CPN_LATENT; ++k) {
-      float wv = __ldg(wz + (size_t)k * CPN_HIDDEN + j);
-      int kk = k < CPN_LATENT ? k : k - CPN_LATENT;
+    for (int c = 0; c < 4; ++c)
 #pragma unroll
-      for (int r = 0; r < PHI_RAYS; ++r) tmp[r] = fmaf(zs[r][kk], wv, tmp[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < PHI_RAYS; ++r) {
-      x[r] += tmp[r];
-      xs[r][j] = x[r];
-    }
+      for (int r = 0; r < 4; ++r) {
+        x[c][r] += tmp[c][r];
+        xt[cq * 4 + c][rg * 4 + r] = x[c][r];
+      }
     __syncthreads();
     // net = fc_0(relu(x)); dx = fc_1(relu(net)); x = x + dx   (lightfield.py:52-62)
-    phi_dense128(W + pw::PHI_F0T + (size_t)blk * CPN_HIDDEN * CPN_HIDDEN, W + pw::PHI_B0 + blk * CPN_HIDDEN, xs, tmp, j,
-                 true);
+    phi_set_bias(W + pw::PHI_B0 + blk * CPN_HIDDEN, cq, tmp);
+    phi_dense<true, false>(W + pw::PHI_F0T + (size_t)blk * CPN_HIDDEN * CPN_HIDDEN, nullptr, CPN_HIDDEN, xt, cq, rg, tmp);
 #pragma unroll
-    for (int r = 0; r < PHI_RAYS; ++r) hs[r][j] = tmp[r];
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) ht[cq * 4 + c][rg * 4 + r] = tmp[c][r];
     __syncthreads();
-    phi_dense128(W + pw::PHI_F1T + (size_t)blk * CPN_HIDDEN * CPN_HIDDEN, W + pw::PHI_B1 + blk * CPN_HIDDEN, hs, tmp, j,
-                 true);
+    phi_set_bias(W + pw::PHI_B1 + blk * CPN_HIDDEN, cq, tmp);
+    phi_dense<true, false>(W + pw::PHI_F1T + (size_t)blk * CPN_HIDDEN * CPN_HIDDEN, nullptr, CPN_HIDDEN, ht, cq, rg, tmp);
 #pragma unroll
-    for (int r = 0; r < PHI_RAYS; ++r) x[r] += tmp[r];
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) x[c][r] += tmp[c][r];
     __syncthreads();
   }
 #pragma unroll
-  for (int r = 0; r < PHI_RAYS; ++r) xs[r][j] = fmaxf(x[r], 0.f);
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) xt[cq * 4 + c][rg * 4 + r] = fmaxf(x[c][r], 0.f);
   __syncthreads();
   // lin_out (3 x 128) + white background for rays with no valid epipolar segment (CoPoNeRF.py:562-566)
-  if (j < PHI_RAYS * 3) {
-    int r = j / 3, c = j % 3;
+  if (t < PHI_RAYS * 3) {
+    int r = t / 3, c = t % 3;
     if (base + r < total) {
       float acc = 0.f;
-      for (int k = 0; k < CPN_HIDDEN; ++k) acc = fmaf(xs[r][k], W[pw::PHI_OUT + c * CPN_HIDDEN + k], acc);
+      for (int k = 0; k < CPN_HIDDEN; ++k) acc = fmaf(xt[k][r], W[pw::PHI_OUT + c * CPN_HIDDEN + k], acc);
       acc += W[pw::PHI_BOUT + c];
-      int b = (base + r) / nr, nl = (base + r) % nr, n = ray0 + nl;
-      const float* sg = seg + ((size_t)(base + r) * 2) * 6;
-      float valid = (sg[4] != 0.f || sg[6 + 4] != 0.f) ? 1.f : 0.f;
-      a.rgb[((size_t)b * a.N + n) * 3 + c] = acc * valid + 1.f * (1.f - valid);
-      if (c == 0) a.valid_mask[(size_t)b * a.N + n] = valid;
-      (void)rgb_raw;
+      float valid = a.valid_mask[base + r];   // written by ray_epilogue_kernel
+      a.rgb[(size_t)(base + r) * 3 + c] = acc * valid + 1.f * (1.f - valid);
     }
   }
 }
@@ -242,17 +261,17 @@ int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, c
   return CPN_OK;
 }
 
-int launch_attn2(const cpn_render_args& a, int nr, const float* q2, const float* qemb, const float* value,
-                 const float* r1, float* z, cudaStream_t st) {
+int launch_attn2(const cpn_render_args& a, int ray0, int nr, const float* q2, const float* qemb, const float* value,
+                 const float* r1, float* z_all, cudaStream_t st) {
   int S2 = 2 * a.S;
-  attn2_kernel<<<a.B * nr, S2, (S2 + 8) * sizeof(float), st>>>(a, nr, q2, qemb, value, r1, z);
+  attn2_kernel<<<a.B * nr, S2, (S2 + 8) * sizeof(float), st>>>(a, ray0, nr, q2, qemb, value, r1, z_all);
   CPN_CHECK_LAUNCH("attn2_kernel");
   return CPN_OK;
 }
 
-int launch_phi(const cpn_render_args& a, int ray0, int nr, const float* z, const float* seg, cudaStream_t st) {
-  int total = a.B * nr;
-  phi_kernel<<<(total + PHI_RAYS - 1) / PHI_RAYS, 128, 0, st>>>(a, ray0, nr, z, seg, nullptr);
+int launch_phi(const cpn_render_args& a, const float* z_all, cudaStream_t st) {
+  int total = a.B * a.N;
+  phi_kernel<<<(total + PHI_RAYS - 1) / PHI_RAYS, 128, 0, st>>>(a, z_all);
   CPN_CHECK_LAUNCH("phi_kernel");
   return CPN_OK;
 }

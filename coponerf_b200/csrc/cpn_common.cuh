@@ -109,10 +109,11 @@ int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias
                      int remap256 = 0);
 int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, const float* qemb, const float* value,
                  const float* rowaux, float* r1, float* wp, cudaStream_t st);
-int launch_attn2(const cpn_render_args& a, int nr, const float* q2, const float* qemb, const float* value,
-                 const float* r1, float* z, cudaStream_t st);
-int launch_phi(const cpn_render_args& a, int ray0, int nr, const float* z, const float* seg, cudaStream_t st);
-int launch_ray_epilogue(const cpn_render_args& a, int ray0, int nr, const float* wp, cudaStream_t st);
+// z_all: (B, N, 416) latent of every ray of the image
+int launch_attn2(const cpn_render_args& a, int ray0, int nr, const float* q2, const float* qemb, const float* value,
+                 const float* r1, float* z_all, cudaStream_t st);
+int launch_phi(const cpn_render_args& a, const float* z_all, cudaStream_t st);
+int launch_ray_epilogue(const cpn_render_args& a, int ray0, int nr, const float* wp, const float* seg, cudaStream_t st);
 
 // tensor-core path (gemm_tc.cu)
 // "Operand image" of an activation matrix [rows x K]: tiles of 128 rows; per tile and 32-wide k-chunk one

@@ -37,7 +37,6 @@ __device__ __forceinline__ Taps make_taps(float gx, float gy, int h, int w, int 
 
 // One warp per (row, branch). Row = ((b*nr + n)*2 + v)*S + s; branch 0 reads view v at the sample
 // position, branch 1 reads view 1-v at the reprojected position.
-template <bool IMAGE>
 __global__ void __launch_bounds__(256) gather_kernel(cpn_render_args a, int nr, const float* __restrict__ rowaux,
                                                      float* __restrict__ A) {
   long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -52,10 +51,6 @@ __global__ void __launch_bounds__(256) gather_kernel(cpn_render_args a, int nr, 
   const float* ra = rowaux + (size_t)row * CPN_ROWAUX;
   float gx = ra[branch * 2 + 0], gy = ra[branch * 2 + 1];
   float* out = A + enc_row((size_t)row, branch) * CPN_KA;
-  // image form: tile (row / 128, branch), row r inside it; lane l owns channels 4l .. 4l+3 of every 128-channel group
-  unsigned char* aimg = reinterpret_cast<unsigned char*>(A);
-  const size_t tile = (size_t)(row >> 7) * 2 + branch;
-  const int r = (int)(row & 127);
   int col = 0;
 #pragma unroll
   for (int l = 0; l < CPN_N_LEVELS; ++l) {
@@ -74,19 +69,69 @@ __global__ void __launch_bounds__(256) gather_kernel(cpn_render_args a, int nr, 
           acc.w += f.w * t.w[k];
         }
       }
-      if (IMAGE) {
+      *reinterpret_cast<float4*>(out + col + c) = acc;
+    }
+    col += C;
+  }
+}
+
+// Operand-image form of the same gather. CTA = 8 warps = 8 consecutive sample rows of one branch; each warp blends
+// its row (lanes along channels: every tap is a coalesced 512-byte read), splits it into fp16 hi/lo and parks it in
+// shared memory; the CTA then writes the image, where the same 8-channel group of 8 consecutive rows is 128
+// contiguous bytes (full-sector, coalesced stores).
+constexpr int GI_ROWS = 8, GI_PITCH = CPN_FEAT_DIM + 8;   // halves per staged row (+8: conflict-free 16-byte reads)
+
+__global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, int nr, const float* __restrict__ rowaux,
+                                                           unsigned char* __restrict__ img) {
+  __shared__ __align__(16) __half sh[2][GI_ROWS][GI_PITCH];   // [hi | lo][row][channel]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int branch = blockIdx.y;
+  const long long nrows = (long long)a.B * nr * 2 * a.S;
+  const long long row0 = (long long)blockIdx.x * GI_ROWS, row = row0 + warp;
+  if (row < nrows) {
+    int v = (int)((row / a.S) & 1);
+    int b = (int)(row / ((long long)2 * a.S * nr));
+    int im = b * 2 + (branch ? 1 - v : v);
+    const float* ra = rowaux + (size_t)row * CPN_ROWAUX;
+    float gx = ra[branch * 2 + 0], gy = ra[branch * 2 + 1];
+    int col = 0;
+#pragma unroll
+    for (int l = 0; l < CPN_N_LEVELS; ++l) {
+      int h = a.feat_h[l], w = a.feat_w[l], C = a.feat_c[l];
+      Taps t = make_taps(gx, gy, h, w, C, branch == 0);
+      const float* base = a.feat[l] + (size_t)im * h * w * C;
+      for (int c = lane * 4; c < C; c += 128) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (t.off[k] >= 0) {
+            float4 f = __ldg(reinterpret_cast<const float4*>(base + t.off[k] + c));
+            acc.x += f.x * t.w[k];
+            acc.y += f.y * t.w[k];
+            acc.z += f.z * t.w[k];
+            acc.w += f.w * t.w[k];
+          }
+        }
         uint2 hi, lo;
         tc::split2(acc.x, acc.y, hi.x, lo.x);
         tc::split2(acc.z, acc.w, hi.y, lo.y);
-        int k = col + c;
-        unsigned char* p = aimg + act_img_off(tile, CPN_KA_IMG / ACT_BK, k & ~7, r) + (k & 7) * 2;
-        *reinterpret_cast<uint2*>(p) = hi;
-        *reinterpret_cast<uint2*>(p + 8192) = lo;
-      } else {
-        *reinterpret_cast<float4*>(out + col + c) = acc;
+        *reinterpret_cast<uint2*>(&sh[0][warp][col + c]) = hi;
+        *reinterpret_cast<uint2*>(&sh[1][warp][col + c]) = lo;
       }
+      col += C;
     }
-    col += C;
+  }
+  __syncthreads();
+  // 104 channel groups x 2 planes; thread -> (group, row): 8 threads write 128 contiguous bytes
+  const size_t tile = (size_t)(row0 >> 7) * 2 + branch;
+  const int r0 = (int)(row0 & 127), rr = threadIdx.x & 7;
+  if (row0 + rr < nrows) {
+    for (int item = threadIdx.x >> 3; item < 2 * (CPN_FEAT_DIM / 8); item += 32) {
+      int plane = item >= CPN_FEAT_DIM / 8, gi = plane ? item - CPN_FEAT_DIM / 8 : item;
+      uint4 val = *reinterpret_cast<const uint4*>(&sh[plane][rr][gi * 8]);
+      unsigned char* p = img + act_img_off(tile, CPN_KA_IMG / ACT_BK, gi * 8, r0 + rr) + plane * 8192;
+      *reinterpret_cast<uint4*>(p) = val;
+    }
   }
 }
 
@@ -113,10 +158,13 @@ int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowau
   (void)ray0;
   long long warps = (long long)a.B * nr * 2 * a.S * 2;
   long long blocks = (warps * 32 + 255) / 256;
-  if (a_image)
-    gather_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(a, nr, rowaux, A);
-  else
-    gather_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(a, nr, rowaux, A);
+  if (a_image) {
+    long long rows = (long long)a.B * nr * 2 * a.S;
+    dim3 grid((unsigned)((rows + GI_ROWS - 1) / GI_ROWS), 2);
+    gather_image_kernel<<<grid, 256, 0, st>>>(a, nr, rowaux, reinterpret_cast<unsigned char*>(A));
+  } else {
+    gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, nr, rowaux, A);
+  }
   CPN_CHECK_LAUNCH("gather_kernel");
   return CPN_OK;
 }

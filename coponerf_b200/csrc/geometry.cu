@@ -461,7 +461,8 @@ __device__ __forceinline__ void project_to_other(const float* invK3, const float
 }
 
 // One thread per (pair, ray). models/CoPoNeRF.py:499-542, utils.flow2kps (utils.py:52-69).
-__global__ void ray_epilogue_kernel(cpn_render_args a, int ray0, int nr, const float* __restrict__ wp) {
+__global__ void ray_epilogue_kernel(cpn_render_args a, int ray0, int nr, const float* __restrict__ wp,
+                                    const float* __restrict__ seg) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.B * nr) return;
   int b = idx / nr, n = ray0 + idx % nr;
@@ -486,6 +487,9 @@ __global__ void ray_epilogue_kernel(cpn_render_args a, int ray0, int nr, const f
   a.C2_pts_to_C1[o * 2 + 0] = (float)kx + a.up_flow2[((size_t)b * 2 + 0) * 65536 + ky * 256 + kx] * fs;
   a.C2_pts_to_C1[o * 2 + 1] = (float)ky + a.up_flow2[((size_t)b * 2 + 1) * 65536 + ky * 256 + kx] * fs;
   a.depth_ray[o] = depth < 0.f ? 0.f : (depth > 10.f ? 10.f : depth);
+  // valid = any view has an epipolar segment inside its image (CoPoNeRF.py:562); phi whites out the rest
+  const float* sg = seg + (size_t)idx * 2 * 6;
+  a.valid_mask[o] = (sg[4] != 0.f || sg[6 + 4] != 0.f) ? 1.f : 0.f;
 }
 
 }  // namespace
@@ -505,9 +509,9 @@ int launch_sample(const cpn_render_args& a, int ray0, int nr, const float* seg, 
   return CPN_OK;
 }
 
-int launch_ray_epilogue(const cpn_render_args& a, int ray0, int nr, const float* wp, cudaStream_t st) {
+int launch_ray_epilogue(const cpn_render_args& a, int ray0, int nr, const float* wp, const float* seg, cudaStream_t st) {
   int total = a.B * nr;
-  ray_epilogue_kernel<<<(total + 127) / 128, 128, 0, st>>>(a, ray0, nr, wp);
+  ray_epilogue_kernel<<<(total + 127) / 128, 128, 0, st>>>(a, ray0, nr, wp, seg);
   CPN_CHECK_LAUNCH("ray_epilogue_kernel");
   return CPN_OK;
 }

@@ -75,7 +75,7 @@ struct ProfScope {  // records an event pair around the enclosed launches when a
 
 // Workspace carve-up for one chunk of `nr` rays of each of B pairs (R = B * nr * 2 * S sample rows).
 struct Workspace {
-  float *seg, *rowaux, *local16, *A, *H1, *E, *V, *K1, *Kk, *Q1, *Qe, *r1, *wp, *zemb, *rbias, *z;
+  float *seg, *rowaux, *local16, *A, *H1, *E, *V, *K1, *Kk, *Q1, *Qe, *r1, *wp, *zemb, *rbias;
   size_t bytes;
 };
 
@@ -103,7 +103,6 @@ Workspace carve(void* base, int B, int nr, int S) {
   w.wp = take(rays * 4);
   w.zemb = take(rays * CPN_HIDDEN);
   w.rbias = take(rays * CPN_HIDDEN);
-  w.z = take(rays * CPN_LATENT);
   w.bytes = off;
   return w;
 }
@@ -151,6 +150,40 @@ int check_args(const cpn_render_args* a) {
     if (_s != CPN_OK) return _s; \
   } while (0)
 
+// ---- chunk lanes -------------------------------------------------------------------------------------------
+// Chunks of rays are independent, so they are issued round-robin on a few internal streams ("lanes"), each with
+// its own workspace: the gather / attention / phi kernels of one chunk (LSU- and latency-bound, no shared memory)
+// then run underneath the tensor-core GEMMs of another. Lanes fork from and join back into the caller's stream
+// through events; the pool is created on first use, per device.
+constexpr int MAX_LANES = 4, MAX_DEVICES = 64;
+struct LanePool {
+  bool ready = false;
+  cudaStream_t stream[MAX_LANES];
+  cudaEvent_t done[MAX_LANES];
+  cudaEvent_t fork;
+};
+LanePool g_pool[MAX_DEVICES];
+
+int get_pool(LanePool** out) {
+  int dev = 0;
+  CPN_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEVICES) {
+    cpn_set_error("device index %d out of range", dev);
+    return CPN_ERR_ARG;
+  }
+  LanePool& p = g_pool[dev];
+  if (!p.ready) {
+    for (int i = 0; i < MAX_LANES; ++i) {
+      CPN_CHECK_CUDA(cudaStreamCreateWithFlags(&p.stream[i], cudaStreamNonBlocking));
+      CPN_CHECK_CUDA(cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming));
+    }
+    CPN_CHECK_CUDA(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+    p.ready = true;
+  }
+  *out = &p;
+  return CPN_OK;
+}
+
 bool use_tc(const cpn_render_args& a) { return !(a.flags & CPN_FLAG_SIMT_ONLY); }
 
 // fp32 CUDA-core layer: C = act(A * Wt + bias)
@@ -162,31 +195,24 @@ int dense_simt(const cpn_render_args& a, const float* A, int lda, size_t wt, siz
 
 }  // namespace
 
-extern "C" size_t cpn_render_workspace_bytes(int B, int chunk_rays, int S) {
-  if (B <= 0 || chunk_rays <= 0 || S <= 0) return 0;
-  return carve(nullptr, B, chunk_rays, S).bytes;
+// image-level part of the workspace: the per-ray latent z of every ray (phi runs once over the whole image)
+size_t image_bytes(int B, int N) { return ((size_t)B * N * CPN_LATENT * sizeof(float) + 255) / 256 * 256; }
+
+extern "C" size_t cpn_render_workspace_bytes(int B, int N, int chunk_rays, int S, int lanes) {
+  if (B <= 0 || N < 0 || chunk_rays <= 0 || S <= 0 || lanes < 1 || lanes > MAX_LANES) return 0;
+  int chunk = chunk_rays < N ? chunk_rays : (N > 0 ? N : 1);
+  return image_bytes(B, N) + carve(nullptr, B, chunk, S).bytes * lanes;
 }
 
 extern "C" int cpn_render_launch_count(const cpn_render_args* a) {
   if (!a || a->chunk_rays <= 0) return 0;
   int chunks = (a->N + a->chunk_rays - 1) / a->chunk_rays;
-  return chunks * 18;
+  return chunks * 17 + 1;
 }
 
-extern "C" int cpn_render_rays(const cpn_render_args* args, void* stream) {
-  CPN_TRY(check_args(args));
-  const cpn_render_args& a = *args;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (a.N == 0) return CPN_OK;
-  int chunk = a.chunk_rays < a.N ? a.chunk_rays : a.N;
-  Workspace w = carve(a.workspace, a.B, chunk, a.S);
-  if (w.bytes > a.workspace_bytes) {
-    cpn_set_error("cpn_render_rays: workspace of %zu bytes needed, %zu given", w.bytes, a.workspace_bytes);
-    return CPN_ERR_WORKSPACE;
-  }
-  const float* W = reinterpret_cast<const float*>(a.weights);
-  for (int ray0 = 0; ray0 < a.N; ray0 += chunk) {
-    int nr = (a.N - ray0) < chunk ? (a.N - ray0) : chunk;
+namespace {
+int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int ray0, int nr, cudaStream_t st) {
+    const float* W = reinterpret_cast<const float*>(a.weights);
     int rays = a.B * nr;
     int R = rays * 2 * a.S;
     CPN_TRY(launch_ray_setup(a, ray0, nr, w.seg, st));
@@ -233,9 +259,53 @@ extern "C" int cpn_render_rays(const cpn_render_args* args, void* stream) {
       CPN_TRY(launch_gemm_tc(a.weights, 6, w.K1, CPN_HIDDEN, w.Kk, CPN_HIDDEN, R, 0, 0, 1, 1, st));
     else
       CPN_TRY(dense_simt(a, w.K1, CPN_HIDDEN, pw::WQR2T, pw::BQR2, w.Kk, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
-    CPN_TRY(launch_attn2(a, nr, w.Kk, w.Qe, w.V, w.r1, w.z, st));
-    CPN_TRY(launch_phi(a, ray0, nr, w.z, w.seg, st));
-    CPN_TRY(launch_ray_epilogue(a, ray0, nr, w.wp, st));
+    CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, w.V, w.r1, z_all, st));
+    CPN_TRY(launch_ray_epilogue(a, ray0, nr, w.wp, w.seg, st));
+    return CPN_OK;
+}
+}  // namespace
+
+extern "C" int cpn_render_rays(const cpn_render_args* args, void* stream) {
+  CPN_TRY(check_args(args));
+  const cpn_render_args& a = *args;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a.N == 0) return CPN_OK;
+  const int chunk = a.chunk_rays < a.N ? a.chunk_rays : a.N;
+  const int nchunks = (a.N + chunk - 1) / chunk;
+  int lanes = a.lanes < 1 ? 1 : a.lanes;
+  if (lanes > MAX_LANES) lanes = MAX_LANES;
+  if (lanes > nchunks) lanes = nchunks;
+  const size_t lane_bytes = carve(nullptr, a.B, chunk, a.S).bytes, img_bytes = image_bytes(a.B, a.N);
+  if (img_bytes + lane_bytes * lanes > a.workspace_bytes) {
+    cpn_set_error("cpn_render_rays: workspace of %zu bytes needed (%d lanes), %zu given", img_bytes + lane_bytes * lanes,
+                  lanes, a.workspace_bytes);
+    return CPN_ERR_WORKSPACE;
   }
-  return CPN_OK;
+  float* z_all = reinterpret_cast<float*>(a.workspace);
+  char* lane_base = reinterpret_cast<char*>(a.workspace) + img_bytes;
+  if (lanes == 1) {
+    Workspace w = carve(lane_base, a.B, chunk, a.S);
+    for (int ray0 = 0; ray0 < a.N; ray0 += chunk)
+      CPN_TRY(render_chunk(a, w, z_all, ray0, (a.N - ray0) < chunk ? (a.N - ray0) : chunk, st));
+    return launch_phi(a, z_all, st);
+  }
+  LanePool* pool = nullptr;
+  CPN_TRY(get_pool(&pool));
+  CPN_CHECK_CUDA(cudaEventRecord(pool->fork, st));
+  Workspace w[MAX_LANES];
+  for (int l = 0; l < lanes; ++l) {
+    w[l] = carve(lane_base + l * lane_bytes, a.B, chunk, a.S);
+    CPN_CHECK_CUDA(cudaStreamWaitEvent(pool->stream[l], pool->fork, 0));
+  }
+  int status = CPN_OK;
+  for (int c = 0; c < nchunks && status == CPN_OK; ++c) {
+    int ray0 = c * chunk;
+    status = render_chunk(a, w[c % lanes], z_all, ray0, (a.N - ray0) < chunk ? (a.N - ray0) : chunk, pool->stream[c % lanes]);
+  }
+  for (int l = 0; l < lanes; ++l) {   // always join, also after an error, so the caller's stream stays ordered
+    cudaEventRecord(pool->done[l], pool->stream[l]);
+    cudaStreamWaitEvent(st, pool->done[l], 0);
+  }
+  if (status != CPN_OK) return status;
+  return launch_phi(a, z_all, st);   // the light-field decoder runs once over every ray of the image
 }

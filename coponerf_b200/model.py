@@ -46,7 +46,7 @@ def pose_inverse_4x4(mat):
 class CoPoNeRF(nn.Module):
     """models/CoPoNeRF.py:19. Only n_view == 2 is supported (the value both reference drivers pass)."""
 
-    def __init__(self, n_view=1, npoints=64, num_hidden_units_phi=128, chunk_rays=2048):
+    def __init__(self, n_view=1, npoints=64, num_hidden_units_phi=128, chunk_rays=2048, lanes=3):
         super().__init__()
         self.n_view = n_view
         self.npoints = npoints if npoints else 64
@@ -75,6 +75,7 @@ class CoPoNeRF(nn.Module):
         self.encode_latent = nn.Conv1d(half, 128, 1)
         self.phi = _ResnetFC(n_view * 9, half * n_view, hidden)
         self.chunk_rays = chunk_rays
+        self.lanes = lanes
         self.pixel_val_on_host = True   # the reference returns out['pixel_val'] as a CPU tensor (CoPoNeRF.py:490)
         self._engine = None
         self._engine_version = None
@@ -92,7 +93,7 @@ class CoPoNeRF(nn.Module):
             raise RuntimeError("coponerf_b200.CoPoNeRF renders on CUDA only: call .cuda() first (no CPU fallback)")
         ver = self._weights_version()
         if self._engine is None or self._engine_version != ver or self._engine.device != dev:
-            self._engine = RenderEngine(self.state_dict(), device=dev, chunk_rays=self.chunk_rays)
+            self._engine = RenderEngine(self.state_dict(), device=dev, chunk_rays=self.chunk_rays, lanes=self.lanes)
             self._engine_version = ver
         return self._engine
 
@@ -131,7 +132,13 @@ class CoPoNeRF(nn.Module):
                   "C2_pts_to_C1"):
             out[k] = o[k]
         out["at_wts"] = [o["at_wt"]]
-        out["pixel_val"] = o["pixel_val"].cpu() if self.pixel_val_on_host else o["pixel_val"]
+        if self.pixel_val_on_host:   # pinned staging (torch's caching host allocator) instead of a pageable .cpu()
+            pv = torch.empty(o["pixel_val"].shape, dtype=torch.float32, pin_memory=True)
+            pv.copy_(o["pixel_val"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            out["pixel_val"] = pv
+        else:
+            out["pixel_val"] = o["pixel_val"]
         out["mask_c2"] = o["mask_c2"].view(torch.bool)
         out["matchability_cycle_mask"] = o["matchability_cycle_mask"].view(torch.bool)
         c = st.consts

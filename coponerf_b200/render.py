@@ -32,12 +32,13 @@ class PairState:
 class RenderEngine:
     """Packed render-path weights + workspace on one CUDA device."""
 
-    def __init__(self, state_dict, device=None, chunk_rays=2048):
+    def __init__(self, state_dict, device=None, chunk_rays=2048, lanes=3):
         if not torch.cuda.is_available():
             raise _lib.CpnError("coponerf_b200 needs a CUDA device: the render path has no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.chunk_rays = int(chunk_rays)
+        self.lanes = int(lanes)   # chunks in flight on the library's internal streams
         self._workspace = None
         self._interval = {}
         self._pair_cache = OrderedDict()
@@ -154,11 +155,12 @@ class RenderEngine:
             }
             if N == 0:
                 return o
-            ws_bytes = self.lib.cpn_render_workspace_bytes(B, chunk, S)
+            lanes = max(1, min(self.lanes, 4, -(-N // chunk)))
+            ws_bytes = self.lib.cpn_render_workspace_bytes(B, N, chunk, S, lanes)
             ws = self._get_workspace(ws_bytes)
             a = _lib.RenderArgs()
             a.B, a.N, a.S, a.H, a.W = B, N, S, st.H, st.W
-            a.flow_h, a.chunk_rays, a.flags = st.flow_h, chunk, self.flags
+            a.flow_h, a.chunk_rays, a.flags, a.lanes = st.flow_h, chunk, self.flags, lanes
             for l, f in enumerate(st.feat):
                 a.feat[l] = f.data_ptr()
                 a.feat_h[l], a.feat_w[l], a.feat_c[l] = f.shape[1], f.shape[2], f.shape[3]

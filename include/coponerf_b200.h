@@ -87,6 +87,8 @@ typedef struct {
   int32_t flow_h;     /* height of flow[1] (for flow2kps' scale 256/flow_h) */
   int32_t chunk_rays; /* rays processed per internal pass (workspace is sized from it) */
   int32_t flags;      /* CPN_FLAG_* */
+  int32_t lanes;      /* chunks in flight on internal streams, 1..4 (workspace scales with it) */
+  int32_t reserved;
   /* inputs */
   const float* feat[CPN_N_LEVELS];   /* channels-last maps (2B, h_l, w_l, C_l) */
   int32_t feat_h[CPN_N_LEVELS], feat_w[CPN_N_LEVELS], feat_c[CPN_N_LEVELS];
@@ -113,7 +115,7 @@ typedef struct {
   size_t workspace_bytes;
 } cpn_render_args;
 
-size_t cpn_render_workspace_bytes(int B, int chunk_rays, int S);
+size_t cpn_render_workspace_bytes(int B, int N, int chunk_rays, int S, int lanes);
 int cpn_render_rays(const cpn_render_args* args, void* stream);
 /* number of kernels one cpn_render_rays call launches (for bench.py's gpu_launches) */
 int cpn_render_launch_count(const cpn_render_args* args);

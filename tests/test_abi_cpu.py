@@ -56,11 +56,12 @@ def test_weight_table_matches_reference_state_dict_names():
 def test_workspace_query_scales_with_rows():
     _ensure_built()
     lib = _lib.load()
-    a = lib.cpn_render_workspace_bytes(1, 256, 64)
-    b = lib.cpn_render_workspace_bytes(2, 256, 64)
-    c = lib.cpn_render_workspace_bytes(1, 256, 128)
-    assert 0 < a < b and abs(b - c) < 0.01 * b
-    assert lib.cpn_render_workspace_bytes(0, 256, 64) == 0
+    a = lib.cpn_render_workspace_bytes(1, 4096, 256, 64, 1)
+    b = lib.cpn_render_workspace_bytes(2, 4096, 256, 64, 1)
+    c = lib.cpn_render_workspace_bytes(1, 4096, 256, 128, 1)
+    assert 0 < a < b and abs(b - c) < 0.05 * b
+    assert a < lib.cpn_render_workspace_bytes(1, 4096, 256, 64, 3) < 3 * a
+    assert lib.cpn_render_workspace_bytes(0, 4096, 256, 64, 1) == 0
 
 
 def test_host_model_keeps_reference_parameter_names():
