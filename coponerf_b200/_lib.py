@@ -14,6 +14,8 @@ LATENT = 416
 HIDDEN = 128
 PAIR_CONSTS_FLOATS = 320
 FLAG_SIMT_ONLY = 1
+FLAG_F16X3 = 2
+TC_F16X3 = 4
 TC_A_IMAGE = 1
 TC_OUT_IMAGE = 2
 ACT_CHUNK_BYTES = 16384

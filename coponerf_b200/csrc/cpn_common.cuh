@@ -99,7 +99,7 @@ void cpn_set_error(const char* fmt, ...);
 
 // launchers implemented across the .cu files (all asynchronous on `st`)
 int launch_ray_setup(const cpn_render_args& a, int ray0, int nr, float* seg, cudaStream_t st);
-// a_image: write the encoder input as the fp16 hi/lo operand image (K = CPN_KA_IMG) instead of fp32 rows of CPN_KA
+// a_image: 0 fp32 rows of CPN_KA; 1 operand image (K = CPN_KA_IMG), f16x3 scheme; 2 operand image, f8 scheme
 int launch_sample(const cpn_render_args& a, int ray0, int nr, const float* seg, float* rowaux, float* local16,
                   float* A, int a_image, cudaStream_t st);
 int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowaux, float* A, int a_image, cudaStream_t st);
@@ -119,13 +119,20 @@ int launch_ray_epilogue(const cpn_render_args& a, int ray0, int nr, const float*
 // "Operand image" of an activation matrix [rows x K]: tiles of 128 rows; per tile and 32-wide k-chunk one
 // 16 KB block [hi | lo] x [4 groups of 8 k][128 rows][8 fp16] -- exactly what the MMA reads from shared memory
 // (K-major, no swizzle), so a consumer stages it with one bulk copy. Block index = tile * (K / 32) + k-chunk.
+// Two precision schemes share the block size: "f16x3" stores [hi fp16 8 KB | lo fp16 8 KB]; the default "f8"
+// scheme stores [hi fp16 8 KB | e4m3(lo * 2^8) 4 KB | e4m3(x * 2^-6) 4 KB] with the 8-bit planes as
+// [2 groups of 16 k][128 rows][16 bytes] (tc_common.cuh).
 constexpr int ACT_BK = 32;
 constexpr int ACT_CHUNK_BYTES = 2 * (ACT_BK / 8) * 128 * 16;
+constexpr int ACT_LO = 8192;      // f16x3: fp16 lo plane
+constexpr int ACT_LO8 = 8192;     // f8: e4m3 remainder plane
+constexpr int ACT_X8 = 12288;     // f8: e4m3 value plane
 constexpr int CPN_TC_LAYERS = 7;
 size_t cpn_packed_fp32_floats();
 size_t cpn_tc_weights_bytes();
 int cpn_pack_tc_weights(const float* raw, void* dst, cudaStream_t st);
 // layer: 0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value, 3 key_map, 4 key_map_2,
 //        5 query_embed_2, 6 query_repeat_embed_2.  mode: CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE.
+//        | CPN_TC_F16X3 (three fp16 MMAs per product instead of fp16 + two fp8 corrections).
 int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,
                    int out_div, int out_kchunks, cudaStream_t st);

@@ -79,11 +79,15 @@ __global__ void __launch_bounds__(256) gather_kernel(cpn_render_args a, int nr, 
 // its row (lanes along channels: every tap is a coalesced 512-byte read), splits it into fp16 hi/lo and parks it in
 // shared memory; the CTA then writes the image, where the same 8-channel group of 8 consecutive rows is 128
 // contiguous bytes (full-sector, coalesced stores).
-constexpr int GI_ROWS = 8, GI_PITCH = CPN_FEAT_DIM + 8;   // halves per staged row (+8: conflict-free 16-byte reads)
+constexpr int GI_ROWS = 8, GI_PITCH = CPN_FEAT_DIM + 24;  // halves per staged row: 1712 B = 428 words, 428 % 32 = 12 -> the 8 rows' 16-byte reads hit distinct banks
+constexpr int GI_B8 = CPN_FEAT_DIM + 16;                  // bytes per e4m3 plane of a staged row
 
+template <bool F8>
 __global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, int nr, const float* __restrict__ rowaux,
                                                            unsigned char* __restrict__ img) {
-  __shared__ __align__(16) __half sh[2][GI_ROWS][GI_PITCH];   // [hi | lo][row][channel]
+  // f16x3: [hi | lo][row][channel] fp16. f8: plane 0 = fp16 hi; plane 1 holds the two byte planes back to back,
+  // e4m3(lo * 2^8) in bytes [0, 832) and e4m3(x * 2^-6) in bytes [848, 1680) of each row.
+  __shared__ __align__(16) __half sh[2][GI_ROWS][GI_PITCH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int branch = blockIdx.y;
   const long long nrows = (long long)a.B * nr * 2 * a.S;
@@ -112,11 +116,21 @@ __global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, in
             acc.w += f.w * t.w[k];
           }
         }
-        uint2 hi, lo;
-        tc::split2(acc.x, acc.y, hi.x, lo.x);
-        tc::split2(acc.z, acc.w, hi.y, lo.y);
-        *reinterpret_cast<uint2*>(&sh[0][warp][col + c]) = hi;
-        *reinterpret_cast<uint2*>(&sh[1][warp][col + c]) = lo;
+        if (F8) {
+          uint2 hi;
+          uint32_t l8, x8;
+          tc::split4_f8(acc, hi, l8, x8);
+          *reinterpret_cast<uint2*>(&sh[0][warp][col + c]) = hi;
+          unsigned char* bp = reinterpret_cast<unsigned char*>(&sh[1][warp][0]);
+          *reinterpret_cast<uint32_t*>(bp + col + c) = l8;
+          *reinterpret_cast<uint32_t*>(bp + GI_B8 + col + c) = x8;
+        } else {
+          uint2 hi, lo;
+          tc::split2(acc.x, acc.y, hi.x, lo.x);
+          tc::split2(acc.z, acc.w, hi.y, lo.y);
+          *reinterpret_cast<uint2*>(&sh[0][warp][col + c]) = hi;
+          *reinterpret_cast<uint2*>(&sh[1][warp][col + c]) = lo;
+        }
       }
       col += C;
     }
@@ -126,11 +140,26 @@ __global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, in
   const size_t tile = (size_t)(row0 >> 7) * 2 + branch;
   const int r0 = (int)(row0 & 127), rr = threadIdx.x & 7;
   if (row0 + rr < nrows) {
-    for (int item = threadIdx.x >> 3; item < 2 * (CPN_FEAT_DIM / 8); item += 32) {
-      int plane = item >= CPN_FEAT_DIM / 8, gi = plane ? item - CPN_FEAT_DIM / 8 : item;
-      uint4 val = *reinterpret_cast<const uint4*>(&sh[plane][rr][gi * 8]);
-      unsigned char* p = img + act_img_off(tile, CPN_KA_IMG / ACT_BK, gi * 8, r0 + rr) + plane * 8192;
-      *reinterpret_cast<uint4*>(p) = val;
+    constexpr int NG8 = CPN_FEAT_DIM / 8, NG16 = CPN_FEAT_DIM / 16;
+    for (int item = threadIdx.x >> 3; item < 2 * NG8; item += 32) {
+      if (F8) {
+        if (item < NG8) {          // fp16 hi: groups of 8 channels
+          uint4 val = *reinterpret_cast<const uint4*>(&sh[0][rr][item * 8]);
+          *reinterpret_cast<uint4*>(img + act_img_off(tile, CPN_KA_IMG / ACT_BK, item * 8, r0 + rr)) = val;
+        } else {                   // byte planes: groups of 16 channels
+          int pl = (item - NG8) >= NG16, gi = item - NG8 - pl * NG16, k = gi * 16;
+          const unsigned char* bp = reinterpret_cast<const unsigned char*>(&sh[1][rr][0]) + pl * GI_B8;
+          uint4 val = *reinterpret_cast<const uint4*>(bp + k);
+          unsigned char* p = img + ((size_t)tile * (CPN_KA_IMG / ACT_BK) + (k >> 5)) * ACT_CHUNK_BYTES +
+                             (pl ? ACT_X8 : ACT_LO8) + ((k & 31) >> 4) * 2048 + (size_t)(r0 + rr) * 16;
+          *reinterpret_cast<uint4*>(p) = val;
+        }
+      } else {
+        int plane = item >= NG8, gi = plane ? item - NG8 : item;
+        uint4 val = *reinterpret_cast<const uint4*>(&sh[plane][rr][gi * 8]);
+        unsigned char* p = img + act_img_off(tile, CPN_KA_IMG / ACT_BK, gi * 8, r0 + rr) + plane * ACT_LO;
+        *reinterpret_cast<uint4*>(p) = val;
+      }
     }
   }
 }
@@ -161,7 +190,10 @@ int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowau
   if (a_image) {
     long long rows = (long long)a.B * nr * 2 * a.S;
     dim3 grid((unsigned)((rows + GI_ROWS - 1) / GI_ROWS), 2);
-    gather_image_kernel<<<grid, 256, 0, st>>>(a, nr, rowaux, reinterpret_cast<unsigned char*>(A));
+    if (a_image == 2)
+      gather_image_kernel<true><<<grid, 256, 0, st>>>(a, nr, rowaux, reinterpret_cast<unsigned char*>(A));
+    else
+      gather_image_kernel<false><<<grid, 256, 0, st>>>(a, nr, rowaux, reinterpret_cast<unsigned char*>(A));
   } else {
     gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, nr, rowaux, A);
   }

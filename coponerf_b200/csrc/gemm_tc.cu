@@ -69,9 +69,15 @@ const TcLayer kLayers[CPN_TC_LAYERS] = {
 };
 constexpr size_t TC_HEADER_BYTES = 256;   // floats [0..7] 1/scale per layer, [8..15] scale, uints [16..23] absmax bits
 
-size_t layer_bytes(int l) { return (size_t)kLayers[l].out * kLayers[l].kpad * 4; }  // hi + lo fp16
-size_t layer_offset(int l) {
-  size_t off = TC_HEADER_BYTES;
+size_t layer_bytes(int l) { return (size_t)kLayers[l].out * kLayers[l].kpad * 4; }  // 4 bytes per weight either scheme
+size_t scheme_bytes() {
+  size_t n = 0;
+  for (int i = 0; i < CPN_TC_LAYERS; ++i) n += layer_bytes(i);
+  return n;
+}
+// scheme 0: f16x3 tiles [w_hi | w_lo] fp16; scheme 1: f8 tiles [w_hi fp16 | e4m3(w_hi 2^-8) | e4m3(w_lo 2^6)]
+size_t layer_offset(int l, int scheme) {
+  size_t off = TC_HEADER_BYTES + (scheme ? scheme_bytes() : 0);
   for (int i = 0; i < l; ++i) off += layer_bytes(i);
   return off;
 }
@@ -94,9 +100,11 @@ __device__ __forceinline__ float layer_scale(unsigned int absmax_bits) {
   return ldexpf(1.f, 10 - e);
 }
 
-// dst tile (nt, kc): [hi | lo] x [BK/8 k-chunks][NT rows][8 halves]
+// dst tile (nt, kc), 128 * NT bytes: f16x3 [hi | lo] x [4 k-groups][NT rows][8 halves];
+// f8 [hi as before | e4m3(hi 2^-8) | e4m3(lo 2^6)] with the byte planes as [2 k-groups of 16][NT rows][16 bytes]
 __global__ void pack_tc_kernel(const float* __restrict__ w, int out, int in, int kpad, int NT, const unsigned int* absmax,
-                               __half* __restrict__ dst, float* __restrict__ header, int layer) {
+                               __half* __restrict__ dst, unsigned char* __restrict__ dst8, float* __restrict__ header,
+                               int layer) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)out * kpad;
   float scale = layer_scale(*absmax);
@@ -116,6 +124,13 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, int out, int in, int
   size_t off = ((size_t)c * NT + nl) * 8 + e;
   dst[tile + off] = hi;
   dst[tile + half_elems + off] = lo;
+  // f8 scheme tile
+  unsigned char* t8 = dst8 + tile * 2;             // same tile size in bytes
+  reinterpret_cast<__half*>(t8)[off] = hi;
+  const float lo_exact = x - __half2float(hi);
+  size_t off8 = ((size_t)((k % BK) / 16) * NT + nl) * 16 + (k % 16);
+  t8[half_elems * 2 + off8] = __nv_cvt_float_to_fp8(__half2float(hi) * F8_W_SCALE, __NV_SATFINITE, __NV_E4M3);
+  t8[half_elems * 3 + off8] = __nv_cvt_float_to_fp8(lo_exact * F8_WLO_SCALE, __NV_SATFINITE, __NV_E4M3);
 }
 
 // ---------------------------------------------------------------------------------------------- the GEMM
@@ -131,6 +146,7 @@ struct GemmArgs {
   const float* inv_scale;        // header[layer]
   int kchunks, NT;
   uint32_t idesc;
+  int f8;                        // 1: fp16 + two e4m3 correction MMAs, 0: three fp16 MMAs
 };
 
 template <bool A_IMAGE, bool OUT_IMAGE>
@@ -197,15 +213,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
           if (sub == 1 && !sub1_valid) break;
           uint32_t a_hi = stage + sub * A_SUB, a_lo = a_hi + A_HALF;
           uint32_t d = tmem + sub * 256;
+          if (g.f8) {
 #pragma unroll
-          for (int j = 0; j < BK / 16; ++j) {
-            uint64_t da_hi = make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128);
-            uint64_t da_lo = make_desc(a_lo + j * 2 * A_LBO, A_LBO, 128);
-            uint64_t db_hi = make_desc(b_hi + j * 2 * NT * 16, NT * 16, 128);
-            uint64_t db_lo = make_desc(b_lo + j * 2 * NT * 16, NT * 16, 128);
-            mma_f16_ss(d, da_hi, db_hi, g.idesc, (i | j) != 0);
-            mma_f16_ss(d, da_hi, db_lo, g.idesc, 1);
-            mma_f16_ss(d, da_lo, db_hi, g.idesc, 1);
+            for (int j = 0; j < BK / 16; ++j)
+              mma_f16_ss(d, make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128), make_desc(b_hi + j * 2 * NT * 16, NT * 16, 128),
+                         g.idesc, (i | j) != 0);
+            // e4m3 planes: K = 32 per instruction = two 16-byte core matrices along k
+            mma_f8_ss(d, make_desc(a_hi + ACT_LO8, A_LBO, 128), make_desc(b_hi + w_half, NT * 16, 128), g.idesc, 1);
+            mma_f8_ss(d, make_desc(a_hi + ACT_X8, A_LBO, 128), make_desc(b_hi + w_half + w_half / 2, NT * 16, 128),
+                      g.idesc, 1);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BK / 16; ++j) {
+              uint64_t da_hi = make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128);
+              uint64_t da_lo = make_desc(a_lo + j * 2 * A_LBO, A_LBO, 128);
+              uint64_t db_hi = make_desc(b_hi + j * 2 * NT * 16, NT * 16, 128);
+              uint64_t db_lo = make_desc(b_lo + j * 2 * NT * 16, NT * 16, 128);
+              mma_f16_ss(d, da_hi, db_hi, g.idesc, (i | j) != 0);
+              mma_f16_ss(d, da_hi, db_lo, g.idesc, 1);
+              mma_f16_ss(d, da_lo, db_hi, g.idesc, 1);
+            }
           }
         }
         mma_commit(empty + 8 * s);   // the stage is free once these MMAs have read it
@@ -243,10 +270,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           int r = rbase + it * 8 + r_in;
-          uint4 hi, lo;
-          split8(v[it][0], v[it][1], hi, lo);
-          *reinterpret_cast<uint4*>(a_hi + c * A_LBO + r * 16) = hi;
-          *reinterpret_cast<uint4*>(a_hi + A_HALF + c * A_LBO + r * 16) = lo;
+          if (g.f8) {   // this thread's 8 k: one 16-byte fp16 group, half of a 16-byte e4m3 group in each byte plane
+            uint2 h0, h1, l8, x8;
+            split4_f8(v[it][0], h0, l8.x, x8.x);
+            split4_f8(v[it][1], h1, l8.y, x8.y);
+            *reinterpret_cast<uint4*>(a_hi + c * A_LBO + r * 16) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+            *reinterpret_cast<uint2*>(a_hi + ACT_LO8 + (c >> 1) * A_LBO + r * 16 + (c & 1) * 8) = l8;
+            *reinterpret_cast<uint2*>(a_hi + ACT_X8 + (c >> 1) * A_LBO + r * 16 + (c & 1) * 8) = x8;
+          } else {
+            uint4 hi, lo;
+            split8(v[it][0], v[it][1], hi, lo);
+            *reinterpret_cast<uint4*>(a_hi + c * A_LBO + r * 16) = hi;
+            *reinterpret_cast<uint4*>(a_hi + A_HALF + c * A_LBO + r * 16) = lo;
+          }
         }
         fence_proxy_async_smem();
         mbar_arrive(full_a + 8 * s);
@@ -298,16 +334,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
           for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (OUT_IMAGE) {
-          // 16 consecutive k of the next layer = two 8-wide k-chunks; lanes are consecutive rows -> 512 B runs
+          // 16 consecutive k of the next layer; lanes are consecutive rows -> every store instruction writes 512 B runs
+          const int k = kbase + c0;
+          unsigned char* chunk = img + (size_t)(k / BK) * ACT_CHUNK_BYTES;
+          if (g.f8) {
+            uint2 h[4];
+            uint4 l8, x8;
+            split4_f8(make_float4(v[0], v[1], v[2], v[3]), h[0], l8.x, x8.x);
+            split4_f8(make_float4(v[4], v[5], v[6], v[7]), h[1], l8.y, x8.y);
+            split4_f8(make_float4(v[8], v[9], v[10], v[11]), h[2], l8.z, x8.z);
+            split4_f8(make_float4(v[12], v[13], v[14], v[15]), h[3], l8.w, x8.w);
+            unsigned char* ph = chunk + ((k % BK) / 8) * A_LBO;
+            *reinterpret_cast<uint4*>(ph) = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
+            *reinterpret_cast<uint4*>(ph + A_LBO) = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
+            *reinterpret_cast<uint4*>(chunk + ACT_LO8 + ((k % BK) / 16) * A_LBO) = l8;
+            *reinterpret_cast<uint4*>(chunk + ACT_X8 + ((k % BK) / 16) * A_LBO) = x8;
+          } else {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            int k = kbase + c0 + h * 8;
-            unsigned char* p = img + (size_t)(k / BK) * ACT_CHUNK_BYTES + ((k % BK) / 8) * A_LBO;
-            uint4 hi, lo;
-            split8(make_float4(v[h * 8], v[h * 8 + 1], v[h * 8 + 2], v[h * 8 + 3]),
-                   make_float4(v[h * 8 + 4], v[h * 8 + 5], v[h * 8 + 6], v[h * 8 + 7]), hi, lo);
-            *reinterpret_cast<uint4*>(p) = hi;
-            *reinterpret_cast<uint4*>(p + A_HALF) = lo;
+            for (int h = 0; h < 2; ++h) {
+              unsigned char* p = chunk + (((k + h * 8) % BK) / 8) * A_LBO;
+              uint4 hi, lo;
+              split8(make_float4(v[h * 8], v[h * 8 + 1], v[h * 8 + 2], v[h * 8 + 3]),
+                     make_float4(v[h * 8 + 4], v[h * 8 + 5], v[h * 8 + 6], v[h * 8 + 7]), hi, lo);
+              *reinterpret_cast<uint4*>(p) = hi;
+              *reinterpret_cast<uint4*>(p + A_HALF) = lo;
+            }
           }
         } else if (row < g.M) {
           float* out = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + n0 + c0;
@@ -324,7 +375,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
 
 }  // namespace
 
-size_t cpn_tc_weights_bytes() { return layer_offset(CPN_TC_LAYERS); }
+size_t cpn_tc_weights_bytes() { return TC_HEADER_BYTES + 2 * scheme_bytes(); }
 
 int cpn_pack_tc_weights(const float* raw, void* dst_v, cudaStream_t st) {
   unsigned char* dst = reinterpret_cast<unsigned char*>(dst_v);
@@ -338,7 +389,8 @@ int cpn_pack_tc_weights(const float* raw, void* dst_v, cudaStream_t st) {
     CPN_CHECK_LAUNCH("absmax_kernel");
     size_t total = (size_t)L.out * L.kpad;
     pack_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(raw + L.raw, L.out, L.in, L.kpad, L.nt, absmax + l,
-                                                                    reinterpret_cast<__half*>(dst + layer_offset(l)), header, l);
+                                                                    reinterpret_cast<__half*>(dst + layer_offset(l, 0)),
+                                                                    dst + layer_offset(l, 1), header, l);
     CPN_CHECK_LAUNCH("pack_tc_kernel");
   }
   return CPN_OK;
@@ -370,7 +422,8 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
   g.relu = relu;
   g.out_div = out_div;
   g.out_kchunks = out_kchunks;
-  g.wtiles = tcw + layer_offset(layer);
+  g.f8 = (mode & CPN_TC_F16X3) ? 0 : 1;
+  g.wtiles = tcw + layer_offset(layer, g.f8);
   g.bias = reinterpret_cast<const float*>(packed) + L.bias;
   g.inv_scale = reinterpret_cast<const float*>(tcw) + layer;
   g.kchunks = L.kpad / BK;

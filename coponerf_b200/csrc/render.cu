@@ -185,6 +185,9 @@ int get_pool(LanePool** out) {
 }
 
 bool use_tc(const cpn_render_args& a) { return !(a.flags & CPN_FLAG_SIMT_ONLY); }
+// encoder-input form for sample / gather: 0 fp32 rows, 1 operand image (f16x3), 2 operand image (f8 scheme)
+int a_form(const cpn_render_args& a) { return !use_tc(a) ? 0 : ((a.flags & CPN_FLAG_F16X3) ? 1 : 2); }
+int tc_scheme(const cpn_render_args& a) { return (a.flags & CPN_FLAG_F16X3) ? CPN_TC_F16X3 : 0; }
 
 // fp32 CUDA-core layer: C = act(A * Wt + bias)
 int dense_simt(const cpn_render_args& a, const float* A, int lda, size_t wt, size_t bias, float* C, int ldc, int M, int N,
@@ -216,26 +219,27 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
     int rays = a.B * nr;
     int R = rays * 2 * a.S;
     CPN_TRY(launch_ray_setup(a, ray0, nr, w.seg, st));
-    CPN_TRY(launch_sample(a, ray0, nr, w.seg, w.rowaux, w.local16, w.A, use_tc(a), st));
-    CPN_TRY(launch_gather(a, ray0, nr, w.rowaux, w.A, use_tc(a), st));
+    CPN_TRY(launch_sample(a, ray0, nr, w.seg, w.rowaux, w.local16, w.A, a_form(a), st));
+    CPN_TRY(launch_gather(a, ray0, nr, w.rowaux, w.A, a_form(a), st));
     const int Rp = (R + 127) / 128 * 128;
     const int KC832 = CPN_FEAT_DIM / ACT_BK, KC128 = CPN_HIDDEN / ACT_BK;
+    const int sch = tc_scheme(a);
     if (use_tc(a)) {
       // per-sample encoder, CoPoNeRF.py:387-397: (835 -> 832 ReLU -> 416) for the primary and the secondary rows.
       // Activations travel between the tensor-core layers as fp16 hi/lo operand images (cpn_common.cuh).
       {
         ProfScope prof(st);
-        CPN_TRY(launch_gemm_tc(a.weights, 0, w.A, 0, w.H1, 0, 2 * Rp, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE, 1, KC832, st));
+        CPN_TRY(launch_gemm_tc(a.weights, 0, w.A, 0, w.H1, 0, 2 * Rp, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 1, KC832, st));
       }
       // the (tile, primary) and (tile, secondary) results land side by side: E image rows = sample rows, K = 832
-      CPN_TRY(launch_gemm_tc(a.weights, 1, w.H1, 0, w.E, 0, 2 * Rp, 0, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE, 2, KC832, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 1, w.H1, 0, w.E, 0, 2 * Rp, 0, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 2, KC832, st));
       // value and key, CoPoNeRF.py:404-408
-      CPN_TRY(launch_gemm_tc(a.weights, 2, w.E, 0, w.V, CPN_LATENT, R, 0, CPN_TC_A_IMAGE, 1, 1, st));
-      CPN_TRY(launch_gemm_tc(a.weights, 3, w.E, 0, w.K1, 0, R, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE, 1, KC128, st));
-      CPN_TRY(launch_gemm_tc(a.weights, 4, w.K1, 0, w.Kk, CPN_HIDDEN, R, 0, CPN_TC_A_IMAGE, 1, 1, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 2, w.E, 0, w.V, CPN_LATENT, R, 0, CPN_TC_A_IMAGE | sch, 1, 1, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 3, w.E, 0, w.K1, 0, R, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 1, KC128, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 4, w.K1, 0, w.Kk, CPN_HIDDEN, R, 0, CPN_TC_A_IMAGE | sch, 1, 1, st));
       // coordinate embedding, CoPoNeRF.py:446
       CPN_TRY(dense_simt(a, w.local16, 16, pw::WQT, pw::BQ, w.Q1, CPN_HIDDEN, R, CPN_HIDDEN, 16, 1, st));
-      CPN_TRY(launch_gemm_tc(a.weights, 5, w.Q1, CPN_HIDDEN, w.Qe, CPN_HIDDEN, R, 0, 0, 1, 1, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 5, w.Q1, CPN_HIDDEN, w.Qe, CPN_HIDDEN, R, 0, sch, 1, 1, st));
     } else {
       {
         ProfScope prof(st);
@@ -256,7 +260,7 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
     CPN_TRY(launch_gemm_simt(w.local16, 16, W + pw::WQRB_T, nullptr, w.rbias, 2 * a.S, w.K1, CPN_HIDDEN, R, CPN_HIDDEN,
                              16, 1, st));
     if (use_tc(a))
-      CPN_TRY(launch_gemm_tc(a.weights, 6, w.K1, CPN_HIDDEN, w.Kk, CPN_HIDDEN, R, 0, 0, 1, 1, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 6, w.K1, CPN_HIDDEN, w.Kk, CPN_HIDDEN, R, 0, tc_scheme(a), 1, 1, st));
     else
       CPN_TRY(dense_simt(a, w.K1, CPN_HIDDEN, pw::WQR2T, pw::BQR2, w.Kk, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
     CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, w.V, w.r1, z_all, st));

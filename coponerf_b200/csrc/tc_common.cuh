@@ -3,6 +3,7 @@
 // Bit layouts follow the PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor" tables.
 #pragma once
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 
 namespace tc {
@@ -97,6 +98,17 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uin
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with e4m3 operands (K = 32 per instruction); the instruction descriptor has the same bit pattern
+__device__ __forceinline__ void mma_f8_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier once every tcgen05 op this thread issued so far has completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -115,6 +127,30 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
   split2(a.z, a.w, hi.y, lo.y);
   split2(b.x, b.y, hi.z, lo.z);
   split2(b.z, b.w, hi.w, lo.w);
+}
+
+// ---- fp16 + fp8-correction split ("f8 scheme") ----------------------------------------------------------------
+// x*w = x_hi*w_hi                         fp16 MMA, exact products, fp32 accumulation
+//     + e4m3(x_lo * 2^8) * e4m3(w_hi * 2^-8)    x_lo = x - x_hi, |x_lo| <= 2^-11 |x|
+//     + e4m3(x * 2^-6)   * e4m3(w_lo * 2^6)     w_lo = w - w_hi
+// The two correction terms only need ~4 significant bits (they are 2^-11 of the product), so they run on the
+// fp8 tensor path at twice the fp16 rate: 2.0 MMA passes per product instead of 3.0. Measured on the reference
+// goldens (scripts/emulate_fp8_scheme.py): rgb max error on well-conditioned rays 1-2e-5 (fp16 alone: 3e-4).
+constexpr float F8_XLO_SCALE = 256.f, F8_W_SCALE = 1.f / 256.f, F8_X_SCALE = 1.f / 64.f, F8_WLO_SCALE = 64.f;
+
+__device__ __forceinline__ uint32_t f8x4(float a, float b, float c, float d) {
+  uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+// 4 values -> 4 fp16 hi (uint2), 4 e4m3 of the scaled remainder, 4 e4m3 of the scaled value
+__device__ __forceinline__ void split4_f8(const float4& x, uint2& hi, uint32_t& lo8, uint32_t& x8) {
+  __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+  float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  hi.x = *reinterpret_cast<uint32_t*>(&h0);
+  hi.y = *reinterpret_cast<uint32_t*>(&h1);
+  lo8 = f8x4((x.x - f0.x) * F8_XLO_SCALE, (x.y - f0.y) * F8_XLO_SCALE, (x.z - f1.x) * F8_XLO_SCALE, (x.w - f1.y) * F8_XLO_SCALE);
+  x8 = f8x4(x.x * F8_X_SCALE, x.y * F8_X_SCALE, x.z * F8_X_SCALE, x.w * F8_X_SCALE);
 }
 
 }  // namespace tc

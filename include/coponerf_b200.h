@@ -37,6 +37,7 @@ typedef enum {
 #define CPN_HIDDEN 128      /* hidden_dim, models/CoPoNeRF.py:78 */
 #define CPN_PAIR_CONSTS_FLOATS 320
 #define CPN_FLAG_SIMT_ONLY 1  /* run the big 1x1 convs on the fp32 CUDA-core GEMM (cross-check path) */
+#define CPN_FLAG_F16X3 2      /* tensor-core GEMMs with three fp16 MMAs per product (default: fp16 + 2 fp8) */
 
 int cpn_version(void);
 const char* cpn_last_error(void);
@@ -135,13 +136,15 @@ int cpn_gemm_simt(const float* A, int lda, const float* wt, const float* bias, f
 
 /* Tensor-core GEMM of one packed layer (0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value,
  * 3 key_map, 4 key_map_2, 5 query_embed_2, 6 query_repeat_embed_2): C[M, N_layer] = act(A[M, K_layer] * W^T + b),
- * operands split into fp16 hi/lo pairs and accumulated in fp32 on tcgen05 (3 MMAs per product).
+ * operands split into an fp16 head plus corrections (e4m3 on the fp8 path by default, fp16 with CPN_TC_F16X3)
+ * and accumulated in fp32 on tcgen05.
  * `packed` is the blob from cpn_pack_weights. mode bit CPN_TC_A_IMAGE: A is an "operand image" (128-row tiles,
  * per 32-wide k-chunk a 16 KB block [hi|lo][4][128][8] of fp16) instead of fp32 row-major; CPN_TC_OUT_IMAGE: C is
  * written as such an image with `out_kchunks` k-chunks per tile, source tile t landing in image tile t / out_div at
  * k offset (t % out_div) * N_layer (how the two branches of a sample row are concatenated). */
 #define CPN_TC_A_IMAGE 1
 #define CPN_TC_OUT_IMAGE 2
+#define CPN_TC_F16X3 4   /* three fp16 MMAs per product; default is fp16 + two e4m3 correction MMAs */
 int cpn_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,
                 int out_div, int out_kchunks, void* stream);
 

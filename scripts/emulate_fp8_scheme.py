@@ -1,0 +1,47 @@
+"""CPU emulation of candidate tensor-core precision schemes inside the oracle, against the reference goldens.
+   scheme 'f16x3' : a_hi*w_hi + a_hi*w_lo + a_lo*w_hi   (what gemm_tc does today)
+   scheme 'f16+f8': a_hi*w_hi (fp16) + e4m3(a_lo 2^p)*e4m3(w_hi 2^-p) + e4m3(a_hi 2^-q)*e4m3(w_lo 2^q)
+"""
+import glob, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from cases import GOLDEN_DIR, make_case, per_ray, SENS_FLOOR
+from coponerf_b200 import synth
+from oracle import render_oracle
+
+BIG = {"query_encode_latent", "query_encode_latent_2", "latent_value", "key_map", "key_map_2", "query_embed_2", "query_repeat_embed_2"}
+f8 = lambda t: t.to(torch.float8_e4m3fn).to(torch.float32)
+SCHEME = sys.argv[1] if len(sys.argv) > 1 else "f16+f8"
+P = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+Q = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+
+def emu(sd, name, x):
+    w = sd[name + ".weight"]; w = w.reshape(w.shape[0], -1); b = sd[name + ".bias"]
+    if name not in BIG:
+        return torch.nn.functional.linear(x, w, b)
+    m = w.abs().max().item(); e = int(np.floor(np.log2(m))) + 1
+    s = 2.0 ** (10 - e)
+    ws = w * s
+    w_hi = ws.half().float(); w_lo = ws - w_hi
+    a_hi = x.half().float(); a_lo = x - a_hi
+    mm = lambda a, bb: (a.double() @ bb.double().T).float()
+    if SCHEME == "f16x3":
+        y = mm(a_hi, w_hi) + mm(a_hi, w_lo.half().float()) + mm(a_lo.half().float(), w_hi)
+    elif SCHEME == "f16":
+        y = mm(a_hi, w_hi)
+    else:
+        y = mm(a_hi, w_hi) + mm(f8(a_lo * 2.0 ** P), f8(w_hi * 2.0 ** -P)) + mm(f8(a_hi * 2.0 ** -Q), f8(w_lo * 2.0 ** Q))
+    return y / s + b
+
+render_oracle._conv = emu
+for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "render_*.npz"))):
+    g = dict(np.load(p)); H, W, n, S, seed, val = [int(v) for v in g["meta"]]
+    inp, z, rel, flow = make_case(H, W, n, seed)
+    out = render_oracle.render_forward(synth.render_state_dict(0), inp, z, rel, flow, H, W, S, bool(val))
+    msg = []
+    for k in ("rgb", "at_wt"):
+        a, b = out[k].numpy(), g[k]; sc = np.abs(b).max()
+        err = per_ray(a.astype(np.float64) - b, k); st = g[k + "_sens"] <= SENS_FLOOR * sc
+        msg.append(f"{k}: max-err-on-stable {err[st].max() / sc:.2e} median {np.median(err) / sc:.2e}")
+    print(os.path.basename(p), SCHEME, P, Q, " | ".join(msg))
