@@ -72,7 +72,7 @@ __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* _
   extern __shared__ float sm[];
   const int S = a.S, S2 = 2 * S;
   float* w = sm;            // [2S]
-  float* red = sm + S2;     // [8]
+  float* red = sm + S2;     // [8] softmax scratch, [8] argmax indices, [8 x 3] weighted-point partials
   const int ray = blockIdx.x;  // b * nr + nl
   const int b = ray / nr, nl = ray % nr, n = ray0 + nl;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31, nwarps = S2 >> 5;
@@ -85,14 +85,55 @@ __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* _
     a.at_wt[(((size_t)(b * 2 + v)) * a.N + n) * S + s] = wt;
   }
   __syncthreads();
-  if (t < 2) {  // torch.argmax: first index of the maximum
-    int best = 0;
-    float bw = w[t * S];
-    for (int s = 1; s < S; ++s) {
-      float x = w[t * S + s];
-      if (x > bw) { bw = x; best = s; }
+  {  // torch.argmax over the S samples of each view: first index of the maximum (ties -> lowest index)
+    float bv = wt;
+    int bi = t % S;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
-    a.at_wt_max[((size_t)(b * 2 + t)) * a.N + n] = best;
+    if (lane == 0) {
+      red[warp] = bv;
+      reinterpret_cast<int*>(red)[8 + warp] = bi;   // red has 8 floats; the int slots live in the 8 after it
+    }
+  }
+  // weighted 3-D point: every thread contributes its own row, reduced per view in the fixed order s = 0..S-1
+  // inside a warp tree and then across the warps of the view
+  float p3[3];
+  {
+    const float* pp = rowaux + (row0 + t) * CPN_ROWAUX + 4;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float x = wt * pp[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      p3[c] = x;
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) red[16 + warp * 3 + c] = p3[c];
+    }
+  }
+  __syncthreads();
+  const int wpv = nwarps / 2;   // warps per view
+  if (t < 2) {
+    float bv = red[t * wpv];
+    int bi = reinterpret_cast<int*>(red)[8 + t * wpv];
+    for (int i = 1; i < wpv; ++i) {
+      float ov = red[t * wpv + i];
+      int oi = reinterpret_cast<int*>(red)[8 + t * wpv + i];
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    a.at_wt_max[((size_t)(b * 2 + t)) * a.N + n] = bi;
+  }
+  if (t >= 32 && t < 35) {
+    int c = t - 32;
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int i = 0; i < wpv; ++i) acc0 += red[16 + i * 3 + c];
+    for (int i = 0; i < wpv; ++i) acc1 += red[16 + (wpv + i) * 3 + c];
+    wp[(size_t)ray * 4 + c] = acc0 + acc1;
   }
   for (int c = t; c < CPN_LATENT; c += S2) {
     const float* vp = value + row0 * CPN_LATENT + c;
@@ -102,14 +143,6 @@ __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* _
 #pragma unroll 8
     for (int s = 0; s < S; ++s) acc1 += vp[(size_t)(S + s) * CPN_LATENT] * w[S + s];
     r1[(size_t)ray * CPN_LATENT + c] = acc0 + acc1;
-  }
-  if (t >= 32 && t < 35) {
-    int c = t - 32;
-    const float* pp = rowaux + row0 * CPN_ROWAUX + 4 + c;
-    float acc0 = 0.f, acc1 = 0.f;
-    for (int s = 0; s < S; ++s) acc0 += w[s] * pp[(size_t)s * CPN_ROWAUX];
-    for (int s = 0; s < S; ++s) acc1 += w[S + s] * pp[(size_t)(S + s) * CPN_ROWAUX];
-    wp[(size_t)ray * 4 + c] = acc0 + acc1;
   }
 }
 
@@ -256,7 +289,7 @@ __global__ void __launch_bounds__(128) phi_kernel(cpn_render_args a, const float
 int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, const float* qemb, const float* value,
                  const float* rowaux, float* r1, float* wp, cudaStream_t st) {
   int S2 = 2 * a.S;
-  attn1_kernel<<<a.B * nr, S2, (S2 + 8) * sizeof(float), st>>>(a, ray0, nr, key, qemb, value, rowaux, r1, wp);
+  attn1_kernel<<<a.B * nr, S2, (S2 + 48) * sizeof(float), st>>>(a, ray0, nr, key, qemb, value, rowaux, r1, wp);
   CPN_CHECK_LAUNCH("attn1_kernel");
   return CPN_OK;
 }

@@ -82,6 +82,18 @@ __global__ void __launch_bounds__(256) gather_kernel(cpn_render_args a, int nr, 
 constexpr int GI_ROWS = 8, GI_PITCH = CPN_FEAT_DIM + 24;  // halves per staged row: 1712 B = 428 words, 428 % 32 = 12 -> the 8 rows' 16-byte reads hit distinct banks
 constexpr int GI_B8 = CPN_FEAT_DIM + 16;                  // bytes per e4m3 plane of a staged row
 
+// make_taps with out-of-range taps turned into (offset 0, weight 0): the blend needs no branches
+__device__ __forceinline__ Taps make_taps_safe(float gx, float gy, int h, int w, int C, bool border) {
+  Taps t = make_taps(gx, gy, h, w, C, border);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (t.off[k] < 0) {
+      t.off[k] = 0;
+      t.w[k] = 0.f;
+    }
+  return t;
+}
+
 template <bool F8>
 __global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, int nr, const float* __restrict__ rowaux,
                                                            unsigned char* __restrict__ img) {
@@ -90,75 +102,88 @@ __global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, in
   __shared__ __align__(16) __half sh[2][GI_ROWS][GI_PITCH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int branch = blockIdx.y;
-  const long long nrows = (long long)a.B * nr * 2 * a.S;
-  const long long row0 = (long long)blockIdx.x * GI_ROWS, row = row0 + warp;
+  const unsigned nrows = (unsigned)(a.B * nr * 2 * a.S);       // < 2^31 (checked by the launcher)
+  const unsigned row0 = blockIdx.x * GI_ROWS, row = row0 + warp;
   if (row < nrows) {
-    int v = (int)((row / a.S) & 1);
-    int b = (int)(row / ((long long)2 * a.S * nr));
-    int im = b * 2 + (branch ? 1 - v : v);
-    const float* ra = rowaux + (size_t)row * CPN_ROWAUX;
-    float gx = ra[branch * 2 + 0], gy = ra[branch * 2 + 1];
+    const unsigned S = (unsigned)a.S;
+    const int v = (int)((row / S) & 1u);
+    const int b = (int)(row / (2u * S * (unsigned)nr));
+    const int im = b * 2 + (branch ? 1 - v : v);
+    const float2 g = *reinterpret_cast<const float2*>(rowaux + (size_t)row * CPN_ROWAUX + branch * 2);
+    __half* sh_hi = &sh[0][warp][0];
+    unsigned char* sh_b = reinterpret_cast<unsigned char*>(&sh[1][warp][0]);
     int col = 0;
 #pragma unroll
     for (int l = 0; l < CPN_N_LEVELS; ++l) {
-      int h = a.feat_h[l], w = a.feat_w[l], C = a.feat_c[l];
-      Taps t = make_taps(gx, gy, h, w, C, branch == 0);
-      const float* base = a.feat[l] + (size_t)im * h * w * C;
-      for (int c = lane * 4; c < C; c += 128) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (t.off[k] >= 0) {
-            float4 f = __ldg(reinterpret_cast<const float4*>(base + t.off[k] + c));
-            acc.x += f.x * t.w[k];
-            acc.y += f.y * t.w[k];
-            acc.z += f.z * t.w[k];
-            acc.w += f.w * t.w[k];
-          }
-        }
+      const int h = a.feat_h[l], w = a.feat_w[l], C = a.feat_c[l];
+      const Taps t = make_taps_safe(g.x, g.y, h, w, C, branch == 0);
+      const float* base = a.feat[l] + (size_t)im * h * w * C + lane * 4;
+      for (int c = lane * 4; c < C; c += 128, base += 128) {
+        const float4 f0 = __ldg(reinterpret_cast<const float4*>(base + t.off[0]));
+        const float4 f1 = __ldg(reinterpret_cast<const float4*>(base + t.off[1]));
+        const float4 f2 = __ldg(reinterpret_cast<const float4*>(base + t.off[2]));
+        const float4 f3 = __ldg(reinterpret_cast<const float4*>(base + t.off[3]));
+        float4 acc;   // same order as the fp32 kernel: ((f0 w0 + f1 w1) + f2 w2) + f3 w3
+        acc.x = fmaf(f3.x, t.w[3], fmaf(f2.x, t.w[2], fmaf(f1.x, t.w[1], f0.x * t.w[0])));
+        acc.y = fmaf(f3.y, t.w[3], fmaf(f2.y, t.w[2], fmaf(f1.y, t.w[1], f0.y * t.w[0])));
+        acc.z = fmaf(f3.z, t.w[3], fmaf(f2.z, t.w[2], fmaf(f1.z, t.w[1], f0.z * t.w[0])));
+        acc.w = fmaf(f3.w, t.w[3], fmaf(f2.w, t.w[2], fmaf(f1.w, t.w[1], f0.w * t.w[0])));
         if (F8) {
           uint2 hi;
           uint32_t l8, x8;
           tc::split4_f8(acc, hi, l8, x8);
-          *reinterpret_cast<uint2*>(&sh[0][warp][col + c]) = hi;
-          unsigned char* bp = reinterpret_cast<unsigned char*>(&sh[1][warp][0]);
-          *reinterpret_cast<uint32_t*>(bp + col + c) = l8;
-          *reinterpret_cast<uint32_t*>(bp + GI_B8 + col + c) = x8;
+          *reinterpret_cast<uint2*>(sh_hi + col + c) = hi;
+          *reinterpret_cast<uint32_t*>(sh_b + col + c) = l8;
+          *reinterpret_cast<uint32_t*>(sh_b + GI_B8 + col + c) = x8;
         } else {
           uint2 hi, lo;
           tc::split2(acc.x, acc.y, hi.x, lo.x);
           tc::split2(acc.z, acc.w, hi.y, lo.y);
-          *reinterpret_cast<uint2*>(&sh[0][warp][col + c]) = hi;
-          *reinterpret_cast<uint2*>(&sh[1][warp][col + c]) = lo;
+          *reinterpret_cast<uint2*>(sh_hi + col + c) = hi;
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(sh_b) + col + c) = lo;
         }
       }
       col += C;
     }
   }
   __syncthreads();
-  // 104 channel groups x 2 planes; thread -> (group, row): 8 threads write 128 contiguous bytes
-  const size_t tile = (size_t)(row0 >> 7) * 2 + branch;
-  const int r0 = (int)(row0 & 127), rr = threadIdx.x & 7;
+  // 208 16-byte groups per row (104 fp16-hi groups of 8 channels + 2 x 52 byte-plane groups of 16 channels, or
+  // 104 + 104 fp16 groups); thread -> (group, row): 8 threads write 128 contiguous bytes
+  const int rr = threadIdx.x & 7;
   if (row0 + rr < nrows) {
     constexpr int NG8 = CPN_FEAT_DIM / 8, NG16 = CPN_FEAT_DIM / 16;
-    for (int item = threadIdx.x >> 3; item < 2 * NG8; item += 32) {
-      if (F8) {
-        if (item < NG8) {          // fp16 hi: groups of 8 channels
-          uint4 val = *reinterpret_cast<const uint4*>(&sh[0][rr][item * 8]);
-          *reinterpret_cast<uint4*>(img + act_img_off(tile, CPN_KA_IMG / ACT_BK, item * 8, r0 + rr)) = val;
-        } else {                   // byte planes: groups of 16 channels
-          int pl = (item - NG8) >= NG16, gi = item - NG8 - pl * NG16, k = gi * 16;
-          const unsigned char* bp = reinterpret_cast<const unsigned char*>(&sh[1][rr][0]) + pl * GI_B8;
-          uint4 val = *reinterpret_cast<const uint4*>(bp + k);
-          unsigned char* p = img + ((size_t)tile * (CPN_KA_IMG / ACT_BK) + (k >> 5)) * ACT_CHUNK_BYTES +
-                             (pl ? ACT_X8 : ACT_LO8) + ((k & 31) >> 4) * 2048 + (size_t)(r0 + rr) * 16;
-          *reinterpret_cast<uint4*>(p) = val;
+    unsigned char* tile = img + ((size_t)(row0 >> 7) * 2 + branch) * ((size_t)(CPN_KA_IMG / ACT_BK) * ACT_CHUNK_BYTES) +
+                          ((row0 & 127) + rr) * 16;
+    const unsigned char* s_hi = reinterpret_cast<const unsigned char*>(&sh[0][rr][0]);
+    const unsigned char* s_b = reinterpret_cast<const unsigned char*>(&sh[1][rr][0]);
+#pragma unroll
+    for (int it = 0; it < (NG8 + 31) / 32; ++it) {   // plane 0: fp16 hi
+      const int gi = it * 32 + (threadIdx.x >> 3);
+      if (gi < NG8) {
+        const int k = gi * 8;
+        *reinterpret_cast<uint4*>(tile + (k >> 5) * ACT_CHUNK_BYTES + ((k & 31) >> 3) * 2048) =
+            *reinterpret_cast<const uint4*>(s_hi + gi * 16);
+      }
+    }
+    if (F8) {
+#pragma unroll
+      for (int it = 0; it < (2 * NG16 + 31) / 32; ++it) {
+        const int item = it * 32 + (threadIdx.x >> 3);
+        if (item < 2 * NG16) {
+          const int pl = item >= NG16, gi = item - pl * NG16, k = gi * 16;
+          *reinterpret_cast<uint4*>(tile + (k >> 5) * ACT_CHUNK_BYTES + (pl ? ACT_X8 : ACT_LO8) + ((k & 31) >> 4) * 2048) =
+              *reinterpret_cast<const uint4*>(s_b + pl * GI_B8 + gi * 16);
         }
-      } else {
-        int plane = item >= NG8, gi = plane ? item - NG8 : item;
-        uint4 val = *reinterpret_cast<const uint4*>(&sh[plane][rr][gi * 8]);
-        unsigned char* p = img + act_img_off(tile, CPN_KA_IMG / ACT_BK, gi * 8, r0 + rr) + plane * ACT_LO;
-        *reinterpret_cast<uint4*>(p) = val;
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < (NG8 + 31) / 32; ++it) {
+        const int gi = it * 32 + (threadIdx.x >> 3);
+        if (gi < NG8) {
+          const int k = gi * 8;
+          *reinterpret_cast<uint4*>(tile + (k >> 5) * ACT_CHUNK_BYTES + ACT_LO + ((k & 31) >> 3) * 2048) =
+              *reinterpret_cast<const uint4*>(s_b + gi * 16);
+        }
       }
     }
   }
@@ -189,6 +214,10 @@ int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowau
   long long blocks = (warps * 32 + 255) / 256;
   if (a_image) {
     long long rows = (long long)a.B * nr * 2 * a.S;
+    if (rows >= (1ll << 31) || (a.S % GI_ROWS) != 0) {
+      cpn_set_error("gather: %lld sample rows per chunk / S=%d unsupported (S must be a multiple of 8)", rows, a.S);
+      return CPN_ERR_ARG;
+    }
     dim3 grid((unsigned)((rows + GI_ROWS - 1) / GI_ROWS), 2);
     if (a_image == 2)
       gather_image_kernel<true><<<grid, 256, 0, st>>>(a, nr, rowaux, reinterpret_cast<unsigned char*>(A));

@@ -117,8 +117,8 @@ int check_args(const cpn_render_args* a) {
                   a->chunk_rays, a->flow_h);
     return CPN_ERR_ARG;
   }
-  if (a->S <= 0 || a->S > 128 || ((2 * a->S) % 32) != 0) {
-    cpn_set_error("cpn_render_rays: S=%d unsupported (2*S must be a multiple of 32, S <= 128)", a->S);
+  if (a->S <= 0 || a->S > 128 || (a->S % 32) != 0) {
+    cpn_set_error("cpn_render_rays: S=%d unsupported (S must be a multiple of 32, S <= 128)", a->S);
     return CPN_ERR_ARG;
   }
   int csum = 0;

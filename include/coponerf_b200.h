@@ -83,7 +83,7 @@ int cpn_pair_prologue(const float* flow0, const float* flow1, int B, int fh, int
 typedef struct {
   int32_t B;          /* stereo pairs */
   int32_t N;          /* target rays per pair */
-  int32_t S;          /* samples per epipolar line (npoints); 2*S must be a multiple of 32, S <= 128 */
+  int32_t S;          /* samples per epipolar line (npoints): 32, 64, 96 or 128 */
   int32_t H, W;       /* context image size (model.H, model.W) */
   int32_t flow_h;     /* height of flow[1] (for flow2kps' scale 256/flow_h) */
   int32_t chunk_rays; /* rays processed per internal pass (workspace is sized from it) */

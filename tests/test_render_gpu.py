@@ -103,7 +103,7 @@ def test_empty_ray_set():
 def test_bad_arguments_fail_loudly():
     from coponerf_b200 import _lib
     with pytest.raises(_lib.CpnError):
-        run_cuda(64, 64, 16, 40, seed=1, val=True)   # 2*S not a multiple of 32
+        run_cuda(64, 64, 16, 40, seed=1, val=True)   # S not a multiple of 32
     lib = _lib.load()
     assert lib.cpn_render_rays(None, None) != 0
     assert b"null" in lib.cpn_last_error()
