@@ -149,7 +149,10 @@ struct GemmArgs {
   int f8;                        // 1: fp16 + two e4m3 correction MMAs, 0: three fp16 MMAs
 };
 
-template <bool A_IMAGE, bool OUT_IMAGE>
+// CLUSTER (> 1, operand-image A only): the CTAs of the N tiles of one 256-row tile form a cluster; each loads
+// 1/CLUSTER of every A stage and multicasts it to all of them, so the shared A operand is read from L2 once per
+// cluster instead of once per N tile (the GEMMs are L2 -> SM bandwidth bound, profiles/).
+template <bool A_IMAGE, bool OUT_IMAGE, int CLUSTER>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bars[3 * STAGES + 1];
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_a + 8 * s, 256);
       mbar_init(full_w + 8 * s, 1);
-      mbar_init(empty + 8 * s, 1);
+      mbar_init(empty + 8 * s, CLUSTER);   // one commit from the MMA warp of every CTA that reads this stage
     }
     mbar_init(accum, 1);
     fence_barrier_init();
@@ -175,8 +178,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), TMEM_COLS);
   tcgen05_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync();   // every CTA's barriers are initialised before any remote arrive / copy
   tcgen05_fence_after();
   const uint32_t tmem = tmem_base_s;
+  const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0;
+  constexpr uint16_t cmask = (uint16_t)((1u << CLUSTER) - 1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -191,7 +197,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
         uint32_t bytes = 2 * w_half + (A_IMAGE ? (sub1_valid ? 2 : 1) * A_SUB : 0);
         mbar_arrive_expect_tx(full_w + 8 * s, bytes);
         bulk_g2s(stage + 2 * A_SUB, wsrc + (size_t)i * 2 * w_half, 2 * w_half, full_w + 8 * s);
-        if (A_IMAGE) {
+        if (A_IMAGE && CLUSTER > 1) {
+          // this CTA's slice of the A stage (both sub-tiles are contiguous 16 KB blocks), multicast to the cluster
+          constexpr uint32_t SLICE = 2 * A_SUB / CLUSTER;
+          const uint32_t off = crank * SLICE, sub = off / A_SUB, in_sub = off % A_SUB;
+          if (sub == 0 || sub1_valid)
+            bulk_g2s_multicast(stage + off, asrc + ((tile0 + sub) * g.kchunks + i) * ACT_CHUNK_BYTES + in_sub, SLICE,
+                               full_w + 8 * s, cmask);
+        } else if (A_IMAGE) {
           bulk_g2s(stage, asrc + (tile0 * g.kchunks + i) * ACT_CHUNK_BYTES, A_SUB, full_w + 8 * s);
           if (sub1_valid)
             bulk_g2s(stage + A_SUB, asrc + ((tile0 + 1) * g.kchunks + i) * ACT_CHUNK_BYTES, A_SUB, full_w + 8 * s);
@@ -235,7 +248,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
             }
           }
         }
-        mma_commit(empty + 8 * s);   // the stage is free once these MMAs have read it
+        // the stage is free once these MMAs have read it (in every CTA of the cluster, for the shared A slices)
+        if (CLUSTER > 1) mma_commit_multicast(empty + 8 * s, cmask); else mma_commit(empty + 8 * s);
       }
       mma_commit(accum);
     }
@@ -370,6 +384,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync();   // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
@@ -430,11 +445,27 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
   g.NT = L.nt;
   g.idesc = make_idesc_f16(128, L.nt);
   dim3 grid(L.out / L.nt, (M + BM - 1) / BM);
-  auto kern = a_img ? (o_img ? gemm_tc_kernel<true, true> : gemm_tc_kernel<true, false>)
-                    : (o_img ? gemm_tc_kernel<false, true> : gemm_tc_kernel<false, false>);
+  const int ntiles = L.out / L.nt;
+  const int cluster = (a_img && (mode & CPN_TC_CLUSTER)) ? ntiles : 1;   // 4, 2 or 1; opt-in: measured slower
+  void (*kern)(GemmArgs);
+  if (cluster == 4) kern = o_img ? gemm_tc_kernel<true, true, 4> : gemm_tc_kernel<true, false, 4>;
+  else if (cluster == 2) kern = o_img ? gemm_tc_kernel<true, true, 2> : gemm_tc_kernel<true, false, 2>;
+  else kern = a_img ? (o_img ? gemm_tc_kernel<true, true, 1> : gemm_tc_kernel<true, false, 1>)
+                    : (o_img ? gemm_tc_kernel<false, true, 1> : gemm_tc_kernel<false, false, 1>);
   CPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(g);
-  CPN_CHECK_LAUNCH("gemm_tc_kernel");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CPN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, g));
   return CPN_OK;
 }
 
