@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk-rays", type=int, default=2048)
-    ap.add_argument("--lanes", type=int, default=3, help="chunks in flight on internal streams")
+    ap.add_argument("--lanes", type=int, default=2, help="chunks in flight on internal streams")
     ap.add_argument("--simt", action="store_true", help="fp32 CUDA-core GEMMs only (cross-check path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -266,10 +266,19 @@ def main():
     for _ in range(args.warmup):
         device_step()
     torch.cuda.synchronize()
-    _lib.check(lib.cpn_prof_begin(chunks * args.steps), "cpn_prof_begin")
     ms_dev = timed(device_step, args.steps, 0)
+    # roofline pass: the dominant kernel timed with CUDA events around each launch. Chunks are issued on one lane
+    # here so that an event pair brackets that kernel alone (with lanes > 1 other chunks' kernels share the GPU
+    # and the bracket would include their time); the step time of this pass gives the kernel's share.
+    prof_steps = min(args.steps, 3)
+    eng.lanes = 1
+    device_step()
+    torch.cuda.synchronize()
+    _lib.check(lib.cpn_prof_begin(chunks * prof_steps), "cpn_prof_begin")
+    ms_prof = timed(device_step, prof_steps, 0)
     dom_ms, dom_n = ctypes.c_float(0), ctypes.c_int(0)
     _lib.check(lib.cpn_prof_end(ctypes.byref(dom_ms), ctypes.byref(dom_n)), "cpn_prof_end")
+    eng.lanes = args.lanes
     launches = args.steps * (eng.last_launch_count + 6)   # + 4 feature re-layouts, pair_setup, pair_prologue
     ms_e2e = timed(e2e_step, args.steps, 2)
     clk = clocks.stop() if clocks else None
@@ -296,7 +305,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "256x256 stereo pair, 65536 rays, S=64 (render half: forward with z given)",
                    "pairs_per_gpu": 1, "chunk_rays": args.chunk_rays, "lanes": args.lanes, "l2": "flushed between timed steps (256 MB write)",
-                   "gemm_path": "simt-fp32" if args.simt else "tcgen05 split-fp16 (3 MMA) + simt-fp32 small layers",
+                   "gemm_path": "simt-fp32" if args.simt else "tcgen05: fp16 head + two e4m3 correction MMAs per product (fp32 accumulate)",
                    "parallelism": f"pairs sharded over {world} GPU(s), one NCCL gather of rgb" if world > 1 else "1 GPU"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
@@ -305,7 +314,9 @@ def main():
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "launches": dom_n.value,
                      "avg_launch_ms": dom_ms.value / max(dom_n.value, 1),
-                     "share_of_step": dom_ms.value / ms_dev if world == 1 else None,
+                     "share_of_step": dom_ms.value / ms_prof,
+                     "measured": f"CUDA events around every launch in a {prof_steps}-step pass with lanes=1 "
+                                 f"({ms_prof / prof_steps:.1f} ms/step)",
                      "flop_per_launch": flop_per_launch,
                      "whole_path_tflops": value * FLOP_PER_RAY / 1e12 / world},
         "clocks": clk,
@@ -333,10 +344,13 @@ def main():
                                 "sample": sample}
         got = state["out"]["rgb"][0, 0].cpu()[idx]
         want = ref["rgb"][0, 0]
-        err = float((got - want).abs().max() / want.abs().max())
+        per_ray_err = (got - want).abs().max(dim=-1).values / want.abs().max()
+        err = float(per_ray_err.max())
         mse = float(((got.clamp(-1, 1) - want.clamp(-1, 1)) ** 2).mean())
         import math
-        line["parity"] = {"rgb_max_rel_err_vs_oracle": err,
+        line["parity"] = {"rgb_max_rel_err_vs_oracle": err, "rgb_median_rel_err_vs_oracle": float(per_ray_err.median()),
+                          "rgb_p99_rel_err_vs_oracle": float(per_ray_err.kthvalue(int(0.99 * len(per_ray_err))).values),
+                          "note": "the max sits on rays where the reference itself is ill-conditioned (DESIGN.md section 2)",
                           "psnr_vs_oracle_db": (-10 * math.log10(mse)) if mse > 0 else None,
                           "rays_checked": CPU_SAMPLE_RAYS}
     print(json.dumps(line), flush=True)

@@ -46,7 +46,7 @@ def pose_inverse_4x4(mat):
 class CoPoNeRF(nn.Module):
     """models/CoPoNeRF.py:19. Only n_view == 2 is supported (the value both reference drivers pass)."""
 
-    def __init__(self, n_view=1, npoints=64, num_hidden_units_phi=128, chunk_rays=2048, lanes=3):
+    def __init__(self, n_view=1, npoints=64, num_hidden_units_phi=128, chunk_rays=2048, lanes=2):
         super().__init__()
         self.n_view = n_view
         self.npoints = npoints if npoints else 64

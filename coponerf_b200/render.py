@@ -32,7 +32,7 @@ class PairState:
 class RenderEngine:
     """Packed render-path weights + workspace on one CUDA device."""
 
-    def __init__(self, state_dict, device=None, chunk_rays=2048, lanes=3):
+    def __init__(self, state_dict, device=None, chunk_rays=2048, lanes=2):
         if not torch.cuda.is_available():
             raise _lib.CpnError("coponerf_b200 needs a CUDA device: the render path has no CPU fallback")
         self.lib = _lib.load()
