@@ -45,6 +45,15 @@ class RenderArgs(ctypes.Structure):
     ]
 
 
+class UfcTailArgs(ctypes.Structure):
+    """cpn_ufc_tail_args (include/coponerf_b200.h)."""
+    _fields_ = [("B", ctypes.c_int32), ("C", ctypes.c_int32), ("out", ctypes.c_int32), ("sizes", ctypes.c_int32 * 3),
+                ("src", ctypes.c_void_p * 3), ("trg", ctypes.c_void_p * 3), ("lin", ctypes.c_void_p),
+                ("c", ctypes.c_void_p), ("flow", ctypes.c_void_p), ("flow_flip", ctypes.c_void_p),
+                ("flow_t_to_s", ctypes.c_void_p), ("flow_s_to_t", ctypes.c_void_p),
+                ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t)]
+
+
 # symbol -> (restype, argtypes); every entry point include/coponerf_b200.h declares
 SIGNATURES = {
     "cpn_version": (ctypes.c_int, []),
@@ -66,6 +75,9 @@ SIGNATURES = {
     "cpn_render_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5),
     "cpn_render_rays": (ctypes.c_int, [ctypes.POINTER(RenderArgs), ctypes.c_void_p]),
     "cpn_render_launch_count": (ctypes.c_int, [ctypes.POINTER(RenderArgs)]),
+    "cpn_ufc_tail_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                       ctypes.POINTER(ctypes.c_int32)]),
+    "cpn_ufc_tail": (ctypes.c_int, [ctypes.POINTER(UfcTailArgs), ctypes.c_void_p]),
     "cpn_gemm_simt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_void_p]),

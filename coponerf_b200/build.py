@@ -25,6 +25,7 @@ SOURCES = [
     ("attention.cu", []),
     ("weights.cu", []),
     ("render.cu", []),
+    ("ufc_tail.cu", []),
 ]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

@@ -106,7 +106,7 @@ int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowau
 // remap256: output row m goes to row (m / 256) * 128 + m % 128 at column offset ((m / 128) & 1) * N (undoes enc_row)
 int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias, const float* rowbias,
                      int rows_per_bias, float* C, int ldc, int M, int N, int K, int relu, cudaStream_t st,
-                     int remap256 = 0);
+                     int remap256 = 0, float out_div = 0.f);   // out_div != 0: result divided by it
 int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, const float* qemb, const float* value,
                  const float* rowaux, float* r1, float* wp, cudaStream_t st);
 // z_all: (B, N, 416) latent of every ray of the image

@@ -14,7 +14,7 @@ constexpr int BM = 128, BN = 128, BK = 16, NT = 256;
 __global__ void __launch_bounds__(NT, 2)
 gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Wt, const float* __restrict__ bias,
                  const float* __restrict__ rowbias, int rows_per_bias, float* __restrict__ C, int ldc, int M, int N,
-                 int K, int relu, int remap256) {
+                 int K, int relu, int remap256, float out_div) {
   __shared__ __align__(16) float As[2][BK][BM];
   __shared__ __align__(16) float Bs[2][BK][BN];
   const int tid = threadIdx.x;
@@ -105,6 +105,9 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
       if (relu) {
         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
       }
+      if (out_div != 0.f) {
+        v.x /= out_div; v.y /= out_div; v.z /= out_div; v.w /= out_div;
+      }
       size_t orow = remap256 ? (size_t)(m >> 8) * 128 + (m & 127) : (size_t)m;
       int ocol = remap256 ? ((m >> 7) & 1) * N + n : n;
       *reinterpret_cast<float4*>(C + orow * ldc + ocol) = v;
@@ -115,7 +118,8 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
 }  // namespace
 
 int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias, const float* rowbias,
-                     int rows_per_bias, float* C, int ldc, int M, int N, int K, int relu, cudaStream_t st, int remap256) {
+                     int rows_per_bias, float* C, int ldc, int M, int N, int K, int relu, cudaStream_t st, int remap256,
+                     float out_div) {
   if (M <= 0) return CPN_OK;
   if ((K & 3) || (N & 3) || (lda & 3) || (ldc & 3)) {
     cpn_set_error("gemm_simt: K, N, lda and ldc must be multiples of 4 (K=%d N=%d lda=%d ldc=%d)", K, N, lda, ldc);
@@ -127,7 +131,7 @@ int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias
     return CPN_ERR_ARG;
   }
   gemm_simt_kernel<<<grid, NT, 0, st>>>(A, lda, wt, bias, rowbias, rows_per_bias > 0 ? rows_per_bias : 1, C, ldc, M, N,
-                                        K, relu, remap256);
+                                        K, relu, remap256, out_div);
   CPN_CHECK_LAUNCH("gemm_simt_kernel");
   return CPN_OK;
 }
@@ -138,5 +142,5 @@ extern "C" int cpn_gemm_simt(const float* A, int lda, const float* wt, const flo
     cpn_set_error("cpn_gemm_simt: null pointer");
     return CPN_ERR_ARG;
   }
-  return launch_gemm_simt(A, lda, wt, bias, nullptr, 1, C, ldc, M, N, K, relu, (cudaStream_t)stream, 0);
+  return launch_gemm_simt(A, lda, wt, bias, nullptr, 1, C, ldc, M, N, K, relu, (cudaStream_t)stream, 0, 0.f);
 }

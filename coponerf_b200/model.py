@@ -76,6 +76,7 @@ class CoPoNeRF(nn.Module):
         self.phi = _ResnetFC(n_view * 9, half * n_view, hidden)
         self.chunk_rays = chunk_rays
         self.lanes = lanes
+        self.native_ufc_tail = True     # get_z(): closing stage of the cost aggregation on cpn_ufc_tail
         self.pixel_val_on_host = True   # the reference returns out['pixel_val'] as a CPU tensor (CoPoNeRF.py:490)
         self._engine = None
         self._engine_version = None
@@ -107,8 +108,21 @@ class CoPoNeRF(nn.Module):
         if self._pair_stage is None:
             raise RuntimeError("get_z() needs the per-pair stage: call attach_pair_stage(reference_model), or pass "
                                "z=, rel_pose=, flow= to forward()")
-        out = self._pair_stage.get_z(input)
-        self.H, self.W = self._pair_stage.H, self._pair_stage.W
+        ref = self._pair_stage
+        fca = ref.feature_cost_aggregation
+        if not self.native_ufc_tail:
+            out = ref.get_z(input)
+        else:
+            # same call, with the closing stage of UFC (correlations of the refined features, 4-D upsampling,
+            # soft-argmax flows: aggregation.py:527-561) routed to cpn_ufc_tail
+            from .ufc import ufc_forward
+            orig = fca.forward
+            fca.forward = lambda feat, nview: ufc_forward(fca, feat, nview)
+            try:
+                out = ref.get_z(input)
+            finally:
+                fca.forward = orig
+        self.H, self.W = ref.H, ref.W
         return out
 
     @torch.no_grad()

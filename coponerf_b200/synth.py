@@ -169,3 +169,22 @@ def make_features(H=256, W=256, seed=1, batch=1):
     # estimated context-1 -> context-2 pose: close to the true one, not equal to it
     rel = np.stack([_pose(0.3, -0.1, 0.01 * b, -0.02) for b in range(batch)])
     return z, f32(rel), flow
+
+
+def ufc_tail_features(sizes=(16, 32, 64), batch=1, seed=12, C=256):
+    """Refined source / target token features for the closing stage of UFC (three (B, n*n, C) tensors each).
+
+    Smooth random maps plus noise; the target is a shifted copy of the source, so neighbouring pixels correlate and
+    the soft-argmax flow has structure instead of being uniform.
+    """
+    import torch.nn.functional as F
+    rng = np.random.default_rng(4000 + seed)
+    src, trg = [], []
+    for n in sizes:
+        base = torch.from_numpy(rng.standard_normal((batch, 8, 8, C))).permute(0, 3, 1, 2).float()
+        up = F.interpolate(base, size=(n, n), mode="bicubic", align_corners=True)
+        shift = torch.roll(up, shifts=(max(1, n // 8), -max(1, n // 16)), dims=(2, 3))
+        noise = lambda: torch.from_numpy(rng.standard_normal((batch, C, n, n))).float() * 0.3
+        src.append((up + noise()).flatten(2).transpose(1, 2).contiguous())
+        trg.append((shift + noise()).flatten(2).transpose(1, 2).contiguous())
+    return src, trg

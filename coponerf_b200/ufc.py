@@ -1,0 +1,99 @@
+"""Host side of the per-pair cost-aggregation kernels (models/aggregation.py). Built so far: the closing stage of
+UFC.forward() -- correlation of the refined features of the three levels, 4-D upsampling, their mean `c`, the two
+soft-argmax flow fields and the conversion to pixel flow (aggregation.py:527,539,549-561) -- as `ufc_tail`."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def ufc_tail(src_feats, trg_feats, sizes=(16, 32, 64), out=64):
+    """src_feats / trg_feats: three CUDA fp32 token tensors (B, sizes[l]^2, C).
+
+    Returns ((flow, flow_flip, flow_t_to_s, flow_s_to_t), c) with the shapes UFC.forward returns:
+    flows (B, 2, out, out), c (B, 1, out, out, out, out).
+    """
+    lib = _lib.load()
+    dev = src_feats[0].device
+    if dev.type != "cuda":
+        raise _lib.CpnError("ufc_tail runs on CUDA only (no CPU fallback)")
+    B, _, C = src_feats[0].shape
+    src = [t.detach().to(torch.float32).contiguous() for t in src_feats]
+    trg = [t.detach().to(torch.float32).contiguous() for t in trg_feats]
+    for l, n in enumerate(sizes):
+        if tuple(src[l].shape) != (B, n * n, C) or tuple(trg[l].shape) != (B, n * n, C):
+            raise ValueError(f"level {l}: expected (B, {n * n}, {C}) token features")
+    with torch.cuda.device(dev):
+        f32 = dict(dtype=torch.float32, device=dev)
+        c = torch.empty((B, 1, out, out, out, out), **f32)
+        flows = [torch.empty((B, 2, out, out), **f32) for _ in range(4)]
+        lin = torch.linspace(-1, 1, out).to(dev)   # built on the host like the reference's
+        a = _lib.UfcTailArgs()
+        a.B, a.C, a.out = B, C, out
+        for l in range(3):
+            a.sizes[l] = sizes[l]
+            a.src[l] = src[l].data_ptr()
+            a.trg[l] = trg[l].data_ptr()
+        a.lin, a.c = lin.data_ptr(), c.data_ptr()
+        a.flow, a.flow_flip, a.flow_t_to_s, a.flow_s_to_t = (f.data_ptr() for f in flows)
+        nbytes = lib.cpn_ufc_tail_workspace_bytes(B, C, out, a.sizes)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+        _lib.check(lib.cpn_ufc_tail(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "cpn_ufc_tail")
+    return tuple(flows), c
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# UFC.forward with the native closing stage. The coarse-to-fine refinement (proj_feat, embedding, the five UFCLayer
+# blocks: aggregation.py:509-549) is not native yet and is delegated to the attached reference module's own
+# submodules; what is replaced is everything after the last UFCLayer.
+def _tokens_to_map(x, n):
+    return x.transpose(1, 2).reshape(x.shape[0], x.shape[2], n, n)
+
+
+def _correlation(src_tok, trg_tok, n, eps=1e-5):
+    """aggregation.py:70-74 on token features."""
+    s, t = _tokens_to_map(src_tok, n), _tokens_to_map(trg_tok, n)
+    s = s / (s.norm(dim=1, p=2, keepdim=True) + eps)
+    t = t / (t.norm(dim=1, p=2, keepdim=True) + eps)
+    return torch.einsum("bchw,bcxy->bhwxy", s, t)[:, None]
+
+
+def _upsample_tokens(x, n_out):
+    """aggregation.py:58-63 (interpolate2d_token)."""
+    n = int(round(x.shape[1] ** 0.5))
+    y = torch.nn.functional.interpolate(_tokens_to_map(x, n), size=(n_out, n_out), mode="bilinear", align_corners=True)
+    return y.flatten(2).transpose(1, 2)
+
+
+def ufc_forward(fca, feat, nview, tail=None):
+    """Drop-in for UFC.forward(feat, nview) (aggregation.py:509-562) of the attached reference module `fca`.
+
+    Returns (feat_list, (flow, flow_flip, flow_t_to_s, flow_s_to_t), c) like the reference. `tail` defaults to the
+    sm_100a closing stage (ufc_tail); tests pass the CPU oracle here to check the orchestration without a GPU.
+    """
+    tail = tail or ufc_tail
+    B = feat[0].shape[0]
+    sizes = [f.shape[-1] for f in feat]
+
+    def side(i, v):
+        x = feat[i].view(B // nview, nview, -1, sizes[i], sizes[i])[:, v]
+        return fca.proj_feat[i](x.flatten(2).transpose(1, 2))
+
+    src = [side(i, 0) for i in range(3)]
+    trg = [side(i, 1) for i in range(3)]
+    feat_list, refined = [], []
+    corr, s, t = None, None, None
+    for lvl in range(3):
+        raw = fca.embedding[lvl](_correlation(src[lvl], trg[lvl], sizes[lvl]))
+        corr = raw if lvl == 0 else corr + raw
+        s = src[lvl] if lvl == 0 else _upsample_tokens(s, sizes[lvl]) + src[lvl]
+        t = trg[lvl] if lvl == 0 else _upsample_tokens(t, sizes[lvl]) + trg[lvl]
+        corr, s, t = fca.layers[lvl](corr, s, t)
+        both = torch.stack((s, t), dim=1).flatten(0, 1)
+        feat_list.append(_tokens_to_map(both, sizes[lvl]))
+        refined.append((s, t))
+    flows, c = tail([r[0] for r in refined], [r[1] for r in refined], tuple(sizes), sizes[-1])
+    return feat_list, flows, c

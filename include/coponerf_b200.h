@@ -121,6 +121,30 @@ int cpn_render_rays(const cpn_render_args* args, void* stream);
 /* number of kernels one cpn_render_rays call launches (for bench.py's gpu_launches) */
 int cpn_render_launch_count(const cpn_render_args* args);
 
+/* ---- closing stage of the per-pair cost aggregation ---------------------------------------------------
+ * Replaces models/aggregation.py:527,539,549-561 (the three correlation_token calls, interpolate4d x3, their mean,
+ * soft_argmax x2 and unnormalise_and_convert_mapping_to_flow x2 of UFC.forward):
+ *   src[l], trg[l]  refined token features of pyramid level l, (B, sizes[l]^2, C) fp32 ("B (H W) C")
+ *   lin             linspace(-1, 1, out), (out) fp32
+ *   c               (B, out, out, out, out) = UFC's third return value [b, hs, ws, ht, wt]
+ *   flow, flow_flip, flow_t_to_s, flow_s_to_t   (B, 2, out, out) = UFC's flow tuple, in that order */
+typedef struct {
+  int32_t B, C, out;
+  int32_t sizes[3];
+  const float* src[3];
+  const float* trg[3];
+  const float* lin;
+  float* c;
+  float* flow;
+  float* flow_flip;
+  float* flow_t_to_s;
+  float* flow_s_to_t;
+  void* workspace;
+  size_t workspace_bytes;
+} cpn_ufc_tail_args;
+size_t cpn_ufc_tail_workspace_bytes(int B, int C, int out, const int* sizes);
+int cpn_ufc_tail(const cpn_ufc_tail_args* args, void* stream);
+
 /* ---- device timing of the dominant kernel (the query_encode_latent GEMM), for roofline reports.
  * Between cpn_prof_begin and cpn_prof_end every launch of that kernel by cpn_render_rays is bracketed
  * by CUDA events on the caller's stream. cpn_prof_end waits for them and returns the summed duration.

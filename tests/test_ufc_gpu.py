@@ -1,0 +1,59 @@
+"""Parity of the native closing stage of UFC (cpn_ufc_tail, through the C-ABI) against the outputs of the
+unmodified reference functions (tests/golden/ufc_tail_*.npz) and against the CPU oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from coponerf_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "ufc_tail_*.npz")))
+NAMES = ("flow", "flow_flip", "flow_t_to_s", "flow_s_to_t")
+
+
+def run(sizes, out, batch, seed):
+    from coponerf_b200.ufc import ufc_tail
+    src, trg = synth.ufc_tail_features(sizes, batch, seed)
+    flows, c = ufc_tail([t.cuda() for t in src], [t.cuda() for t in trg], sizes, out)
+    torch.cuda.synchronize()
+    return [f.cpu() for f in flows], c.cpu(), (src, trg)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_ufc_tail_matches_reference_golden(case):
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    sizes, out, batch, seed = tuple(int(v) for v in g["meta"][:3]), int(g["meta"][3]), int(g["meta"][4]), int(g["meta"][5])
+    flows, c, _ = run(sizes, out, batch, seed)
+    # c is a cosine correlation in [-1, 1]: absolute gate
+    assert np.abs(c.reshape(-1)[g["c_idx"]].numpy() - g["c_val"]).max() <= 2e-6
+    assert abs(float(c.double().mean()) - float(g["c_mean"])) <= 1e-7
+    assert abs(float((c.double() ** 2).mean()) - float(g["c_sq"])) <= 1e-7
+    # the softmax temperature 0.02 amplifies errors of c by 50: 1e-4 on the [-1, 1] grid, 1e-4 * out pixels on flows
+    for name, got in zip(NAMES, flows):
+        tol = 1e-4 if "_to_" in name else 1e-4 * out
+        err = np.abs(got.numpy() - g[name]).max()
+        assert err <= tol, (name, err)
+
+
+def test_ufc_tail_matches_oracle_small_batch():
+    from oracle import ufc_oracle
+    sizes, out = (4, 8, 16), 16
+    flows, c, (src, trg) = run(sizes, out, 3, 21)
+    ref_flows, ref_c = ufc_oracle.ufc_tail(src, trg, sizes, out)
+    assert c.shape == ref_c.shape and (c - ref_c).abs().max() <= 2e-6
+    for name, got, want in zip(NAMES, flows, ref_flows):
+        assert got.shape == want.shape
+        assert (got - want).abs().max() <= (1e-4 if "_to_" in name else 1e-4 * out), name
+
+
+def test_ufc_tail_bad_arguments():
+    from coponerf_b200 import _lib
+    from coponerf_b200.ufc import ufc_tail
+    src, trg = synth.ufc_tail_features((4, 8, 16), 1, 3)
+    with pytest.raises(ValueError):
+        ufc_tail([t.cuda() for t in src], [t.cuda() for t in trg], (4, 8, 8), 16)
+    assert _lib.load().cpn_ufc_tail(None, None) != 0

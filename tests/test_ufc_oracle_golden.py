@@ -1,0 +1,31 @@
+"""Pin the UFC closing-stage oracle against outputs of the unmodified reference functions (tests/golden/ufc_tail_*.npz)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from coponerf_b200 import synth
+from oracle import ufc_oracle
+
+CASES = sorted(os.path.basename(p)[:-4] for p in
+               glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ufc_tail_*.npz")))
+
+
+def run_case(g):
+    sizes, out, batch, seed = tuple(int(v) for v in g["meta"][:3]), int(g["meta"][3]), int(g["meta"][4]), int(g["meta"][5])
+    src, trg = synth.ufc_tail_features(sizes, batch, seed)
+    return ufc_oracle.ufc_tail(src, trg, sizes, out)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_ufc_tail_oracle_matches_reference(case, golden_dir):
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    (flow, flow_flip, t2s, s2t), c = run_case(g)
+    assert np.abs(c.reshape(-1)[g["c_idx"]].numpy() - g["c_val"]).max() <= 1e-6
+    assert abs(float(c.double().mean()) - float(g["c_mean"])) <= 1e-8
+    assert abs(float((c.double() ** 2).mean()) - float(g["c_sq"])) <= 1e-8
+    for name, got in (("flow", flow), ("flow_flip", flow_flip), ("flow_t_to_s", t2s), ("flow_s_to_t", s2t)):
+        assert got.shape == g[name].shape
+        tol = 1e-5 if name.startswith("flow_") and "_to_" in name else 1e-5 * g[name].shape[-1]
+        assert np.abs(got.numpy() - g[name]).max() <= tol, name
