@@ -54,6 +54,13 @@ class UfcTailArgs(ctypes.Structure):
                 ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t)]
 
 
+class Conv4dArgs(ctypes.Structure):
+    """cpn_conv4d_args (include/coponerf_b200.h)."""
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "Ci", "Co", "Hq", "Hs", "k", "stride", "pad", "norm_relu", "reserved")] + \
+               [(n, ctypes.c_void_p) for n in ("x", "wq", "bq", "ws", "bs", "gamma", "beta", "y", "workspace")] + \
+               [("workspace_bytes", ctypes.c_size_t)]
+
+
 # symbol -> (restype, argtypes); every entry point include/coponerf_b200.h declares
 SIGNATURES = {
     "cpn_version": (ctypes.c_int, []),
@@ -78,6 +85,8 @@ SIGNATURES = {
     "cpn_ufc_tail_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                        ctypes.POINTER(ctypes.c_int32)]),
     "cpn_ufc_tail": (ctypes.c_int, [ctypes.POINTER(UfcTailArgs), ctypes.c_void_p]),
+    "cpn_conv4d_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 6),
+    "cpn_conv4d": (ctypes.c_int, [ctypes.POINTER(Conv4dArgs), ctypes.c_void_p]),
     "cpn_gemm_simt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_void_p]),

@@ -26,6 +26,7 @@ SOURCES = [
     ("weights.cu", []),
     ("render.cu", []),
     ("ufc_tail.cu", []),
+    ("conv4d.cu", []),
 ]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

@@ -1,0 +1,220 @@
+// Centre-pivot 4-D convolution block of the cost aggregation: Conv4d -> GroupNorm(1 group) -> ReLU
+// (models/conv4d.py:57-135 Conv4d, :7-32 MaxPool4d, :138-163 Encoder4D; 63 calls per stereo pair).
+//
+// Conv4d is the sum of a 2-D convolution over the query axes and one over the support axes; with stride s the
+// branch that convolves one pair of axes first max-pools the other pair by s (ceil_mode). Here one thread owns one
+// output position (b, hq, wq, hs, ws) and all Co output channels: every input tap is read (and pooled on the fly)
+// once, the weights sit in shared memory as [ci][tap][co] and are read as warp-wide broadcasts. No rearranged or
+// pooled copy of the 4-D volume is ever materialised (the reference's einops rearranges are 44 % of its UFC time).
+// GroupNorm over all Co x positions of a sample is a two-phase reduction: per-CTA (sum, sum of squares) in
+// double, then a normalise + ReLU pass over the 2-8 MB output.
+#include <math.h>
+#include "cpn_common.cuh"
+
+namespace {
+
+constexpr int C4_THREADS = 128;
+
+template <int CO>
+__global__ void __launch_bounds__(C4_THREADS) conv4d_kernel(cpn_conv4d_args a, int oq, int os, double* __restrict__ partials) {
+  extern __shared__ float wsm[];   // [2 branches][Ci][k*k][CO]
+  const int k = a.k, kk = k * k, s = a.stride, p = a.pad, Ci = a.Ci, Hq = a.Hq, Hs = a.Hs;
+  for (int i = threadIdx.x; i < 2 * Ci * kk * CO; i += C4_THREADS) {
+    int co = i % CO, tap = (i / CO) % kk, ci = (i / (CO * kk)) % Ci, br = i / (CO * kk * Ci);
+    const float* w = br ? a.ws : a.wq;   // (Co, Ci, k, k)
+    wsm[i] = w[((size_t)co * Ci + ci) * kk + tap];
+  }
+  __syncthreads();
+  const int P = oq * oq * os * os;
+  const int pos = blockIdx.x * C4_THREADS + threadIdx.x, b = blockIdx.y;
+  float acc[CO];
+#pragma unroll
+  for (int co = 0; co < CO; ++co) acc[co] = 0.f;
+  const bool live = pos < P;
+  if (live) {
+    const int ws_ = pos % os, hs = (pos / os) % os, wq = (pos / (os * os)) % oq, hq = pos / (os * os * oq);
+    const size_t sHs = (size_t)Hs, plane = (size_t)Hq * Hq * Hs * Hs;
+    const float* xb = a.x + (size_t)b * Ci * plane;
+    for (int ci = 0; ci < Ci; ++ci) {
+      const float* xc = xb + (size_t)ci * plane;
+      // query branch: conv over (Hq, Wq) of the input max-pooled over the support window of this output position
+      for (int dy = 0; dy < k; ++dy) {
+        const int qy = hq * s + dy - p;
+        if (qy < 0 || qy >= Hq) continue;
+        for (int dx = 0; dx < k; ++dx) {
+          const int qx = wq * s + dx - p;
+          if (qx < 0 || qx >= Hq) continue;
+          const float* base = xc + ((size_t)qy * Hq + qx) * sHs * sHs;
+          float v = -INFINITY;
+          for (int i = 0; i < s; ++i) {
+            const int y = hs * s + i;
+            if (y >= Hs) break;
+            for (int j = 0; j < s; ++j) {
+              const int x = ws_ * s + j;
+              if (x >= Hs) break;
+              v = fmaxf(v, __ldg(base + (size_t)y * Hs + x));
+            }
+          }
+          const float* w = wsm + ((size_t)(0 * Ci + ci) * kk + dy * k + dx) * CO;
+#pragma unroll
+          for (int co = 0; co < CO; ++co) acc[co] = fmaf(v, w[co], acc[co]);
+        }
+      }
+      // support branch: conv over (Hs, Ws) of the input max-pooled over the query window
+      for (int dy = 0; dy < k; ++dy) {
+        const int sy = hs * s + dy - p;
+        if (sy < 0 || sy >= Hs) continue;
+        for (int dx = 0; dx < k; ++dx) {
+          const int sx = ws_ * s + dx - p;
+          if (sx < 0 || sx >= Hs) continue;
+          float v = -INFINITY;
+          for (int i = 0; i < s; ++i) {
+            const int y = hq * s + i;
+            if (y >= Hq) break;
+            for (int j = 0; j < s; ++j) {
+              const int x = wq * s + j;
+              if (x >= Hq) break;
+              v = fmaxf(v, __ldg(xc + (((size_t)y * Hq + x) * sHs + sy) * sHs + sx));
+            }
+          }
+          const float* w = wsm + ((size_t)(1 * Ci + ci) * kk + dy * k + dx) * CO;
+#pragma unroll
+          for (int co = 0; co < CO; ++co) acc[co] = fmaf(v, w[co], acc[co]);
+        }
+      }
+    }
+  }
+  double sum = 0.0, sq = 0.0;
+  if (live) {
+    float* yb = a.y + (size_t)b * CO * P + pos;
+#pragma unroll
+    for (int co = 0; co < CO; ++co) {
+      float v = acc[co] + (a.bq[co] + a.bs[co]);
+      yb[(size_t)co * P] = v;
+      sum += (double)v;
+      sq += (double)v * (double)v;
+    }
+  }
+  // per-CTA partial sums for GroupNorm (fixed order: warp tree, then warps in order)
+  __shared__ double red[2][C4_THREADS / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = sum;
+    red[1][threadIdx.x >> 5] = sq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int i = 0; i < C4_THREADS / 32; ++i) {
+      t0 += red[0][i];
+      t1 += red[1][i];
+    }
+    partials[((size_t)b * gridDim.x + blockIdx.x) * 2 + 0] = t0;
+    partials[((size_t)b * gridDim.x + blockIdx.x) * 2 + 1] = t1;
+  }
+}
+
+// GroupNorm(1, Co) (biased variance, eps 1e-5, per-channel affine) + ReLU, in place.
+__global__ void __launch_bounds__(256) gn_relu_kernel(float* __restrict__ y, const double* __restrict__ partials, int nparts,
+                                                      int Co, int P, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta) {
+  __shared__ double red[2][8];
+  __shared__ float stat[2];
+  const int b = blockIdx.y;
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += 256) {
+    s0 += partials[((size_t)b * nparts + i) * 2 + 0];
+    s1 += partials[((size_t)b * nparts + i) * 2 + 1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s0;
+    red[1][threadIdx.x >> 5] = s1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int i = 0; i < 8; ++i) {
+      t0 += red[0][i];
+      t1 += red[1][i];
+    }
+    const double n = (double)Co * (double)P, mean = t0 / n, var = t1 / n - mean * mean;
+    stat[0] = (float)mean;
+    stat[1] = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + 1e-5));
+  }
+  __syncthreads();
+  const float mean = stat[0], rstd = stat[1];
+  const size_t total = (size_t)Co * P;
+  float* yb = y + (size_t)b * total;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int co = (int)(i / P);
+    float v = (yb[i] - mean) * rstd * gamma[co] + beta[co];
+    yb[i] = fmaxf(v, 0.f);
+  }
+}
+
+int out_size(int H, int k, int s, int p) { return (H + 2 * p - k) / s + 1; }
+
+}  // namespace
+
+extern "C" size_t cpn_conv4d_workspace_bytes(int B, int Hq, int Hs, int k, int stride, int pad) {
+  if (B <= 0 || Hq <= 0 || Hs <= 0 || k <= 0 || stride <= 0) return 0;
+  int oq = out_size(Hq, k, stride, pad), os = out_size(Hs, k, stride, pad);
+  size_t P = (size_t)oq * oq * os * os;
+  return (size_t)B * ((P + C4_THREADS - 1) / C4_THREADS) * 2 * sizeof(double);
+}
+
+extern "C" int cpn_conv4d(const cpn_conv4d_args* args, void* stream) {
+  if (!args) {
+    cpn_set_error("cpn_conv4d: null args");
+    return CPN_ERR_ARG;
+  }
+  const cpn_conv4d_args& a = *args;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a.B <= 0 || a.Ci <= 0 || (a.Co != 8 && a.Co != 32) || a.Hq <= 0 || a.Hs <= 0 || a.k <= 0 || a.stride <= 0 || a.pad < 0 ||
+      !a.x || !a.wq || !a.bq || !a.ws || !a.bs || !a.y || !a.workspace || (a.norm_relu && (!a.gamma || !a.beta))) {
+    cpn_set_error("cpn_conv4d: bad argument (Co must be 8 or 32)");
+    return CPN_ERR_ARG;
+  }
+  const int oq = out_size(a.Hq, a.k, a.stride, a.pad), os = out_size(a.Hs, a.k, a.stride, a.pad);
+  // the pooled axes must give the same output size as the convolved ones (MaxPool4d, ceil_mode)
+  if (oq <= 0 || os <= 0 || (a.Hq + a.stride - 1) / a.stride != oq || (a.Hs + a.stride - 1) / a.stride != os) {
+    cpn_set_error("cpn_conv4d: inconsistent output sizes for Hq=%d Hs=%d k=%d stride=%d pad=%d", a.Hq, a.Hs, a.k, a.stride, a.pad);
+    return CPN_ERR_ARG;
+  }
+  const size_t need = cpn_conv4d_workspace_bytes(a.B, a.Hq, a.Hs, a.k, a.stride, a.pad);
+  if (need > a.workspace_bytes) {
+    cpn_set_error("cpn_conv4d: workspace of %zu bytes needed, %zu given", need, a.workspace_bytes);
+    return CPN_ERR_WORKSPACE;
+  }
+  const int P = oq * oq * os * os, nblk = (P + C4_THREADS - 1) / C4_THREADS;
+  const size_t smem = (size_t)2 * a.Ci * a.k * a.k * a.Co * sizeof(float);
+  if (smem > 96 * 1024) {
+    cpn_set_error("cpn_conv4d: weights of %zu bytes do not fit in shared memory", smem);
+    return CPN_ERR_ARG;
+  }
+  double* partials = reinterpret_cast<double*>(a.workspace);
+  dim3 grid(nblk, a.B);
+  if (a.Co == 8) {
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(conv4d_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv4d_kernel<8><<<grid, C4_THREADS, smem, st>>>(a, oq, os, partials);
+  } else {
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(conv4d_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv4d_kernel<32><<<grid, C4_THREADS, smem, st>>>(a, oq, os, partials);
+  }
+  CPN_CHECK_LAUNCH("conv4d_kernel");
+  if (a.norm_relu) {
+    dim3 g2(256, a.B);
+    gn_relu_kernel<<<g2, 256, 0, st>>>(a.y, partials, nblk, a.Co, P, a.gamma, a.beta);
+    CPN_CHECK_LAUNCH("gn_relu_kernel");
+  }
+  return CPN_OK;
+}

@@ -113,8 +113,8 @@ class CoPoNeRF(nn.Module):
         if not self.native_ufc_tail:
             out = ref.get_z(input)
         else:
-            # same call, with the closing stage of UFC (correlations of the refined features, 4-D upsampling,
-            # soft-argmax flows: aggregation.py:527-561) routed to cpn_ufc_tail
+            # same call, with every Encoder4D block (cpn_conv4d) and the closing stage of UFC (correlations of the
+            # refined features, 4-D upsampling, soft-argmax flows: aggregation.py:527-561, cpn_ufc_tail) native
             from .ufc import ufc_forward
             orig = fca.forward
             fca.forward = lambda feat, nview: ufc_forward(fca, feat, nview)

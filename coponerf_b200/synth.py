@@ -188,3 +188,27 @@ def ufc_tail_features(sizes=(16, 32, 64), batch=1, seed=12, C=256):
         src.append((up + noise()).flatten(2).transpose(1, 2).contiguous())
         trg.append((shift + noise()).flatten(2).transpose(1, 2).contiguous())
     return src, trg
+
+
+# (name, B, [channels...], k, stride, pad, input size) of the Encoder4D blocks UFC uses (models/aggregation.py:209-318,436-480)
+CONV4D_CASES = {
+    "conv4d_embed16": (2, (1, 8), 3, 1, 1, 16),        # embedding[0] / feat_to_corr of level 0
+    "conv4d_mlp16": (1, (8, 32, 8), 3, 1, 1, 16),      # mlp_corr / mlp_refine_corr: two blocks
+    "conv4d_embed32": (1, (1, 8), 3, 2, 1, 32),        # embedding[1]: stride 2 with MaxPool4d(2)
+    "conv4d_embed64": (1, (1, 8), 5, 4, 2, 64),        # embedding[2]: kernel 5, stride 4 with MaxPool4d(4)
+}
+
+
+def conv4d_case(name):
+    """Seeded input volume and Encoder4D parameters for one CONV4D_CASES entry (numpy PCG64: same bytes everywhere)."""
+    B, chans, k, stride, pad, n = CONV4D_CASES[name]
+    rng = np.random.default_rng(5000 + sorted(CONV4D_CASES).index(name))
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    x = f32(rng.standard_normal((B, chans[0], n, n, n, n), dtype=np.float32))
+    layers = []
+    for ci, co in zip(chans[:-1], chans[1:]):
+        bound = 1.5 / math.sqrt(ci * k * k)
+        layers.append(dict(wq=f32(rng.uniform(-bound, bound, (co, ci, k, k))), bq=f32(rng.uniform(-0.2, 0.2, co)),
+                           ws=f32(rng.uniform(-bound, bound, (co, ci, k, k))), bs=f32(rng.uniform(-0.2, 0.2, co)),
+                           gamma=f32(rng.uniform(0.5, 1.5, co)), beta=f32(rng.uniform(-0.3, 0.3, co))))
+    return x, layers, stride, pad

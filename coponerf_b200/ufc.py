@@ -45,6 +45,38 @@ def ufc_tail(src_feats, trg_feats, sizes=(16, 32, 64), out=64):
     return tuple(flows), c
 
 
+def conv4d_block(x, wq, bq, ws, bs, gamma=None, beta=None, stride=1, pad=1):
+    """One Encoder4D block (models/conv4d.py:149-153): Conv4d -> GroupNorm(1 group) -> ReLU on CUDA; without
+    gamma / beta the plain Conv4d. x (B, Ci, Hq, Hq, Hs, Hs) -> (B, Co, oq, oq, os, os)."""
+    lib = _lib.load()
+    dev = x.device
+    if dev.type != "cuda":
+        raise _lib.CpnError("conv4d_block runs on CUDA only (no CPU fallback)")
+    f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    x, wq, bq, ws, bs = f(x), f(wq), f(bq), f(ws), f(bs)
+    B, Ci, Hq, Wq, Hs, Ws = x.shape
+    Co, _, k, _ = wq.shape
+    if Hq != Wq or Hs != Ws or tuple(ws.shape) != tuple(wq.shape) or wq.shape[1] != Ci:
+        raise ValueError("conv4d_block: square query / support axes and matching (Co, Ci, k, k) weights expected")
+    oq, os_ = (Hq + 2 * pad - k) // stride + 1, (Hs + 2 * pad - k) // stride + 1
+    with torch.cuda.device(dev):
+        y = torch.empty((B, Co, oq, oq, os_, os_), dtype=torch.float32, device=dev)
+        a = _lib.Conv4dArgs()
+        a.B, a.Ci, a.Co, a.Hq, a.Hs, a.k, a.stride, a.pad = B, Ci, Co, Hq, Hs, k, stride, pad
+        a.norm_relu = int(gamma is not None)
+        keep = [x, wq, bq, ws, bs]
+        a.x, a.wq, a.bq, a.ws, a.bs, a.y = (t.data_ptr() for t in (x, wq, bq, ws, bs, y))
+        if gamma is not None:
+            g, bt = f(gamma), f(beta)
+            keep += [g, bt]
+            a.gamma, a.beta = g.data_ptr(), bt.data_ptr()
+        nbytes = lib.cpn_conv4d_workspace_bytes(B, Hq, Hs, k, stride, pad)
+        wsb = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        a.workspace, a.workspace_bytes = wsb.data_ptr(), nbytes
+        _lib.check(lib.cpn_conv4d(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "cpn_conv4d")
+    return y
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # UFC.forward with the native closing stage. The coarse-to-fine refinement (proj_feat, embedding, the five UFCLayer
 # blocks: aggregation.py:509-549) is not native yet and is delegated to the attached reference module's own
@@ -68,13 +100,48 @@ def _upsample_tokens(x, n_out):
     return y.flatten(2).transpose(1, 2)
 
 
-def ufc_forward(fca, feat, nview, tail=None):
+def _encoder4d_forward(enc, block_fn):
+    """forward() for a reference Encoder4D module (conv4d.py:156-163) that runs every
+    Conv4d -> GroupNorm -> ReLU block through `block_fn` (conv4d_block on CUDA)."""
+    def forward(x):
+        for blk in enc.conv4d:
+            c4, gn = blk[0], blk[1]
+            x = block_fn(x, c4.query_conv.weight, c4.query_conv.bias, c4.supp_conv.weight, c4.supp_conv.bias,
+                         gn.weight, gn.bias, c4.stride[0], c4.padding[0])
+        return x
+    return forward
+
+
+class _patched_encoders:
+    """Context manager: route every Encoder4D inside `root` through `block_fn` for the duration of a call."""
+
+    def __init__(self, root, block_fn):
+        self.mods = [m for m in root.modules() if type(m).__name__ == "Encoder4D"]
+        self.block_fn = block_fn
+
+    def __enter__(self):
+        for m in self.mods:
+            m.forward = _encoder4d_forward(m, self.block_fn)
+
+    def __exit__(self, *exc):
+        for m in self.mods:
+            del m.forward          # back to the class's own forward
+        return False
+
+
+def ufc_forward(fca, feat, nview, tail=None, conv_block=None):
     """Drop-in for UFC.forward(feat, nview) (aggregation.py:509-562) of the attached reference module `fca`.
 
-    Returns (feat_list, (flow, flow_flip, flow_t_to_s, flow_s_to_t), c) like the reference. `tail` defaults to the
-    sm_100a closing stage (ufc_tail); tests pass the CPU oracle here to check the orchestration without a GPU.
+    Returns (feat_list, (flow, flow_flip, flow_t_to_s, flow_s_to_t), c) like the reference. Native so far: every
+    Encoder4D block (63 Conv4d + GroupNorm + ReLU per pair, `conv_block`, default conv4d_block) and the closing
+    stage (`tail`, default ufc_tail). Tests pass the CPU oracles for both to check the orchestration without a GPU.
     """
     tail = tail or ufc_tail
+    with _patched_encoders(fca, conv_block or conv4d_block):
+        return _ufc_forward(fca, feat, nview, tail)
+
+
+def _ufc_forward(fca, feat, nview, tail):
     B = feat[0].shape[0]
     sizes = [f.shape[-1] for f in feat]
 

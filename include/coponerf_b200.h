@@ -145,6 +145,27 @@ typedef struct {
 size_t cpn_ufc_tail_workspace_bytes(int B, int C, int out, const int* sizes);
 int cpn_ufc_tail(const cpn_ufc_tail_args* args, void* stream);
 
+/* ---- centre-pivot 4-D convolution block ----------------------------------------------------------------------
+ * Replaces models/conv4d.py:57-135 (Conv4d, with its MaxPool4d for stride > 1) and, with norm_relu, the
+ * GroupNorm(1, Co) + ReLU that follow it in Encoder4D (conv4d.py:138-163).
+ *   x (B, Ci, Hq, Hq, Hs, Hs); wq, ws (Co, Ci, k, k) = query_conv / supp_conv weights; bq, bs (Co);
+ *   gamma, beta (Co) = GroupNorm affine; y (B, Co, oq, oq, os, os), o = (H + 2 pad - k) / stride + 1; Co is 8 or 32. */
+typedef struct {
+  int32_t B, Ci, Co, Hq, Hs, k, stride, pad, norm_relu, reserved;
+  const float* x;
+  const float* wq;
+  const float* bq;
+  const float* ws;
+  const float* bs;
+  const float* gamma;
+  const float* beta;
+  float* y;
+  void* workspace;
+  size_t workspace_bytes;
+} cpn_conv4d_args;
+size_t cpn_conv4d_workspace_bytes(int B, int Hq, int Hs, int k, int stride, int pad);
+int cpn_conv4d(const cpn_conv4d_args* args, void* stream);
+
 /* ---- device timing of the dominant kernel (the query_encode_latent GEMM), for roofline reports.
  * Between cpn_prof_begin and cpn_prof_end every launch of that kernel by cpn_render_rays is bracketed
  * by CUDA events on the caller's stream. cpn_prof_end waits for them and returns the summed duration.

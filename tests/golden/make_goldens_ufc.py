@@ -48,5 +48,29 @@ def main():
         print(name, "c range", float(c.min()), float(c.max()), "flow range", float(flow.min()), float(flow.max()))
 
 
+def conv4d_goldens():
+    """Encoder4D blocks of the unmodified reference (models/conv4d.py) on the seeded volumes of synth.conv4d_case."""
+    from models.conv4d import Encoder4D
+    for name, (B, chans, k, stride, pad, n) in synth.CONV4D_CASES.items():
+        x, layers, stride, pad = synth.conv4d_case(name)
+        nl = len(chans) - 1
+        m = Encoder4D(chans, ((k,) * 4,) * nl, ((stride,) * 4,) * nl, ((pad,) * 4,) * nl, (1,) * nl).eval()
+        for blk, p in zip(m.conv4d, layers):
+            c4, gn = blk[0], blk[1]
+            with torch.no_grad():
+                c4.query_conv.weight.copy_(p["wq"]); c4.query_conv.bias.copy_(p["bq"])
+                c4.supp_conv.weight.copy_(p["ws"]); c4.supp_conv.bias.copy_(p["bs"])
+                gn.weight.copy_(p["gamma"]); gn.bias.copy_(p["beta"])
+        with torch.no_grad():
+            y = m(x)
+        rng = np.random.default_rng(77)
+        idx = rng.integers(0, y.numel(), size=16384)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), idx=idx, val=y.reshape(-1)[idx].numpy(),
+                            mean=np.float64(y.double().mean()), sq=np.float64((y.double() ** 2).mean()),
+                            shape=np.array(y.shape, dtype=np.int64))
+        print(name, tuple(y.shape), "mean", float(y.mean()), "max", float(y.max()))
+
+
 if __name__ == "__main__":
     main()
+    conv4d_goldens()

@@ -57,3 +57,36 @@ def test_ufc_tail_bad_arguments():
     with pytest.raises(ValueError):
         ufc_tail([t.cuda() for t in src], [t.cuda() for t in trg], (4, 8, 8), 16)
     assert _lib.load().cpn_ufc_tail(None, None) != 0
+
+
+CONV_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "conv4d_*.npz")))
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv4d_block_matches_reference_golden(case):
+    """cpn_conv4d (Conv4d + MaxPool4d + GroupNorm + ReLU) against the reference's Encoder4D outputs."""
+    from coponerf_b200.ufc import conv4d_block
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    x, layers, stride, pad = synth.conv4d_case(case)
+    y = x.cuda()
+    for p in layers:
+        y = conv4d_block(y, p["wq"], p["bq"], p["ws"], p["bs"], p["gamma"], p["beta"], stride, pad)
+    torch.cuda.synchronize()
+    y = y.cpu()
+    assert tuple(y.shape) == tuple(g["shape"])
+    scale = max(1.0, float(np.abs(g["val"]).max()))
+    err = np.abs(y.reshape(-1)[g["idx"]].numpy() - g["val"]).max()
+    assert err <= 2e-5 * scale, err
+    assert abs(float(y.double().mean()) - float(g["mean"])) <= 1e-5
+    assert abs(float((y.double() ** 2).mean()) - float(g["sq"])) <= 1e-4 * float(g["sq"])
+
+
+def test_conv4d_plain_matches_oracle():
+    """Without GroupNorm / ReLU (plain Conv4d, models/conv4d.py:108-135) against the CPU oracle."""
+    from coponerf_b200.ufc import conv4d_block
+    from oracle import conv4d_oracle
+    x, layers, stride, pad = synth.conv4d_case("conv4d_embed32")
+    p = layers[0]
+    want = conv4d_oracle.conv4d(x, p["wq"], p["bq"], p["ws"], p["bs"], stride, pad)
+    got = conv4d_block(x.cuda(), p["wq"], p["bq"], p["ws"], p["bs"], None, None, stride, pad).cpu()
+    assert got.shape == want.shape and (got - want).abs().max() <= 2e-5 * float(want.abs().max())

@@ -29,3 +29,20 @@ def test_ufc_tail_oracle_matches_reference(case, golden_dir):
         assert got.shape == g[name].shape
         tol = 1e-5 if name.startswith("flow_") and "_to_" in name else 1e-5 * g[name].shape[-1]
         assert np.abs(got.numpy() - g[name]).max() <= tol, name
+
+
+CONV_CASES = sorted(os.path.basename(p)[:-4] for p in
+                    glob.glob(os.path.join(os.path.dirname(__file__), "golden", "conv4d_*.npz")))
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv4d_oracle_matches_reference(case, golden_dir):
+    from oracle import conv4d_oracle
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    x, layers, stride, pad = synth.conv4d_case(case)
+    y = x
+    for p in layers:
+        y = conv4d_oracle.encoder4d_layer(y, p, stride, pad)
+    assert tuple(y.shape) == tuple(g["shape"])
+    assert np.abs(y.reshape(-1)[g["idx"]].numpy() - g["val"]).max() <= 1e-5
+    assert abs(float(y.double().mean()) - float(g["mean"])) <= 1e-6

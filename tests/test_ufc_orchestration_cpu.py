@@ -16,7 +16,10 @@ def test_ufc_forward_matches_reference_module():
     import_reference()
     from models.aggregation import UFC
     from coponerf_b200.ufc import ufc_forward
-    from oracle import ufc_oracle
+    from oracle import conv4d_oracle, ufc_oracle
+
+    def conv_block(x, wq, bq, ws, bs, gamma, beta, stride, pad):
+        return conv4d_oracle.encoder4d_layer(x, dict(wq=wq, bq=bq, ws=ws, bs=bs, gamma=gamma, beta=beta), stride, pad)
     torch.manual_seed(0)
     fca = UFC().eval()
     g = torch.Generator().manual_seed(3)
@@ -24,7 +27,8 @@ def test_ufc_forward_matches_reference_module():
             torch.randn(2, 128, 64, 64, generator=g)]
     with torch.no_grad():
         ref_feats, ref_flows, ref_c = fca(feat, 2)
-        got_feats, got_flows, got_c = ufc_forward(fca, feat, 2, tail=ufc_oracle.ufc_tail)
+        got_feats, got_flows, got_c = ufc_forward(fca, feat, 2, tail=ufc_oracle.ufc_tail, conv_block=conv_block)
+    assert all('forward' not in m.__dict__ for m in fca.modules())   # patches removed
     for a, b in zip(got_feats, ref_feats):
         assert a.shape == b.shape and torch.allclose(a, b, atol=1e-5, rtol=1e-5)
     assert got_c.shape == ref_c.shape and (got_c - ref_c).abs().max() <= 1e-5
