@@ -87,6 +87,9 @@ SIGNATURES = {
     "cpn_ufc_tail": (ctypes.c_int, [ctypes.POINTER(UfcTailArgs), ctypes.c_void_p]),
     "cpn_conv4d_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 6),
     "cpn_conv4d": (ctypes.c_int, [ctypes.POINTER(Conv4dArgs), ctypes.c_void_p]),
+    "cpn_linear_attention_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),
+    "cpn_linear_attention": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 +
+                             [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "cpn_gemm_simt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_void_p]),

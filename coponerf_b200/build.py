@@ -27,6 +27,7 @@ SOURCES = [
     ("render.cu", []),
     ("ufc_tail.cu", []),
     ("conv4d.cu", []),
+    ("linear_attention.cu", []),
 ]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

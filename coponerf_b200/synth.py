@@ -212,3 +212,16 @@ def conv4d_case(name):
                            ws=f32(rng.uniform(-bound, bound, (co, ci, k, k))), bs=f32(rng.uniform(-0.2, 0.2, co)),
                            gamma=f32(rng.uniform(0.5, 1.5, co)), beta=f32(rng.uniform(-0.3, 0.3, co))))
     return x, layers, stride, pad
+
+
+# (N, L = S, Dv) of the LinearAttention calls in UFCLayer.forward_attention (models/aggregation.py:296-297)
+LINATT_CASES = {"linatt_256_feat": (2, 256, 32), "linatt_256_corr": (2, 256, 256), "linatt_1024_corr": (1, 1024, 256),
+                "linatt_4096_feat": (1, 4096, 32)}
+
+
+def linatt_case(name, H=8, D=32):
+    N, L, Dv = LINATT_CASES[name]
+    rng = np.random.default_rng(6000 + sorted(LINATT_CASES).index(name))
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return (f32(rng.standard_normal((N, L, H, D))), f32(rng.standard_normal((N, L, H, D))),
+            f32(rng.standard_normal((N, L, H, Dv))))

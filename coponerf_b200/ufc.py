@@ -77,6 +77,27 @@ def conv4d_block(x, wq, bq, ws, bs, gamma=None, beta=None, stride=1, pad=1):
     return y
 
 
+def linear_attention(queries, keys, values):
+    """LinearAttention.forward (models/aggregation.py:84-117) on CUDA: (N, L, H, 32), (N, S, H, 32), (N, S, H, Dv)."""
+    lib = _lib.load()
+    dev = queries.device
+    if dev.type != "cuda":
+        raise _lib.CpnError("linear_attention runs on CUDA only (no CPU fallback)")
+    f = lambda t: t.detach().to(torch.float32).contiguous()
+    q, k, v = f(queries), f(keys), f(values)
+    N, L, H, D = q.shape
+    S, Dv = k.shape[1], v.shape[-1]
+    with torch.cuda.device(dev):
+        out = torch.empty((N, L, H, Dv), dtype=torch.float32, device=dev)
+        nbytes = lib.cpn_linear_attention_workspace_bytes(N, H, Dv)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(lib.cpn_linear_attention(p(q), p(k), p(v), N, L, S, H, D, Dv, p(out), p(ws), nbytes,
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "cpn_linear_attention")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # UFC.forward with the native closing stage. The coarse-to-fine refinement (proj_feat, embedding, the five UFCLayer
 # blocks: aggregation.py:509-549) is not native yet and is delegated to the attached reference module's own
@@ -112,32 +133,37 @@ def _encoder4d_forward(enc, block_fn):
     return forward
 
 
-class _patched_encoders:
-    """Context manager: route every Encoder4D inside `root` through `block_fn` for the duration of a call."""
+class _patched_modules:
+    """Context manager: for the duration of a call, route every Encoder4D inside `root` through `block_fn` and
+    every LinearAttention through `attention_fn`."""
 
-    def __init__(self, root, block_fn):
-        self.mods = [m for m in root.modules() if type(m).__name__ == "Encoder4D"]
-        self.block_fn = block_fn
+    def __init__(self, root, block_fn, attention_fn):
+        self.enc = [m for m in root.modules() if type(m).__name__ == "Encoder4D"]
+        self.att = [m for m in root.modules() if type(m).__name__ == "LinearAttention"]
+        self.block_fn, self.attention_fn = block_fn, attention_fn
 
     def __enter__(self):
-        for m in self.mods:
+        for m in self.enc:
             m.forward = _encoder4d_forward(m, self.block_fn)
+        for m in self.att:
+            m.forward = lambda q, k, v, q_mask=None, kv_mask=None, _f=self.attention_fn: _f(q, k, v)
 
     def __exit__(self, *exc):
-        for m in self.mods:
+        for m in self.enc + self.att:
             del m.forward          # back to the class's own forward
         return False
 
 
-def ufc_forward(fca, feat, nview, tail=None, conv_block=None):
+def ufc_forward(fca, feat, nview, tail=None, conv_block=None, attention=None):
     """Drop-in for UFC.forward(feat, nview) (aggregation.py:509-562) of the attached reference module `fca`.
 
     Returns (feat_list, (flow, flow_flip, flow_t_to_s, flow_s_to_t), c) like the reference. Native so far: every
-    Encoder4D block (63 Conv4d + GroupNorm + ReLU per pair, `conv_block`, default conv4d_block) and the closing
-    stage (`tail`, default ufc_tail). Tests pass the CPU oracles for both to check the orchestration without a GPU.
+    Encoder4D block (63 Conv4d + GroupNorm + ReLU per pair, `conv_block`, default conv4d_block), every
+    LinearAttention (20 per pair, `attention`, default linear_attention) and the closing stage (`tail`, default
+    ufc_tail). Tests pass the CPU oracles for all three to check the orchestration without a GPU.
     """
     tail = tail or ufc_tail
-    with _patched_encoders(fca, conv_block or conv4d_block):
+    with _patched_modules(fca, conv_block or conv4d_block, attention or linear_attention):
         return _ufc_forward(fca, feat, nview, tail)
 
 

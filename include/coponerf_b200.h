@@ -166,6 +166,13 @@ typedef struct {
 size_t cpn_conv4d_workspace_bytes(int B, int Hq, int Hs, int k, int stride, int pad);
 int cpn_conv4d(const cpn_conv4d_args* args, void* stream);
 
+/* ---- linear attention ------------------------------------------------------------------------------------------
+ * Replaces LinearAttention.forward (models/aggregation.py:84-117): q (N, L, H, D), k (N, S, H, D), v (N, S, H, Dv)
+ * -> out (N, L, H, Dv), elu(x)+1 feature map, D = 32. */
+size_t cpn_linear_attention_workspace_bytes(int N, int H, int Dv);
+int cpn_linear_attention(const float* q, const float* k, const float* v, int N, int L, int S, int H, int D, int Dv,
+                         float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- device timing of the dominant kernel (the query_encode_latent GEMM), for roofline reports.
  * Between cpn_prof_begin and cpn_prof_end every launch of that kernel by cpn_render_rays is bracketed
  * by CUDA events on the caller's stream. cpn_prof_end waits for them and returns the summed duration.

@@ -71,6 +71,23 @@ def conv4d_goldens():
         print(name, tuple(y.shape), "mean", float(y.mean()), "max", float(y.max()))
 
 
+def linatt_goldens():
+    """LinearAttention of the unmodified reference (models/aggregation.py:84-117)."""
+    from models.aggregation import LinearAttention
+    att = LinearAttention()
+    for name in synth.LINATT_CASES:
+        q, k, v = synth.linatt_case(name)
+        with torch.no_grad():
+            y = att(q, k, v)
+        rng = np.random.default_rng(78)
+        idx = rng.integers(0, y.numel(), size=16384)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), idx=idx, val=y.reshape(-1)[idx].numpy(),
+                            mean=np.float64(y.double().mean()), sq=np.float64((y.double() ** 2).mean()),
+                            shape=np.array(y.shape, dtype=np.int64))
+        print(name, tuple(y.shape), "max", float(y.abs().max()))
+
+
 if __name__ == "__main__":
     main()
     conv4d_goldens()
+    linatt_goldens()

@@ -90,3 +90,19 @@ def test_conv4d_plain_matches_oracle():
     want = conv4d_oracle.conv4d(x, p["wq"], p["bq"], p["ws"], p["bs"], stride, pad)
     got = conv4d_block(x.cuda(), p["wq"], p["bq"], p["ws"], p["bs"], None, None, stride, pad).cpu()
     assert got.shape == want.shape and (got - want).abs().max() <= 2e-5 * float(want.abs().max())
+
+
+LINATT = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "linatt_*.npz")))
+
+
+@pytest.mark.parametrize("case", LINATT)
+def test_linear_attention_matches_reference_golden(case):
+    from coponerf_b200.ufc import linear_attention
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    q, k, v = synth.linatt_case(case)
+    y = linear_attention(q.cuda(), k.cuda(), v.cuda()).cpu()
+    assert tuple(y.shape) == tuple(g["shape"])
+    scale = float(np.abs(g["val"]).max())
+    err = np.abs(y.reshape(-1)[g["idx"]].numpy() - g["val"]).max()
+    assert err <= 1e-5 * scale, (err, scale)
+    assert abs(float((y.double() ** 2).mean()) - float(g["sq"])) <= 1e-4 * float(g["sq"])

@@ -46,3 +46,15 @@ def test_conv4d_oracle_matches_reference(case, golden_dir):
     assert tuple(y.shape) == tuple(g["shape"])
     assert np.abs(y.reshape(-1)[g["idx"]].numpy() - g["val"]).max() <= 1e-5
     assert abs(float(y.double().mean()) - float(g["mean"])) <= 1e-6
+
+
+LINATT = sorted(os.path.basename(p)[:-4] for p in
+                glob.glob(os.path.join(os.path.dirname(__file__), "golden", "linatt_*.npz")))
+
+
+@pytest.mark.parametrize("case", LINATT)
+def test_linear_attention_oracle_matches_reference(case, golden_dir):
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    y = ufc_oracle.linear_attention(*synth.linatt_case(case))
+    assert tuple(y.shape) == tuple(g["shape"])
+    assert np.abs(y.reshape(-1)[g["idx"]].numpy() - g["val"]).max() <= 1e-6 * float(np.abs(g["val"]).max())

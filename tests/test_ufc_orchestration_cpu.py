@@ -27,7 +27,8 @@ def test_ufc_forward_matches_reference_module():
             torch.randn(2, 128, 64, 64, generator=g)]
     with torch.no_grad():
         ref_feats, ref_flows, ref_c = fca(feat, 2)
-        got_feats, got_flows, got_c = ufc_forward(fca, feat, 2, tail=ufc_oracle.ufc_tail, conv_block=conv_block)
+        got_feats, got_flows, got_c = ufc_forward(fca, feat, 2, tail=ufc_oracle.ufc_tail, conv_block=conv_block,
+                                                      attention=ufc_oracle.linear_attention)
     assert all('forward' not in m.__dict__ for m in fca.modules())   # patches removed
     for a, b in zip(got_feats, ref_feats):
         assert a.shape == b.shape and torch.allclose(a, b, atol=1e-5, rtol=1e-5)
