@@ -90,6 +90,16 @@ SIGNATURES = {
     "cpn_linear_attention_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),
     "cpn_linear_attention": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 +
                              [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "cpn_layernorm": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 2 + [ctypes.c_void_p]),
+    "cpn_corr_to_tokens": (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 7 + [ctypes.c_void_p]),
+    "cpn_tokens_to_corr": (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 5 + [ctypes.c_void_p]),
+    "cpn_transpose_pq": (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 3 + [ctypes.c_void_p]),
+    "cpn_dwconv_gelu": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 3 + [ctypes.c_void_p]),
+    "cpn_resample_tokens": (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 5 + [ctypes.c_void_p]),
+    "cpn_cross_attention": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 5 + [ctypes.c_void_p]),
+    "cpn_correlation_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),
+    "cpn_correlation": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_size_t,
+                                                                                   ctypes.c_void_p]),
     "cpn_gemm_simt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_void_p]),

@@ -28,6 +28,7 @@ SOURCES = [
     ("ufc_tail.cu", []),
     ("conv4d.cu", []),
     ("linear_attention.cu", []),
+    ("ufc_ops.cu", []),
 ]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

@@ -154,6 +154,16 @@ __global__ void __launch_bounds__(1024) ufc_softargmax_cols_kernel(const float* 
   }
 }
 
+}  // namespace
+
+int launch_ufc_normalize(const float* in, float* out, int tokens, int C, cudaStream_t st) {
+  ufc_normalize_kernel<<<(tokens * 32 + 255) / 256, 256, 0, st>>>(in, out, tokens, C);
+  CPN_CHECK_LAUNCH("ufc_normalize_kernel");
+  return CPN_OK;
+}
+
+namespace {
+
 struct TailWs {
   float *ntok[2][3], *S, *Tt;
   size_t bytes;

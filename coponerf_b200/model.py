@@ -76,7 +76,8 @@ class CoPoNeRF(nn.Module):
         self.phi = _ResnetFC(n_view * 9, half * n_view, hidden)
         self.chunk_rays = chunk_rays
         self.lanes = lanes
-        self.native_ufc_tail = True     # get_z(): closing stage of the cost aggregation on cpn_ufc_tail
+        self.native_ufc = True          # get_z(): cost aggregation (UFC) on the sm_100a operators
+        self._ufc_ops = None
         self.pixel_val_on_host = True   # the reference returns out['pixel_val'] as a CPU tensor (CoPoNeRF.py:490)
         self._engine = None
         self._engine_version = None
@@ -110,14 +111,18 @@ class CoPoNeRF(nn.Module):
                                "z=, rel_pose=, flow= to forward()")
         ref = self._pair_stage
         fca = ref.feature_cost_aggregation
-        if not self.native_ufc_tail:
+        if not self.native_ufc:
             out = ref.get_z(input)
         else:
-            # same call, with every Encoder4D block (cpn_conv4d) and the closing stage of UFC (correlations of the
-            # refined features, 4-D upsampling, soft-argmax flows: aggregation.py:527-561, cpn_ufc_tail) native
-            from .ufc import ufc_forward
+            # same call, with the cost aggregation (UFC.forward, aggregation.py:509-562) running on the sm_100a
+            # operators: only the module's parameters are used, none of its Python code
+            from . import ufc_native
+            from .ufc_ops import CudaOps
+            if self._ufc_ops is None:
+                self._ufc_ops = CudaOps()
+            sd = dict(fca.state_dict())
             orig = fca.forward
-            fca.forward = lambda feat, nview: ufc_forward(fca, feat, nview)
+            fca.forward = lambda feat, nview: ufc_native.ufc_forward(sd, feat, nview, self._ufc_ops)
             try:
                 out = ref.get_z(input)
             finally:

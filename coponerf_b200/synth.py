@@ -225,3 +225,73 @@ def linatt_case(name, H=8, D=32):
     f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
     return (f32(rng.standard_normal((N, L, H, D))), f32(rng.standard_normal((N, L, H, D))),
             f32(rng.standard_normal((N, L, H, Dv))))
+
+
+def ufc_param_shapes():
+    """name -> shape of every parameter of the reference UFC module (models/aggregation.py:358-490), without the
+    'feature_cost_aggregation.' prefix. 439 entries."""
+    sh = {}
+
+    def enc(prefix, chans, k):
+        for i, (ci, co) in enumerate(zip(chans[:-1], chans[1:])):
+            for br in ("query_conv", "supp_conv"):
+                sh[f"{prefix}.conv4d.{i}.0.{br}.weight"] = (co, ci, k, k)
+                sh[f"{prefix}.conv4d.{i}.0.{br}.bias"] = (co,)
+            sh[f"{prefix}.conv4d.{i}.1.weight"] = (co,)
+            sh[f"{prefix}.conv4d.{i}.1.bias"] = (co,)
+
+    def lin(prefix, o, i):
+        sh[prefix + ".weight"] = (o, i)
+        sh[prefix + ".bias"] = (o,)
+
+    for lvl, (nlayers, n, k) in enumerate(((2, 16, 3), (2, 32, 3), (1, 64, 5))):
+        for j in range(nlayers):
+            p = f"layers.{lvl}.{j}"
+            sh[p + ".pos_embed"] = (1, n * n, 1, 32)
+            lin(p + ".q_proj", 256, 2304)
+            lin(p + ".k_proj", 256, 2304)
+            lin(p + ".v_proj", 256, 256)
+            enc(p + ".v_proj_corr", (8, 8), 3)
+            for m in ("mlp", "mlp_cross"):
+                lin(f"{p}.{m}.0", 1024, 256)
+                sh[f"{p}.{m}.1.dwconv.weight"] = (1024, 1, 3, 3)
+                sh[f"{p}.{m}.1.dwconv.bias"] = (1024,)
+                lin(f"{p}.{m}.3", 256, 1024)
+            for m in ("mlp_corr", "mlp_refine_corr", "mlp_refine_corr2"):
+                enc(f"{p}.{m}", (8, 32, 8), 3)
+            enc(p + ".feat_to_corr1", (1, 8), k)
+            enc(p + ".feat_to_corr2", (1, 8), k)
+            for m in ("norm1", "norm2", "norm_cross1", "norm_cross2"):
+                sh[f"{p}.{m}.weight"] = (256,)
+                sh[f"{p}.{m}.bias"] = (256,)
+            lin(p + ".v_cross", 256, 256)
+    for lvl, k in enumerate((3, 3, 5)):
+        enc(f"embedding.{lvl}", (1, 8), k)
+    for lvl, cin in enumerate((512, 256, 128)):
+        lin(f"proj_feat.{lvl}.0", 256, cin)
+    return sh
+
+
+def ufc_state_dict(seed=0):
+    """Seeded random parameters with the reference UFC's names and shapes (numpy PCG64)."""
+    rng = np.random.default_rng(7000 + seed)
+    sd = {}
+    for name, shape in ufc_param_shapes().items():
+        if name.endswith("pos_embed"):
+            a = rng.normal(0, 0.02, shape)
+        elif ".conv4d." in name and name.endswith(".1.weight") or ".norm" in name and name.endswith("weight"):
+            a = rng.uniform(0.7, 1.3, shape)          # GroupNorm / LayerNorm scales
+        elif name.endswith(".bias"):
+            a = rng.uniform(-0.1, 0.1, shape)
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            a = rng.uniform(-1, 1, shape) * (1.2 / math.sqrt(fan_in))
+        sd[name] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return sd
+
+
+def ufc_inputs(seed=0, batch=1):
+    """Encoder feature pyramid as UFC.forward receives it: [(2B,512,16,16), (2B,256,32,32), (2B,128,64,64)]."""
+    rng = np.random.default_rng(7500 + seed)
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return [f32(rng.standard_normal((2 * batch, c, n, n))) for c, n in ((512, 16), (256, 32), (128, 64))]

@@ -173,6 +173,29 @@ size_t cpn_linear_attention_workspace_bytes(int N, int H, int Dv);
 int cpn_linear_attention(const float* q, const float* k, const float* v, int N, int L, int S, int H, int D, int Dv,
                          float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- small operators of the cost aggregation (models/aggregation.py) ----------------------------------------
+ * Tokens are (B, L = n*n, C) row-major; correlation volumes (B, H, hs, hs, q, q).
+ * cpn_layernorm        nn.LayerNorm(C), eps 1e-5 (aggregation.py:257-263)
+ * cpn_corr_to_tokens   'B H Hs Ws Ht Wt -> B (H Ht Wt) Hs Ws', bilinear (align_corners) to n x n, '-> B (Hs Ws) C'
+ *                      (aggregation.py:283-285,291-293); written at column col0 of rows of length ld
+ * cpn_tokens_to_corr   the inverse path (aggregation.py:298-300)
+ * cpn_transpose_pq     batched (P x Q) -> (Q x P); 'B H Hs Ws Ht Wt -> B H Ht Wt Hs Ws' with P = Q = hs*hs (:344-346)
+ * cpn_dwconv_gelu      DWConv 3x3 + nn.GELU on the n x n token map (aggregation.py:18-29,186-187)
+ * cpn_resample_tokens  mode 0 interpolate2d_token (:58-63), 1 einops mean-pool (:316-319), 2 einops repeat (:327-332)
+ * cpn_cross_attention  softmax(corr, -1) @ trg_v and softmax(corr, -2)^T @ src_v per head (:314,324-325)
+ * cpn_correlation      cosine correlation of token features (:70-80), out (B, L, L) */
+int cpn_layernorm(const float* x, const float* gamma, const float* beta, float* y, int tokens, int C, void* stream);
+int cpn_corr_to_tokens(const float* corr, float* tok, int B, int H, int hs, int q, int n, int ld, int col0, void* stream);
+int cpn_tokens_to_corr(const float* tok, float* corr, int B, int H, int hs, int q, int n, void* stream);
+int cpn_transpose_pq(const float* in, float* out, int batch, int P, int Q, void* stream);
+int cpn_dwconv_gelu(const float* x, const float* w, const float* bias, float* y, int B, int n, int C, void* stream);
+int cpn_resample_tokens(const float* x, float* y, int B, int n, int m_or_pool, int C, int mode, void* stream);
+int cpn_cross_attention(const float* corr, const float* src_v, const float* trg_v, float* src_attn, float* trg_attn, int B,
+                        int H, int S, int T, int D, void* stream);
+size_t cpn_correlation_workspace_bytes(int B, int L, int C);
+int cpn_correlation(const float* src, const float* trg, float* out, int B, int L, int C, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 /* ---- device timing of the dominant kernel (the query_encode_latent GEMM), for roofline reports.
  * Between cpn_prof_begin and cpn_prof_end every launch of that kernel by cpn_render_rays is bracketed
  * by CUDA events on the caller's stream. cpn_prof_end waits for them and returns the summed duration.

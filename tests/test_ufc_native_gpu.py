@@ -1,0 +1,71 @@
+"""The complete native UFC (coponerf_b200.ufc_native.ufc_forward over CudaOps: every operator a C-ABI call) against
+the same state_dict-driven orchestration over the PyTorch restatement of the operators (oracle/ufc_ops_torch.py),
+which tests/test_ufc_orchestration_cpu.py pins to the unmodified reference UFC. Also operator-by-operator."""
+import numpy as np
+import pytest
+import torch
+
+from coponerf_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from coponerf_b200.ufc_ops import CudaOps
+    from oracle.ufc_ops_torch import TorchOps
+    return CudaOps(), TorchOps()
+
+
+def _close(a, b, tol=2e-5):
+    a, b = a.cpu().double(), b.double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = float((a - b).abs().max() / max(1e-30, float(b.abs().max())))
+    assert err <= tol, err
+
+
+def test_operators_match_torch_restatement():
+    cu, th = _ops()
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.randn(*s, generator=g)
+    x = r(2, 1024, 256)
+    w, b = r(256) * 0.2 + 1, r(256) * 0.1
+    _close(cu.layernorm(x.cuda(), w.cuda(), b.cuda()), th.layernorm(x, w, b))
+    W, bb = r(512, 256) * 0.1, r(512) * 0.1
+    _close(cu.linear(x.cuda(), W.cuda(), bb.cuda(), act="relu"), th.linear(x, W, bb, act="relu"))
+    corr = r(2, 8, 16, 16, 16, 16)
+    for n in (16, 32, 64):
+        _close(cu.corr_to_tokens(corr.cuda(), n), th.corr_to_tokens(corr, n))
+        tok = r(1, n * n, 2048)
+        _close(cu.tokens_to_corr(tok.cuda(), n, 8, 16), th.tokens_to_corr(tok, n, 8, 16))
+    _close(cu.transpose4d(corr.cuda()), th.transpose4d(corr))
+    xm, wd, bd = r(2, 32 * 32, 1024), r(1024, 1, 3, 3) * 0.3, r(1024) * 0.1
+    _close(cu.dwconv_gelu(xm.cuda(), wd.cuda(), bd.cuda(), 32), th.dwconv_gelu(xm, wd, bd, 32))
+    s, t = r(2, 1024, 256), r(2, 1024, 256)
+    _close(cu.correlation(s.cuda(), t.cuda(), 32), th.correlation(s, t, 32), tol=1e-5)
+    _close(cu.upsample_tokens(s.cuda(), 64), th.upsample_tokens(s, 64))
+    _close(cu.avgpool_tokens(s.cuda(), 32, 2), th.avgpool_tokens(s, 32, 2))
+    small = r(2, 256, 256)
+    _close(cu.repeat_tokens(small.cuda(), 16, 4), th.repeat_tokens(small, 16, 4))
+    sv, tv = r(2, 256, 8, 32), r(2, 256, 8, 32)
+    cc = corr * 3
+    a1, a2 = cu.cross_attention(cc.cuda(), sv.cuda(), tv.cuda())
+    b1, b2 = th.cross_attention(cc, sv, tv)
+    _close(a1, b1)
+    _close(a2, b2)
+
+
+def test_native_ufc_forward_matches_restatement():
+    from coponerf_b200 import ufc_native
+    cu, th = _ops()
+    sd = synth.ufc_state_dict(0)
+    feat = synth.ufc_inputs(0)
+    ref_feats, ref_flows, ref_c = ufc_native.ufc_forward(sd, feat, 2, th)
+    sd_d = {k: v.cuda() for k, v in sd.items()}
+    got_feats, got_flows, got_c = ufc_native.ufc_forward(sd_d, [f.cuda() for f in feat], 2, cu)
+    torch.cuda.synchronize()
+    for a, b in zip(got_feats, ref_feats):
+        _close(a, b, tol=1e-4)
+    assert float((got_c.cpu() - ref_c).abs().max()) <= 2e-5
+    for a, b in zip(got_flows, ref_flows):
+        assert a.shape == b.shape
+        assert float((a.cpu() - b).abs().max()) <= 2e-3 * 64   # soft-argmax at temperature 0.02 amplifies c by 50
