@@ -13,12 +13,14 @@
 
 namespace {
 
-constexpr int C4_THREADS = 128;
+constexpr int C4_THREADS = 64;   // 16^4 outputs -> 1024 CTAs: ~7 per SM so loads of several CTAs overlap
 
-template <int CO>
+// K, S: kernel size and stride as compile-time constants (0 = take them from the arguments), so that the tap and
+// pooling loops unroll for the three geometries UFC uses: (3, 1), (3, 2), (5, 4).
+template <int CO, int K, int S>
 __global__ void __launch_bounds__(C4_THREADS) conv4d_kernel(cpn_conv4d_args a, int oq, int os, double* __restrict__ partials) {
   extern __shared__ float wsm[];   // [2 branches][Ci][k*k][CO]
-  const int k = a.k, kk = k * k, s = a.stride, p = a.pad, Ci = a.Ci, Hq = a.Hq, Hs = a.Hs;
+  const int k = K ? K : a.k, kk = k * k, s = S ? S : a.stride, p = a.pad, Ci = a.Ci, Hq = a.Hq, Hs = a.Hs;
   for (int i = threadIdx.x; i < 2 * Ci * kk * CO; i += C4_THREADS) {
     int co = i % CO, tap = (i / CO) % kk, ci = (i / (CO * kk)) % Ci, br = i / (CO * kk * Ci);
     const float* w = br ? a.ws : a.wq;   // (Co, Ci, k, k)
@@ -38,17 +40,21 @@ __global__ void __launch_bounds__(C4_THREADS) conv4d_kernel(cpn_conv4d_args a, i
     for (int ci = 0; ci < Ci; ++ci) {
       const float* xc = xb + (size_t)ci * plane;
       // query branch: conv over (Hq, Wq) of the input max-pooled over the support window of this output position
+#pragma unroll
       for (int dy = 0; dy < k; ++dy) {
         const int qy = hq * s + dy - p;
         if (qy < 0 || qy >= Hq) continue;
+#pragma unroll
         for (int dx = 0; dx < k; ++dx) {
           const int qx = wq * s + dx - p;
           if (qx < 0 || qx >= Hq) continue;
           const float* base = xc + ((size_t)qy * Hq + qx) * sHs * sHs;
           float v = -INFINITY;
+#pragma unroll
           for (int i = 0; i < s; ++i) {
             const int y = hs * s + i;
             if (y >= Hs) break;
+#pragma unroll
             for (int j = 0; j < s; ++j) {
               const int x = ws_ * s + j;
               if (x >= Hs) break;
@@ -61,16 +67,20 @@ __global__ void __launch_bounds__(C4_THREADS) conv4d_kernel(cpn_conv4d_args a, i
         }
       }
       // support branch: conv over (Hs, Ws) of the input max-pooled over the query window
+#pragma unroll
       for (int dy = 0; dy < k; ++dy) {
         const int sy = hs * s + dy - p;
         if (sy < 0 || sy >= Hs) continue;
+#pragma unroll
         for (int dx = 0; dx < k; ++dx) {
           const int sx = ws_ * s + dx - p;
           if (sx < 0 || sx >= Hs) continue;
           float v = -INFINITY;
+#pragma unroll
           for (int i = 0; i < s; ++i) {
             const int y = hq * s + i;
             if (y >= Hq) break;
+#pragma unroll
             for (int j = 0; j < s; ++j) {
               const int x = wq * s + j;
               if (x >= Hq) break;
@@ -203,13 +213,15 @@ extern "C" int cpn_conv4d(const cpn_conv4d_args* args, void* stream) {
   }
   double* partials = reinterpret_cast<double*>(a.workspace);
   dim3 grid(nblk, a.B);
-  if (a.Co == 8) {
-    CPN_CHECK_CUDA(cudaFuncSetAttribute(conv4d_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv4d_kernel<8><<<grid, C4_THREADS, smem, st>>>(a, oq, os, partials);
-  } else {
-    CPN_CHECK_CUDA(cudaFuncSetAttribute(conv4d_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv4d_kernel<32><<<grid, C4_THREADS, smem, st>>>(a, oq, os, partials);
-  }
+  void (*kern)(cpn_conv4d_args, int, int, double*);
+  const int ks = a.k * 10 + a.stride;
+  if (a.Co == 8)
+    kern = ks == 31 ? conv4d_kernel<8, 3, 1> : ks == 32 ? conv4d_kernel<8, 3, 2> : ks == 54 ? conv4d_kernel<8, 5, 4>
+                                                                                           : conv4d_kernel<8, 0, 0>;
+  else
+    kern = ks == 31 ? conv4d_kernel<32, 3, 1> : conv4d_kernel<32, 0, 0>;
+  CPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, C4_THREADS, smem, st>>>(a, oq, os, partials);
   CPN_CHECK_LAUNCH("conv4d_kernel");
   if (a.norm_relu) {
     dim3 g2(256, a.B);

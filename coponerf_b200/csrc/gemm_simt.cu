@@ -115,6 +115,91 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
   }
 }
 
+// 64 x 64 tiles, 4 x 4 per thread: for problems whose 128 x 128 tiling would leave most of the 148 SMs idle (the
+// per-pair layers of the cost aggregation: M = 256 .. 4096 tokens). Same k order per output as the large kernel, so
+// both give bit-identical results.
+constexpr int SBM = 64, SBN = 64;
+
+__global__ void __launch_bounds__(NT, 2)
+gemm_simt_small_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Wt, const float* __restrict__ bias,
+                       const float* __restrict__ rowbias, int rows_per_bias, float* __restrict__ C, int ldc, int M, int N,
+                       int K, int relu, int remap256, float out_div) {
+  __shared__ __align__(16) float As[2][BK][SBM];
+  __shared__ __align__(16) float Bs[2][BK][SBN];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+  const int a_row = tid & (SBM - 1), a_k = (tid >> 6) * 4;          // 64 rows x 4 groups of 4 k
+  const bool a_ok = (m0 + a_row) < M;
+  const float* a_ptr = A + (size_t)(m0 + a_row) * lda + a_k;
+  const int b_k = tid >> 4, b_n = (tid & 15) * 4;                   // 16 k rows x 16 float4 columns
+  const bool b_ok = (n0 + b_n) < N;
+  const float* b_ptr = Wt + (size_t)b_k * N + n0 + b_n;
+  float4 ra, rb;
+  auto load_tiles = [&](int k0) {
+    ra = (a_ok && k0 + a_k < K) ? *reinterpret_cast<const float4*>(a_ptr + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = (b_ok && k0 + b_k < K) ? *reinterpret_cast<const float4*>(b_ptr + (size_t)k0 * N) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto store_tiles = [&](int buf) {
+    As[buf][a_k + 0][a_row] = ra.x;
+    As[buf][a_k + 1][a_row] = ra.y;
+    As[buf][a_k + 2][a_row] = ra.z;
+    As[buf][a_k + 3][a_row] = ra.w;
+    *reinterpret_cast<float4*>(&Bs[buf][b_k][b_n]) = rb;
+  };
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    const bool more = (k0 + BK) < K;
+    if (more) load_tiles(k0 + BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i, n = n0 + tx * 4;
+    if (m >= M || n >= N) continue;
+    float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    if (bias) {
+      float4 bb = *reinterpret_cast<const float4*>(bias + n);
+      v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+    }
+    if (rowbias) {
+      float4 bb = *reinterpret_cast<const float4*>(rowbias + (size_t)(m / rows_per_bias) * N + n);
+      v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+    }
+    if (relu) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    if (out_div != 0.f) {
+      v.x /= out_div; v.y /= out_div; v.z /= out_div; v.w /= out_div;
+    }
+    size_t orow = remap256 ? (size_t)(m >> 8) * 128 + (m & 127) : (size_t)m;
+    int ocol = remap256 ? ((m >> 7) & 1) * N + n : n;
+    *reinterpret_cast<float4*>(C + orow * ldc + ocol) = v;
+  }
+}
+
 }  // namespace
 
 int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias, const float* rowbias,
@@ -126,6 +211,13 @@ int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias
     return CPN_ERR_ARG;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  if ((long long)grid.x * grid.y < 148) {   // too few large tiles to fill the GPU
+    dim3 g2((N + SBN - 1) / SBN, (M + SBM - 1) / SBM);
+    gemm_simt_small_kernel<<<g2, NT, 0, st>>>(A, lda, wt, bias, rowbias, rows_per_bias > 0 ? rows_per_bias : 1, C, ldc, M,
+                                              N, K, relu, remap256, out_div);
+    CPN_CHECK_LAUNCH("gemm_simt_small_kernel");
+    return CPN_OK;
+  }
   if (grid.y > 65535) {
     cpn_set_error("gemm_simt: M=%d too large for one launch", M);
     return CPN_ERR_ARG;

@@ -16,23 +16,29 @@ __device__ __forceinline__ float elu1(float x) { return (x > 0.f ? x : expm1f(x)
 
 // KV[n][h][d][v] for a 32-wide v slice; the v-slice-0 CTA also writes Ksum[n][h][d].
 // block (32, 8): threadIdx.x = v within the slice, threadIdx.y = 4-row group of d; loop over keys in tiles of 32.
+// The keys are split into `nsplit` contiguous ranges (blockIdx.z = n * nsplit + split); each CTA writes a partial
+// KV / Ksum, la_reduce_kernel adds the partials in split order.
 __global__ void __launch_bounds__(256) la_kv_kernel(const float* __restrict__ k, const float* __restrict__ v, int S, int H,
-                                                    int Dv, float* __restrict__ KV, float* __restrict__ Ksum) {
+                                                    int Dv, int nsplit, float* __restrict__ KV, float* __restrict__ Ksum) {
   __shared__ float ks[32][LA_D + 1];   // [key in tile][d]
   __shared__ float vs[32][33];         // [key in tile][v in slice]
-  const int n = blockIdx.z, h = blockIdx.y, v0 = blockIdx.x * 32;
+  const int n = blockIdx.z / nsplit, split = blockIdx.z % nsplit, h = blockIdx.y, v0 = blockIdx.x * 32;
+  const int per = ((S + nsplit - 1) / nsplit + 31) / 32 * 32, s_begin = split * per, s_end = min(S, s_begin + per);
+  const int N = gridDim.z / nsplit;
+  KV += (size_t)split * N * H * LA_D * Dv;
+  Ksum += (size_t)split * N * H * LA_D;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   float ksum = 0.f;   // threads with ty == 0 accumulate Ksum[d = tx]
   const float invS = (float)S;
-  for (int s0 = 0; s0 < S; s0 += 32) {
+  for (int s0 = s_begin; s0 < s_end; s0 += 32) {
     for (int i = tid; i < 32 * LA_D; i += 256) {
       int sk = i / LA_D, d = i % LA_D;
-      ks[sk][d] = (s0 + sk < S) ? elu1(k[(((size_t)n * S + s0 + sk) * H + h) * LA_D + d]) : 0.f;
+      ks[sk][d] = (s0 + sk < s_end) ? elu1(k[(((size_t)n * S + s0 + sk) * H + h) * LA_D + d]) : 0.f;
     }
     for (int i = tid; i < 32 * 32; i += 256) {
       int sk = i / 32, vv = i % 32;
-      vs[sk][vv] = (s0 + sk < S && v0 + vv < Dv) ? v[(((size_t)n * S + s0 + sk) * H + h) * Dv + v0 + vv] / invS : 0.f;
+      vs[sk][vv] = (s0 + sk < s_end && v0 + vv < Dv) ? v[(((size_t)n * S + s0 + sk) * H + h) * Dv + v0 + vv] / invS : 0.f;
     }
     __syncthreads();
 #pragma unroll 8
@@ -49,6 +55,14 @@ __global__ void __launch_bounds__(256) la_kv_kernel(const float* __restrict__ k,
     for (int j = 0; j < 4; ++j) KV[(((size_t)n * H + h) * LA_D + ty * 4 + j) * Dv + v0 + tx] = acc[j];
   }
   if (blockIdx.x == 0 && ty == 0) Ksum[((size_t)n * H + h) * LA_D + tx] = ksum;
+}
+
+__global__ void la_reduce_kernel(float* __restrict__ buf, size_t count, int nsplit) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float s = buf[i];
+  for (int j = 1; j < nsplit; ++j) s += buf[i + (size_t)j * count];
+  buf[i] = s;
 }
 
 // out[n][l][h][v]: one warp per (n, l, h); lanes stride over v
@@ -80,9 +94,12 @@ __global__ void __launch_bounds__(256) la_out_kernel(const float* __restrict__ q
 
 }  // namespace
 
+constexpr int LA_MAX_SPLIT = 32;
+static int la_splits(int S) { int n = (S + 127) / 128; return n < 1 ? 1 : (n > LA_MAX_SPLIT ? LA_MAX_SPLIT : n); }
+
 extern "C" size_t cpn_linear_attention_workspace_bytes(int N, int H, int Dv) {
   if (N <= 0 || H <= 0 || Dv <= 0) return 0;
-  return ((size_t)N * H * LA_D * Dv + (size_t)N * H * LA_D) * sizeof(float);
+  return ((size_t)N * H * LA_D * Dv + (size_t)N * H * LA_D) * sizeof(float) * LA_MAX_SPLIT;
 }
 
 extern "C" int cpn_linear_attention(const float* q, const float* k, const float* v, int N, int L, int S, int H, int D,
@@ -96,11 +113,18 @@ extern "C" int cpn_linear_attention(const float* q, const float* k, const float*
     return CPN_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  const int nsplit = la_splits(S);
+  const size_t kv_count = (size_t)N * H * LA_D * Dv, ks_count = (size_t)N * H * LA_D;
   float* KV = reinterpret_cast<float*>(workspace);
-  float* Ksum = KV + (size_t)N * H * LA_D * Dv;
-  dim3 g1((Dv + 31) / 32, H, N), b1(32, 8);
-  la_kv_kernel<<<g1, b1, 0, st>>>(k, v, S, H, Dv, KV, Ksum);
+  float* Ksum = KV + kv_count * LA_MAX_SPLIT;
+  dim3 g1((Dv + 31) / 32, H, N * nsplit), b1(32, 8);
+  la_kv_kernel<<<g1, b1, 0, st>>>(k, v, S, H, Dv, nsplit, KV, Ksum);
   CPN_CHECK_LAUNCH("la_kv_kernel");
+  if (nsplit > 1) {
+    la_reduce_kernel<<<(unsigned)((kv_count + 255) / 256), 256, 0, st>>>(KV, kv_count, nsplit);
+    la_reduce_kernel<<<(unsigned)((ks_count + 255) / 256), 256, 0, st>>>(Ksum, ks_count, nsplit);
+    CPN_CHECK_LAUNCH("la_reduce_kernel");
+  }
   long long warps = (long long)N * L * H;
   la_out_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(q, KV, Ksum, L, S, H, Dv, N, out);
   CPN_CHECK_LAUNCH("la_out_kernel");
