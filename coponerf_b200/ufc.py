@@ -8,6 +8,17 @@ import torch
 from . import _lib
 
 
+_LIN = {}
+
+
+def _linspace(n, dev):
+    """linspace(-1, 1, n), built on the host like the reference's and cached per device (graph-capture safe)."""
+    key = (n, str(dev))
+    if key not in _LIN:
+        _LIN[key] = torch.linspace(-1, 1, n).to(dev)
+    return _LIN[key]
+
+
 def ufc_tail(src_feats, trg_feats, sizes=(16, 32, 64), out=64):
     """src_feats / trg_feats: three CUDA fp32 token tensors (B, sizes[l]^2, C).
 
@@ -28,7 +39,7 @@ def ufc_tail(src_feats, trg_feats, sizes=(16, 32, 64), out=64):
         f32 = dict(dtype=torch.float32, device=dev)
         c = torch.empty((B, 1, out, out, out, out), **f32)
         flows = [torch.empty((B, 2, out, out), **f32) for _ in range(4)]
-        lin = torch.linspace(-1, 1, out).to(dev)   # built on the host like the reference's
+        lin = _linspace(out, dev)
         a = _lib.UfcTailArgs()
         a.B, a.C, a.out = B, C, out
         for l in range(3):

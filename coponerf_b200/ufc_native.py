@@ -95,6 +95,7 @@ def ufc_forward(sd, feat, nview, ops):
     feat: [(2B, 512, 16, 16), (2B, 256, 32, 32), (2B, 128, 64, 64)]. Returns what UFC.forward returns."""
     B2 = feat[0].shape[0]
     sizes = [f.shape[-1] for f in feat]
+    launches0 = getattr(ops, "launches", 0)
 
     def side(i, v):
         x = feat[i].reshape(B2 // nview, nview, -1, sizes[i] * sizes[i])[:, v].transpose(1, 2)   # 'B C H W -> B (H W) C'
@@ -117,4 +118,6 @@ def ufc_forward(sd, feat, nview, ops):
         feat_list.append(both.transpose(1, 2).reshape(both.shape[0], both.shape[2], n, n))
         refined.append((s, t))
     flows, c = ops.tail([r[0] for r in refined], [r[1] for r in refined], tuple(sizes), sizes[-1])
+    if hasattr(ops, "launches"):
+        ops.launches_per_forward = ops.launches - launches0
     return feat_list, flows, c

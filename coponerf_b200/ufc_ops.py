@@ -24,6 +24,8 @@ class CudaOps:
     def __init__(self):
         self.lib = _lib.load()
         self._wt = {}      # weight tensor -> transposed [K][N] copy for the GEMM (made once per weight)
+        self.launches = 0  # kernels launched so far (bench.py's gpu_launches)
+        self.launches_per_forward = 0
 
     def _check_dev(self, t):
         if t.device.type != "cuda":
@@ -45,6 +47,7 @@ class CudaOps:
         x = _c(x)
         self._check_dev(x)
         y = torch.empty_like(x)
+        self.launches += 1
         _lib.check(self.lib.cpn_layernorm(_p(x), _p(_c(w)), _p(_c(b)), _p(y), x.numel() // x.shape[-1], x.shape[-1], _st()),
                    "cpn_layernorm")
         return y
@@ -56,6 +59,7 @@ class CudaOps:
         M = x.numel() // K
         wt, bias = self._transposed(w), _c(b)
         y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
+        self.launches += 1
         _lib.check(self.lib.cpn_gemm_simt(_p(x), K, _p(wt), _p(bias), _p(y), N, M, N, K, int(act == "relu"), _st()),
                    "cpn_gemm_simt")
         return y
@@ -66,6 +70,7 @@ class CudaOps:
         self._check_dev(corr)
         B, H, hs, _, q, _ = corr.shape
         tok = torch.empty((B, n * n, H * q * q), dtype=torch.float32, device=corr.device)
+        self.launches += 1
         _lib.check(self.lib.cpn_corr_to_tokens(_p(corr), _p(tok), B, H, hs, q, n, H * q * q, 0, _st()), "cpn_corr_to_tokens")
         return tok
 
@@ -75,6 +80,7 @@ class CudaOps:
         B, L, CH = tok.shape
         q = int(round((CH // H) ** 0.5))
         corr = torch.empty((B, H, hs, hs, q, q), dtype=torch.float32, device=tok.device)
+        self.launches += 1
         _lib.check(self.lib.cpn_tokens_to_corr(_p(tok), _p(corr), B, H, hs, q, n, _st()), "cpn_tokens_to_corr")
         return corr
 
@@ -83,11 +89,13 @@ class CudaOps:
         self._check_dev(corr)
         B, H, hs, ws, ht, wt = corr.shape
         out = torch.empty((B, H, ht, wt, hs, ws), dtype=torch.float32, device=corr.device)
+        self.launches += 1
         _lib.check(self.lib.cpn_transpose_pq(_p(corr), _p(out), B * H, hs * ws, ht * wt, _st()), "cpn_transpose_pq")
         return out
 
     def encoder4d(self, x, blocks, stride, pad):
         for p in blocks:
+            self.launches += 2      # conv4d_kernel + gn_relu_kernel
             x = conv4d_block(x, p["wq"], p["bq"], p["ws"], p["bs"], p["gamma"], p["beta"], stride, pad)
         return x
 
@@ -98,11 +106,13 @@ class CudaOps:
         out = torch.empty((B, 1, n, n, n, n), dtype=torch.float32, device=src.device)
         nbytes = self.lib.cpn_correlation_workspace_bytes(B, L, C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=src.device)
+        self.launches += 3 + B      # two normalisations, one transpose, one GEMM per pair
         _lib.check(self.lib.cpn_correlation(_p(src), _p(trg), _p(out), B, L, C, _p(ws), nbytes, _st()), "cpn_correlation")
         return out
 
     # ------------------------------------------------------------------ attention
     def linear_attention(self, q, k, v):
+        self.launches += 2 + (2 if k.shape[1] > 128 else 0)     # kv, (two partial reductions), out
         return linear_attention(q, k, v)
 
     def cross_attention(self, corr, src_v, trg_v):
@@ -113,6 +123,7 @@ class CudaOps:
         D = src_v.shape[-1]
         src_attn = torch.empty((B, S, H * D), dtype=torch.float32, device=corr.device)
         trg_attn = torch.empty((B, T, H * D), dtype=torch.float32, device=corr.device)
+        self.launches += 2
         _lib.check(self.lib.cpn_cross_attention(_p(corr), _p(src_v), _p(trg_v), _p(src_attn), _p(trg_attn), B, H, S, T, D,
                                                 _st()), "cpn_cross_attention")
         return src_attn, trg_attn
@@ -123,6 +134,7 @@ class CudaOps:
         self._check_dev(x)
         B, L, C = x.shape
         y = torch.empty_like(x)
+        self.launches += 1
         _lib.check(self.lib.cpn_dwconv_gelu(_p(x), _p(_c(w)), _p(_c(b)), _p(y), B, n, C, _st()), "cpn_dwconv_gelu")
         return y
 
@@ -131,6 +143,7 @@ class CudaOps:
         self._check_dev(x)
         B, L, C = x.shape
         y = torch.empty((B, m * m, C), dtype=torch.float32, device=x.device)
+        self.launches += 1
         _lib.check(self.lib.cpn_resample_tokens(_p(x), _p(y), B, n, arg, C, mode, _st()), "cpn_resample_tokens")
         return y
 
@@ -145,4 +158,5 @@ class CudaOps:
         return x if pool == 1 else self._resample(x, hs, pool, hs * pool, 2)
 
     def tail(self, src, trg, sizes, out):
+        self.launches += 12 + src[0].shape[0] + 2     # 6 normalisations, 6 upsample-packs, one GEMM per pair, 2 soft-argmax
         return ufc_tail(src, trg, sizes, out)
