@@ -211,7 +211,7 @@ int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias
     return CPN_ERR_ARG;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  if ((long long)grid.x * grid.y < 148) {   // too few large tiles to fill the GPU
+  if ((long long)grid.x * grid.y < 96) {   // too few large tiles to fill the 148 SMs
     dim3 g2((N + SBN - 1) / SBN, (M + SBM - 1) / SBM);
     gemm_simt_small_kernel<<<g2, NT, 0, st>>>(A, lda, wt, bias, rowbias, rows_per_bias > 0 ? rows_per_bias : 1, C, ldc, M,
                                               N, K, relu, remap256, out_div);

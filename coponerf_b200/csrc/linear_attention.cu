@@ -65,30 +65,44 @@ __global__ void la_reduce_kernel(float* __restrict__ buf, size_t count, int nspl
   buf[i] = s;
 }
 
-// out[n][l][h][v]: one warp per (n, l, h); lanes stride over v
+// out[n][l][h][:] = (Q[n,l,h,:] KV[n,h]) * Z * S. CTA = (n, h, 64 consecutive l): KV[n,h] (32 x Dv) and Ksum sit in
+// shared memory; each of the 8 warps handles 8 positions, lane = d for the feature map / normaliser and lane = v
+// (in up to 8 chunks of 32, accumulated together) for the output.
+constexpr int LA_LT = 64, LA_MAXC = 8;
 __global__ void __launch_bounds__(256) la_out_kernel(const float* __restrict__ q, const float* __restrict__ KV,
-                                                     const float* __restrict__ Ksum, int L, int S, int H, int Dv, int N,
+                                                     const float* __restrict__ Ksum, int L, int S, int H, int Dv,
                                                      float* __restrict__ out) {
-  const long long w = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= (long long)N * L * H) return;
-  const int h = (int)(w % H);
-  const long long nl = w / H;
-  const int n = (int)(nl / L);
-  const float qd = elu1(q[(size_t)w * LA_D + lane]);      // lane = d
-  float dot = qd * Ksum[((size_t)n * H + h) * LA_D + lane];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  const float z = 1.f / (dot + 1e-6f);
+  extern __shared__ float kvs[];   // [32][Dv] + [32]
+  float* ksum_s = kvs + LA_D * Dv;
+  const int n = blockIdx.z, h = blockIdx.y, l0 = blockIdx.x * LA_LT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* kv = KV + ((size_t)n * H + h) * LA_D * Dv;
-  for (int v0 = 0; v0 < Dv; v0 += 32) {
-    float acc = 0.f;
+  for (int i = threadIdx.x; i < LA_D * Dv; i += 256) kvs[i] = kv[i];
+  if (threadIdx.x < LA_D) ksum_s[threadIdx.x] = Ksum[((size_t)n * H + h) * LA_D + threadIdx.x];
+  __syncthreads();
+  const int nchunk = (Dv + 31) / 32;
+  for (int li = warp; li < LA_LT; li += 8) {
+    const int l = l0 + li;
+    if (l >= L) break;
+    const size_t row = ((size_t)n * L + l) * H + h;
+    const float qd = elu1(q[row * LA_D + lane]);
+    float dot = qd * ksum_s[lane];
 #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float z = 1.f / (dot + 1e-6f);
+    float acc[LA_MAXC];
+#pragma unroll
+    for (int c = 0; c < LA_MAXC; ++c) acc[c] = 0.f;
+#pragma unroll 4
     for (int d = 0; d < LA_D; ++d) {
-      float qv = __shfl_sync(0xffffffffu, qd, d);
-      if (v0 + lane < Dv) acc = fmaf(qv, kv[(size_t)d * Dv + v0 + lane], acc);
+      const float qv = __shfl_sync(0xffffffffu, qd, d);
+#pragma unroll
+      for (int c = 0; c < LA_MAXC; ++c)
+        if (c < nchunk && c * 32 + lane < Dv) acc[c] = fmaf(qv, kvs[d * Dv + c * 32 + lane], acc[c]);
     }
-    if (v0 + lane < Dv) out[(size_t)w * Dv + v0 + lane] = acc * z * (float)S;
+#pragma unroll
+    for (int c = 0; c < LA_MAXC; ++c)
+      if (c < nchunk && c * 32 + lane < Dv) out[row * Dv + c * 32 + lane] = acc[c] * z * (float)S;
   }
 }
 
@@ -125,8 +139,12 @@ extern "C" int cpn_linear_attention(const float* q, const float* k, const float*
     la_reduce_kernel<<<(unsigned)((ks_count + 255) / 256), 256, 0, st>>>(Ksum, ks_count, nsplit);
     CPN_CHECK_LAUNCH("la_reduce_kernel");
   }
-  long long warps = (long long)N * L * H;
-  la_out_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(q, KV, Ksum, L, S, H, Dv, N, out);
+  if (Dv > 32 * LA_MAXC) {
+    cpn_set_error("cpn_linear_attention: Dv=%d above %d unsupported", Dv, 32 * LA_MAXC);
+    return CPN_ERR_ARG;
+  }
+  dim3 g2((L + LA_LT - 1) / LA_LT, H, N);
+  la_out_kernel<<<g2, 256, (LA_D * Dv + LA_D) * sizeof(float), st>>>(q, KV, Ksum, L, S, H, Dv, out);
   CPN_CHECK_LAUNCH("la_out_kernel");
   return CPN_OK;
 }
