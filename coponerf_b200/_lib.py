@@ -17,6 +17,7 @@ FLAG_SIMT_ONLY = 1
 FLAG_F16X3 = 2
 TC_F16X3 = 4
 TC_CLUSTER = 8
+TC_PAIR = 16
 TC_A_IMAGE = 1
 TC_OUT_IMAGE = 2
 ACT_CHUNK_BYTES = 16384

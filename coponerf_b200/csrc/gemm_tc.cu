@@ -75,9 +75,10 @@ size_t scheme_bytes() {
   for (int i = 0; i < CPN_TC_LAYERS; ++i) n += layer_bytes(i);
   return n;
 }
-// scheme 0: f16x3 tiles [w_hi | w_lo] fp16; scheme 1: f8 tiles [w_hi fp16 | e4m3(w_hi 2^-8) | e4m3(w_lo 2^6)]
+// scheme 0: f16x3 tiles [w_hi | w_lo] fp16; scheme 1: f8 tiles [w_hi fp16 | e4m3(w_hi 2^-8) | e4m3(w_lo 2^6)];
+// scheme 2: the f8 planes again in half tiles of NT / 2 rows (one per CTA of a cta_group::2 pair)
 size_t layer_offset(int l, int scheme) {
-  size_t off = TC_HEADER_BYTES + (scheme ? scheme_bytes() : 0);
+  size_t off = TC_HEADER_BYTES + (size_t)scheme * scheme_bytes();
   for (int i = 0; i < l; ++i) off += layer_bytes(i);
   return off;
 }
@@ -103,8 +104,8 @@ __device__ __forceinline__ float layer_scale(unsigned int absmax_bits) {
 // dst tile (nt, kc), 128 * NT bytes: f16x3 [hi | lo] x [4 k-groups][NT rows][8 halves];
 // f8 [hi as before | e4m3(hi 2^-8) | e4m3(lo 2^6)] with the byte planes as [2 k-groups of 16][NT rows][16 bytes]
 __global__ void pack_tc_kernel(const float* __restrict__ w, int out, int in, int kpad, int NT, const unsigned int* absmax,
-                               __half* __restrict__ dst, unsigned char* __restrict__ dst8, float* __restrict__ header,
-                               int layer) {
+                               __half* __restrict__ dst, unsigned char* __restrict__ dst8,
+                               unsigned char* __restrict__ dstp, float* __restrict__ header, int layer) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)out * kpad;
   float scale = layer_scale(*absmax);
@@ -129,8 +130,17 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, int out, int in, int
   reinterpret_cast<__half*>(t8)[off] = hi;
   const float lo_exact = x - __half2float(hi);
   size_t off8 = ((size_t)((k % BK) / 16) * NT + nl) * 16 + (k % 16);
-  t8[half_elems * 2 + off8] = __nv_cvt_float_to_fp8(__half2float(hi) * F8_W_SCALE, __NV_SATFINITE, __NV_E4M3);
-  t8[half_elems * 3 + off8] = __nv_cvt_float_to_fp8(lo_exact * F8_WLO_SCALE, __NV_SATFINITE, __NV_E4M3);
+  const unsigned char w8 = __nv_cvt_float_to_fp8(__half2float(hi) * F8_W_SCALE, __NV_SATFINITE, __NV_E4M3);
+  const unsigned char wl8 = __nv_cvt_float_to_fp8(lo_exact * F8_WLO_SCALE, __NV_SATFINITE, __NV_E4M3);
+  t8[half_elems * 2 + off8] = w8;
+  t8[half_elems * 3 + off8] = wl8;
+  // pair tiles: (nt, half, kc) with NH = NT / 2 rows: [hi: 4 groups x NH x 16 B | w8: 2 x NH x 16 | w_lo8: 2 x NH x 16]
+  const int NH = NT / 2, hf = nl / NH, nh = nl % NH;
+  unsigned char* tp = dstp + (((size_t)nt * 2 + hf) * kchunks + kc) * (size_t)NH * 128;
+  reinterpret_cast<__half*>(tp)[((size_t)c * NH + nh) * 8 + e] = hi;
+  const size_t offp = ((size_t)((k % BK) / 16) * NH + nh) * 16 + (k % 16);
+  tp[(size_t)NH * 64 + offp] = w8;
+  tp[(size_t)NH * 96 + offp] = wl8;
 }
 
 // ---------------------------------------------------------------------------------------------- the GEMM
@@ -148,6 +158,74 @@ struct GemmArgs {
   uint32_t idesc;
   int f8;                        // 1: fp16 + two e4m3 correction MMAs, 0: three fp16 MMAs
 };
+
+// Drain one 128-row accumulator sub-tile: TMEM -> registers -> scale, bias, ReLU -> fp32 rows or the operand image
+// of the next layer. Warp quadrant q owns TMEM lanes 32 q .. 32 q + 31.
+template <bool OUT_IMAGE>
+__device__ __forceinline__ void drain_subtile(const GemmArgs& g, uint32_t tmem, int m0, int n_tile, int esub, int q,
+                                              int lane) {
+  const int NT = g.NT;
+  const int rloc = q * 32 + lane;                  // row inside the 128-row sub-tile
+  const int row = m0 + esub * 128 + rloc;
+  const float inv = *g.inv_scale;
+  const int n0 = n_tile * NT;
+  const uint32_t tsrc = tmem + esub * 256 + ((uint32_t)(q * 32) << 16);
+  unsigned char* img = nullptr;   // this thread's row inside the output image tile
+  int kbase = 0;                  // k of the next layer that column n0 of this tile maps to
+  if (OUT_IMAGE) {
+    int t = m0 / 128 + esub;
+    img = reinterpret_cast<unsigned char*>(g.C) + (size_t)(t / g.out_div) * g.out_kchunks * ACT_CHUNK_BYTES + rloc * 16;
+    kbase = (t % g.out_div) * g.N + n0;
+  }
+  for (int c0 = 0; c0 < NT; c0 += 16) {
+    float v[16];
+    tmem_ld16(tsrc + c0, v);
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      float4 b = *reinterpret_cast<const float4*>(g.bias + n0 + c0 + j);
+      v[j] = v[j] * inv + b.x;
+      v[j + 1] = v[j + 1] * inv + b.y;
+      v[j + 2] = v[j + 2] * inv + b.z;
+      v[j + 3] = v[j + 3] * inv + b.w;
+    }
+    if (g.relu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (OUT_IMAGE) {
+      // 16 consecutive k of the next layer; lanes are consecutive rows -> every store instruction writes 512 B runs
+      const int k = kbase + c0;
+      unsigned char* chunk = img + (size_t)(k / BK) * ACT_CHUNK_BYTES;
+      if (g.f8) {
+        uint2 h[4];
+        uint4 l8, x8;
+        split4_f8(make_float4(v[0], v[1], v[2], v[3]), h[0], l8.x, x8.x);
+        split4_f8(make_float4(v[4], v[5], v[6], v[7]), h[1], l8.y, x8.y);
+        split4_f8(make_float4(v[8], v[9], v[10], v[11]), h[2], l8.z, x8.z);
+        split4_f8(make_float4(v[12], v[13], v[14], v[15]), h[3], l8.w, x8.w);
+        unsigned char* ph = chunk + ((k % BK) / 8) * A_LBO;
+        *reinterpret_cast<uint4*>(ph) = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
+        *reinterpret_cast<uint4*>(ph + A_LBO) = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
+        *reinterpret_cast<uint4*>(chunk + ACT_LO8 + ((k % BK) / 16) * A_LBO) = l8;
+        *reinterpret_cast<uint4*>(chunk + ACT_X8 + ((k % BK) / 16) * A_LBO) = x8;
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          unsigned char* p = chunk + (((k + h * 8) % BK) / 8) * A_LBO;
+          uint4 hi, lo;
+          split8(make_float4(v[h * 8], v[h * 8 + 1], v[h * 8 + 2], v[h * 8 + 3]),
+                 make_float4(v[h * 8 + 4], v[h * 8 + 5], v[h * 8 + 6], v[h * 8 + 7]), hi, lo);
+          *reinterpret_cast<uint4*>(p) = hi;
+          *reinterpret_cast<uint4*>(p + A_HALF) = lo;
+        }
+      }
+    } else if (row < g.M) {
+      float* out = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + n0 + c0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+}
 
 // CLUSTER (> 1, operand-image A only): the CTAs of the N tiles of one 256-row tile form a cluster; each loads
 // 1/CLUSTER of every A stage and multicasts it to all of them, so the shared A operand is read from L2 once per
@@ -320,66 +398,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
     if (esub == 0 || sub1_valid) {
       mbar_wait(accum, 0);
       tcgen05_fence_after();
-      const int rloc = q * 32 + lane;                  // row inside the 128-row sub-tile
-      const int row = m0 + esub * 128 + rloc;
-      const float inv = *g.inv_scale;
-      const int n0 = n_tile * NT;
-      const uint32_t tsrc = tmem + esub * 256 + ((uint32_t)(q * 32) << 16);
-      unsigned char* img = nullptr;   // this thread's row inside the output image tile
-      int kbase = 0;                  // k of the next layer that column n0 of this tile maps to
-      if (OUT_IMAGE) {
-        int t = m0 / 128 + esub;
-        img = reinterpret_cast<unsigned char*>(g.C) + (size_t)(t / g.out_div) * g.out_kchunks * ACT_CHUNK_BYTES + rloc * 16;
-        kbase = (t % g.out_div) * g.N + n0;
-      }
-      for (int c0 = 0; c0 < NT; c0 += 16) {
-        float v[16];
-        tmem_ld16(tsrc + c0, v);
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 b = *reinterpret_cast<const float4*>(g.bias + n0 + c0 + j);
-          v[j] = v[j] * inv + b.x;
-          v[j + 1] = v[j + 1] * inv + b.y;
-          v[j + 2] = v[j + 2] * inv + b.z;
-          v[j + 3] = v[j + 3] * inv + b.w;
-        }
-        if (g.relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (OUT_IMAGE) {
-          // 16 consecutive k of the next layer; lanes are consecutive rows -> every store instruction writes 512 B runs
-          const int k = kbase + c0;
-          unsigned char* chunk = img + (size_t)(k / BK) * ACT_CHUNK_BYTES;
-          if (g.f8) {
-            uint2 h[4];
-            uint4 l8, x8;
-            split4_f8(make_float4(v[0], v[1], v[2], v[3]), h[0], l8.x, x8.x);
-            split4_f8(make_float4(v[4], v[5], v[6], v[7]), h[1], l8.y, x8.y);
-            split4_f8(make_float4(v[8], v[9], v[10], v[11]), h[2], l8.z, x8.z);
-            split4_f8(make_float4(v[12], v[13], v[14], v[15]), h[3], l8.w, x8.w);
-            unsigned char* ph = chunk + ((k % BK) / 8) * A_LBO;
-            *reinterpret_cast<uint4*>(ph) = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
-            *reinterpret_cast<uint4*>(ph + A_LBO) = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
-            *reinterpret_cast<uint4*>(chunk + ACT_LO8 + ((k % BK) / 16) * A_LBO) = l8;
-            *reinterpret_cast<uint4*>(chunk + ACT_X8 + ((k % BK) / 16) * A_LBO) = x8;
-          } else {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              unsigned char* p = chunk + (((k + h * 8) % BK) / 8) * A_LBO;
-              uint4 hi, lo;
-              split8(make_float4(v[h * 8], v[h * 8 + 1], v[h * 8 + 2], v[h * 8 + 3]),
-                     make_float4(v[h * 8 + 4], v[h * 8 + 5], v[h * 8 + 6], v[h * 8 + 7]), hi, lo);
-              *reinterpret_cast<uint4*>(p) = hi;
-              *reinterpret_cast<uint4*>(p + A_HALF) = lo;
-            }
-          }
-        } else if (row < g.M) {
-          float* out = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + n0 + c0;
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-      }
+      drain_subtile<OUT_IMAGE>(g, tmem, m0, n_tile, esub, q, lane);
     }
   }
   tcgen05_fence_before();
@@ -388,9 +407,114 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// ---- CTA-pair version (cta_group::2, operand-image A, f8 scheme) -------------------------------------------------
+// Two CTAs of a cluster own 2 x 256 rows and the same N tile. Every MMA spans both (M = 256: 128 rows from each
+// CTA's A stage) and reads half of the weight tile from each CTA's shared memory, so each SM stages only NT / 2
+// weight rows per k-chunk: 45.3 KB instead of 58.6 KB cross the L2 -> SM fabric per chunk and SM (the bound of
+// this GEMM), and the smaller stage allows a 4-deep ring. The leader CTA's MMA thread issues for the pair; the
+// peer relays "my stage has landed" to the leader with a remote mbarrier arrive; tcgen05.commit multicasts
+// "stage free" / "accumulators ready" to both CTAs.
+constexpr int PSTAGES = 4;
+constexpr int PW_STAGE_MAX = (NT_MAX / 2) * 128;                 // bytes of half a weight tile per k-chunk
+constexpr int PSTAGE_BYTES = 2 * A_SUB + PW_STAGE_MAX;
+constexpr int PSMEM_BYTES = PSTAGES * PSTAGE_BYTES + 256;
+
+template <bool OUT_IMAGE>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_pair_kernel(GemmArgs g) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[3 * PSTAGES + 1];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n_tile = blockIdx.y, m0 = (blockIdx.z * 2 + (int)rank) * BM;
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t full = smem_u32(&bars[0]), peer_full = smem_u32(&bars[PSTAGES]), empty = smem_u32(&bars[2 * PSTAGES]),
+                 accum = smem_u32(&bars[3 * PSTAGES]);
+  const int NT = g.NT, NH = NT / 2;
+  const uint32_t wh = (uint32_t)(BK / 8) * NH * 16;          // fp16 plane of this CTA's half tile; e4m3 planes wh / 2 each
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PSTAGES; ++s) {
+      mbar_init(full + 8 * s, 1);
+      mbar_init(peer_full + 8 * s, 1);
+      mbar_init(empty + 8 * s, 1);
+    }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(smem_u32(&tmem_base_s), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // this CTA's half of the weight tile and its own two A sub-tiles
+      const unsigned char* wsrc = g.wtiles + ((size_t)n_tile * 2 + rank) * g.kchunks * 2 * wh;
+      const unsigned char* asrc = reinterpret_cast<const unsigned char*>(g.A);
+      const size_t tile0 = (size_t)(m0 / 128);
+      for (int i = 0; i < g.kchunks; ++i) {
+        int s = i % PSTAGES;
+        uint32_t u = i / PSTAGES;
+        mbar_wait_cluster(empty + 8 * s, (u & 1) ^ 1);
+        uint32_t stage = smem0 + s * PSTAGE_BYTES;
+        mbar_arrive_expect_tx(full + 8 * s, 2 * wh + 2 * A_SUB);
+        bulk_g2s(stage + 2 * A_SUB, wsrc + (size_t)i * 2 * wh, 2 * wh, full + 8 * s);
+        bulk_g2s(stage, asrc + (tile0 * g.kchunks + i) * ACT_CHUNK_BYTES, A_SUB, full + 8 * s);
+        bulk_g2s(stage + A_SUB, asrc + ((tile0 + 1) * g.kchunks + i) * ACT_CHUNK_BYTES, A_SUB, full + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 1) {
+      // peer: tell the leader when a stage of this CTA has landed
+      for (int i = 0; i < g.kchunks; ++i) {
+        int s = i % PSTAGES;
+        uint32_t u = i / PSTAGES;
+        mbar_wait(full + 8 * s, u & 1);
+        mbar_arrive_remote(peer_full + 8 * s, 0);
+      }
+    } else if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(256, NT);
+      for (int i = 0; i < g.kchunks; ++i) {
+        int s = i % PSTAGES;
+        uint32_t u = i / PSTAGES;
+        mbar_wait(full + 8 * s, u & 1);
+        mbar_wait_cluster(peer_full + 8 * s, u & 1);
+        tcgen05_fence_after();
+        uint32_t stage = smem0 + s * PSTAGE_BYTES;
+        uint32_t b_hi = stage + 2 * A_SUB;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          uint32_t a_hi = stage + sub * A_SUB;
+          uint32_t d = tmem + sub * 256;
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j)
+            mma_f16_ss_pair(d, make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128), make_desc(b_hi + j * 2 * NH * 16, NH * 16, 128),
+                            idesc, (i | j) != 0);
+          mma_f8_ss_pair(d, make_desc(a_hi + ACT_LO8, A_LBO, 128), make_desc(b_hi + wh, NH * 16, 128), idesc, 1);
+          mma_f8_ss_pair(d, make_desc(a_hi + ACT_X8, A_LBO, 128), make_desc(b_hi + wh + wh / 2, NH * 16, 128), idesc, 1);
+        }
+        mma_commit_pair(empty + 8 * s, 3);   // both CTAs may refill the stage once these MMAs have read it
+      }
+      mma_commit_pair(accum, 3);
+    }
+  } else {
+    const int pwarp = warp - 2, esub = pwarp >> 2, q = warp & 3;
+    mbar_wait_cluster(accum, 0);
+    tcgen05_fence_after();
+    drain_subtile<OUT_IMAGE>(g, tmem, m0, n_tile, esub, q, lane);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 1) tmem_dealloc_pair(tmem, TMEM_COLS);
+}
+
 }  // namespace
 
-size_t cpn_tc_weights_bytes() { return TC_HEADER_BYTES + 2 * scheme_bytes(); }
+size_t cpn_tc_weights_bytes() { return TC_HEADER_BYTES + 3 * scheme_bytes(); }
 
 int cpn_pack_tc_weights(const float* raw, void* dst_v, cudaStream_t st) {
   unsigned char* dst = reinterpret_cast<unsigned char*>(dst_v);
@@ -405,7 +529,7 @@ int cpn_pack_tc_weights(const float* raw, void* dst_v, cudaStream_t st) {
     size_t total = (size_t)L.out * L.kpad;
     pack_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(raw + L.raw, L.out, L.in, L.kpad, L.nt, absmax + l,
                                                                     reinterpret_cast<__half*>(dst + layer_offset(l, 0)),
-                                                                    dst + layer_offset(l, 1), header, l);
+                                                                    dst + layer_offset(l, 1), dst + layer_offset(l, 2), header, l);
     CPN_CHECK_LAUNCH("pack_tc_kernel");
   }
   return CPN_OK;
@@ -446,6 +570,27 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
   g.idesc = make_idesc_f16(128, L.nt);
   dim3 grid(L.out / L.nt, (M + BM - 1) / BM);
   const int ntiles = L.out / L.nt;
+  if (a_img && g.f8 && (mode & CPN_TC_PAIR) && (M % (2 * BM)) == 0) {
+    // CTA pairs (cta_group::2), opt-in: measured 20-28 % slower than independent CTAs; needs whole
+    // 512-row pairs, other shapes take the single-CTA kernel below
+    g.wtiles = tcw + layer_offset(layer, 2);
+    void (*pk)(GemmArgs) = o_img ? gemm_tc_pair_kernel<true> : gemm_tc_pair_kernel<false>;
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, PSMEM_BYTES));
+    cudaLaunchConfig_t pc = {};
+    pc.gridDim = dim3(2, ntiles, M / (2 * BM));
+    pc.blockDim = dim3(NUM_THREADS);
+    pc.dynamicSmemBytes = PSMEM_BYTES;
+    pc.stream = st;
+    cudaLaunchAttribute pa[1];
+    pa[0].id = cudaLaunchAttributeClusterDimension;
+    pa[0].val.clusterDim.x = 2;
+    pa[0].val.clusterDim.y = 1;
+    pa[0].val.clusterDim.z = 1;
+    pc.attrs = pa;
+    pc.numAttrs = 1;
+    CPN_CHECK_CUDA(cudaLaunchKernelEx(&pc, pk, g));
+    return CPN_OK;
+  }
   const int cluster = (a_img && (mode & CPN_TC_CLUSTER)) ? ntiles : 1;   // 4, 2 or 1; opt-in: measured slower
   void (*kern)(GemmArgs);
   if (cluster == 4) kern = o_img ? gemm_tc_kernel<true, true, 4> : gemm_tc_kernel<true, false, 4>;

@@ -220,6 +220,8 @@ int cpn_gemm_simt(const float* A, int lda, const float* wt, const float* bias, f
 #define CPN_TC_A_IMAGE 1
 #define CPN_TC_OUT_IMAGE 2
 #define CPN_TC_F16X3 4   /* three fp16 MMAs per product; default is fp16 + two e4m3 correction MMAs */
+#define CPN_TC_PAIR 16   /* experiment: cta_group::2 CTA pairs, each SM stages half of every weight tile (f8 scheme,
+                          * M % 512 == 0); correct, but measured 20-28 % slower than independent CTAs on B200 */
 #define CPN_TC_CLUSTER 8 /* experiment: the N-tile CTAs of a row tile form a cluster and multicast the A operand
                           * (halves L2 reads, but measured 8-18 % slower than independent CTAs on B200) */
 int cpn_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,

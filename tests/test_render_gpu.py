@@ -180,7 +180,7 @@ def test_gemm_tc_against_torch_fp64(layer, name, relu, scheme):
     N, K = Wm.shape
     lda = 848 if K == 835 else K
     torch.manual_seed(layer)
-    for M in (1, 128, 300, 1000):
+    for M in (1, 128, 300, 1000, 1024):
         A = torch.zeros(M, lda, device="cuda")
         A[:, :K] = torch.randn(M, K, device="cuda") * 3
         C = torch.full((M, N), float("nan"), device="cuda")
@@ -193,8 +193,9 @@ def test_gemm_tc_against_torch_fp64(layer, name, relu, scheme):
         assert e < (1e-5 if scheme else 6e-5), (name, M, e)
 
 
-@pytest.mark.parametrize("scheme", [0, 4, 8], ids=["f16+f8", "f16x3", "f16+f8/cluster-multicast"])
-def test_gemm_tc_operand_image_chain(scheme):
+@pytest.mark.parametrize("R", [300, 1024], ids=["ragged", "whole-pairs"])
+@pytest.mark.parametrize("scheme", [0, 4, 12, 16], ids=["f16+f8", "f16x3", "f16x3/cluster-multicast", "f16+f8/cta-pairs"])
+def test_gemm_tc_operand_image_chain(scheme, R):
     """fp32 -> [GEMM1] -> hi/lo operand image -> [GEMM2, two branches side by side] -> image -> [latent_value] -> fp32,
     the way cpn_render_rays chains the encoder layers, against fp64."""
     from coponerf_b200 import _lib
@@ -202,7 +203,6 @@ def test_gemm_tc_operand_image_chain(scheme):
     _, _, W2, b2 = _tc_setup("query_encode_latent_2")
     _, _, WV, bV = _tc_setup("latent_value")
     torch.manual_seed(7)
-    R = 300                                   # sample rows; 3 tiles of 128 with a ragged tail
     Rp = (R + 127) // 128 * 128
     x = torch.randn(2, R, 835, device="cuda")  # [branch][row]
     A = torch.zeros(2 * Rp, 848, device="cuda")
