@@ -18,6 +18,7 @@ FLAG_F16X3 = 2
 TC_F16X3 = 4
 TC_CLUSTER = 8
 TC_PAIR = 16
+TC_OUT_CB16 = 32
 TC_A_IMAGE = 1
 TC_OUT_IMAGE = 2
 ACT_CHUNK_BYTES = 16384
@@ -83,6 +84,9 @@ SIGNATURES = {
     "cpn_render_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5),
     "cpn_render_rays": (ctypes.c_int, [ctypes.POINTER(RenderArgs), ctypes.c_void_p]),
     "cpn_render_launch_count": (ctypes.c_int, [ctypes.POINTER(RenderArgs)]),
+    "cpn_gemm_tc_rowdot": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                          ctypes.c_void_p]),
     "cpn_ufc_tail_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                        ctypes.POINTER(ctypes.c_int32)]),
     "cpn_ufc_tail": (ctypes.c_int, [ctypes.POINTER(UfcTailArgs), ctypes.c_void_p]),

@@ -68,7 +68,8 @@ __device__ __forceinline__ float block_softmax(float logit, float* red, int warp
 // (2B, N, S) layout, r1 (rays,416), wp (rays,4) = sum_v sum_s w * clamp(pt, +-100).
 __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* __restrict__ key,
                              const float* __restrict__ qemb, const float* __restrict__ value,
-                             const float* __restrict__ rowaux, float* __restrict__ r1, float* __restrict__ wp) {
+                             const float* __restrict__ rowaux, float* __restrict__ r1, float* __restrict__ wp,
+                             const float* __restrict__ logits) {
   extern __shared__ float sm[];
   const int S = a.S, S2 = 2 * S;
   float* w = sm;            // [2S]
@@ -77,7 +78,7 @@ __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* _
   const int b = ray / nr, nl = ray % nr, n = ray0 + nl;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31, nwarps = S2 >> 5;
   const size_t row0 = (size_t)ray * S2;
-  float logit = warp_row_logits(key, qemb, row0, warp, lane);
+  float logit = logits ? logits[row0 + t] : warp_row_logits(key, qemb, row0, warp, lane);
   float wt = block_softmax(logit, red, warp, lane, nwarps);
   w[t] = wt;
   {
@@ -149,7 +150,7 @@ __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* _
 // Round 2. z = sum_v (sum_s w2 * V + R1) = R2 + 2 R1.
 __global__ void attn2_kernel(cpn_render_args a, int ray0, int nr, const float* __restrict__ q2,
                              const float* __restrict__ qemb, const float* __restrict__ value,
-                             const float* __restrict__ r1, float* __restrict__ z_all) {
+                             const float* __restrict__ r1, float* __restrict__ z_all, const float* __restrict__ logits) {
   extern __shared__ float sm[];
   const int S = a.S, S2 = 2 * S;
   float* w = sm;
@@ -157,7 +158,7 @@ __global__ void attn2_kernel(cpn_render_args a, int ray0, int nr, const float* _
   const int ray = blockIdx.x;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31, nwarps = S2 >> 5;
   const size_t row0 = (size_t)ray * S2;
-  float logit = warp_row_logits(q2, qemb, row0, warp, lane);
+  float logit = logits ? logits[row0 + t] : warp_row_logits(q2, qemb, row0, warp, lane);
   w[t] = block_softmax(logit, red, warp, lane, nwarps);
   __syncthreads();
   for (int c = t; c < CPN_LATENT; c += S2) {
@@ -287,17 +288,17 @@ __global__ void __launch_bounds__(128) phi_kernel(cpn_render_args a, const float
 }  // namespace
 
 int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, const float* qemb, const float* value,
-                 const float* rowaux, float* r1, float* wp, cudaStream_t st) {
+                 const float* rowaux, float* r1, float* wp, cudaStream_t st, const float* logits) {
   int S2 = 2 * a.S;
-  attn1_kernel<<<a.B * nr, S2, (S2 + 48) * sizeof(float), st>>>(a, ray0, nr, key, qemb, value, rowaux, r1, wp);
+  attn1_kernel<<<a.B * nr, S2, (S2 + 48) * sizeof(float), st>>>(a, ray0, nr, key, qemb, value, rowaux, r1, wp, logits);
   CPN_CHECK_LAUNCH("attn1_kernel");
   return CPN_OK;
 }
 
 int launch_attn2(const cpn_render_args& a, int ray0, int nr, const float* q2, const float* qemb, const float* value,
-                 const float* r1, float* z_all, cudaStream_t st) {
+                 const float* r1, float* z_all, cudaStream_t st, const float* logits) {
   int S2 = 2 * a.S;
-  attn2_kernel<<<a.B * nr, S2, (S2 + 8) * sizeof(float), st>>>(a, ray0, nr, q2, qemb, value, r1, z_all);
+  attn2_kernel<<<a.B * nr, S2, (S2 + 8) * sizeof(float), st>>>(a, ray0, nr, q2, qemb, value, r1, z_all, logits);
   CPN_CHECK_LAUNCH("attn2_kernel");
   return CPN_OK;
 }

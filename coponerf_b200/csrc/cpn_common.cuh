@@ -107,11 +107,12 @@ int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowau
 int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias, const float* rowbias,
                      int rows_per_bias, float* C, int ldc, int M, int N, int K, int relu, cudaStream_t st,
                      int remap256 = 0, float out_div = 0.f);   // out_div != 0: result divided by it
+// logits != nullptr: one precomputed logit per sample row (key / qemb unused); else <key, qemb> / 11.31 is computed here
 int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, const float* qemb, const float* value,
-                 const float* rowaux, float* r1, float* wp, cudaStream_t st);
+                 const float* rowaux, float* r1, float* wp, cudaStream_t st, const float* logits = nullptr);
 // z_all: (B, N, 416) latent of every ray of the image
 int launch_attn2(const cpn_render_args& a, int ray0, int nr, const float* q2, const float* qemb, const float* value,
-                 const float* r1, float* z_all, cudaStream_t st);
+                 const float* r1, float* z_all, cudaStream_t st, const float* logits = nullptr);
 int launch_phi(const cpn_render_args& a, const float* z_all, cudaStream_t st);
 int launch_ray_epilogue(const cpn_render_args& a, int ray0, int nr, const float* wp, const float* seg, cudaStream_t st);
 
@@ -134,5 +135,6 @@ int cpn_pack_tc_weights(const float* raw, void* dst, cudaStream_t st);
 // layer: 0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value, 3 key_map, 4 key_map_2,
 //        5 query_embed_2, 6 query_repeat_embed_2.  mode: CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE.
 //        | CPN_TC_F16X3 (three fp16 MMAs per product instead of fp16 + two fp8 corrections).
+// CPN_TC_OUT_CB16: fp32 output as [row tile][16-col block][128][16]; CPN_TC_OUT_ROWDOT: C[row] = <out row, dotv row> / dot_div
 int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,
-                   int out_div, int out_kchunks, cudaStream_t st);
+                   int out_div, int out_kchunks, cudaStream_t st, const float* dotv = nullptr, float dot_div = 1.f);

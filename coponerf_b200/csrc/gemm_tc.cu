@@ -157,6 +157,9 @@ struct GemmArgs {
   int kchunks, NT;
   uint32_t idesc;
   int f8;                        // 1: fp16 + two e4m3 correction MMAs, 0: three fp16 MMAs
+  int out_kind;                  // fp32 output: 0 row-major, 2 column-blocked (CB16), 3 per-row dot with `dotv`
+  const float* dotv;             // CB16 matrix the rows are dotted with (out_kind 3); C then holds one float per row
+  float dot_div;
 };
 
 // Drain one 128-row accumulator sub-tile: TMEM -> registers -> scale, bias, ReLU -> fp32 rows or the operand image
@@ -177,6 +180,10 @@ __device__ __forceinline__ void drain_subtile(const GemmArgs& g, uint32_t tmem, 
     img = reinterpret_cast<unsigned char*>(g.C) + (size_t)(t / g.out_div) * g.out_kchunks * ACT_CHUNK_BYTES + rloc * 16;
     kbase = (t % g.out_div) * g.N + n0;
   }
+  // CB16: fp32 [row tile][16-column block][128 rows][16], so that a thread's 16 columns are 64 contiguous bytes and the
+  // 32 rows of a warp 2 KB: coalesced for this epilogue and for a consumer that owns one row per thread
+  const size_t cb_row = ((size_t)(m0 / 128 + esub) * (g.N / 16)) * 128 * 16 + (size_t)rloc * 16;
+  float dot = 0.f;
   for (int c0 = 0; c0 < NT; c0 += 16) {
     float v[16];
     tmem_ld16(tsrc + c0, v);
@@ -219,12 +226,24 @@ __device__ __forceinline__ void drain_subtile(const GemmArgs& g, uint32_t tmem, 
           *reinterpret_cast<uint4*>(p + A_HALF) = lo;
         }
       }
+    } else if (g.out_kind == 2) {
+      float* out = reinterpret_cast<float*>(g.C) + cb_row + (size_t)((n0 + c0) / 16) * 128 * 16;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else if (g.out_kind == 3) {
+      const float4* qv = reinterpret_cast<const float4*>(g.dotv + cb_row + (size_t)((n0 + c0) / 16) * 128 * 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 x = __ldg(qv + j);
+        dot = fmaf(v[4 * j + 3], x.w, fmaf(v[4 * j + 2], x.z, fmaf(v[4 * j + 1], x.y, fmaf(v[4 * j], x.x, dot))));
+      }
     } else if (row < g.M) {
       float* out = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + n0 + c0;
 #pragma unroll
       for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
   }
+  if (!OUT_IMAGE && g.out_kind == 3 && row < g.M) reinterpret_cast<float*>(g.C)[row] = dot / g.dot_div;
 }
 
 // CLUSTER (> 1, operand-image A only): the CTAs of the N tiles of one 256-row tile form a cluster; each loads
@@ -536,9 +555,9 @@ int cpn_pack_tc_weights(const float* raw, void* dst_v, cudaStream_t st) {
 }
 
 int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,
-                   int out_div, int out_kchunks, cudaStream_t st) {
+                   int out_div, int out_kchunks, cudaStream_t st, const float* dotv, float dot_div) {
   const bool a_img = mode & CPN_TC_A_IMAGE, o_img = mode & CPN_TC_OUT_IMAGE;
-  if (!packed || !A || !C || layer < 0 || layer >= CPN_TC_LAYERS || M < 0 || (!a_img && (lda & 3)) || (!o_img && (ldc & 3)) ||
+  if (!packed || !A || !C || layer < 0 || layer >= CPN_TC_LAYERS || M < 0 || (!a_img && (lda & 3)) || (!o_img && !(mode & (CPN_TC_OUT_ROWDOT | CPN_TC_OUT_CB16)) && (ldc & 3)) ||
       (o_img && (out_div < 1 || out_kchunks < 1))) {
     cpn_set_error("gemm_tc: bad argument (layer=%d M=%d lda=%d ldc=%d mode=%d)", layer, M, lda, ldc, mode);
     return CPN_ERR_ARG;
@@ -562,6 +581,13 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
   g.out_div = out_div;
   g.out_kchunks = out_kchunks;
   g.f8 = (mode & CPN_TC_F16X3) ? 0 : 1;
+  g.out_kind = (mode & CPN_TC_OUT_ROWDOT) ? 3 : ((mode & CPN_TC_OUT_CB16) ? 2 : 0);
+  g.dotv = dotv;
+  g.dot_div = dot_div;
+  if (g.out_kind && (o_img || L.out != L.nt || (g.out_kind == 3 && !dotv))) {
+    cpn_set_error("gemm_tc: CB16 / row-dot outputs need a single-N-tile layer and fp32 output");
+    return CPN_ERR_ARG;
+  }
   g.wtiles = tcw + layer_offset(layer, g.f8);
   g.bias = reinterpret_cast<const float*>(packed) + L.bias;
   g.inv_scale = reinterpret_cast<const float*>(tcw) + layer;
@@ -616,5 +642,11 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
 
 extern "C" int cpn_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu,
                            int mode, int out_div, int out_kchunks, void* stream) {
-  return launch_gemm_tc(packed, layer, A, lda, C, ldc, M, relu, mode, out_div, out_kchunks, (cudaStream_t)stream);
+  return launch_gemm_tc(packed, layer, A, lda, C, ldc, M, relu, mode, out_div, out_kchunks, (cudaStream_t)stream, nullptr, 1.f);
+}
+
+extern "C" int cpn_gemm_tc_rowdot(const void* packed, int layer, const void* A, int lda, const float* dotv_cb16, float* out,
+                                  int M, int relu, int mode, float div, void* stream) {
+  return launch_gemm_tc(packed, layer, A, lda, out, 0, M, relu, mode | CPN_TC_OUT_ROWDOT, 1, 1, (cudaStream_t)stream, dotv_cb16,
+                        div);
 }

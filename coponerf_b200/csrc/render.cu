@@ -75,7 +75,7 @@ struct ProfScope {  // records an event pair around the enclosed launches when a
 
 // Workspace carve-up for one chunk of `nr` rays of each of B pairs (R = B * nr * 2 * S sample rows).
 struct Workspace {
-  float *seg, *rowaux, *local16, *A, *H1, *E, *V, *K1, *Kk, *Q1, *Qe, *r1, *wp, *zemb, *rbias;
+  float *seg, *rowaux, *local16, *A, *H1, *E, *V, *K1, *Kk, *Q1, *Qe, *r1, *wp, *zemb, *rbias, *lg1, *lg2;
   size_t bytes;
 };
 
@@ -103,6 +103,8 @@ Workspace carve(void* base, int B, int nr, int S) {
   w.wp = take(rays * 4);
   w.zemb = take(rays * CPN_HIDDEN);
   w.rbias = take(rays * CPN_HIDDEN);
+  w.lg1 = take(R);   // attention logits of round 1 / round 2, one per sample row
+  w.lg2 = take(R);
   w.bytes = off;
   return w;
 }
@@ -236,10 +238,12 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
       // value and key, CoPoNeRF.py:404-408
       CPN_TRY(launch_gemm_tc(a.weights, 2, w.E, 0, w.V, CPN_LATENT, R, 0, CPN_TC_A_IMAGE | sch, 1, 1, st));
       CPN_TRY(launch_gemm_tc(a.weights, 3, w.E, 0, w.K1, 0, R, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 1, KC128, st));
-      CPN_TRY(launch_gemm_tc(a.weights, 4, w.K1, 0, w.Kk, CPN_HIDDEN, R, 0, CPN_TC_A_IMAGE | sch, 1, 1, st));
-      // coordinate embedding, CoPoNeRF.py:446
+      // coordinate embedding, CoPoNeRF.py:446; written column-blocked so the two logit epilogues read it coalesced
       CPN_TRY(dense_simt(a, w.local16, 16, pw::WQT, pw::BQ, w.Q1, CPN_HIDDEN, R, CPN_HIDDEN, 16, 1, st));
-      CPN_TRY(launch_gemm_tc(a.weights, 5, w.Q1, CPN_HIDDEN, w.Qe, CPN_HIDDEN, R, 0, sch, 1, 1, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 5, w.Q1, CPN_HIDDEN, w.Qe, 0, R, 0, sch | CPN_TC_OUT_CB16, 1, 1, st));
+      // key_map_2 with the round-1 logits <K, Q> / 11.31 (CoPoNeRF.py:450) as its epilogue: K itself is never stored
+      CPN_TRY(launch_gemm_tc(a.weights, 4, w.K1, 0, w.lg1, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_ROWDOT, 1, 1, st, w.Qe,
+                             11.31f));
     } else {
       {
         ProfScope prof(st);
@@ -252,18 +256,19 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
       CPN_TRY(dense_simt(a, w.local16, 16, pw::WQT, pw::BQ, w.Q1, CPN_HIDDEN, R, CPN_HIDDEN, 16, 1, st));
       CPN_TRY(dense_simt(a, w.Q1, CPN_HIDDEN, pw::WQ2T, pw::BQ2, w.Qe, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
     }
-    CPN_TRY(launch_attn1(a, ray0, nr, w.Kk, w.Qe, w.V, w.rowaux, w.r1, w.wp, st));
+    CPN_TRY(launch_attn1(a, ray0, nr, w.Kk, w.Qe, w.V, w.rowaux, w.r1, w.wp, st, use_tc(a) ? w.lg1 : nullptr));
     // round 2, CoPoNeRF.py:467-473: query_repeat_embed(cat(encode_latent(R1), local_coords)); the z_embed
     // channels are the same for every sample of a ray, so they enter as a per-ray bias.
     CPN_TRY(dense_simt(a, w.r1, CPN_LATENT, pw::WET, pw::BE, w.zemb, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_LATENT, 0, st));
     CPN_TRY(dense_simt(a, w.zemb, CPN_HIDDEN, pw::WQRA_T, pw::BQR, w.rbias, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_HIDDEN, 0, st));
     CPN_TRY(launch_gemm_simt(w.local16, 16, W + pw::WQRB_T, nullptr, w.rbias, 2 * a.S, w.K1, CPN_HIDDEN, R, CPN_HIDDEN,
                              16, 1, st));
-    if (use_tc(a))
-      CPN_TRY(launch_gemm_tc(a.weights, 6, w.K1, CPN_HIDDEN, w.Kk, CPN_HIDDEN, R, 0, tc_scheme(a), 1, 1, st));
+    if (use_tc(a))   // query_repeat_embed_2 with the round-2 logits <Q2, Q> / 11.31 (CoPoNeRF.py:474) as its epilogue
+      CPN_TRY(launch_gemm_tc(a.weights, 6, w.K1, CPN_HIDDEN, w.lg2, 0, R, 0, tc_scheme(a) | CPN_TC_OUT_ROWDOT, 1, 1, st, w.Qe,
+                             11.31f));
     else
       CPN_TRY(dense_simt(a, w.K1, CPN_HIDDEN, pw::WQR2T, pw::BQR2, w.Kk, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
-    CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, w.V, w.r1, z_all, st));
+    CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, w.V, w.r1, z_all, st, use_tc(a) ? w.lg2 : nullptr));
     CPN_TRY(launch_ray_epilogue(a, ray0, nr, w.wp, w.seg, st));
     return CPN_OK;
 }

@@ -222,10 +222,17 @@ int cpn_gemm_simt(const float* A, int lda, const float* wt, const float* bias, f
 #define CPN_TC_F16X3 4   /* three fp16 MMAs per product; default is fp16 + two e4m3 correction MMAs */
 #define CPN_TC_PAIR 16   /* experiment: cta_group::2 CTA pairs, each SM stages half of every weight tile (f8 scheme,
                           * M % 512 == 0); correct, but measured 20-28 % slower than independent CTAs on B200 */
+#define CPN_TC_OUT_CB16 32  /* fp32 output column-blocked: [row tile of 128][16-column block][row][16] (N = 128 layers) */
+#define CPN_TC_OUT_ROWDOT 64 /* set by cpn_gemm_tc_rowdot */
 #define CPN_TC_CLUSTER 8 /* experiment: the N-tile CTAs of a row tile form a cluster and multicast the A operand
                           * (halves L2 reads, but measured 8-18 % slower than independent CTAs on B200) */
 int cpn_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,
                 int out_div, int out_kchunks, void* stream);
+/* The same GEMM for a 128-wide layer whose output is only needed dotted with another (M, 128) matrix, row by row:
+ * out[m] = <act(A W^T + b)[m, :], dotv[m, :]> / div, with dotv in the CB16 layout (CPN_TC_OUT_CB16). Replaces
+ * key_map_2 / query_repeat_embed_2 followed by the einsum('bijk,bijk->bjk') / 11.31 of models/CoPoNeRF.py:450,474. */
+int cpn_gemm_tc_rowdot(const void* packed, int layer, const void* A, int lda, const float* dotv_cb16, float* out, int M,
+                       int relu, int mode, float div, void* stream);
 
 #ifdef __cplusplus
 }

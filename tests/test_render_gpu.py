@@ -249,3 +249,27 @@ def test_config4_shape_512_s128_properties():
     err = (sub["rgb"] - ref["rgb"]).abs().amax(dim=-1)[0, 0] / ref["rgb"].abs().max()
     assert float(err.median()) < 1e-5 and float(err.kthvalue(int(0.9 * 256)).values) < 1e-4
     assert torch.equal(sub["rgb"], out["rgb"][:, :, :256])
+
+
+def test_gemm_tc_cb16_and_rowdot_epilogues():
+    """query_embed_2 written column-blocked (CB16) and key_map_2 fused with the per-row dot product of the attention
+    logits (models/CoPoNeRF.py:446,450) against fp64."""
+    from coponerf_b200 import _lib
+    lib, eng, Wq, bq = _tc_setup("query_embed_2")
+    _, _, Wk, bk = _tc_setup("key_map_2")
+    torch.manual_seed(3)
+    M = 700
+    Mp = (M + 127) // 128 * 128
+    x = torch.randn(M, 128, device="cuda")
+    k1 = torch.randn(M, 128, device="cuda").relu()
+    qcb = torch.zeros(Mp * 128, device="cuda")
+    w = _p(eng.weights)
+    _lib.check(lib.cpn_gemm_tc(w, 5, _p(x), 128, _p(qcb), 0, M, 0, _lib.TC_OUT_CB16, 1, 1, _st()), "qe cb16")
+    qe = torch.nn.functional.linear(x.double(), Wq.double(), bq.double())
+    got = qcb.view(Mp // 128, 8, 128, 16).permute(0, 2, 1, 3).reshape(Mp, 128)[:M]
+    assert rel_err(got.cpu().numpy(), qe.cpu().numpy()) < 6e-5
+    out = torch.full((M,), float("nan"), device="cuda")
+    _lib.check(lib.cpn_gemm_tc_rowdot(w, 4, _p(k1), 128, _p(qcb), _p(out), M, 0, 0, 11.31, _st()), "rowdot")
+    kk = torch.nn.functional.linear(k1.double(), Wk.double(), bk.double())
+    ref = (kk * qe).sum(-1) / 11.31
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 1e-4
