@@ -65,22 +65,23 @@ __global__ void la_reduce_kernel(float* __restrict__ buf, size_t count, int nspl
   buf[i] = s;
 }
 
-// out[n][l][h][:] = (Q[n,l,h,:] KV[n,h]) * Z * S. CTA = (n, h, 64 consecutive l): KV[n,h] (32 x Dv) and Ksum sit in
-// shared memory; each of the 8 warps handles 8 positions, lane = d for the feature map / normaliser and lane = v
-// (in up to 8 chunks of 32, accumulated together) for the output.
-constexpr int LA_LT = 64, LA_MAXC = 8;
+// out[n][l][h][:] = (Q[n,l,h,:] KV[n,h]) * Z * S. CTA = (n, h, 64 consecutive l, one 256-wide slice of Dv): that slice of
+// KV[n,h] (32 x 256) and Ksum sit in shared memory; each of the 8 warps handles 8 positions, lane = d for the feature
+// map / normaliser and lane = v (8 chunks of 32, accumulated together) for the output.
+constexpr int LA_LT = 64, LA_MAXC = 8, LA_VS = 32 * LA_MAXC;
 __global__ void __launch_bounds__(256) la_out_kernel(const float* __restrict__ q, const float* __restrict__ KV,
                                                      const float* __restrict__ Ksum, int L, int S, int H, int Dv,
-                                                     float* __restrict__ out) {
-  extern __shared__ float kvs[];   // [32][Dv] + [32]
-  float* ksum_s = kvs + LA_D * Dv;
-  const int n = blockIdx.z, h = blockIdx.y, l0 = blockIdx.x * LA_LT;
+                                                     int vpasses, float* __restrict__ out) {
+  __shared__ float kvs[LA_D * LA_VS];
+  __shared__ float ksum_s[LA_D];
+  const int n = blockIdx.z / vpasses, vbase = (blockIdx.z % vpasses) * LA_VS, h = blockIdx.y, l0 = blockIdx.x * LA_LT;
+  const int vw = min(LA_VS, Dv - vbase);                       // width of this slice
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* kv = KV + ((size_t)n * H + h) * LA_D * Dv;
-  for (int i = threadIdx.x; i < LA_D * Dv; i += 256) kvs[i] = kv[i];
+  for (int i = threadIdx.x; i < LA_D * vw; i += 256) kvs[(i / vw) * LA_VS + i % vw] = kv[(size_t)(i / vw) * Dv + vbase + i % vw];
   if (threadIdx.x < LA_D) ksum_s[threadIdx.x] = Ksum[((size_t)n * H + h) * LA_D + threadIdx.x];
   __syncthreads();
-  const int nchunk = (Dv + 31) / 32;
+  const int nchunk = (vw + 31) / 32;
   for (int li = warp; li < LA_LT; li += 8) {
     const int l = l0 + li;
     if (l >= L) break;
@@ -98,11 +99,11 @@ __global__ void __launch_bounds__(256) la_out_kernel(const float* __restrict__ q
       const float qv = __shfl_sync(0xffffffffu, qd, d);
 #pragma unroll
       for (int c = 0; c < LA_MAXC; ++c)
-        if (c < nchunk && c * 32 + lane < Dv) acc[c] = fmaf(qv, kvs[d * Dv + c * 32 + lane], acc[c]);
+        if (c < nchunk && c * 32 + lane < vw) acc[c] = fmaf(qv, kvs[d * LA_VS + c * 32 + lane], acc[c]);
     }
 #pragma unroll
     for (int c = 0; c < LA_MAXC; ++c)
-      if (c < nchunk && c * 32 + lane < Dv) out[row * Dv + c * 32 + lane] = acc[c] * z * (float)S;
+      if (c < nchunk && c * 32 + lane < vw) out[row * Dv + vbase + c * 32 + lane] = acc[c] * z * (float)S;
   }
 }
 
@@ -139,12 +140,9 @@ extern "C" int cpn_linear_attention(const float* q, const float* k, const float*
     la_reduce_kernel<<<(unsigned)((ks_count + 255) / 256), 256, 0, st>>>(Ksum, ks_count, nsplit);
     CPN_CHECK_LAUNCH("la_reduce_kernel");
   }
-  if (Dv > 32 * LA_MAXC) {
-    cpn_set_error("cpn_linear_attention: Dv=%d above %d unsupported", Dv, 32 * LA_MAXC);
-    return CPN_ERR_ARG;
-  }
-  dim3 g2((L + LA_LT - 1) / LA_LT, H, N);
-  la_out_kernel<<<g2, 256, (LA_D * Dv + LA_D) * sizeof(float), st>>>(q, KV, Ksum, L, S, H, Dv, out);
+  const int vpasses = (Dv + LA_VS - 1) / LA_VS;
+  dim3 g2((L + LA_LT - 1) / LA_LT, H, N * vpasses);
+  la_out_kernel<<<g2, 256, 0, st>>>(q, KV, Ksum, L, S, H, Dv, vpasses, out);
   CPN_CHECK_LAUNCH("la_out_kernel");
   return CPN_OK;
 }

@@ -227,10 +227,13 @@ def linatt_case(name, H=8, D=32):
             f32(rng.standard_normal((N, L, H, Dv))))
 
 
-def ufc_param_shapes():
+def ufc_param_shapes(sizes=(16, 32, 64)):
     """name -> shape of every parameter of the reference UFC module (models/aggregation.py:358-490), without the
-    'feature_cost_aggregation.' prefix. 439 entries."""
+    'feature_cost_aggregation.' prefix. 439 entries. `sizes` are the feature-map sizes of the three levels; the
+    correlation volumes live at sizes[0] (16 at 256x256, the only geometry the reference itself supports; 32 for the
+    512x512 restatement of BASELINE config 4, where q_proj / k_proj take 256 + 8 * 32^2 inputs)."""
     sh = {}
+    corr = sizes[0]
 
     def enc(prefix, chans, k):
         for i, (ci, co) in enumerate(zip(chans[:-1], chans[1:])):
@@ -244,12 +247,12 @@ def ufc_param_shapes():
         sh[prefix + ".weight"] = (o, i)
         sh[prefix + ".bias"] = (o,)
 
-    for lvl, (nlayers, n, k) in enumerate(((2, 16, 3), (2, 32, 3), (1, 64, 5))):
+    for lvl, (nlayers, n, k) in enumerate(((2, sizes[0], 3), (2, sizes[1], 3), (1, sizes[2], 5))):
         for j in range(nlayers):
             p = f"layers.{lvl}.{j}"
             sh[p + ".pos_embed"] = (1, n * n, 1, 32)
-            lin(p + ".q_proj", 256, 2304)
-            lin(p + ".k_proj", 256, 2304)
+            lin(p + ".q_proj", 256, 256 + 8 * corr * corr)
+            lin(p + ".k_proj", 256, 256 + 8 * corr * corr)
             lin(p + ".v_proj", 256, 256)
             enc(p + ".v_proj_corr", (8, 8), 3)
             for m in ("mlp", "mlp_cross"):
@@ -272,11 +275,11 @@ def ufc_param_shapes():
     return sh
 
 
-def ufc_state_dict(seed=0):
+def ufc_state_dict(seed=0, sizes=(16, 32, 64)):
     """Seeded random parameters with the reference UFC's names and shapes (numpy PCG64)."""
     rng = np.random.default_rng(7000 + seed)
     sd = {}
-    for name, shape in ufc_param_shapes().items():
+    for name, shape in ufc_param_shapes(sizes).items():
         if name.endswith("pos_embed"):
             a = rng.normal(0, 0.02, shape)
         elif ".conv4d." in name and name.endswith(".1.weight") or ".norm" in name and name.endswith("weight"):
@@ -290,8 +293,8 @@ def ufc_state_dict(seed=0):
     return sd
 
 
-def ufc_inputs(seed=0, batch=1):
+def ufc_inputs(seed=0, batch=1, sizes=(16, 32, 64)):
     """Encoder feature pyramid as UFC.forward receives it: [(2B,512,16,16), (2B,256,32,32), (2B,128,64,64)]."""
     rng = np.random.default_rng(7500 + seed)
     f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
-    return [f32(rng.standard_normal((2 * batch, c, n, n))) for c, n in ((512, 16), (256, 32), (128, 64))]
+    return [f32(rng.standard_normal((2 * batch, c, n, n), dtype=np.float32)) for c, n in zip((512, 256, 128), sizes)]

@@ -69,3 +69,26 @@ def test_native_ufc_forward_matches_restatement():
     for a, b in zip(got_flows, ref_flows):
         assert a.shape == b.shape
         assert float((a.cpu() - b).abs().max()) <= 2e-3 * 64   # soft-argmax at temperature 0.02 amplifies c by 50
+
+
+def test_native_ufc_forward_at_512_sizes():
+    """BASELINE config 4: the cost aggregation at 512x512 (feature sizes 32 / 64 / 128, correlation size 32, a 128^4
+    = 1.07 GB volume `c`). The reference UFC is hard-wired to 256x256, so the oracle here is the
+    size-generic restatement that tests/test_ufc_orchestration_cpu.py pins to the reference at 256x256."""
+    from coponerf_b200 import ufc_native
+    cu, th = _ops()
+    sizes = (32, 64, 128)
+    sd = synth.ufc_state_dict(1, sizes)
+    feat = synth.ufc_inputs(1, 1, sizes)
+    ref_feats, ref_flows, ref_c = ufc_native.ufc_forward(sd, feat, 2, th)
+    sd_d = {k: v.cuda() for k, v in sd.items()}
+    got_feats, got_flows, got_c = ufc_native.ufc_forward(sd_d, [f.cuda() for f in feat], 2, cu)
+    torch.cuda.synchronize()
+    assert got_c.shape == (1, 1, 128, 128, 128, 128)
+    for a, b in zip(got_feats, ref_feats):
+        _close(a, b, tol=1e-4)
+    idx = torch.randint(0, ref_c.numel(), (1 << 20,), generator=torch.Generator().manual_seed(0))
+    assert float((got_c.reshape(-1)[idx.cuda()].cpu() - ref_c.reshape(-1)[idx]).abs().max()) <= 2e-5
+    for a, b in zip(got_flows, ref_flows):
+        assert a.shape == b.shape
+        assert float((a.cpu() - b).abs().max()) <= 2e-3 * 128
