@@ -5,11 +5,11 @@
 
 Workload (BASELINE.json configs[1]): one RealEstate10K-shape 256x256 stereo pair, all 65 536 target rays,
 S = 64 samples per epipolar line; at N > 1 one such pair per rank (configs[2]: pairs shard across ranks,
-one NCCL gather of the final pixels to rank 0, weak scaling). A "step" renders the whole image(s): the
-per-pair cost aggregation (UFC.forward on the encoder's feature pyramid -> refined features, flows), per-pair
-setup, and every ray through CoPoNeRF.forward(z=..., rel_pose=..., flow=...). The ResNet34 encoder and the pose
-head stay reference PyTorch modules (BASELINE.json) and are not in the timed path: their outputs (the feature
-pyramid, conv_map and rel_pose) are the synthetic inputs. `--stage render` times the render half alone.
+one NCCL gather of the final pixels to rank 0, weak scaling). A "step" (default `--stage full`) is the whole
+drop-in call on one pair, images in, pixels out: get_z() (ResNet-34 encoder + conv_map in PyTorch/cuDNN, which
+BASELINE.json says stays; cost aggregation, pose features and pose head on the sm_100a operators) followed by
+forward(val=True) over every ray with the estimated pose. `--stage pair` starts from the encoder's feature pyramid
+(cost aggregation + render), `--stage render` times the render half alone (z, rel_pose, flow given).
 
 `value`  : inputs resident in HBM, timed on the device with CUDA events, L2 flushed between steps.
 `e2e`    : the same through the drop-in forward() with HOST inputs: pinned host -> device copies of the
@@ -49,9 +49,40 @@ def parse():
     ap.add_argument("--lanes", type=int, default=2, help="chunks in flight on internal streams")
     ap.add_argument("--simt", action="store_true", help="fp32 CUDA-core GEMMs only (cross-check path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--stage", default="pair", choices=["pair", "render"],
-                    help="pair: cost aggregation (UFC) + render per step; render: render half only (z given)")
+    ap.add_argument("--stage", default="full", choices=["full", "pair", "render"],
+                    help="full: get_z (encoder, cost aggregation, pose) + render per step; pair: cost aggregation "
+                         "(UFC) + render from a given feature pyramid; render: render half only (z given)")
     return ap.parse_args()
+
+
+WORKLOADS = {
+    "full": "256x256 stereo pair, 65536 rays, S=64: get_z (ResNet-34 encoder, cost aggregation, pose features + pose "
+            "head) + forward(val=True), images in, pixels out",
+    "pair": "256x256 stereo pair, 65536 rays, S=64: cost aggregation (UFC) + render; encoder and pose head outputs are inputs",
+    "render": "256x256 stereo pair, 65536 rays, S=64 (render half: forward with z given)",
+}
+
+
+def cpu_pair_stage(stage, seed, timings=None):
+    """Seconds the CPU restatement needs for the per-pair work of one image (reference formulation, incl. the
+    Python positional-encoding loop of backbone.py:269-273), and its outputs (z, rel_pose, flow) for `full`."""
+    from coponerf_b200 import synth, ufc_native
+    from oracle.ufc_ops_torch import TorchOps
+    if stage == "full":
+        from oracle import pair_oracle
+        sd = synth.full_state_dict(0)
+        inp = synth.make_input(H, W, None, seed=seed, pose_set="frontal")
+        pair_oracle.get_z(sd, inp, fast_pos=True)        # warm-up (thread pools, allocator)
+        t0 = time.perf_counter()
+        res = pair_oracle.get_z(sd, inp, fast_pos=False, timings=timings)
+        return time.perf_counter() - t0, res
+    if stage == "pair":
+        sdc, pyc = synth.ufc_state_dict(0), synth.ufc_inputs(seed)
+        ufc_native.ufc_forward(sdc, pyc, 2, TorchOps())
+        t0 = time.perf_counter()
+        ufc_native.ufc_forward(sdc, pyc, 2, TorchOps())
+        return time.perf_counter() - t0, None
+    return 0.0, None
 
 
 def workload(seed):
@@ -128,6 +159,9 @@ def run_reference(args, rank):
     torch.set_num_threads(cores)
     inp, z, rel_pose, flow = workload(10)
     sd = synth.render_state_dict(0)
+    t_pair, res = cpu_pair_stage(args.stage, 10)
+    if res is not None:       # render from the restatement's own features / estimated pose / flows
+        z, rel_pose, flow = res
     sub = {"context": inp["context"], "query": dict(inp["query"])}
     idx = torch.arange(0, N_RAYS, N_RAYS // CPU_SAMPLE_RAYS)[:CPU_SAMPLE_RAYS]
     sub["query"]["uv"] = inp["query"]["uv"][:, :, idx].contiguous()
@@ -142,27 +176,15 @@ def run_reference(args, rank):
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    t_ufc = 0.0
-    if args.stage == "pair":   # the per-pair cost aggregation, once per image (CPU restatement of UFC.forward)
-        from coponerf_b200 import ufc_native
-        from oracle.ufc_ops_torch import TorchOps
-        ufc_sd, pyr = synth.ufc_state_dict(0), synth.ufc_inputs(10)
-        ufc_native.ufc_forward(ufc_sd, pyr, 2, TorchOps())
-        t1 = time.perf_counter()
-        ufc_native.ufc_forward(ufc_sd, pyr, 2, TorchOps())
-        t_ufc = time.perf_counter() - t1
-    # whole-image rate: one cost aggregation + 65536 rays at the sampled per-ray cost
-    v = N_RAYS / (t_ufc + (N_RAYS / CPU_SAMPLE_RAYS) * dt / args.steps)
+    # whole-image rate: the per-pair work once + 65536 rays at the sampled per-ray cost
+    v = N_RAYS / (t_pair + (N_RAYS / CPU_SAMPLE_RAYS) * dt / args.steps)
     sample = (f"{CPU_SAMPLE_RAYS} evenly strided rays of the 65536-ray image per step (chunks of 512), torch CPU fp32, "
-              f"extrapolated to the image; cost aggregation timed once ({t_ufc * 1e3:.0f} ms)")
+              f"extrapolated to the image; per-pair stage ({args.stage}) timed once ({t_pair * 1e3:.0f} ms)")
     line = {
         "impl": "reference", "metric": "rendered rays/sec at 256x256 stereo", "value": v, "unit": "rays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": ("256x256 stereo pair, 65536 rays, S=64: cost aggregation (UFC) + render; encoder and "
-                                "pose head outputs are inputs" if args.stage == "pair" else
-                                "256x256 stereo pair, 65536 rays, S=64 (render half: forward with z given)"),
-                   "stage": args.stage, "sample": sample},
+        "config": {"workload": WORKLOADS[args.stage], "stage": args.stage, "sample": sample},
         "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -195,7 +217,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     model = CoPoNeRF(n_view=2, npoints=S, chunk_rays=args.chunk_rays, lanes=args.lanes)
-    model.load_state_dict(synth.render_state_dict(0), strict=False)
+    full = args.stage == "full"
+    if full:
+        model.load_state_dict(synth.full_state_dict(0), strict=True)
+    else:
+        model.load_state_dict(synth.render_state_dict(0), strict=False)
     model = model.to(dev).eval()
     model.H, model.W = H, W
     eng = model.engine()
@@ -236,7 +262,11 @@ def main():
     def device_step():
         # feature re-layout included every step (the cache would hide it): new pair state each image
         eng._feat_cache.clear()
-        if with_ufc:   # refined features + flows of this pair; conv_map (z[3]) comes from the encoder side
+        if full:       # images -> features, estimated pose, flows -> pixels
+            z, rel, flows = model.get_z(inp_d)
+            state["z"], state["flow"], state["rel"] = z, flows, rel
+            st = eng.prepare_pair(inp_d, z, rel, flows, H, W, True)
+        elif with_ufc:   # refined features + flows of this pair; conv_map (z[3]) comes from the encoder side
             feats, flows, _c = ufc_native.ufc_forward(ufc_sd, pyr_d, 2, ufc_ops)
             state["z"], state["flow"] = feats + [z_d[3]], flows
             st = eng.prepare_pair(inp_d, state["z"], rel_d, flows, H, W, True)
@@ -254,6 +284,12 @@ def main():
         eng._feat_cache.clear()
         inp = {"context": {k: todev(v) for k, v in host["context"].items()},
                "query": {k: todev(v) for k, v in host["query"].items()}}
+        if full:       # the call a user makes: forward(input, val=True) with z=None
+            out = model(inp, val=True)
+            if world > 1:
+                dist.gather(out["rgb"], gather_buf, dst=0)
+            rgb_pinned.copy_(out["rgb"], non_blocking=True)
+            return out
         if with_ufc:
             feats, fl, _c = ufc_native.ufc_forward(ufc_sd, [todev(t) for t in pyr_host], 2, ufc_ops)
             z = feats + [todev(z_host[3])]
@@ -268,8 +304,9 @@ def main():
 
     h2d = sum(t.numel() * t.element_size() for d in host.values() for t in d.values())
     nbytes = lambda ts: sum(t.numel() * t.element_size() for t in ts)
-    h2d += (nbytes(pyr_host) + nbytes([z_host[3]])) if with_ufc else (nbytes(z_host) + nbytes(flow_host))
-    h2d += rel_host.numel() * 4
+    if not full:
+        h2d += (nbytes(pyr_host) + nbytes([z_host[3]])) if with_ufc else (nbytes(z_host) + nbytes(flow_host))
+        h2d += rel_host.numel() * 4
     d2h = N_RAYS * 3 * 4 + 2 * N_RAYS * S * 2 * 4    # rgb + the reference's out['pixel_val'].cpu()
 
     def barrier():
@@ -319,6 +356,10 @@ def main():
     launches = args.steps * (eng.last_launch_count + 6)   # + 4 feature re-layouts, pair_setup, pair_prologue
     if with_ufc:
         launches += args.steps * ufc_ops.launches_per_forward
+    if full:       # cost aggregation + pose operators of one get_z (the cuDNN encoder kernels are not ours: not counted)
+        n0 = model._ufc_ops.launches
+        model.get_z(inp_d)
+        launches += args.steps * (model._ufc_ops.launches - n0)
     ms_e2e = timed(e2e_step, args.steps, 2)
     clk = clocks.stop() if clocks else None
 
@@ -342,10 +383,7 @@ def main():
         "metric": "rendered rays/sec at 256x256 stereo", "value": value, "unit": "rays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": ("256x256 stereo pair, 65536 rays, S=64: cost aggregation (UFC) + render; encoder and "
-                                "pose head outputs are inputs" if with_ufc else
-                                "256x256 stereo pair, 65536 rays, S=64 (render half: forward with z given)"),
-                   "stage": args.stage, "pairs_per_gpu": 1, "chunk_rays": args.chunk_rays, "lanes": args.lanes, "l2": "flushed between timed steps (256 MB write)",
+        "config": {"workload": WORKLOADS[args.stage], "stage": args.stage, "pairs_per_gpu": 1, "chunk_rays": args.chunk_rays, "lanes": args.lanes, "l2": "flushed between timed steps (256 MB write)",
                    "gemm_path": "simt-fp32" if args.simt else "tcgen05: fp16 head + two e4m3 correction MMAs per product (fp32 accumulate)",
                    "parallelism": f"pairs sharded over {world} GPU(s), one NCCL gather of rgb" if world > 1 else "1 GPU"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -374,9 +412,10 @@ def main():
         sd = synth.render_state_dict(0)
         # the oracle renders from the same per-pair state the CUDA path used (the native UFC's outputs when the
         # cost aggregation is part of the step; its own parity is covered by tests/test_ufc_*_gpu.py)
-        z_cpu = [t.detach().float().cpu().contiguous() for t in state["z"]] if with_ufc else z_h
-        flow_cpu = tuple(t.detach().cpu() for t in state["flow"]) if with_ufc else flow_h
-        run = lambda: render_oracle.render_forward(sd, sub, z_cpu, rel_h, flow_cpu, H, W, S, True, chunk=512)
+        z_cpu = [t.detach().float().cpu().contiguous() for t in state["z"]] if (with_ufc or full) else z_h
+        flow_cpu = tuple(t.detach().cpu() for t in state["flow"]) if (with_ufc or full) else flow_h
+        rel_cpu = state["rel"].detach().cpu() if full else rel_h
+        run = lambda: render_oracle.render_forward(sd, sub, z_cpu, rel_cpu, flow_cpu, H, W, S, True, chunk=512)
         run()
         t0 = time.perf_counter()
         ref = run()
@@ -384,18 +423,20 @@ def main():
         ref = run()
         t2 = time.perf_counter()
         dt = min(t1 - t0, t2 - t1)
-        t_ufc = 0.0
-        if with_ufc:
-            from oracle.ufc_ops_torch import TorchOps
-            sdc, pyc = synth.ufc_state_dict(0), synth.ufc_inputs(10)
-            ufc_native.ufc_forward(sdc, pyc, 2, TorchOps())
-            t3 = time.perf_counter()
-            ufc_native.ufc_forward(sdc, pyc, 2, TorchOps())
-            t_ufc = time.perf_counter() - t3
+        tm = {}
+        t_pair, pair_res = cpu_pair_stage(args.stage, 10, tm)
         sample = (f"{CPU_SAMPLE_RAYS} evenly strided rays of the same image (chunks of 512), best of 2, extrapolated to "
-                  f"the image; cost aggregation timed once ({t_ufc * 1e3:.0f} ms)")
-        line["cpu_baseline"] = {"value": N_RAYS / (t_ufc + (N_RAYS / CPU_SAMPLE_RAYS) * dt), "unit": "rays/s",
+                  f"the image; per-pair stage ({args.stage}) timed once ({t_pair * 1e3:.0f} ms"
+                  + (f": encoder {tm['encoder'] * 1e3:.0f}, cost aggregation {tm['ufc'] * 1e3:.0f}, pose {tm['pose'] * 1e3:.0f}"
+                     if tm else "") + ")")
+        line["cpu_baseline"] = {"value": N_RAYS / (t_pair + (N_RAYS / CPU_SAMPLE_RAYS) * dt), "unit": "rays/s",
                                 "cores": cores, "kind": "port", "sample": sample}
+        if pair_res is not None:     # get_z parity of this very step against the CPU restatement
+            zc, pc, fc = pair_res
+            line["pair_parity"] = {
+                "rel_pose_max_abs_err": float((state["rel"].cpu() - pc).abs().max()),
+                "z_max_rel_err": max(float((a.cpu() - b).abs().max() / b.abs().max()) for a, b in zip(state["z"], zc)),
+                "flow_max_abs_err_px": max(float((a.cpu() - b).abs().max()) for a, b in zip(state["flow"][:2], fc[:2]))}
         got = state["out"]["rgb"][0, 0].cpu()[idx]
         want = ref["rgb"][0, 0]
         per_ray_err = (got - want).abs().max(dim=-1).values / want.abs().max()

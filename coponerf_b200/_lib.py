@@ -63,6 +63,13 @@ class Conv4dArgs(ctypes.Structure):
                [("workspace_bytes", ctypes.c_size_t)]
 
 
+class PoseHeadArgs(ctypes.Structure):
+    """cpn_pose_head_args (include/coponerf_b200.h)."""
+    _fields_ = [("B", ctypes.c_int32), ("reserved", ctypes.c_int32)] + \
+               [(n, ctypes.c_void_p) for n in ("h0", "w2", "b2", "w4", "b4", "rw1", "rb1", "rw3", "rb3", "rw5", "rb5",
+                                               "tw1", "tb1", "tw3", "tb3", "tw5", "tb5", "rel_pose")]
+
+
 # symbol -> (restype, argtypes); every entry point include/coponerf_b200.h declares
 SIGNATURES = {
     "cpn_version": (ctypes.c_int, []),
@@ -105,6 +112,17 @@ SIGNATURES = {
     "cpn_correlation_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),
     "cpn_correlation": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_size_t,
                                                                                    ctypes.c_void_p]),
+    "cpn_dual_softmax_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 2),
+    "cpn_dual_softmax": (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 2 + [ctypes.c_void_p, ctypes.c_size_t,
+                                                                                    ctypes.c_void_p]),
+    "cpn_gemm_tn_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),
+    "cpn_gemm_tn": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                   ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_void_p, ctypes.c_size_t,
+                                                                           ctypes.c_void_p]),
+    "cpn_linear_skinny_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),
+    "cpn_linear_skinny": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_size_t,
+                                                                                    ctypes.c_void_p]),
+    "cpn_pose_head": (ctypes.c_int, [ctypes.POINTER(PoseHeadArgs), ctypes.c_void_p]),
     "cpn_gemm_simt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_void_p]),

@@ -29,6 +29,7 @@ SOURCES = [
     ("conv4d.cu", []),
     ("linear_attention.cu", []),
     ("ufc_ops.cu", []),
+    ("pose_feat.cu", []),
 ]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

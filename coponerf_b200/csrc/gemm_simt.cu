@@ -11,6 +11,9 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16, NT = 256;
 
+// activation code `relu`: 0 none, 1 ReLU, 2 exact GELU (nn.GELU default, erf form)
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+
 __global__ void __launch_bounds__(NT, 2)
 gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Wt, const float* __restrict__ bias,
                  const float* __restrict__ rowbias, int rows_per_bias, float* __restrict__ C, int ldc, int M, int N,
@@ -102,8 +105,10 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
         float4 bb = *reinterpret_cast<const float4*>(rbp + n);
         v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
       }
-      if (relu) {
+      if (relu == 1) {
         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      } else if (relu == 2) {
+        v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
       }
       if (out_div != 0.f) {
         v.x /= out_div; v.y /= out_div; v.z /= out_div; v.w /= out_div;
@@ -188,8 +193,10 @@ gemm_simt_small_kernel(const float* __restrict__ A, int lda, const float* __rest
       float4 bb = *reinterpret_cast<const float4*>(rowbias + (size_t)(m / rows_per_bias) * N + n);
       v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
     }
-    if (relu) {
+    if (relu == 1) {
       v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    } else if (relu == 2) {
+      v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
     }
     if (out_div != 0.f) {
       v.x /= out_div; v.y /= out_div; v.z /= out_div; v.w /= out_div;

@@ -2,14 +2,16 @@
 render path, get_z()/forward() signatures and output dictionary (models/CoPoNeRF.py:19-104,159-576),
 whose per-ray stage runs on the sm_100a kernels of libcoponerf_b200.so.
 
-The image encoder, pose head and (for now) the cost aggregation stay the reference's own PyTorch modules
-(BASELINE.json: "models/backbone.py and the train/test drivers stay"); they are attached with
-`attach_pair_stage()` from a reference model instance, or get_z() results are passed in through
-forward(z=..., rel_pose=..., flow=...) exactly as test.py:173-189 does.
+get_z() is standalone too (coponerf_b200/pair_stage.py): the ResNet-34 image encoder stays PyTorch/cuDNN
+(BASELINE.json: "models/backbone.py and the train/test drivers stay"), the cost aggregation and the pose
+features / pose head run on the sm_100a operators. The module carries all 744 state_dict keys of the reference
+model, so `load_state_dict(torch.load(ckpt)['model'], strict=False)` (test.py:143) works unchanged.
+`attach_pair_stage(reference_model)` is kept for A/B runs against the reference's own get_z().
 """
 import torch
 import torch.nn as nn
 
+from . import pair_stage
 from .render import RenderEngine
 
 
@@ -54,6 +56,9 @@ class CoPoNeRF(nn.Module):
         hidden = 128
         if num_hidden_units_phi != hidden:
             raise ValueError("the sm_100a render path is built for num_hidden_units_phi == 128")
+        # per-pair stage: encoder, conv_map, feature_cost_aggregation, cross_attention, pose / rotation / translation
+        # regressors (models/CoPoNeRF.py:31-69) as parameter containers with the reference's names
+        pair_stage.PairStage.build_into(self)
         # render-path parameters, same names and shapes as models/CoPoNeRF.py:71-104
         self.query_encode_latent = nn.Conv2d(latent + 3, latent, 1)
         self.query_encode_latent_2 = nn.Conv2d(latent, latent // 2, 1)
@@ -105,10 +110,16 @@ class CoPoNeRF(nn.Module):
 
     # ------------------------------------------------------------------ reference API
     def get_z(self, input, val=False):
-        """models/CoPoNeRF.py:159-206. Delegates to the attached per-pair stage."""
+        """models/CoPoNeRF.py:159-206: image features, estimated relative pose, correspondence fields."""
         if self._pair_stage is None:
-            raise RuntimeError("get_z() needs the per-pair stage: call attach_pair_stage(reference_model), or pass "
-                               "z=, rel_pose=, flow= to forward()")
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("coponerf_b200.CoPoNeRF.get_z() runs on CUDA only: call .cuda() first (no CPU fallback)")
+            if self._ufc_ops is None:
+                from .ufc_ops import CudaOps
+                self._ufc_ops = CudaOps()
+            with torch.cuda.device(dev):
+                return pair_stage.get_z(self, input, self._ufc_ops)
         ref = self._pair_stage
         fca = ref.feature_cost_aggregation
         if not self.native_ufc:

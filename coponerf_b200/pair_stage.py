@@ -1,0 +1,156 @@
+"""The per-pair stage behind CoPoNeRF.get_z() (models/CoPoNeRF.py:159-206), standalone: no reference code is
+needed at run time, and a reference checkpoint loads key for key.
+
+  image encoder     torchvision ResNet-34 without the first max-pool, conv_map 7x7 (models/backbone.py:10-104,
+                    models/CoPoNeRF.py:66-69): stays PyTorch/cuDNN, as BASELINE.json asks ("models/backbone.py ...
+                    stay"); run in strict fp32 (TF32 off) so the features equal the reference's fp32 ones
+  cost aggregation  ufc_native.ufc_forward over the sm_100a operators (models/aggregation.py)
+  pose features     pose_native: CrossBlock + regressors over the sm_100a operators (models/backbone.py:262-431)
+
+Parameters live in containers that only reproduce the reference's state_dict names and shapes; none of the
+reference's module code exists here.
+"""
+import torch
+import torch.nn as nn
+
+from . import pose_native, synth, ufc_native
+
+
+class ParamTree(nn.Module):
+    """Parameters registered under dotted state_dict names ('layers.0.1.q_proj.weight'): one nested container per
+    name component. Initialisation is generic (inference framework: real values come from a checkpoint)."""
+
+    def __init__(self, shapes=None):
+        super().__init__()
+        for name, shape in (shapes or {}).items():
+            self._add(name.split("."), shape)
+
+    def _add(self, parts, shape):
+        if len(parts) == 1:
+            self.register_parameter(parts[0], nn.Parameter(_init(parts[0], shape)))
+            return
+        if parts[0] not in self._modules:
+            self.add_module(parts[0], ParamTree())
+        self._modules[parts[0]]._add(parts[1:], shape)
+
+
+def _init(leaf, shape):
+    if len(shape) == 1:
+        return torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
+    t = torch.empty(shape)
+    if leaf == "pos_embed":
+        return nn.init.trunc_normal_(t, std=0.02)
+    fan_in = 1
+    for s in shape[1:]:
+        fan_in *= s
+    bound = 1.0 / fan_in ** 0.5
+    return t.uniform_(-bound, bound)
+
+
+# name -> shape of the pose-half parameters (models/CoPoNeRF.py:33-52, models/backbone.py:262-277,383-398)
+POSE_PARAM_SHAPES = {
+    "cross_attention.norm1.weight": (256,), "cross_attention.norm1.bias": (256,),
+    "cross_attention.cross_attn.qkv.weight": (768, 256),               # unused by forward (noess=False), kept for the state_dict
+    "cross_attention.cross_attn.proj_fundamental.weight": (256, 262),
+    "cross_attention.cross_attn.proj_fundamental.bias": (256,),
+    "cross_attention.norm2.weight": (256,), "cross_attention.norm2.bias": (256,),
+    "cross_attention.mlp.fc1.weight": (1024, 256), "cross_attention.mlp.fc1.bias": (1024,),
+    "cross_attention.mlp.fc2.weight": (256, 1024), "cross_attention.mlp.fc2.bias": (256,),
+    "cross_attention.norm.weight": (256,), "cross_attention.norm.bias": (256,),
+    "pose_regressor.0.weight": (512, (16 * 16 + 6) * 256 * 2), "pose_regressor.0.bias": (512,),
+    "pose_regressor.2.weight": (256, 512), "pose_regressor.2.bias": (256,),
+    "pose_regressor.4.weight": (256, 256), "pose_regressor.4.bias": (256,),
+    "rotation_regressor.1.weight": (64, 128), "rotation_regressor.1.bias": (64,),
+    "rotation_regressor.3.weight": (32, 64), "rotation_regressor.3.bias": (32,),
+    "rotation_regressor.5.weight": (6, 32), "rotation_regressor.5.bias": (6,),
+    "translation_regressor.1.weight": (64, 128), "translation_regressor.1.bias": (64,),
+    "translation_regressor.3.weight": (32, 64), "translation_regressor.3.bias": (32,),
+    "translation_regressor.5.weight": (3, 32), "translation_regressor.5.bias": (3,),
+}
+
+
+class SpatialEncoder(nn.Module):
+    """models/backbone.py:10-104 as CoPoNeRF configures it (resnet34, num_layers=5, use_first_pool=False): returns
+    the three coarsest ResNet stages, coarsest first. Parameter names: 'model.<torchvision resnet34 names>'."""
+
+    def __init__(self):
+        super().__init__()
+        import torchvision
+        self.model = torchvision.models.resnet34(weights=None)
+        self.model.fc = nn.Sequential()
+        self.model.avgpool = nn.Sequential()
+
+    def forward(self, x):
+        m = self.model
+        x = m.relu(m.bn1(m.conv1(x)))
+        x = m.layer1(x)                       # no max-pool (use_first_pool=False)
+        l2 = m.layer2(x)
+        l3 = m.layer3(l2)
+        l4 = m.layer4(l3)
+        return [l4, l3, l2]
+
+
+class PairStage(nn.Module):
+    """Owns every parameter of get_z(): 'encoder.*', 'conv_map.*', 'feature_cost_aggregation.*', 'cross_attention.*',
+    '{pose,rotation,translation}_regressor.*'. It is mixed into coponerf_b200.model.CoPoNeRF so the names carry no prefix."""
+
+    @staticmethod
+    def build_into(module):
+        module.encoder = SpatialEncoder()
+        module.conv_map = nn.Conv2d(3, 64, kernel_size=7, stride=1, padding=3)
+        module.feature_cost_aggregation = ParamTree(synth.ufc_param_shapes())
+        pose = {}
+        for k, v in POSE_PARAM_SHAPES.items():
+            pose.setdefault(k.split(".")[0], {})[k.split(".", 1)[1]] = v
+        for top, shapes in pose.items():
+            setattr(module, top, ParamTree(shapes))
+
+
+_IMAGENET_MEAN = (0.485, 0.456, 0.406)
+_IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def encode_images(model, rgb):
+    """rgb (B, n_ctxt, H, W, 3) in [-1, 1] -> (ResNet pyramid [3 tensors], conv_map features). CoPoNeRF.py:171-184
+    with utils.normalize_imagenet (utils_training/utils.py:247-257)."""
+    x = torch.flatten(rgb, 0, 1).permute(0, 3, 1, 2).to(torch.float32)
+    x = (x + 1) / 2.
+    mean = torch.tensor(_IMAGENET_MEAN, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(_IMAGENET_STD, device=x.device).view(1, 3, 1, 1)
+    x = (x - mean) / std
+    if x.is_cuda:
+        with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
+            return model.encoder(x), model.conv_map(x)
+    return model.encoder(x), model.conv_map(x)
+
+
+def _sub_state(model, prefix):
+    return {k[len(prefix) + 1:]: v for k, v in model.state_dict(keep_vars=True).items() if k.startswith(prefix + ".")}
+
+
+@torch.no_grad()
+def get_z(model, input, ops):
+    """models/CoPoNeRF.py:159-206. Returns (z list of 4 feature maps, rel_pose (B, 4, 4), flow tuple)."""
+    ctx = input["context"]
+    dev = next(model.parameters()).device
+    rgb = ctx["rgb"].to(dev)
+    B, n_ctxt, H, W, _ = rgb.shape
+    if n_ctxt != 2:
+        raise ValueError("the per-pair stage is built for two context views")
+    model.H, model.W = H, W
+    if model.training:
+        raise RuntimeError("coponerf_b200 is an inference path: call .eval() (BatchNorm must use running statistics)")
+    z, z_conv = encode_images(model, rgb)
+    cache = model.__dict__.setdefault("_sd_cache", {})
+    ver = tuple((p.data_ptr(), p._version) for p in model.parameters())
+    if cache.get("ver") != ver:
+        cache["ver"] = ver
+        cache["ufc"] = _sub_state(model, "feature_cost_aggregation")
+        full = model.state_dict(keep_vars=True)
+        cache["pose"] = {k: v for k, v in full.items()
+                         if k.split(".")[0] in ("cross_attention", "pose_regressor", "rotation_regressor",
+                                                "translation_regressor")}
+    feats, flows, c = ufc_native.ufc_forward(cache["ufc"], z, model.n_view, ops)
+    tokens = feats[-1].flatten(-2, -1).transpose(-1, -2)            # (2B, L, 256)
+    rel_pose = pose_native.pose_from_features(cache["pose"], tokens, c, ctx["intrinsics"], H, ops)
+    return feats + [z_conv], rel_pose, flows

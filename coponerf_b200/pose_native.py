@@ -1,0 +1,146 @@
+"""Pose half of the per-pair stage, re-stated as functions of the model's state_dict over an operator set:
+CrossBlock / CrossAttention (models/backbone.py:262-431), get_positional_encodings (:209-278) and the pose,
+rotation and translation regressors with r6d2mat (models/CoPoNeRF.py:33-52,106-128,194-204).
+
+`ops` supplies the operators. The product backend is `coponerf_b200.ufc_ops.CudaOps` (sm_100a kernels behind the
+C-ABI); tests check this orchestration on CPU against the unmodified reference with the PyTorch restatement of the
+same operators (oracle/ufc_ops_torch.py).
+
+What changes against the reference's formulation (results equal up to fp32 summation order):
+  * attn_fundamental_2 is the transpose of attn_fundamental_1 (both are softmax(-1) * softmax(-2) of the same
+    matrix), so only P = attn_fundamental_1 is formed and
+        fundamental_1 = v1^T (P v1),   fundamental_2 = (P v2)^T v2;
+    P v1 and P v2 are one (L x L) x (L x 2(C+6)) product.
+  * the Python double loop that builds the positional encodings (4096 tiny matmuls, ~0.3 s per call; SURVEY.md
+    section 8(f) rank 1) is one batched matmul, memoised by the intrinsics values.
+"""
+from collections import OrderedDict
+
+import torch
+
+_POS_CACHE = OrderedDict()
+
+
+def positional_encodings(B, N, intr, device=None):
+    """get_positional_encodings (backbone.py:209-278): (B, N, 6) = (y'^2, x'^2, x'y', y', x', 1) with
+    [x', y', w'] = K^-1 [x, y, 1] on the linspace(-1, 1) grid, stored at index k * w + j for grid point
+    (x_k, y_j) exactly as the reference does. `intr` = [fx, fy, cx, cy], each (B, 1), of view 0, rows 0-1 of K
+    divided by H. Memoised by value (the intrinsics of a dataset rarely change between pairs)."""
+    vals = torch.stack([t.detach().reshape(-1) for t in intr]).to("cpu", torch.float32)     # (4, B)
+    key = (B, N, vals.numpy().tobytes(), str(device))
+    hit = _POS_CACHE.get(key)
+    if hit is not None:
+        _POS_CACHE.move_to_end(key)
+        return hit
+    h, w = 48, 64
+    if N == 64 * 64:
+        h, w = 64, 64
+    elif N != 48 * 64:
+        side = int(round(N ** 0.5))
+        if side * side != N:
+            raise ValueError(f"unexpected resolution for positional encoding: N = {N}")
+        h = w = side            # resolution-generic restatement (the reference asserts on anything else)
+    fx, fy, cx, cy = vals
+    if float(cx[0] * cy[0]) == 0.0:
+        raise ValueError("principal point is in the upper left corner: the reference stops in pdb here "
+                         "(backbone.py:244-246)")
+    hpix, wpix = cy * 2, cx * 2
+    K = torch.zeros(B, 3, 3)
+    K[:, 0, 0] = (fx / wpix) * 2
+    K[:, 1, 1] = (fy / hpix) * 2
+    K[:, 0, 2] = (cx / wpix) * 2 - 1
+    K[:, 1, 2] = (cy / hpix) * 2 - 1
+    K[:, 2, 2] = 1
+    Kinv = torch.inverse(K)
+    ys = torch.linspace(-1, 1, steps=h)
+    xs = torch.linspace(-1, 1, steps=w)
+    p3 = ys.unsqueeze(0).repeat(B, w)
+    p4 = xs.repeat_interleave(h).unsqueeze(0).repeat(B, 1)
+    kk, jj = torch.meshgrid(torch.arange(w), torch.arange(h), indexing="ij")
+    kk, jj = kk.reshape(-1), jj.reshape(-1)
+    pts = torch.stack((xs[kk], ys[jj], torch.ones(kk.numel())))        # (3, w*h)
+    wv = Kinv @ pts                                                     # (B, 3, w*h)
+    idx = kk * w + jj
+    p3[:, idx] = wv[:, 1] / wv[:, 2]
+    p4[:, idx] = wv[:, 0] / wv[:, 2]
+    pos = torch.ones(B, N, 6)
+    pos[:, :, :5] = torch.stack((p3 * p3, p4 * p4, p3 * p4, p3, p4), dim=2)
+    if device is not None:
+        pos = pos.to(device)
+    _POS_CACHE[key] = pos
+    while len(_POS_CACHE) > 16:
+        _POS_CACHE.popitem(last=False)
+    return pos
+
+
+def _padded_proj(sd, p, D, cache):
+    """proj_fundamental.weight (C, C+6) as the zero-padded [C+6 -> D][C] matrix the A^T B operator takes."""
+    w = sd[p + ".cross_attn.proj_fundamental.weight"]
+    key = (w.data_ptr(), w._version, D)
+    hit = cache.get(key)
+    if hit is None:
+        wt = torch.zeros(D, w.shape[0], dtype=torch.float32, device=w.device)
+        wt[:w.shape[1]] = w.detach().t()
+        cache.clear()
+        hit = cache[key] = (wt, w)
+    return hit[0]
+
+
+_PROJ_CACHE = {}
+
+
+@torch.no_grad()
+def cross_block(sd, p, x, corr, pos, ops):
+    """CrossBlock.forward (backbone.py:400-420) with CrossAttention.forward (:279-330) inlined.
+
+    x: (2B, L, C) tokens of both views ('(b v) l c'), corr: the averaged correlation (B, 1, hs, ws, ht, wt) with
+    hs * ws = ht * wt = L, pos: (B, L, 6). Returns the flattened pose feature (B, 2 * (C + 6) * C)."""
+    B2, L, C = x.shape
+    B = B2 // 2
+    E = C + 6
+    D = (E + 3) // 4 * 4                      # operand width padded to a multiple of 4 floats (zero columns)
+    xn = ops.layernorm(x, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"]).reshape(B, 2, L, C)
+    v = torch.zeros(B, L, 2 * D, dtype=torch.float32, device=x.device)     # [v1 | v2] side by side
+    for i in range(2):
+        v[:, :, i * D:i * D + C] = xn[:, i]
+        v[:, :, i * D + C:i * D + E] = pos
+    P = ops.dual_softmax(corr.reshape(B, L, L))
+    wpt = _padded_proj(sd, p, D, _PROJ_CACHE)
+    bp = sd[p + ".cross_attn.proj_fundamental.bias"]
+    fund = torch.empty(B, 2, E, C, dtype=torch.float32, device=x.device)
+    for b in range(B):
+        G = ops.matmul(P[b], v[b])                                     # (L, 2D) = [P v1 | P v2]
+        F1 = ops.matmul_tn(v[b, :, :D], G[:, :D])                     # v1^T (P v1)
+        F2 = ops.matmul_tn(G[:, D:], v[b, :, D:])                     # (P v2)^T v2
+        # reshape(B, E, E).transpose(-2, -1) then Linear(E -> C): rows of F^T times W^T
+        f1 = ops.matmul_tn(F1, wpt, bias=bp)
+        f2 = ops.matmul_tn(F2, wpt, bias=bp)
+        fund[b, 0] = f2[:E]                                            # CrossAttention returns (fundamental_2, fundamental_1)
+        fund[b, 1] = f1[:E]
+    fund = fund.reshape(B2, E, C)
+    h = ops.layernorm(fund, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"])
+    h = ops.linear(h, sd[p + ".mlp.fc1.weight"], sd[p + ".mlp.fc1.bias"], act="gelu")
+    h = ops.linear(h, sd[p + ".mlp.fc2.weight"], sd[p + ".mlp.fc2.bias"])
+    fund = fund + h
+    return ops.layernorm(fund, sd[p + ".norm.weight"], sd[p + ".norm.bias"]).reshape(B, -1)
+
+
+@torch.no_grad()
+def pose_head(sd, pose_feat, ops):
+    """pose_regressor -> [:, :128] -> rotation / translation regressors -> r6d2mat -> (B, 4, 4)
+    (models/CoPoNeRF.py:33-52,106-128,198-204)."""
+    h0 = ops.linear_skinny(pose_feat, sd["pose_regressor.0.weight"], sd["pose_regressor.0.bias"], act="relu")
+    return ops.pose_head(h0, sd)
+
+
+@torch.no_grad()
+def pose_from_features(sd, feat_tokens, corr, intrinsics, H, ops):
+    """The pose half of get_z (models/CoPoNeRF.py:188-204): feat_tokens (2B, L, 256) are the finest refined
+    features, corr the averaged correlation volume, intrinsics context['intrinsics'] (B, n_ctxt, 4, 4)."""
+    B = intrinsics.shape[0]
+    k = intrinsics[:, 0].detach().to(torch.float32)
+    intr = [(k[:, 0, 0] / H).reshape(B, 1), (k[:, 1, 1] / H).reshape(B, 1),
+            (k[:, 0, 2] / H).reshape(B, 1), (k[:, 1, 2] / H).reshape(B, 1)]
+    pos = positional_encodings(B, feat_tokens.shape[1], intr, device=feat_tokens.device)
+    feat = cross_block(sd, "cross_attention", feat_tokens, corr, pos, ops)
+    return pose_head(sd, feat, ops)

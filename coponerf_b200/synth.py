@@ -298,3 +298,69 @@ def ufc_inputs(seed=0, batch=1, sizes=(16, 32, 64)):
     rng = np.random.default_rng(7500 + seed)
     f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
     return [f32(rng.standard_normal((2 * batch, c, n, n), dtype=np.float32)) for c, n in zip((512, 256, 128), sizes)]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the rest of the model: image encoder, conv_map, pose features and pose head (models/CoPoNeRF.py:31-69)
+
+# parameters the reference constructs but never reads in forward() (SURVEY.md section 8(a) notes)
+UNUSED_PARAM_SHAPES = {
+    "corr_embed.weight": (832, 4096, 1, 1), "corr_embed.bias": (832,),
+    "latent_avg_query.weight": (128, 25, 1, 1), "latent_avg_query.bias": (128,),
+    "latent_avg_query_2.weight": (128, 128, 1, 1), "latent_avg_query_2.bias": (128,),
+    "latent_avg_key.weight": (128, 416, 1, 1), "latent_avg_key.bias": (128,),
+    "latent_avg_key_2.weight": (128, 128, 1, 1), "latent_avg_key_2.bias": (128,),
+    "latent_avg_repeat_query.weight": (128, 153, 1, 1), "latent_avg_repeat_query.bias": (128,),
+    "latent_avg_repeat_query_2.weight": (128, 128, 1, 1), "latent_avg_repeat_query_2.bias": (128,),
+}
+
+
+def encoder_param_shapes():
+    """'encoder.model.*' = torchvision resnet34 without fc (models/backbone.py:52-58): name -> (shape, dtype)."""
+    import torchvision
+    net = torchvision.models.resnet34(weights=None)
+    return {"encoder.model." + k: (tuple(v.shape), v.dtype) for k, v in net.state_dict().items() if not k.startswith("fc.")}
+
+
+def pair_state_dict(seed=0):
+    """Seeded parameters of everything get_z() reads besides the cost aggregation (numpy PCG64): the ResNet-34
+    encoder with non-trivial BatchNorm statistics, conv_map, CrossBlock and the three regressors. Output scales are
+    chosen so the estimated pose is a moderate rotation / translation instead of saturating."""
+    from .pair_stage import POSE_PARAM_SHAPES
+    rng = np.random.default_rng(9000 + seed)
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    sd = {}
+    for name, (shape, dtype) in encoder_param_shapes().items():
+        if name.endswith("num_batches_tracked"):
+            sd[name] = torch.zeros(shape, dtype=dtype)
+        elif name.endswith("running_mean"):
+            sd[name] = f32(rng.normal(0, 0.1, shape))
+        elif name.endswith("running_var"):
+            sd[name] = f32(rng.uniform(0.75, 1.25, shape))
+        elif len(shape) == 1:
+            sd[name] = f32(rng.uniform(0.7, 1.3, shape) if name.endswith("weight") else rng.uniform(-0.1, 0.1, shape))
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            sd[name] = f32(rng.uniform(-1, 1, shape) * (1.7 / math.sqrt(fan_in)))
+    sd["conv_map.weight"] = f32(rng.uniform(-1, 1, (64, 3, 7, 7)) * (1.7 / math.sqrt(147)))
+    sd["conv_map.bias"] = f32(rng.uniform(-0.1, 0.1, 64))
+    for name, shape in POSE_PARAM_SHAPES.items():
+        if ".norm" in name:
+            a = rng.uniform(0.7, 1.3, shape) if name.endswith("weight") else rng.uniform(-0.1, 0.1, shape)
+        elif name.endswith(".bias"):
+            a = rng.uniform(-0.1, 0.1, shape)
+        else:
+            a = rng.uniform(-1, 1, shape, ) * (1.7 / math.sqrt(shape[1]))
+        sd[name] = f32(a)
+    return sd
+
+
+def full_state_dict(seed=0):
+    """All 744 state_dict entries of the reference model (models/CoPoNeRF.py:19-104), seeded."""
+    sd = dict(render_state_dict(seed))
+    sd.update({"feature_cost_aggregation." + k: v for k, v in ufc_state_dict(seed).items()})
+    sd.update(pair_state_dict(seed))
+    rng = np.random.default_rng(9500 + seed)
+    for name, shape in UNUSED_PARAM_SHAPES.items():
+        sd[name] = torch.from_numpy(rng.uniform(-0.05, 0.05, shape).astype(np.float32))
+    return sd

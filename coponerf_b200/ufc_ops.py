@@ -20,9 +20,13 @@ def _c(t):
     return t.detach().to(torch.float32).contiguous()
 
 
+_ACT = {None: 0, "relu": 1, "gelu": 2}
+
+
 class CudaOps:
     def __init__(self):
         self.lib = _lib.load()
+        self._ws = None    # scratch for the split reductions (stream-ordered reuse)
         self._wt = {}      # weight tensor -> transposed [K][N] copy for the GEMM (made once per weight)
         self.launches = 0  # kernels launched so far (bench.py's gpu_launches)
         self.launches_per_forward = 0
@@ -60,9 +64,92 @@ class CudaOps:
         wt, bias = self._transposed(w), _c(b)
         y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
         self.launches += 1
-        _lib.check(self.lib.cpn_gemm_simt(_p(x), K, _p(wt), _p(bias), _p(y), N, M, N, K, int(act == "relu"), _st()),
+        _lib.check(self.lib.cpn_gemm_simt(_p(x), K, _p(wt), _p(bias), _p(y), N, M, N, K, _ACT[act], _st()),
                    "cpn_gemm_simt")
         return y
+
+    def matmul(self, a, b):
+        """(M, K) @ (K, N), fp32, both row-major."""
+        a, b = _c(a), _c(b)
+        self._check_dev(a)
+        M, K = a.shape
+        N = b.shape[1]
+        y = torch.empty((M, N), dtype=torch.float32, device=a.device)
+        self.launches += 1
+        _lib.check(self.lib.cpn_gemm_simt(_p(a), K, _p(b), None, _p(y), N, M, N, K, 0, _st()), "cpn_gemm_simt")
+        return y
+
+    def _scratch(self, nbytes, dev):
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
+            self._ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        return self._ws
+
+    def matmul_tn(self, a, b, bias=None, act=None):
+        """a^T @ b (+ bias, activation) for a (L, Mi), b (L, Nj); rows may be strided views of wider matrices."""
+        self._check_dev(a)
+        if a.dtype != torch.float32 or b.dtype != torch.float32 or a.stride(1) != 1 or b.stride(1) != 1:
+            a, b = _c(a), _c(b)
+        L, Mi = a.shape
+        Nj = b.shape[1]
+        y = torch.empty((Mi, Nj), dtype=torch.float32, device=a.device)
+        nbytes = self.lib.cpn_gemm_tn_workspace_bytes(Mi, Nj, L)
+        ws = self._scratch(nbytes, a.device)
+        self.launches += 2
+        _lib.check(self.lib.cpn_gemm_tn(_p(a), a.stride(0), _p(b), b.stride(0), _p(_c(bias)) if bias is not None else None,
+                                        _p(y), Nj, Mi, Nj, L, _ACT[act], _p(ws), ws.numel(), _st()), "cpn_gemm_tn")
+        return y
+
+    def linear_skinny(self, x, w, b, act=None):
+        """act(x W^T + b) for a few rows and a very long K, W as stored (N, K)."""
+        x, w, b = _c(x), _c(w), _c(b)
+        self._check_dev(x)
+        M, K = x.shape
+        N = w.shape[0]
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        for m0 in range(0, M, 8):
+            m = min(8, M - m0)
+            nbytes = self.lib.cpn_linear_skinny_workspace_bytes(m, N, K)
+            ws = self._scratch(nbytes, x.device)
+            self.launches += 2
+            _lib.check(self.lib.cpn_linear_skinny(_p(x[m0:m0 + m]), _p(w), _p(b), _p(y[m0:m0 + m]), m, N, K, _ACT[act],
+                                                  _p(ws), ws.numel(), _st()), "cpn_linear_skinny")
+        return y
+
+    # ------------------------------------------------------------------ pose features (models/backbone.py)
+    def dual_softmax(self, c):
+        c = _c(c)
+        self._check_dev(c)
+        B, L, _ = c.shape
+        P = torch.empty_like(c)
+        nbytes = self.lib.cpn_dual_softmax_workspace_bytes(B, L)
+        ws = self._scratch(nbytes, c.device)
+        self.launches += 4
+        _lib.check(self.lib.cpn_dual_softmax(_p(c), _p(P), B, L, _p(ws), ws.numel(), _st()), "cpn_dual_softmax")
+        return P
+
+    def pose_head(self, h0, sd):
+        h0 = _c(h0)
+        self._check_dev(h0)
+        B = h0.shape[0]
+        out = torch.empty((B, 4, 4), dtype=torch.float32, device=h0.device)
+        a = _lib.PoseHeadArgs()
+        a.B = B
+        a.h0, a.rel_pose = h0.data_ptr(), out.data_ptr()
+        keep = []
+        for field, key in (("w2", "pose_regressor.2.weight"), ("b2", "pose_regressor.2.bias"),
+                           ("w4", "pose_regressor.4.weight"), ("b4", "pose_regressor.4.bias"),
+                           ("rw1", "rotation_regressor.1.weight"), ("rb1", "rotation_regressor.1.bias"),
+                           ("rw3", "rotation_regressor.3.weight"), ("rb3", "rotation_regressor.3.bias"),
+                           ("rw5", "rotation_regressor.5.weight"), ("rb5", "rotation_regressor.5.bias"),
+                           ("tw1", "translation_regressor.1.weight"), ("tb1", "translation_regressor.1.bias"),
+                           ("tw3", "translation_regressor.3.weight"), ("tb3", "translation_regressor.3.bias"),
+                           ("tw5", "translation_regressor.5.weight"), ("tb5", "translation_regressor.5.bias")):
+            t = _c(sd[key])
+            keep.append(t)
+            setattr(a, field, t.data_ptr())
+        self.launches += 1
+        _lib.check(self.lib.cpn_pose_head(ctypes.byref(a), _st()), "cpn_pose_head")
+        return out
 
     # ------------------------------------------------------------------ correlation volume <-> tokens
     def corr_to_tokens(self, corr, n):

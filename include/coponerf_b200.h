@@ -196,6 +196,35 @@ size_t cpn_correlation_workspace_bytes(int B, int L, int C);
 int cpn_correlation(const float* src, const float* trg, float* out, int B, int L, int C, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* ---- per-pair pose features and pose head ---------------------------------------
+ * cpn_dual_softmax   P = softmax(c, -1) * softmax(c, -2) for c (B, L, L): attn_fundamental_1 of CrossAttention.forward
+ *                    (models/backbone.py:282-291); attn_fundamental_2 is its transpose and is never formed. L % 4 == 0.
+ * cpn_gemm_tn        C[Mi, Nj] = act(A^T B + bias), A (L, Mi) with row stride lda, B (L, Nj) with row stride ldb; the L
+ *                    range is split over CTAs and reduced in a fixed order. Replaces the v^T (attn v) products of
+ *                    backbone.py:311-312 and proj_fundamental applied to the transposed matrix (:318-324).
+ * cpn_linear_skinny  y[M, N] = act(x[M, K] W[N, K]^T + bias) for M <= 8 rows and long K, W as stored in the state_dict
+ *                    (pose_regressor[0], models/CoPoNeRF.py:34: 134 144 -> 512).
+ * cpn_pose_head      pose_regressor[2:], [:, :128], rotation_regressor, translation_regressor, r6d2mat and the 4 x 4
+ *                    assembly of models/CoPoNeRF.py:34-52,106-128,198-204: h0 (B, 512) -> rel_pose (B, 4, 4).
+ * act: 0 none, 1 ReLU, 2 exact GELU. */
+size_t cpn_dual_softmax_workspace_bytes(int B, int L);
+int cpn_dual_softmax(const float* c, float* P, int B, int L, void* workspace, size_t workspace_bytes, void* stream);
+size_t cpn_gemm_tn_workspace_bytes(int Mi, int Nj, int L);
+int cpn_gemm_tn(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int Mi, int Nj,
+                int L, int act, void* workspace, size_t workspace_bytes, void* stream);
+size_t cpn_linear_skinny_workspace_bytes(int M, int N, int K);
+int cpn_linear_skinny(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, int act,
+                      void* workspace, size_t workspace_bytes, void* stream);
+typedef struct {
+  int32_t B, reserved;
+  const float* h0;                       /* (B, 512) = relu(pose_regressor[0](pose_feat)) */
+  const float *w2, *b2, *w4, *b4;        /* pose_regressor.2 (256, 512), pose_regressor.4 (256, 256) */
+  const float *rw1, *rb1, *rw3, *rb3, *rw5, *rb5;   /* rotation_regressor.{1,3,5} */
+  const float *tw1, *tb1, *tw3, *tb3, *tw5, *tb5;   /* translation_regressor.{1,3,5} */
+  float* rel_pose;                       /* (B, 4, 4) out */
+} cpn_pose_head_args;
+int cpn_pose_head(const cpn_pose_head_args* args, void* stream);
+
 /* ---- device timing of the dominant kernel (the query_encode_latent GEMM), for roofline reports.
  * Between cpn_prof_begin and cpn_prof_end every launch of that kernel by cpn_render_rays is bracketed
  * by CUDA events on the caller's stream. cpn_prof_end waits for them and returns the summed duration.
@@ -207,7 +236,7 @@ int cpn_prof_end(float* total_ms, int* launches);
  * C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]); fp32 row-major, lda/ldc in floats.
  * `wt` is W transposed to [K,N] (fp32, as produced by cpn_pack_weights for SIMT layers). */
 int cpn_gemm_simt(const float* A, int lda, const float* wt, const float* bias, float* C, int ldc,
-                  int M, int N, int K, int relu, void* stream);
+                  int M, int N, int K, int relu /* 0 none, 1 ReLU, 2 exact GELU */, void* stream);
 
 /* Tensor-core GEMM of one packed layer (0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value,
  * 3 key_map, 4 key_map_2, 5 query_embed_2, 6 query_repeat_embed_2): C[M, N_layer] = act(A[M, K_layer] * W^T + b),

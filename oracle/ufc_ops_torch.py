@@ -16,7 +16,40 @@ class TorchOps:
 
     def linear(self, x, w, b, act=None):
         y = F.linear(x, w, b)
-        return F.relu(y) if act == "relu" else y
+        return F.relu(y) if act == "relu" else F.gelu(y) if act == "gelu" else y
+
+    # ---- operators of coponerf_b200/pose_native.py (models/backbone.py:279-330, models/CoPoNeRF.py:33-52,106-128)
+    def matmul(self, a, b):
+        return a @ b
+
+    def matmul_tn(self, a, b, bias=None, act=None):
+        y = a.transpose(0, 1) @ b
+        if bias is not None:
+            y = y + bias
+        return F.relu(y) if act == "relu" else F.gelu(y) if act == "gelu" else y
+
+    def linear_skinny(self, x, w, b, act=None):
+        return self.linear(x, w, b, act)
+
+    def dual_softmax(self, c):                          # backbone.py:290-291
+        return c.softmax(dim=-1) * c.softmax(dim=-2)
+
+    def pose_head(self, h0, sd):                        # CoPoNeRF.py:33-52,106-128,198-204; h0 = relu(pose_regressor[0](x))
+        h = F.relu(F.linear(h0, sd["pose_regressor.2.weight"], sd["pose_regressor.2.bias"]))
+        h = F.relu(F.linear(h, sd["pose_regressor.4.weight"], sd["pose_regressor.4.bias"]))[:, :128]
+
+        def head(name):
+            y = F.relu(h)
+            y = F.relu(F.linear(y, sd[name + ".1.weight"], sd[name + ".1.bias"]))
+            y = F.relu(F.linear(y, sd[name + ".3.weight"], sd[name + ".3.bias"]))
+            return F.linear(y, sd[name + ".5.weight"], sd[name + ".5.bias"])
+        d6, tr = head("rotation_regressor"), head("translation_regressor")
+        a1, a2 = d6[..., :3], d6[..., 3:]
+        b1 = F.normalize(a1, dim=-1)
+        b2 = F.normalize(a2 - (b1 * a2).sum(-1, keepdim=True) * b1, dim=-1)
+        R = torch.stack((b1, b2, torch.cross(b1, b2, dim=-1)), dim=-2)
+        bottom = torch.tensor([0.0, 0.0, 0.0, 1.0]).expand(h0.shape[0], 1, -1).to(h0.device)
+        return torch.cat((torch.cat((R, tr.unsqueeze(-1)), dim=-1), bottom), dim=1)
 
     def corr_to_tokens(self, corr, n):                  # aggregation.py:283-285
         B, H, hs, ws, ht, wt = corr.shape

@@ -1,0 +1,91 @@
+"""The CPU restatement of get_z() (oracle/pair_oracle.py) and the state_dict-driven orchestration of the product
+(coponerf_b200/pair_stage.py with the PyTorch operator set) against the outputs of the unmodified reference stored in
+tests/golden/pair_256.npz (tests/golden/make_goldens_pair.py). Runs without a GPU and without /root/reference."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from coponerf_b200 import synth  # noqa: E402
+from make_goldens_pair import C_STRIDE, CASE, Z_STRIDE  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return dict(np.load(os.path.join(HERE, "golden", "pair_256.npz")))
+
+
+@pytest.fixture(scope="module")
+def case():
+    sd = synth.full_state_dict(CASE["weights_seed"])
+    inp = synth.make_input(CASE["H"], CASE["W"], CASE["n_rays"], seed=CASE["seed"], pose_set=CASE["pose_set"])
+    return sd, inp
+
+
+def check_pair_outputs(z, rel_pose, flow, golden, tol_z=2e-5, tol_pose=2e-5, tol_flow=2e-3):
+    """z relative to max|ref|, rel_pose absolute, flows in units of the 64-pixel grid (flow[0:2]) / [-1, 1] (flow[2:4])."""
+    for i, (t, (sc, sy, sx)) in enumerate(zip(z, Z_STRIDE)):
+        a, b = t[:, ::sc, ::sy, ::sx].cpu().numpy(), golden[f"z{i}"]
+        assert a.shape == b.shape
+        assert np.abs(a - b).max() <= tol_z * np.abs(b).max(), (i, np.abs(a - b).max(), np.abs(b).max())
+    assert np.abs(rel_pose.cpu().numpy() - golden["rel_pose"]).max() <= tol_pose
+    for i, f in enumerate(flow):
+        scale = 64.0 if i < 2 else 2.0
+        assert np.abs(f.cpu().numpy() - golden[f"flow{i}"]).max() <= tol_flow * scale, i
+
+
+def test_pair_oracle_matches_reference_golden(case, golden):
+    from oracle import pair_oracle
+    sd, inp = case
+    z, rel_pose, flow = pair_oracle.get_z(sd, inp, fast_pos=True)
+    check_pair_outputs(z, rel_pose, flow, golden)
+
+
+def test_positional_encodings_loop_equals_batched():
+    """The reference's 4096-iteration Python loop (backbone.py:269-273) and the single batched matmul give the same table."""
+    from coponerf_b200 import pose_native
+    from oracle import pair_oracle
+    intr = [torch.tensor([[0.9]]), torch.tensor([[0.85]]), torch.tensor([[0.5]]), torch.tensor([[0.45]])]
+    slow = pair_oracle.positional_encodings(1, 4096, intr, fast_pos=False)
+    fast = pair_oracle.positional_encodings(1, 4096, intr, fast_pos=True)
+    ours = pose_native.positional_encodings(1, 4096, intr)
+    assert torch.allclose(slow, fast, atol=1e-6, rtol=1e-6)
+    assert torch.allclose(slow, ours, atol=1e-6, rtol=1e-6)
+    assert pose_native.positional_encodings(1, 4096, intr) is ours      # memoised by value
+
+
+def test_product_orchestration_on_torch_ops_matches_golden(case, golden):
+    """pair_stage.get_z (the code the GPU path runs) with every operator swapped for its PyTorch restatement."""
+    from coponerf_b200 import pair_stage
+    from coponerf_b200.model import CoPoNeRF
+    from oracle.ufc_ops_torch import TorchOps
+    sd, inp = case
+    m = CoPoNeRF(n_view=2).eval()
+    m.load_state_dict(sd, strict=True)          # every one of the 744 reference keys, nothing else
+    z, rel_pose, flow = pair_stage.get_z(m, inp, TorchOps())
+    check_pair_outputs(z, rel_pose, flow, golden)
+    assert (m.H, m.W) == (256, 256)
+
+
+def test_get_z_refuses_cpu():
+    from coponerf_b200.model import CoPoNeRF
+    m = CoPoNeRF(n_view=2).eval()
+    inp = synth.make_input(256, 256, 8, seed=1)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m.get_z(inp)
+
+
+def test_pipeline_oracle_matches_reference_golden(case, golden):
+    """get_z restatement -> render oracle == the reference's get_z -> forward(val=True) (BASELINE config 5)."""
+    from oracle import pair_oracle, render_oracle
+    sd, inp = case
+    z, rel_pose, flow = pair_oracle.get_z(sd, inp, fast_pos=True)
+    out = render_oracle.render_forward(sd, inp, z, rel_pose, flow, CASE["H"], CASE["W"], 64, True)
+    scale = np.abs(golden["rgb"]).max()
+    err = np.abs(out["rgb"].numpy() - golden["rgb"]).max(axis=-1)[0, 0] / scale
+    assert np.median(err) <= 2e-5 and np.quantile(err, 0.9) <= 1e-3, (np.median(err), np.quantile(err, 0.9), err.max())
+    assert np.array_equal(out["valid_mask"].numpy(), golden["valid_mask"])
