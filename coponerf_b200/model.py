@@ -82,6 +82,7 @@ class CoPoNeRF(nn.Module):
         self.chunk_rays = chunk_rays
         self.lanes = lanes
         self.native_ufc = True          # get_z(): cost aggregation (UFC) on the sm_100a operators
+        self.graph_get_z = True         # get_z(): replay the per-pair stage from a CUDA graph (same kernels, same bits)
         self._ufc_ops = None
         self.pixel_val_on_host = True   # the reference returns out['pixel_val'] as a CPU tensor (CoPoNeRF.py:490)
         self._engine = None
@@ -119,7 +120,7 @@ class CoPoNeRF(nn.Module):
                 from .ufc_ops import CudaOps
                 self._ufc_ops = CudaOps()
             with torch.cuda.device(dev):
-                return pair_stage.get_z(self, input, self._ufc_ops)
+                return pair_stage.get_z(self, input, self._ufc_ops, use_graph=self.graph_get_z)
         ref = self._pair_stage
         fca = ref.feature_cost_aggregation
         if not self.native_ufc:

@@ -108,6 +108,15 @@ class PairStage(nn.Module):
 
 _IMAGENET_MEAN = (0.485, 0.456, 0.406)
 _IMAGENET_STD = (0.229, 0.224, 0.225)
+_NORM_CONST = {}
+
+
+def _norm_const(dev):
+    key = str(dev)
+    if key not in _NORM_CONST:      # built once per device, outside any graph capture
+        _NORM_CONST[key] = (torch.tensor(_IMAGENET_MEAN, device=dev).view(1, 3, 1, 1),
+                            torch.tensor(_IMAGENET_STD, device=dev).view(1, 3, 1, 1))
+    return _NORM_CONST[key]
 
 
 def encode_images(model, rgb):
@@ -115,8 +124,7 @@ def encode_images(model, rgb):
     with utils.normalize_imagenet (utils_training/utils.py:247-257)."""
     x = torch.flatten(rgb, 0, 1).permute(0, 3, 1, 2).to(torch.float32)
     x = (x + 1) / 2.
-    mean = torch.tensor(_IMAGENET_MEAN, device=x.device).view(1, 3, 1, 1)
-    std = torch.tensor(_IMAGENET_STD, device=x.device).view(1, 3, 1, 1)
+    mean, std = _norm_const(x.device)
     x = (x - mean) / std
     if x.is_cuda:
         with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
@@ -128,29 +136,79 @@ def _sub_state(model, prefix):
     return {k[len(prefix) + 1:]: v for k, v in model.state_dict(keep_vars=True).items() if k.startswith(prefix + ".")}
 
 
-@torch.no_grad()
-def get_z(model, input, ops):
-    """models/CoPoNeRF.py:159-206. Returns (z list of 4 feature maps, rel_pose (B, 4, 4), flow tuple)."""
-    ctx = input["context"]
-    dev = next(model.parameters()).device
-    rgb = ctx["rgb"].to(dev)
-    B, n_ctxt, H, W, _ = rgb.shape
-    if n_ctxt != 2:
-        raise ValueError("the per-pair stage is built for two context views")
-    model.H, model.W = H, W
-    if model.training:
-        raise RuntimeError("coponerf_b200 is an inference path: call .eval() (BatchNorm must use running statistics)")
-    z, z_conv = encode_images(model, rgb)
+def _state_cache(model):
     cache = model.__dict__.setdefault("_sd_cache", {})
     ver = tuple((p.data_ptr(), p._version) for p in model.parameters())
     if cache.get("ver") != ver:
+        cache.clear()
         cache["ver"] = ver
         cache["ufc"] = _sub_state(model, "feature_cost_aggregation")
         full = model.state_dict(keep_vars=True)
         cache["pose"] = {k: v for k, v in full.items()
                          if k.split(".")[0] in ("cross_attention", "pose_regressor", "rotation_regressor",
                                                 "translation_regressor")}
+    return cache
+
+
+def _pair_body(model, cache, rgb, pos, ops):
+    """Everything of get_z() that runs on the device, as one stream-ordered sequence with no host dependence
+    (so it can be captured into a CUDA graph): encoder, cost aggregation, pose features, pose head."""
+    z, z_conv = encode_images(model, rgb)
     feats, flows, c = ufc_native.ufc_forward(cache["ufc"], z, model.n_view, ops)
     tokens = feats[-1].flatten(-2, -1).transpose(-1, -2)            # (2B, L, 256)
-    rel_pose = pose_native.pose_from_features(cache["pose"], tokens, c, ctx["intrinsics"], H, ops)
+    pose_feat = pose_native.cross_block(cache["pose"], "cross_attention", tokens, c, pos, ops)
+    rel_pose = pose_native.pose_head(cache["pose"], pose_feat, ops)
     return feats + [z_conv], rel_pose, flows
+
+
+class _PairGraph:
+    """get_z()'s device work for one input geometry captured once and replayed: ~800 short kernels (the per-pair
+    stage is launch-latency bound) become one graph launch. Outputs are cloned out of the graph's
+    static buffers, so callers own what they get, as with the reference."""
+
+    def __init__(self, model, cache, ops, shape, n_tokens, dev):
+        self.static_rgb = torch.zeros(shape, dtype=torch.float32, device=dev)
+        self.static_pos = torch.zeros((shape[0], n_tokens, 6), dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):          # warm-up: weight-layout caches, scratch buffers, cuDNN handles
+                _pair_body(model, cache, self.static_rgb, self.static_pos, ops)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = _pair_body(model, cache, self.static_rgb, self.static_pos, ops)
+
+    def run(self, rgb, pos):
+        self.static_rgb.copy_(rgb, non_blocking=True)
+        self.static_pos.copy_(pos, non_blocking=True)
+        self.graph.replay()
+        z, rel_pose, flows = self.out
+        return [t.clone() for t in z], rel_pose.clone(), tuple(t.clone() for t in flows)
+
+
+@torch.no_grad()
+def get_z(model, input, ops, use_graph=False):
+    """models/CoPoNeRF.py:159-206. Returns (z list of 4 feature maps, rel_pose (B, 4, 4), flow tuple)."""
+    ctx = input["context"]
+    dev = next(model.parameters()).device
+    rgb = ctx["rgb"]
+    B, n_ctxt, H, W, _ = rgb.shape
+    if n_ctxt != 2:
+        raise ValueError("the per-pair stage is built for two context views")
+    model.H, model.W = H, W
+    if model.training:
+        raise RuntimeError("coponerf_b200 is an inference path: call .eval() (BatchNorm must use running statistics)")
+    cache = _state_cache(model)
+    n_tokens = (H // 4) * (W // 4)                                  # the finest refined level (ResNet layer2)
+    pos = pose_native.positional_encodings_for(ctx["intrinsics"], n_tokens, H, dev)
+    if not (use_graph and dev.type == "cuda"):
+        return _pair_body(model, cache, rgb.to(dev), pos, ops)
+    key = (B, H, W, str(dev))
+    g = cache.get("graph")
+    if g is None or cache.get("graph_key") != key:
+        cache["graph"] = cache["graph_key"] = None                  # free the old pool before capturing anew
+        g = cache["graph"] = _PairGraph(model, cache, ops, (B, n_ctxt, H, W, 3), n_tokens, dev)
+        cache["graph_key"] = key
+    return g.run(rgb, pos)

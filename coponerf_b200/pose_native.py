@@ -73,20 +73,16 @@ def positional_encodings(B, N, intr, device=None):
     return pos
 
 
-def _padded_proj(sd, p, D, cache):
-    """proj_fundamental.weight (C, C+6) as the zero-padded [C+6 -> D][C] matrix the A^T B operator takes."""
-    w = sd[p + ".cross_attn.proj_fundamental.weight"]
-    key = (w.data_ptr(), w._version, D)
-    hit = cache.get(key)
-    if hit is None:
+def _padded_proj(sd, p, D):
+    """proj_fundamental.weight (C, C+6) as the zero-padded [C+6 -> D][C] matrix the A^T B operator takes. Kept in
+    `sd` (the per-model parameter view, rebuilt when the weights change) so a captured graph never outlives it."""
+    key = f"_{p}.proj_fundamental.padded_t.{D}"
+    if key not in sd:
+        w = sd[p + ".cross_attn.proj_fundamental.weight"]
         wt = torch.zeros(D, w.shape[0], dtype=torch.float32, device=w.device)
         wt[:w.shape[1]] = w.detach().t()
-        cache.clear()
-        hit = cache[key] = (wt, w)
-    return hit[0]
-
-
-_PROJ_CACHE = {}
+        sd[key] = wt
+    return sd[key]
 
 
 @torch.no_grad()
@@ -105,7 +101,7 @@ def cross_block(sd, p, x, corr, pos, ops):
         v[:, :, i * D:i * D + C] = xn[:, i]
         v[:, :, i * D + C:i * D + E] = pos
     P = ops.dual_softmax(corr.reshape(B, L, L))
-    wpt = _padded_proj(sd, p, D, _PROJ_CACHE)
+    wpt = _padded_proj(sd, p, D)
     bp = sd[p + ".cross_attn.proj_fundamental.bias"]
     fund = torch.empty(B, 2, E, C, dtype=torch.float32, device=x.device)
     for b in range(B):
@@ -133,14 +129,20 @@ def pose_head(sd, pose_feat, ops):
     return ops.pose_head(h0, sd)
 
 
-@torch.no_grad()
-def pose_from_features(sd, feat_tokens, corr, intrinsics, H, ops):
-    """The pose half of get_z (models/CoPoNeRF.py:188-204): feat_tokens (2B, L, 256) are the finest refined
-    features, corr the averaged correlation volume, intrinsics context['intrinsics'] (B, n_ctxt, 4, 4)."""
+def positional_encodings_for(intrinsics, n_tokens, H, device=None):
+    """The table for context['intrinsics'] (B, n_ctxt, 4, 4) as get_z prepares them (CoPoNeRF.py:188-191: rows 0-1
+    divided by H, view 0's fx, fy, cx, cy)."""
     B = intrinsics.shape[0]
     k = intrinsics[:, 0].detach().to(torch.float32)
     intr = [(k[:, 0, 0] / H).reshape(B, 1), (k[:, 1, 1] / H).reshape(B, 1),
             (k[:, 0, 2] / H).reshape(B, 1), (k[:, 1, 2] / H).reshape(B, 1)]
-    pos = positional_encodings(B, feat_tokens.shape[1], intr, device=feat_tokens.device)
+    return positional_encodings(B, n_tokens, intr, device=device)
+
+
+@torch.no_grad()
+def pose_from_features(sd, feat_tokens, corr, intrinsics, H, ops):
+    """The pose half of get_z (models/CoPoNeRF.py:188-204): feat_tokens (2B, L, 256) are the finest refined
+    features, corr the averaged correlation volume, intrinsics context['intrinsics'] (B, n_ctxt, 4, 4)."""
+    pos = positional_encodings_for(intrinsics, feat_tokens.shape[1], H, feat_tokens.device)
     feat = cross_block(sd, "cross_attention", feat_tokens, corr, pos, ops)
     return pose_head(sd, feat, ops)

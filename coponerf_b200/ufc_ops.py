@@ -27,6 +27,7 @@ class CudaOps:
     def __init__(self):
         self.lib = _lib.load()
         self._ws = None    # scratch for the split reductions (stream-ordered reuse)
+        self._ws_old = []
         self._wt = {}      # weight tensor -> transposed [K][N] copy for the GEMM (made once per weight)
         self.launches = 0  # kernels launched so far (bench.py's gpu_launches)
         self.launches_per_forward = 0
@@ -81,7 +82,9 @@ class CudaOps:
 
     def _scratch(self, nbytes, dev):
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
-            self._ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+            if self._ws is not None:
+                self._ws_old.append(self._ws)   # a captured graph may still point at it: never hand it back
+            self._ws = torch.empty(max(nbytes, 8 << 20), dtype=torch.uint8, device=dev)
         return self._ws
 
     def matmul_tn(self, a, b, bias=None, act=None):

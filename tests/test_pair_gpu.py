@@ -104,7 +104,7 @@ def test_get_z_matches_reference_golden_and_cpu_restatement(model, golden):
     assert (rel_pose.cpu() - pr).abs().max() <= 5e-5
     for i, (a, b) in enumerate(zip(flow, fr)):
         assert (a.cpu() - b).abs().max() <= 2e-3 * (64.0 if i < 2 else 2.0)
-    assert model._ufc_ops.launches > 900          # the native operators ran (no library / eager fallback)
+    assert model._ufc_ops.launches > 400          # the native operators ran (no library / eager fallback)
 
 
 def test_get_z_accepts_host_input_and_batches(model):
@@ -133,3 +133,23 @@ def test_full_forward_matches_reference_golden(model, golden):
     assert np.array_equal(out["valid_mask"].cpu().numpy(), golden["valid_mask"])
     assert np.abs(out["rel_pose"].cpu().numpy() - golden["rel_pose"]).max() <= 5e-5
     assert len(out["z"]) == 4 and len(out["flow"]) == 4
+
+
+def test_graph_replay_of_get_z_is_bit_identical_to_eager(model):
+    inp = to_device(_inp(), "cuda:0")
+    model.graph_get_z = False
+    ze, pe, fe = model.get_z(inp)
+    model.graph_get_z = True
+    try:
+        for _ in range(2):          # capture, then a pure replay
+            zg, pg, fg = model.get_z(inp)
+    finally:
+        model.graph_get_z = True
+    torch.cuda.synchronize()
+    for a, b in zip(zg + [pg] + list(fg), ze + [pe] + list(fe)):
+        assert torch.equal(a, b)
+    # a different image through the same graph: results follow the input, and earlier outputs are not overwritten
+    inp2 = to_device(_inp(), "cuda:0")
+    inp2["context"]["rgb"] = inp2["context"]["rgb"].flip(-2).contiguous()
+    z2, p2, f2 = model.get_z(inp2)
+    assert not torch.equal(z2[0], zg[0]) and torch.equal(zg[0], ze[0])
