@@ -357,11 +357,9 @@ def main():
     if with_ufc:
         launches += args.steps * ufc_ops.launches_per_forward
     if full:       # cost aggregation + pose operators of one get_z (the cuDNN encoder kernels are not ours: not counted)
-        model.graph_get_z = False     # count them on one eager call; the timed steps replay the same kernels from a graph
         n0 = model._ufc_ops.launches
         model.get_z(inp_d)
         launches += args.steps * (model._ufc_ops.launches - n0)
-        model.graph_get_z = True
     ms_e2e = timed(e2e_step, args.steps, 2)
     clk = clocks.stop() if clocks else None
 

@@ -12,6 +12,7 @@ reference's module code exists here.
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import pose_native, synth, ufc_native
 
@@ -119,17 +120,59 @@ def _norm_const(dev):
     return _NORM_CONST[key]
 
 
-def encode_images(model, rgb):
+def _fold_bn(conv, bn):
+    """Eval-mode BatchNorm folded into the preceding bias-free convolution: w' = w g / sqrt(var + eps),
+    b' = beta - mean g / sqrt(var + eps). Same function, one kernel instead of two."""
+    scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+    w = conv.weight.detach() * scale.view(-1, 1, 1, 1)
+    b = bn.bias.detach() - bn.running_mean * scale
+    return w.contiguous(), b.contiguous(), conv.stride, conv.padding
+
+
+def fold_encoder(encoder):
+    """SpatialEncoder parameters as a list of folded convolutions, in execution order (stem, then per BasicBlock
+    conv1, conv2 and the optional 1x1 downsample)."""
+    m = encoder.model
+    plan = {"stem": _fold_bn(m.conv1, m.bn1), "layers": []}
+    for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
+        blocks = []
+        for blk in layer:
+            down = _fold_bn(blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None
+            blocks.append((_fold_bn(blk.conv1, blk.bn1), _fold_bn(blk.conv2, blk.bn2), down))
+        plan["layers"].append(blocks)
+    return plan
+
+
+def _conv(x, p, relu):
+    y = F.conv2d(x, p[0], p[1], stride=p[2], padding=p[3])
+    return F.relu_(y) if relu else y
+
+
+def run_folded_encoder(plan, x):
+    """torchvision BasicBlock ResNet-34 forward (no max-pool) over the folded convolutions -> [l4, l3, l2]."""
+    x = _conv(x, plan["stem"], True)
+    outs = []
+    for blocks in plan["layers"]:
+        for c1, c2, down in blocks:
+            idt = x if down is None else _conv(x, down, False)
+            x = F.relu_(_conv(_conv(x, c1, True), c2, False).add_(idt))
+        outs.append(x)
+    return [outs[3], outs[2], outs[1]]
+
+
+def encode_images(model, rgb, plan=None):
     """rgb (B, n_ctxt, H, W, 3) in [-1, 1] -> (ResNet pyramid [3 tensors], conv_map features). CoPoNeRF.py:171-184
-    with utils.normalize_imagenet (utils_training/utils.py:247-257)."""
+    with utils.normalize_imagenet (utils_training/utils.py:247-257). With `plan` (fold_encoder) the BatchNorms are
+    folded into their convolutions; strict fp32 (TF32 off) either way, cuDNN autotuned per shape."""
     x = torch.flatten(rgb, 0, 1).permute(0, 3, 1, 2).to(torch.float32)
     x = (x + 1) / 2.
     mean, std = _norm_const(x.device)
     x = (x - mean) / std
+    enc = (lambda t: run_folded_encoder(plan, t)) if plan is not None else model.encoder
     if x.is_cuda:
-        with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
-            return model.encoder(x), model.conv_map(x)
-    return model.encoder(x), model.conv_map(x)
+        with torch.backends.cudnn.flags(enabled=True, benchmark=True, deterministic=False, allow_tf32=False):
+            return enc(x), model.conv_map(x)
+    return enc(x), model.conv_map(x)
 
 
 def _sub_state(model, prefix):
@@ -143,6 +186,7 @@ def _state_cache(model):
         cache.clear()
         cache["ver"] = ver
         cache["ufc"] = _sub_state(model, "feature_cost_aggregation")
+        cache["encoder"] = fold_encoder(model.encoder)
         full = model.state_dict(keep_vars=True)
         cache["pose"] = {k: v for k, v in full.items()
                          if k.split(".")[0] in ("cross_attention", "pose_regressor", "rotation_regressor",
@@ -153,7 +197,7 @@ def _state_cache(model):
 def _pair_body(model, cache, rgb, pos, ops):
     """Everything of get_z() that runs on the device, as one stream-ordered sequence with no host dependence
     (so it can be captured into a CUDA graph): encoder, cost aggregation, pose features, pose head."""
-    z, z_conv = encode_images(model, rgb)
+    z, z_conv = encode_images(model, rgb, cache["encoder"])
     feats, flows, c = ufc_native.ufc_forward(cache["ufc"], z, model.n_view, ops)
     tokens = feats[-1].flatten(-2, -1).transpose(-1, -2)            # (2B, L, 256)
     pose_feat = pose_native.cross_block(cache["pose"], "cross_attention", tokens, c, pos, ops)
