@@ -82,8 +82,8 @@ class CoPoNeRF(nn.Module):
         self.chunk_rays = chunk_rays
         self.lanes = lanes
         self.native_ufc = True          # get_z(): cost aggregation (UFC) on the sm_100a operators
-        self.graph_get_z = False        # get_z(): replay the per-pair stage from a CUDA graph (same kernels, same bits;
-                                        # measured no faster on B200: the stage is GPU-time bound, not launch bound)
+        self.graph_get_z = True         # get_z(): replay the per-pair stage (~800 short kernels) from a CUDA graph: same
+                                        # kernels, same bits; keeps the stage at its GPU time when the host is slow
         self._ufc_ops = None
         self.pixel_val_on_host = True   # the reference returns out['pixel_val'] as a CPU tensor (CoPoNeRF.py:490)
         self._engine = None

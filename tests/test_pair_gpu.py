@@ -144,16 +144,12 @@ def test_graph_replay_of_get_z_is_bit_identical_to_eager(model):
         for _ in range(2):          # capture, then a pure replay
             zg, pg, fg = model.get_z(inp)
     finally:
-        model.graph_get_z = False
+        model.graph_get_z = True
     torch.cuda.synchronize()
     for a, b in zip(zg + [pg] + list(fg), ze + [pe] + list(fe)):
         assert torch.equal(a, b)
     # a different image through the same graph: results follow the input, and earlier outputs are not overwritten
     inp2 = to_device(_inp(), "cuda:0")
     inp2["context"]["rgb"] = inp2["context"]["rgb"].flip(-2).contiguous()
-    model.graph_get_z = True
-    try:
-        z2, p2, f2 = model.get_z(inp2)
-    finally:
-        model.graph_get_z = False
+    z2, p2, f2 = model.get_z(inp2)
     assert not torch.equal(z2[0], zg[0]) and torch.equal(zg[0], ze[0])
