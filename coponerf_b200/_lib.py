@@ -15,6 +15,7 @@ HIDDEN = 128
 PAIR_CONSTS_FLOATS = 320
 FLAG_SIMT_ONLY = 1
 FLAG_F16X3 = 2
+FLAG_NO_FOLD = 4
 TC_F16X3 = 4
 TC_CLUSTER = 8
 TC_PAIR = 16

@@ -42,7 +42,13 @@ constexpr size_t PHI_F1T = PHI_B0 + 3 * 128;     // 3 x [128][128] phi.blocks.i.
 constexpr size_t PHI_B1 = PHI_F1T + 3 * 128 * 128;
 constexpr size_t PHI_OUT = PHI_B1 + 3 * 128;     // [3][128]    phi.lin_out (not transposed)
 constexpr size_t PHI_BOUT = PHI_OUT + 3 * 128;   // [3] (+1 pad)
-constexpr size_t FP32_END = PHI_BOUT + 4;
+// query_encode_latent_2 folded into latent_value / key_map (no nonlinearity between them, CoPoNeRF.py:393-408):
+// row-major (N, K = 1664) like the state_dict tensors; K index = branch * 832 + k of the 832-wide hidden layer
+constexpr size_t WVF = PHI_BOUT + 4;             // [416][1664]
+constexpr size_t BVF = WVF + 416 * 1664;         // [416]
+constexpr size_t WKF = BVF + 416;                // [128][1664]
+constexpr size_t BKF = WKF + 128 * 1664;         // [128]
+constexpr size_t FP32_END = BKF + 128;
 }  // namespace pw
 
 // ---- per-pair constants (floats), written by cpn_pair_setup ---------------------------------
@@ -128,12 +134,13 @@ constexpr int ACT_CHUNK_BYTES = 2 * (ACT_BK / 8) * 128 * 16;
 constexpr int ACT_LO = 8192;      // f16x3: fp16 lo plane
 constexpr int ACT_LO8 = 8192;     // f8: e4m3 remainder plane
 constexpr int ACT_X8 = 12288;     // f8: e4m3 value plane
-constexpr int CPN_TC_LAYERS = 7;
+constexpr int CPN_TC_LAYERS = 9;
 size_t cpn_packed_fp32_floats();
 size_t cpn_tc_weights_bytes();
-int cpn_pack_tc_weights(const float* raw, void* dst, cudaStream_t st);
+int cpn_pack_tc_weights(const float* raw, const float* packed_fp32, void* dst, cudaStream_t st);
 // layer: 0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value, 3 key_map, 4 key_map_2,
-//        5 query_embed_2, 6 query_repeat_embed_2.  mode: CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE.
+//        5 query_embed_2, 6 query_repeat_embed_2, 7 latent_value o query_encode_latent_2 (K = 1664: the hidden
+//        layer of the primary branch then of the secondary one), 8 key_map o query_encode_latent_2.  mode: CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE.
 //        | CPN_TC_F16X3 (three fp16 MMAs per product instead of fp16 + two fp8 corrections).
 // CPN_TC_OUT_CB16: fp32 output as [row tile][16-col block][128][16]; CPN_TC_OUT_ROWDOT: C[row] = <out row, dotv row> / dot_div
 int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,

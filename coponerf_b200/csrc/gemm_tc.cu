@@ -45,8 +45,9 @@ struct TcLayer {
   int out, in;     // weight shape
   int kpad;        // K padded to a multiple of BK (zero weights beyond `in`)
   int nt;          // N tile
-  size_t raw;      // offset of the weight in the raw state_dict blob (floats)
+  size_t raw;      // offset of the weight in the raw state_dict blob (floats); folded layers: in the packed fp32 section
   size_t bias;     // offset of the fp32 bias in the packed fp32 section
+  bool folded;     // weight computed by cpn_pack_weights (pw::WVF / pw::WKF) instead of read from the state_dict
 };
 // raw blob offsets (floats), see weights.cu kTensors
 constexpr size_t RAW_W1 = 0;
@@ -59,15 +60,18 @@ constexpr size_t RAW_WQ2 = RAW_WQ + 128 * 16 + 128;
 constexpr size_t RAW_WQR = RAW_WQ2 + 128 * 128 + 128;
 constexpr size_t RAW_WQR2 = RAW_WQR + 128 * 144 + 128;
 const TcLayer kLayers[CPN_TC_LAYERS] = {
-    {832, 835, 864, 208, RAW_W1, pw::B1},      // 0 query_encode_latent
-    {416, 832, 832, 208, RAW_W2, pw::B2},      // 1 query_encode_latent_2
-    {416, 832, 832, 208, RAW_WV, pw::BV},      // 2 latent_value
-    {128, 832, 832, 128, RAW_WK, pw::BK},      // 3 key_map
-    {128, 128, 128, 128, RAW_WK2, pw::BK2},    // 4 key_map_2
-    {128, 128, 128, 128, RAW_WQ2, pw::BQ2},    // 5 query_embed_2
-    {128, 128, 128, 128, RAW_WQR2, pw::BQR2},  // 6 query_repeat_embed_2
+    {832, 835, 864, 208, RAW_W1, pw::B1, false},      // 0 query_encode_latent
+    {416, 832, 832, 208, RAW_W2, pw::B2, false},      // 1 query_encode_latent_2
+    {416, 832, 832, 208, RAW_WV, pw::BV, false},      // 2 latent_value
+    {128, 832, 832, 128, RAW_WK, pw::BK, false},      // 3 key_map
+    {128, 128, 128, 128, RAW_WK2, pw::BK2, false},    // 4 key_map_2
+    {128, 128, 128, 128, RAW_WQ2, pw::BQ2, false},    // 5 query_embed_2
+    {128, 128, 128, 128, RAW_WQR2, pw::BQR2, false},  // 6 query_repeat_embed_2
+    {416, 1664, 1664, 208, pw::WVF, pw::BVF, true},   // 7 latent_value o query_encode_latent_2 (both branches)
+    {128, 1664, 1664, 128, pw::WKF, pw::BKF, true},   // 8 key_map o query_encode_latent_2
 };
-constexpr size_t TC_HEADER_BYTES = 256;   // floats [0..7] 1/scale per layer, [8..15] scale, uints [16..23] absmax bits
+constexpr size_t TC_HEADER_BYTES = 256;   // floats [0..15] 1/scale per layer, [16..31] scale, uints [32..47] absmax bits
+static_assert(CPN_TC_LAYERS <= 16, "header slots");
 
 size_t layer_bytes(int l) { return (size_t)kLayers[l].out * kLayers[l].kpad * 4; }  // 4 bytes per weight either scheme
 size_t scheme_bytes() {
@@ -111,7 +115,7 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, int out, int in, int
   float scale = layer_scale(*absmax);
   if (i == 0) {
     header[layer] = 1.f / scale;
-    header[8 + layer] = scale;
+    header[16 + layer] = scale;
   }
   if (i >= total) return;
   int k = (int)(i % kpad), n = (int)(i / kpad);
@@ -535,18 +539,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_pair_kernel(GemmArgs g
 
 size_t cpn_tc_weights_bytes() { return TC_HEADER_BYTES + 3 * scheme_bytes(); }
 
-int cpn_pack_tc_weights(const float* raw, void* dst_v, cudaStream_t st) {
+int cpn_pack_tc_weights(const float* raw, const float* packed_fp32, void* dst_v, cudaStream_t st) {
   unsigned char* dst = reinterpret_cast<unsigned char*>(dst_v);
   float* header = reinterpret_cast<float*>(dst);
-  unsigned int* absmax = reinterpret_cast<unsigned int*>(dst) + 16;
+  unsigned int* absmax = reinterpret_cast<unsigned int*>(dst) + 32;
   CPN_CHECK_CUDA(cudaMemsetAsync(dst, 0, cpn_tc_weights_bytes(), st));
   for (int l = 0; l < CPN_TC_LAYERS; ++l) {
     const TcLayer& L = kLayers[l];
     size_t n = (size_t)L.out * L.in;
-    absmax_kernel<<<64, 256, 0, st>>>(raw + L.raw, n, absmax + l);
+    const float* w = (L.folded ? packed_fp32 : raw) + L.raw;
+    absmax_kernel<<<64, 256, 0, st>>>(w, n, absmax + l);
     CPN_CHECK_LAUNCH("absmax_kernel");
     size_t total = (size_t)L.out * L.kpad;
-    pack_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(raw + L.raw, L.out, L.in, L.kpad, L.nt, absmax + l,
+    pack_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, L.out, L.in, L.kpad, L.nt, absmax + l,
                                                                     reinterpret_cast<__half*>(dst + layer_offset(l, 0)),
                                                                     dst + layer_offset(l, 1), dst + layer_offset(l, 2), header, l);
     CPN_CHECK_LAUNCH("pack_tc_kernel");

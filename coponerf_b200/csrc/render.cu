@@ -212,7 +212,7 @@ extern "C" size_t cpn_render_workspace_bytes(int B, int N, int chunk_rays, int S
 extern "C" int cpn_render_launch_count(const cpn_render_args* a) {
   if (!a || a->chunk_rays <= 0) return 0;
   int chunks = (a->N + a->chunk_rays - 1) / a->chunk_rays;
-  return chunks * 17 + 1;
+  return chunks * (((a->flags & CPN_FLAG_NO_FOLD) || (a->flags & CPN_FLAG_SIMT_ONLY)) ? 17 : 16) + 1;
 }
 
 namespace {
@@ -233,11 +233,20 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
         ProfScope prof(st);
         CPN_TRY(launch_gemm_tc(a.weights, 0, w.A, 0, w.H1, 0, 2 * Rp, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 1, KC832, st));
       }
-      // the (tile, primary) and (tile, secondary) results land side by side: E image rows = sample rows, K = 832
-      CPN_TRY(launch_gemm_tc(a.weights, 1, w.H1, 0, w.E, 0, 2 * Rp, 0, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 2, KC832, st));
-      // value and key, CoPoNeRF.py:404-408
-      CPN_TRY(launch_gemm_tc(a.weights, 2, w.E, 0, w.V, CPN_LATENT, R, 0, CPN_TC_A_IMAGE | sch, 1, 1, st));
-      CPN_TRY(launch_gemm_tc(a.weights, 3, w.E, 0, w.K1, 0, R, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 1, KC128, st));
+      if (a.flags & CPN_FLAG_NO_FOLD) {
+        // the (tile, primary) and (tile, secondary) results land side by side: E image rows = sample rows, K = 832
+        CPN_TRY(launch_gemm_tc(a.weights, 1, w.H1, 0, w.E, 0, 2 * Rp, 0, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 2, KC832, st));
+        // value and key, CoPoNeRF.py:404-408
+        CPN_TRY(launch_gemm_tc(a.weights, 2, w.E, 0, w.V, CPN_LATENT, R, 0, CPN_TC_A_IMAGE | sch, 1, 1, st));
+        CPN_TRY(launch_gemm_tc(a.weights, 3, w.E, 0, w.K1, 0, R, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 1, KC128, st));
+      } else {
+        // query_encode_latent_2 has no activation (CoPoNeRF.py:393-397), so it is folded into latent_value and
+        // key_map at pack time: V = WVF [h_p ; h_s], K1 = relu(WKF [h_p ; h_s]) with K = 1664. The H1 image is
+        // already that operand: a sample tile's primary and secondary hidden tiles are adjacent, 2 x 26 k-chunks.
+        // 21 % fewer MACs than the three layers, and the E image is never written or read.
+        CPN_TRY(launch_gemm_tc(a.weights, 7, w.H1, 0, w.V, CPN_LATENT, R, 0, CPN_TC_A_IMAGE | sch, 1, 1, st));
+        CPN_TRY(launch_gemm_tc(a.weights, 8, w.H1, 0, w.K1, 0, R, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 1, KC128, st));
+      }
       // coordinate embedding, CoPoNeRF.py:446; written column-blocked so the two logit epilogues read it coalesced
       CPN_TRY(dense_simt(a, w.local16, 16, pw::WQT, pw::BQ, w.Q1, CPN_HIDDEN, R, CPN_HIDDEN, 16, 1, st));
       CPN_TRY(launch_gemm_tc(a.weights, 5, w.Q1, CPN_HIDDEN, w.Qe, 0, R, 0, sch | CPN_TC_OUT_CB16, 1, 1, st));

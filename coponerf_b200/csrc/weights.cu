@@ -50,6 +50,25 @@ __global__ void transpose_pack_kernel(const float* __restrict__ src, int src_ld,
   dst[i] = (k < K) ? src[(size_t)n * src_ld + col0 + k] : 0.f;
 }
 
+// Folded layer: WF[n][b * 832 + k] = sum_j Wx[n][b * 416 + j] * W2[j][k] (b = primary / secondary branch) and
+// bF[n] = bx[n] + sum_b sum_j Wx[n][b * 416 + j] * b2[j]: x -> Wx [W2 h_p + b2 ; W2 h_s + b2] + bx as one layer on
+// [h_p ; h_s]. Accumulated in double, so the folded weights are the correctly rounded products.
+__global__ void fold_kernel(const float* __restrict__ Wx, const float* __restrict__ bx, const float* __restrict__ W2,
+                            const float* __restrict__ b2, int N, float* __restrict__ WF, float* __restrict__ bF) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 1664) return;
+  const int n = i / 1664, col = i % 1664, b = col / 832, k = col % 832;
+  const float* wx = Wx + (size_t)n * 832 + b * 416;
+  double acc = 0.0;
+  for (int j = 0; j < 416; ++j) acc += (double)wx[j] * (double)W2[(size_t)j * 832 + k];
+  WF[i] = (float)acc;
+  if (col == 0) {
+    double bb = (double)bx[n];
+    for (int j = 0; j < 832; ++j) bb += (double)Wx[(size_t)n * 832 + j] * (double)b2[j % 416];
+    bF[n] = (float)bb;
+  }
+}
+
 struct Job {
   int tensor, col0, K, Kpad;  // K == 0: plain copy of the whole tensor
   size_t dst;
@@ -110,5 +129,13 @@ extern "C" int cpn_pack_weights(const float* src, void* dst_v, void* stream) {
       CPN_CHECK_LAUNCH("transpose_pack_kernel");
     }
   }
-  return cpn_pack_tc_weights(src, reinterpret_cast<char*>(dst_v) + cpn_packed_fp32_floats() * sizeof(float), st);
+  // query_encode_latent_2 folded into latent_value and key_map
+  const float *W2 = src + tensor_offset(2), *b2 = src + tensor_offset(3);
+  fold_kernel<<<(416 * 1664 + 255) / 256, 256, 0, st>>>(src + tensor_offset(4), src + tensor_offset(5), W2, b2, 416,
+                                                        dst + pw::WVF, dst + pw::BVF);
+  CPN_CHECK_LAUNCH("fold_kernel");
+  fold_kernel<<<(128 * 1664 + 255) / 256, 256, 0, st>>>(src + tensor_offset(6), src + tensor_offset(7), W2, b2, 128,
+                                                        dst + pw::WKF, dst + pw::BKF);
+  CPN_CHECK_LAUNCH("fold_kernel");
+  return cpn_pack_tc_weights(src, dst, reinterpret_cast<char*>(dst_v) + cpn_packed_fp32_floats() * sizeof(float), st);
 }

@@ -38,6 +38,8 @@ typedef enum {
 #define CPN_PAIR_CONSTS_FLOATS 320
 #define CPN_FLAG_SIMT_ONLY 1  /* run the big 1x1 convs on the fp32 CUDA-core GEMM (cross-check path) */
 #define CPN_FLAG_F16X3 2      /* tensor-core GEMMs with three fp16 MMAs per product (default: fp16 + 2 fp8) */
+#define CPN_FLAG_NO_FOLD 4    /* keep query_encode_latent_2, latent_value and key_map as three GEMMs (default: the
+                               * activation-free query_encode_latent_2 is folded into the other two at pack time) */
 
 int cpn_version(void);
 const char* cpn_last_error(void);
@@ -239,7 +241,8 @@ int cpn_gemm_simt(const float* A, int lda, const float* wt, const float* bias, f
                   int M, int N, int K, int relu /* 0 none, 1 ReLU, 2 exact GELU */, void* stream);
 
 /* Tensor-core GEMM of one packed layer (0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value,
- * 3 key_map, 4 key_map_2, 5 query_embed_2, 6 query_repeat_embed_2): C[M, N_layer] = act(A[M, K_layer] * W^T + b),
+ * 3 key_map, 4 key_map_2, 5 query_embed_2, 6 query_repeat_embed_2, 7 latent_value o query_encode_latent_2,
+ * 8 key_map o query_encode_latent_2, both with K = 1664): C[M, N_layer] = act(A[M, K_layer] * W^T + b),
  * operands split into an fp16 head plus corrections (e4m3 on the fp8 path by default, fp16 with CPN_TC_F16X3)
  * and accumulated in fp32 on tcgen05.
  * `packed` is the blob from cpn_pack_weights. mode bit CPN_TC_A_IMAGE: A is an "operand image" (128-row tiles,

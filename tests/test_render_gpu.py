@@ -273,3 +273,52 @@ def test_gemm_tc_cb16_and_rowdot_epilogues():
     kk = torch.nn.functional.linear(k1.double(), Wk.double(), bk.double())
     ref = (kk * qe).sum(-1) / 11.31
     assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_unfolded_encoder_tail_matches_reference_golden(case):
+    """CPN_FLAG_NO_FOLD: query_encode_latent_2, latent_value and key_map as three GEMMs (the default folds the
+    activation-free query_encode_latent_2 into the other two at pack time)."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, case + ".npz")))
+    H, W, n_rays, S, seed, val = [int(v) for v in g["meta"]]
+    out = run_cuda(H, W, n_rays, S, seed, val, flags=4)
+    check_against(out, g, case + "/no-fold")
+
+
+@pytest.mark.parametrize("R", [300, 1024], ids=["ragged", "whole-pairs"])
+@pytest.mark.parametrize("scheme", [0, 4], ids=["f16+f8", "f16x3"])
+def test_gemm_tc_folded_value_and_key_layers(scheme, R):
+    """fp32 -> [GEMM1] -> H1 image -> folded layers 7 (latent_value o query_encode_latent_2) and 8 (key_map o
+    query_encode_latent_2) reading the H1 image as a K = 1664 operand, against the unfolded chain in fp64."""
+    from coponerf_b200 import _lib
+    lib, eng, W1, b1 = _tc_setup("query_encode_latent")
+    _, _, W2, b2 = _tc_setup("query_encode_latent_2")
+    _, _, WV, bV = _tc_setup("latent_value")
+    _, _, WK, bK = _tc_setup("key_map")
+    torch.manual_seed(11)
+    Rp = (R + 127) // 128 * 128
+    x = torch.randn(2, R, 835, device="cuda")  # [branch][row]
+    A = torch.zeros(2 * Rp, 848, device="cuda")
+    rows = torch.arange(R, device="cuda")
+    for br in range(2):
+        A[(rows // 128) * 256 + br * 128 + rows % 128, :835] = x[br]
+    chunk = _lib.ACT_CHUNK_BYTES
+    H1 = torch.empty(2 * Rp // 128 * 26 * chunk, dtype=torch.uint8, device="cuda")
+    K1 = torch.empty(Rp // 128 * 4 * chunk, dtype=torch.uint8, device="cuda")
+    V = torch.full((R, 416), float("nan"), device="cuda")
+    Kk = torch.full((R, 128), float("nan"), device="cuda")
+    w = _p(eng.weights)
+    _lib.check(lib.cpn_gemm_tc(w, 0, _p(A), 848, _p(H1), 0, 2 * Rp, 1, _lib.TC_OUT_IMAGE | scheme, 1, 26, _st()), "gemm1")
+    _lib.check(lib.cpn_gemm_tc(w, 7, _p(H1), 0, _p(V), 416, R, 0, _lib.TC_A_IMAGE | scheme, 1, 1, _st()), "gemmVF")
+    _lib.check(lib.cpn_gemm_tc(w, 8, _p(H1), 0, _p(K1), 0, R, 1, _lib.TC_A_IMAGE | _lib.TC_OUT_IMAGE | scheme, 1, 4, _st()), "gemmKF")
+    _lib.check(lib.cpn_gemm_tc(w, 4, _p(K1), 0, _p(Kk), 128, R, 0, _lib.TC_A_IMAGE | scheme, 1, 1, _st()), "gemmK2")
+    lin = torch.nn.functional.linear
+    h = lin(x.double(), W1.double(), b1.double()).relu()
+    e = lin(h, W2.double(), b2.double())                      # (2, R, 416)
+    cat = torch.cat((e[0], e[1]), dim=-1)
+    ref_v = lin(cat, WV.double(), bV.double())
+    _, _, WK2, bK2 = _tc_setup("key_map_2")
+    ref_k = lin(lin(cat, WK.double(), bK.double()).relu(), WK2.double(), bK2.double())
+    ev, ek = rel_err(V.cpu().numpy(), ref_v.cpu().numpy()), rel_err(Kk.cpu().numpy(), ref_k.cpu().numpy())
+    print(f"folded layers scheme={scheme}: V rel err {ev:.2e}, key rel err {ek:.2e}")
+    assert ev < (2e-5 if scheme == 4 else 1e-4) and ek < (2e-5 if scheme == 4 else 1e-4), (ev, ek)
