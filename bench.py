@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--lanes", type=int, default=2, help="chunks in flight on internal streams")
     ap.add_argument("--simt", action="store_true", help="fp32 CUDA-core GEMMs only (cross-check path)")
     ap.add_argument("--no-fold", action="store_true", help="keep query_encode_latent_2 / latent_value / key_map as three GEMMs")
+    ap.add_argument("--early-v", action="store_true", help="form V per sample (GEMM over all sample rows) instead of the late readout")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager-get-z", action="store_true", help="launch get_z()'s kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--stage", default="full", choices=["full", "pair", "render"],
@@ -228,7 +229,8 @@ def main():
     model.graph_get_z = not args.eager_get_z
     model.H, model.W = H, W
     eng = model.engine()
-    eng.flags = (_lib.FLAG_SIMT_ONLY if args.simt else 0) | (_lib.FLAG_NO_FOLD if args.no_fold else 0)
+    eng.flags = (_lib.FLAG_SIMT_ONLY if args.simt else 0) | (_lib.FLAG_NO_FOLD if args.no_fold else 0) | \
+        (_lib.FLAG_EARLY_V if args.early_v else 0)
     lib = _lib.load()
 
     # ---- cost aggregation (per-pair stage): seeded UFC parameters and encoder pyramid
@@ -390,7 +392,8 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.stage], "stage": args.stage, "get_z": "eager launches" if args.eager_get_z else "CUDA graph replay", "pairs_per_gpu": 1, "chunk_rays": args.chunk_rays, "lanes": args.lanes, "l2": "flushed between timed steps (256 MB write)",
                    "gemm_path": "simt-fp32" if args.simt else "tcgen05: fp16 head + two e4m3 correction MMAs per product (fp32 accumulate)"
-                                + ("" if args.no_fold else "; query_encode_latent_2 folded into latent_value / key_map"),
+                                + ("" if args.no_fold else "; query_encode_latent_2 folded into latent_value / key_map")
+                                + ("" if (args.no_fold or args.early_v or args.simt) else "; attention reads out the hidden layer, latent_value per ray"),
                    "parallelism": f"pairs sharded over {world} GPU(s), one NCCL gather of rgb" if world > 1 else "1 GPU"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},

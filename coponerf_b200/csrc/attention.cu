@@ -6,6 +6,8 @@
 // view 0 samples, then view 1 samples). Reductions run in a fixed order per ray, so the result of a
 // ray does not depend on which chunk or rank renders it.
 #include <math.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include "cpn_common.cuh"
 
 namespace {
@@ -69,7 +71,7 @@ __device__ __forceinline__ float block_softmax(float logit, float* red, int warp
 __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* __restrict__ key,
                              const float* __restrict__ qemb, const float* __restrict__ value,
                              const float* __restrict__ rowaux, float* __restrict__ r1, float* __restrict__ wp,
-                             const float* __restrict__ logits) {
+                             const float* __restrict__ logits, float* __restrict__ wts_out) {
   extern __shared__ float sm[];
   const int S = a.S, S2 = 2 * S;
   float* w = sm;            // [2S]
@@ -81,6 +83,7 @@ __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* _
   float logit = logits ? logits[row0 + t] : warp_row_logits(key, qemb, row0, warp, lane);
   float wt = block_softmax(logit, red, warp, lane, nwarps);
   w[t] = wt;
+  if (wts_out) wts_out[row0 + t] = wt;   // late readout (readout_image_kernel): the weights leave, V is never formed
   {
     int v = t / S, s = t % S;
     a.at_wt[(((size_t)(b * 2 + v)) * a.N + n) * S + s] = wt;
@@ -136,6 +139,7 @@ __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* _
     for (int i = 0; i < wpv; ++i) acc1 += red[16 + (wpv + i) * 3 + c];
     wp[(size_t)ray * 4 + c] = acc0 + acc1;
   }
+  if (!value) return;
   for (int c = t; c < CPN_LATENT; c += S2) {
     const float* vp = value + row0 * CPN_LATENT + c;
     float acc0 = 0.f, acc1 = 0.f;
@@ -150,7 +154,8 @@ __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* _
 // Round 2. z = sum_v (sum_s w2 * V + R1) = R2 + 2 R1.
 __global__ void attn2_kernel(cpn_render_args a, int ray0, int nr, const float* __restrict__ q2,
                              const float* __restrict__ qemb, const float* __restrict__ value,
-                             const float* __restrict__ r1, float* __restrict__ z_all, const float* __restrict__ logits) {
+                             const float* __restrict__ r1, float* __restrict__ z_all, const float* __restrict__ logits,
+                             float* __restrict__ wts_out) {
   extern __shared__ float sm[];
   const int S = a.S, S2 = 2 * S;
   float* w = sm;
@@ -160,6 +165,8 @@ __global__ void attn2_kernel(cpn_render_args a, int ray0, int nr, const float* _
   const size_t row0 = (size_t)ray * S2;
   float logit = logits ? logits[row0 + t] : warp_row_logits(q2, qemb, row0, warp, lane);
   w[t] = block_softmax(logit, red, warp, lane, nwarps);
+  if (wts_out) wts_out[row0 + t] = w[t];
+  if (!value) return;
   __syncthreads();
   for (int c = t; c < CPN_LATENT; c += S2) {
     const float* vp = value + row0 * CPN_LATENT + c;
@@ -172,6 +179,89 @@ __global__ void attn2_kernel(cpn_render_args a, int ray0, int nr, const float* _
     const int b = ray / nr, n = ray0 + ray % nr;
     z_all[((size_t)b * a.N + n) * CPN_LATENT + c] = (acc0 + r) + (acc1 + r);
   }
+}
+
+// ---- late readout -----------------------------------------------------------------------------------------------
+// latent_value (folded with query_encode_latent_2: V = WVF [h_p ; h_s] + b) is linear and the softmax weights of a ray
+// sum to one, so  sum_rows w V = WVF (sum_rows w [h_p ; h_s]) + b : the attention reads out the 1664-wide hidden
+// layer straight from its operand image (fp16 head + correction plane, the same bytes the GEMM would consume) and the
+// 416 x 1664 layer runs once per RAY instead of once per SAMPLE (128x fewer rows). V is never formed.
+//   hbar[ray][br * 832 + k] = sum_{r < 2S} w[ray * 2S + r] * h_br[row r of the ray][k],  rows in ascending order.
+// Thread -> (branch, k-chunk, group of 8 k): 208 threads per ray. Eight consecutive rows of a group are one 128-byte
+// line of the image, fetched by eight back-to-back 16-byte loads.
+template <bool F8>
+__global__ void __launch_bounds__(224) readout_image_kernel(const unsigned char* __restrict__ img,
+                                                            const float* __restrict__ wts, int S2,
+                                                            float* __restrict__ hbar) {
+  extern __shared__ float sm[];   // [2S] weights of this ray
+  const int ray = blockIdx.x, t = threadIdx.x;
+  const size_t row0 = (size_t)ray * S2;
+  for (int i = t; i < S2; i += blockDim.x) sm[i] = wts[row0 + i];
+  __syncthreads();
+  constexpr int KC = CPN_FEAT_DIM / ACT_BK;   // 26 k-chunks per hidden tile
+  if (t >= 2 * KC * 4) return;
+  const int br = t / (KC * 4), kc = (t % (KC * 4)) >> 2, g = t & 3;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int r0 = 0; r0 < S2; r0 += 8) {          // 2S % 64 == 0 and row0 % 64 == 0: the 8 rows share a tile
+    const size_t row = row0 + r0;
+    const unsigned char* blk = img + (((row >> 7) * 2 + br) * KC + kc) * (size_t)ACT_CHUNK_BYTES + (row & 127) * 16;
+    uint4 hi[8];
+    uint4 lo16[F8 ? 1 : 8];
+    uint2 lo8[F8 ? 8 : 1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      hi[i] = __ldg(reinterpret_cast<const uint4*>(blk + g * 2048 + i * 16));
+      if (F8) lo8[i] = __ldg(reinterpret_cast<const uint2*>(blk + ACT_LO8 + (g >> 1) * 2048 + i * 16 + (g & 1) * 8));
+      else lo16[i] = __ldg(reinterpret_cast<const uint4*>(blk + ACT_LO + g * 2048 + i * 16));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float w = sm[r0 + i];
+      const uint32_t hw[4] = {hi[i].x, hi[i].y, hi[i].z, hi[i].w};
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+        x[2 * j] = f.x;
+        x[2 * j + 1] = f.y;
+      }
+      if (F8) {
+        const uint32_t lw[2] = {lo8[i].x, lo8[i].y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __half2_raw h2 = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((lw[j >> 1] >> ((j & 1) * 16)) & 0xffffu), __NV_E4M3);
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+          x[2 * j] = fmaf(f.x, 1.f / 256.f, x[2 * j]);          // e4m3((x - hi) * 2^8), tc_common.cuh
+          x[2 * j + 1] = fmaf(f.y, 1.f / 256.f, x[2 * j + 1]);
+        }
+      } else {
+        const uint32_t lw[4] = {lo16[i].x, lo16[i].y, lo16[i].z, lo16[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
+          x[2 * j] += f.x;
+          x[2 * j + 1] += f.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, x[j], acc[j]);
+    }
+  }
+  float* out = hbar + (size_t)ray * (2 * CPN_FEAT_DIM) + br * CPN_FEAT_DIM + kc * ACT_BK + g * 8;
+  *reinterpret_cast<float4*>(out) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  *reinterpret_cast<float4*>(out + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+// z = sum_v (R2 + R1) = R2 + 2 R1 (CoPoNeRF.py:481-485), R2 = WVF hbar2 + b from the late readout of round 2
+__global__ void combine_z_kernel(cpn_render_args a, int ray0, int nr, const float* __restrict__ r2,
+                                 const float* __restrict__ r1, float* __restrict__ z_all) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.B * nr * CPN_LATENT) return;
+  const int ray = i / CPN_LATENT, c = i % CPN_LATENT, b = ray / nr, n = ray0 + ray % nr;
+  const float r = r1[i];
+  z_all[((size_t)b * a.N + n) * CPN_LATENT + c] = (r2[i] + r) + r;
 }
 
 // phi. One CTA of 128 threads renders PHI_RAYS = 16 rays. Thread (cq = t % 32, rg = t / 32) owns a 4-channel x
@@ -288,18 +378,44 @@ __global__ void __launch_bounds__(128) phi_kernel(cpn_render_args a, const float
 }  // namespace
 
 int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, const float* qemb, const float* value,
-                 const float* rowaux, float* r1, float* wp, cudaStream_t st, const float* logits) {
+                 const float* rowaux, float* r1, float* wp, cudaStream_t st, const float* logits, float* wts_out) {
   int S2 = 2 * a.S;
-  attn1_kernel<<<a.B * nr, S2, (S2 + 48) * sizeof(float), st>>>(a, ray0, nr, key, qemb, value, rowaux, r1, wp, logits);
+  attn1_kernel<<<a.B * nr, S2, (S2 + 48) * sizeof(float), st>>>(a, ray0, nr, key, qemb, value, rowaux, r1, wp, logits,
+                                                                wts_out);
   CPN_CHECK_LAUNCH("attn1_kernel");
   return CPN_OK;
 }
 
 int launch_attn2(const cpn_render_args& a, int ray0, int nr, const float* q2, const float* qemb, const float* value,
-                 const float* r1, float* z_all, cudaStream_t st, const float* logits) {
+                 const float* r1, float* z_all, cudaStream_t st, const float* logits, float* wts_out) {
   int S2 = 2 * a.S;
-  attn2_kernel<<<a.B * nr, S2, (S2 + 8) * sizeof(float), st>>>(a, ray0, nr, q2, qemb, value, r1, z_all, logits);
+  attn2_kernel<<<a.B * nr, S2, (S2 + 8) * sizeof(float), st>>>(a, ray0, nr, q2, qemb, value, r1, z_all, logits, wts_out);
   CPN_CHECK_LAUNCH("attn2_kernel");
+  return CPN_OK;
+}
+
+int launch_readout_image(const cpn_render_args& a, int nr, const void* h1_image, const float* wts, float* hbar, int f8,
+                         cudaStream_t st) {
+  const int S2 = 2 * a.S;
+  if (S2 % 64) {
+    cpn_set_error("readout_image: S=%d unsupported (S must be a multiple of 32)", a.S);
+    return CPN_ERR_ARG;
+  }
+  if (f8)
+    readout_image_kernel<true><<<a.B * nr, 224, S2 * sizeof(float), st>>>(reinterpret_cast<const unsigned char*>(h1_image),
+                                                                           wts, S2, hbar);
+  else
+    readout_image_kernel<false><<<a.B * nr, 224, S2 * sizeof(float), st>>>(reinterpret_cast<const unsigned char*>(h1_image),
+                                                                            wts, S2, hbar);
+  CPN_CHECK_LAUNCH("readout_image_kernel");
+  return CPN_OK;
+}
+
+int launch_combine_z(const cpn_render_args& a, int ray0, int nr, const float* r2, const float* r1, float* z_all,
+                     cudaStream_t st) {
+  const int total = a.B * nr * CPN_LATENT;
+  combine_z_kernel<<<(total + 255) / 256, 256, 0, st>>>(a, ray0, nr, r2, r1, z_all);
+  CPN_CHECK_LAUNCH("combine_z_kernel");
   return CPN_OK;
 }
 

@@ -115,10 +115,16 @@ int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias
                      int remap256 = 0, float out_div = 0.f);   // out_div != 0: result divided by it
 // logits != nullptr: one precomputed logit per sample row (key / qemb unused); else <key, qemb> / 11.31 is computed here
 int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, const float* qemb, const float* value,
-                 const float* rowaux, float* r1, float* wp, cudaStream_t st, const float* logits = nullptr);
+                 const float* rowaux, float* r1, float* wp, cudaStream_t st, const float* logits = nullptr,
+                 float* wts_out = nullptr);   // value == nullptr: no readout here, the weights go to wts_out
 // z_all: (B, N, 416) latent of every ray of the image
 int launch_attn2(const cpn_render_args& a, int ray0, int nr, const float* q2, const float* qemb, const float* value,
-                 const float* r1, float* z_all, cudaStream_t st, const float* logits = nullptr);
+                 const float* r1, float* z_all, cudaStream_t st, const float* logits = nullptr, float* wts_out = nullptr);
+// late readout: hbar (rays, 1664) = sum over a ray's rows of w * [h_p ; h_s] read from the hidden-layer operand image
+int launch_readout_image(const cpn_render_args& a, int nr, const void* h1_image, const float* wts, float* hbar, int f8,
+                         cudaStream_t st);
+int launch_combine_z(const cpn_render_args& a, int ray0, int nr, const float* r2, const float* r1, float* z_all,
+                     cudaStream_t st);
 int launch_phi(const cpn_render_args& a, const float* z_all, cudaStream_t st);
 int launch_ray_epilogue(const cpn_render_args& a, int ray0, int nr, const float* wp, const float* seg, cudaStream_t st);
 

@@ -75,7 +75,8 @@ struct ProfScope {  // records an event pair around the enclosed launches when a
 
 // Workspace carve-up for one chunk of `nr` rays of each of B pairs (R = B * nr * 2 * S sample rows).
 struct Workspace {
-  float *seg, *rowaux, *local16, *A, *H1, *E, *V, *K1, *Kk, *Q1, *Qe, *r1, *wp, *zemb, *rbias, *lg1, *lg2;
+  float *seg, *rowaux, *local16, *A, *H1, *E, *V, *K1, *Kk, *Q1, *Qe, *r1, *wp, *zemb, *rbias, *lg1, *lg2, *wt1, *wt2,
+      *hbar, *r2;
   size_t bytes;
 };
 
@@ -105,6 +106,10 @@ Workspace carve(void* base, int B, int nr, int S) {
   w.rbias = take(rays * CPN_HIDDEN);
   w.lg1 = take(R);   // attention logits of round 1 / round 2, one per sample row
   w.lg2 = take(R);
+  w.wt1 = take(R);   // late readout: softmax weights of round 1 / round 2, weighted hidden layer, round-2 latent
+  w.wt2 = take(R);
+  w.hbar = take(rays * 2 * CPN_FEAT_DIM);
+  w.r2 = take(rays * CPN_LATENT);
   w.bytes = off;
   return w;
 }
@@ -212,7 +217,9 @@ extern "C" size_t cpn_render_workspace_bytes(int B, int N, int chunk_rays, int S
 extern "C" int cpn_render_launch_count(const cpn_render_args* a) {
   if (!a || a->chunk_rays <= 0) return 0;
   int chunks = (a->N + a->chunk_rays - 1) / a->chunk_rays;
-  return chunks * (((a->flags & CPN_FLAG_NO_FOLD) || (a->flags & CPN_FLAG_SIMT_ONLY)) ? 17 : 16) + 1;
+  const bool unfolded = (a->flags & CPN_FLAG_NO_FOLD) || (a->flags & CPN_FLAG_SIMT_ONLY);
+  const int per_chunk = unfolded ? 17 : ((a->flags & CPN_FLAG_EARLY_V) ? 16 : 20);
+  return chunks * per_chunk + 1;
 }
 
 namespace {
@@ -226,6 +233,8 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
     const int Rp = (R + 127) / 128 * 128;
     const int KC832 = CPN_FEAT_DIM / ACT_BK, KC128 = CPN_HIDDEN / ACT_BK;
     const int sch = tc_scheme(a);
+    // late readout (attention.cu): the attention reads out the hidden layer and the folded latent_value runs per ray
+    const bool late_v = use_tc(a) && !(a.flags & (CPN_FLAG_NO_FOLD | CPN_FLAG_EARLY_V));
     if (use_tc(a)) {
       // per-sample encoder, CoPoNeRF.py:387-397: (835 -> 832 ReLU -> 416) for the primary and the secondary rows.
       // Activations travel between the tensor-core layers as fp16 hi/lo operand images (cpn_common.cuh).
@@ -244,7 +253,8 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
         // key_map at pack time: V = WVF [h_p ; h_s], K1 = relu(WKF [h_p ; h_s]) with K = 1664. The H1 image is
         // already that operand: a sample tile's primary and secondary hidden tiles are adjacent, 2 x 26 k-chunks.
         // 21 % fewer MACs than the three layers, and the E image is never written or read.
-        CPN_TRY(launch_gemm_tc(a.weights, 7, w.H1, 0, w.V, CPN_LATENT, R, 0, CPN_TC_A_IMAGE | sch, 1, 1, st));
+        if (!late_v)
+          CPN_TRY(launch_gemm_tc(a.weights, 7, w.H1, 0, w.V, CPN_LATENT, R, 0, CPN_TC_A_IMAGE | sch, 1, 1, st));
         CPN_TRY(launch_gemm_tc(a.weights, 8, w.H1, 0, w.K1, 0, R, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 1, KC128, st));
       }
       // coordinate embedding, CoPoNeRF.py:446; written column-blocked so the two logit epilogues read it coalesced
@@ -265,7 +275,13 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
       CPN_TRY(dense_simt(a, w.local16, 16, pw::WQT, pw::BQ, w.Q1, CPN_HIDDEN, R, CPN_HIDDEN, 16, 1, st));
       CPN_TRY(dense_simt(a, w.Q1, CPN_HIDDEN, pw::WQ2T, pw::BQ2, w.Qe, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
     }
-    CPN_TRY(launch_attn1(a, ray0, nr, w.Kk, w.Qe, w.V, w.rowaux, w.r1, w.wp, st, use_tc(a) ? w.lg1 : nullptr));
+    if (late_v) {
+      CPN_TRY(launch_attn1(a, ray0, nr, w.Kk, w.Qe, nullptr, w.rowaux, w.r1, w.wp, st, w.lg1, w.wt1));
+      CPN_TRY(launch_readout_image(a, nr, w.H1, w.wt1, w.hbar, a_form(a) == 2, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 7, w.hbar, 2 * CPN_FEAT_DIM, w.r1, CPN_LATENT, rays, 0, sch, 1, 1, st));
+    } else {
+      CPN_TRY(launch_attn1(a, ray0, nr, w.Kk, w.Qe, w.V, w.rowaux, w.r1, w.wp, st, use_tc(a) ? w.lg1 : nullptr));
+    }
     // round 2, CoPoNeRF.py:467-473: query_repeat_embed(cat(encode_latent(R1), local_coords)); the z_embed
     // channels are the same for every sample of a ray, so they enter as a per-ray bias.
     CPN_TRY(dense_simt(a, w.r1, CPN_LATENT, pw::WET, pw::BE, w.zemb, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_LATENT, 0, st));
@@ -277,7 +293,14 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
                              11.31f));
     else
       CPN_TRY(dense_simt(a, w.K1, CPN_HIDDEN, pw::WQR2T, pw::BQR2, w.Kk, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
-    CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, w.V, w.r1, z_all, st, use_tc(a) ? w.lg2 : nullptr));
+    if (late_v) {
+      CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, nullptr, w.r1, z_all, st, w.lg2, w.wt2));
+      CPN_TRY(launch_readout_image(a, nr, w.H1, w.wt2, w.hbar, a_form(a) == 2, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 7, w.hbar, 2 * CPN_FEAT_DIM, w.r2, CPN_LATENT, rays, 0, sch, 1, 1, st));
+      CPN_TRY(launch_combine_z(a, ray0, nr, w.r2, w.r1, z_all, st));
+    } else {
+      CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, w.V, w.r1, z_all, st, use_tc(a) ? w.lg2 : nullptr));
+    }
     CPN_TRY(launch_ray_epilogue(a, ray0, nr, w.wp, w.seg, st));
     return CPN_OK;
 }

@@ -31,6 +31,9 @@ typedef enum {
   CPN_ERR_CUDA = -3        /* a CUDA runtime call or launch failed */
 } cpn_status;
 
+#define CPN_FLAG_EARLY_V 8    /* form V = latent_value(...) per sample (one GEMM over all sample rows) and let the attention
+                               * read it; default: the attention reads out the hidden layer and the (linear) folded
+                               * latent_value runs once per ray ("late readout") */
 #define CPN_N_LEVELS 4      /* feature maps per view: 3 refined ResNet levels + conv_map */
 #define CPN_FEAT_DIM 832    /* 256*3 + 64, models/CoPoNeRF.py:68 */
 #define CPN_LATENT 416      /* latent_dim // 2, models/CoPoNeRF.py:74 */

@@ -322,3 +322,22 @@ def test_gemm_tc_folded_value_and_key_layers(scheme, R):
     ev, ek = rel_err(V.cpu().numpy(), ref_v.cpu().numpy()), rel_err(Kk.cpu().numpy(), ref_k.cpu().numpy())
     print(f"folded layers scheme={scheme}: V rel err {ev:.2e}, key rel err {ek:.2e}")
     assert ev < (2e-5 if scheme == 4 else 1e-4) and ek < (2e-5 if scheme == 4 else 1e-4), (ev, ek)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_early_value_path_matches_reference_golden(case):
+    """CPN_FLAG_EARLY_V: V formed per sample by one GEMM and read by the attention kernels (the default reads out the
+    hidden layer and applies the folded latent_value once per ray)."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, case + ".npz")))
+    H, W, n_rays, S, seed, val = [int(v) for v in g["meta"]]
+    out = run_cuda(H, W, n_rays, S, seed, val, flags=8)
+    check_against(out, g, case + "/early-v")
+
+
+@pytest.mark.parametrize("case", CASES[:2])
+def test_late_readout_with_f16x3_images(case):
+    """The late readout reading [fp16 hi | fp16 lo] operand images (CPN_FLAG_F16X3)."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, case + ".npz")))
+    H, W, n_rays, S, seed, val = [int(v) for v in g["meta"]]
+    out = run_cuda(H, W, n_rays, S, seed, val, flags=2)
+    check_against(out, g, case + "/late-f16x3")
