@@ -9,6 +9,7 @@
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 #include "cpn_common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -186,40 +187,34 @@ __global__ void attn2_kernel(cpn_render_args a, int ray0, int nr, const float* _
 // sum to one, so  sum_rows w V = WVF (sum_rows w [h_p ; h_s]) + b : the attention reads out the 1664-wide hidden
 // layer straight from its operand image (fp16 head + correction plane, the same bytes the GEMM would consume) and the
 // 416 x 1664 layer runs once per RAY instead of once per SAMPLE (128x fewer rows). V is never formed.
-//   hbar[ray][br * 832 + k] = sum_{r < 2S} w[ray * 2S + r] * h_br[row r of the ray][k],  rows in ascending order.
-// Thread -> (branch, k-chunk, group of 8 k): 208 threads per ray. Eight consecutive rows of a group are one 128-byte
-// line of the image, fetched by eight back-to-back 16-byte loads.
+//   hbar[ray][br * 832 + k] = sum_{r < 2S} w[ray * 2S + r] * h_br[row r of the ray][k],  rows in ascending order,
+// written as the operand image of the per-ray GEMM (K = 1664, rows = rays).
+// CTA -> (ray, branch), 4 warps; warp -> a (k-chunk, group of 8 k) unit at a time, lane -> row: a warp load is 32
+// consecutive 16-byte rows = 512 contiguous bytes (lanes along k-groups instead made every load 32 wavefronts and
+// the L1 data pipe, not HBM, the limit: 83 % LSU-wavefront utilisation at 3.9 TB/s). Each lane accumulates its rows
+// r = lane, lane + 32, ..., then the 8 sums are reduced over the lanes with a halving butterfly (9 shuffles).
 template <bool F8>
-__global__ void __launch_bounds__(224) readout_image_kernel(const unsigned char* __restrict__ img,
+__global__ void __launch_bounds__(128) readout_image_kernel(const unsigned char* __restrict__ img,
                                                             const float* __restrict__ wts, int S2,
                                                             float* __restrict__ hbar) {
-  extern __shared__ float sm[];   // [2S] weights of this ray
-  const int ray = blockIdx.x, t = threadIdx.x;
+  extern __shared__ float sm[];   // [2S] weights of this ray, [832] weighted sums of this branch
+  float* hb = sm + S2;
+  const int ray = blockIdx.x, br = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const size_t row0 = (size_t)ray * S2;
   for (int i = t; i < S2; i += blockDim.x) sm[i] = wts[row0 + i];
   __syncthreads();
   constexpr int KC = CPN_FEAT_DIM / ACT_BK;   // 26 k-chunks per hidden tile
-  if (t >= 2 * KC * 4) return;
-  const int br = t / (KC * 4), kc = (t % (KC * 4)) >> 2, g = t & 3;
-  float acc[8];
+  for (int u = warp; u < KC * 4; u += 4) {
+    const int kc = u >> 2, g = u & 3;
+    float acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int r0 = 0; r0 < S2; r0 += 8) {          // 2S % 64 == 0 and row0 % 64 == 0: the 8 rows share a tile
-    const size_t row = row0 + r0;
-    const unsigned char* blk = img + (((row >> 7) * 2 + br) * KC + kc) * (size_t)ACT_CHUNK_BYTES + (row & 127) * 16;
-    uint4 hi[8];
-    uint4 lo16[F8 ? 1 : 8];
-    uint2 lo8[F8 ? 8 : 1];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      hi[i] = __ldg(reinterpret_cast<const uint4*>(blk + g * 2048 + i * 16));
-      if (F8) lo8[i] = __ldg(reinterpret_cast<const uint2*>(blk + ACT_LO8 + (g >> 1) * 2048 + i * 16 + (g & 1) * 8));
-      else lo16[i] = __ldg(reinterpret_cast<const uint4*>(blk + ACT_LO + g * 2048 + i * 16));
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float w = sm[r0 + i];
-      const uint32_t hw[4] = {hi[i].x, hi[i].y, hi[i].z, hi[i].w};
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 4
+    for (int r = lane; r < S2; r += 32) {
+      const size_t row = row0 + r;
+      const unsigned char* p = img + (((row >> 7) * 2 + br) * KC + kc) * (size_t)ACT_CHUNK_BYTES + (row & 127) * 16;
+      const uint4 hi = __ldg(reinterpret_cast<const uint4*>(p + g * 2048));
+      const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w};
       float x[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -228,7 +223,8 @@ __global__ void __launch_bounds__(224) readout_image_kernel(const unsigned char*
         x[2 * j + 1] = f.y;
       }
       if (F8) {
-        const uint32_t lw[2] = {lo8[i].x, lo8[i].y};
+        const uint2 lo = __ldg(reinterpret_cast<const uint2*>(p + ACT_LO8 + (g >> 1) * 2048 + (g & 1) * 8));
+        const uint32_t lw[2] = {lo.x, lo.y};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const __half2_raw h2 = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((lw[j >> 1] >> ((j & 1) * 16)) & 0xffffu), __NV_E4M3);
@@ -237,7 +233,8 @@ __global__ void __launch_bounds__(224) readout_image_kernel(const unsigned char*
           x[2 * j + 1] = fmaf(f.y, 1.f / 256.f, x[2 * j + 1]);
         }
       } else {
-        const uint32_t lw[4] = {lo16[i].x, lo16[i].y, lo16[i].z, lo16[i].w};
+        const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p + ACT_LO + g * 2048));
+        const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
@@ -245,13 +242,50 @@ __global__ void __launch_bounds__(224) readout_image_kernel(const unsigned char*
           x[2 * j + 1] += f.y;
         }
       }
+      const float w = sm[r];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, x[j], acc[j]);
     }
+    // halving butterfly: after the xor-16 / 8 / 4 steps every lane holds one of the 8 values (index from lane bits
+    // 4, 3, 2), summed over 8 lanes; xor-2 and xor-1 finish it. Fixed order, independent of chunking.
+    float a4[4], a2[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float send = (lane & 16) ? acc[j] : acc[j + 4], keep = (lane & 16) ? acc[j + 4] : acc[j];
+      a4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float send = (lane & 8) ? a4[j] : a4[j + 2], keep = (lane & 8) ? a4[j + 2] : a4[j];
+      a2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float send = (lane & 4) ? a2[0] : a2[1], keep = (lane & 4) ? a2[1] : a2[0];
+    float a1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    if ((lane & 3) == 0) hb[u * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = a1;
   }
-  float* out = hbar + (size_t)ray * (2 * CPN_FEAT_DIM) + br * CPN_FEAT_DIM + kc * ACT_BK + g * 8;
-  *reinterpret_cast<float4*>(out) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  *reinterpret_cast<float4*>(out + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  __syncthreads();
+  if (t >= KC * 4) return;
+  // hbar leaves as the operand image of the per-ray GEMM (rows = rays, 52 k-chunks per 128-ray tile): thread t's
+  // 8 values are exactly one 16-byte fp16 group plus half a 16-byte group in each correction plane
+  const int kc = t >> 2, g = t & 3;
+  const float4 v0 = *reinterpret_cast<const float4*>(hb + t * 8), v1 = *reinterpret_cast<const float4*>(hb + t * 8 + 4);
+  unsigned char* oblk = reinterpret_cast<unsigned char*>(hbar) +
+                        (((size_t)(ray >> 7) * (2 * KC) + br * KC + kc) * (size_t)ACT_CHUNK_BYTES) + (ray & 127) * 16;
+  if (F8) {
+    uint2 h0, h1, l8, x8;
+    tc::split4_f8(v0, h0, l8.x, x8.x);
+    tc::split4_f8(v1, h1, l8.y, x8.y);
+    *reinterpret_cast<uint4*>(oblk + g * 2048) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    *reinterpret_cast<uint2*>(oblk + ACT_LO8 + (g >> 1) * 2048 + (g & 1) * 8) = l8;
+    *reinterpret_cast<uint2*>(oblk + ACT_X8 + (g >> 1) * 2048 + (g & 1) * 8) = x8;
+  } else {
+    uint4 hi4, lo4;
+    tc::split8(v0, v1, hi4, lo4);
+    *reinterpret_cast<uint4*>(oblk + g * 2048) = hi4;
+    *reinterpret_cast<uint4*>(oblk + ACT_LO + g * 2048) = lo4;
+  }
 }
 
 // z = sum_v (R2 + R1) = R2 + 2 R1 (CoPoNeRF.py:481-485), R2 = WVF hbar2 + b from the late readout of round 2
@@ -402,10 +436,10 @@ int launch_readout_image(const cpn_render_args& a, int nr, const void* h1_image,
     return CPN_ERR_ARG;
   }
   if (f8)
-    readout_image_kernel<true><<<a.B * nr, 224, S2 * sizeof(float), st>>>(reinterpret_cast<const unsigned char*>(h1_image),
+    readout_image_kernel<true><<<dim3(a.B * nr, 2), 128, (S2 + CPN_FEAT_DIM) * sizeof(float), st>>>(reinterpret_cast<const unsigned char*>(h1_image),
                                                                            wts, S2, hbar);
   else
-    readout_image_kernel<false><<<a.B * nr, 224, S2 * sizeof(float), st>>>(reinterpret_cast<const unsigned char*>(h1_image),
+    readout_image_kernel<false><<<dim3(a.B * nr, 2), 128, (S2 + CPN_FEAT_DIM) * sizeof(float), st>>>(reinterpret_cast<const unsigned char*>(h1_image),
                                                                             wts, S2, hbar);
   CPN_CHECK_LAUNCH("readout_image_kernel");
   return CPN_OK;

@@ -108,7 +108,7 @@ Workspace carve(void* base, int B, int nr, int S) {
   w.lg2 = take(R);
   w.wt1 = take(R);   // late readout: softmax weights of round 1 / round 2, weighted hidden layer, round-2 latent
   w.wt2 = take(R);
-  w.hbar = take(rays * 2 * CPN_FEAT_DIM);
+  w.hbar = take((rays + 127) / 128 * 128 * 2 * CPN_FEAT_DIM);   // operand image, whole 128-ray tiles
   w.r2 = take(rays * CPN_LATENT);
   w.bytes = off;
   return w;
@@ -278,7 +278,7 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
     if (late_v) {
       CPN_TRY(launch_attn1(a, ray0, nr, w.Kk, w.Qe, nullptr, w.rowaux, w.r1, w.wp, st, w.lg1, w.wt1));
       CPN_TRY(launch_readout_image(a, nr, w.H1, w.wt1, w.hbar, a_form(a) == 2, st));
-      CPN_TRY(launch_gemm_tc(a.weights, 7, w.hbar, 2 * CPN_FEAT_DIM, w.r1, CPN_LATENT, rays, 0, sch, 1, 1, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 7, w.hbar, 0, w.r1, CPN_LATENT, rays, 0, CPN_TC_A_IMAGE | sch, 1, 1, st));
     } else {
       CPN_TRY(launch_attn1(a, ray0, nr, w.Kk, w.Qe, w.V, w.rowaux, w.r1, w.wp, st, use_tc(a) ? w.lg1 : nullptr));
     }
@@ -296,7 +296,7 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
     if (late_v) {
       CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, nullptr, w.r1, z_all, st, w.lg2, w.wt2));
       CPN_TRY(launch_readout_image(a, nr, w.H1, w.wt2, w.hbar, a_form(a) == 2, st));
-      CPN_TRY(launch_gemm_tc(a.weights, 7, w.hbar, 2 * CPN_FEAT_DIM, w.r2, CPN_LATENT, rays, 0, sch, 1, 1, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 7, w.hbar, 0, w.r2, CPN_LATENT, rays, 0, CPN_TC_A_IMAGE | sch, 1, 1, st));
       CPN_TRY(launch_combine_z(a, ray0, nr, w.r2, w.r1, z_all, st));
     } else {
       CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, w.V, w.r1, z_all, st, use_tc(a) ? w.lg2 : nullptr));
