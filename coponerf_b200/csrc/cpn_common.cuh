@@ -113,6 +113,9 @@ int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowau
 int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias, const float* rowbias,
                      int rows_per_bias, float* C, int ldc, int M, int N, int K, int relu, cudaStream_t st,
                      int remap256 = 0, float out_div = 0.f);   // out_div != 0: result divided by it
+// 16 -> 128 ReLU layer (+ per-ray bias) written as the operand image (K = 128) of the tensor-core layer that follows
+int launch_mlp16_image(const float* x, const float* wt, const float* bias, const float* rowbias, int rows_per_bias, int M,
+                       void* img, int f8, cudaStream_t st);
 // logits != nullptr: one precomputed logit per sample row (key / qemb unused); else <key, qemb> / 11.31 is computed here
 int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, const float* qemb, const float* value,
                  const float* rowaux, float* r1, float* wp, cudaStream_t st, const float* logits = nullptr,

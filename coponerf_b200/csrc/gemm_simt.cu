@@ -6,6 +6,7 @@
 // The k-loop order is fixed and independent of the tile a row lands in, so a ray's result does not
 // depend on the chunk or rank that renders it.
 #include "cpn_common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -207,7 +208,85 @@ gemm_simt_small_kernel(const float* __restrict__ A, int lda, const float* __rest
   }
 }
 
+// ---- 16 -> 128 ReLU layer written straight as the operand image of the 128 -> 128 layer that follows -------------
+// query_embed (CoPoNeRF.py:446) and the local_coords half of query_repeat_embed (:467-473, the z_embed half enters as
+// a per-ray bias): out[row][n] = relu(sum_j x[row][j] * Wt[j][n] + bias[n] + rowbias[row / rows_per_bias][n]).
+// With fp32 output the consumer GEMM has to convert its A operand itself (producer warps, DRAM-latency bound); the
+// image form lets it bulk-copy 16 KB blocks. CTA = one 128-row tile, thread -> (row, half of the 128 outputs).
+template <bool F8>
+__global__ void __launch_bounds__(256) mlp16_image_kernel(const float* __restrict__ x, const float* __restrict__ Wt,
+                                                          const float* __restrict__ bias, const float* __restrict__ rowbias,
+                                                          int rows_per_bias, int M, unsigned char* __restrict__ img) {
+  __shared__ __align__(16) float ws[16][CPN_HIDDEN];
+  __shared__ __align__(16) float bs[CPN_HIDDEN];
+  const int t = threadIdx.x, rloc = t & 127, half = t >> 7;
+  for (int i = t; i < 16 * CPN_HIDDEN; i += 256) ws[i / CPN_HIDDEN][i % CPN_HIDDEN] = Wt[i];
+  if (t < CPN_HIDDEN) bs[t] = bias ? bias[t] : 0.f;
+  __syncthreads();
+  const size_t tile = blockIdx.x, row = tile * 128 + rloc;
+  if (row >= (size_t)M) return;
+  float in[16];
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * 16 + j));
+    in[j] = v.x; in[j + 1] = v.y; in[j + 2] = v.z; in[j + 3] = v.w;
+  }
+  const float* rb = rowbias ? rowbias + (row / rows_per_bias) * CPN_HIDDEN : nullptr;
+  unsigned char* base = img + tile * (size_t)(CPN_HIDDEN / ACT_BK) * ACT_CHUNK_BYTES + rloc * 16;
+#pragma unroll 2
+  for (int n0 = half * 64; n0 < half * 64 + 64; n0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = bs[n0 + c];
+    if (rb) {
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(rb + n0)), r1 = __ldg(reinterpret_cast<const float4*>(rb + n0 + 4));
+      acc[0] += r0.x; acc[1] += r0.y; acc[2] += r0.z; acc[3] += r0.w;
+      acc[4] += r1.x; acc[5] += r1.y; acc[6] += r1.z; acc[7] += r1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&ws[j][n0]), w1 = *reinterpret_cast<const float4*>(&ws[j][n0 + 4]);
+      acc[0] = fmaf(in[j], w0.x, acc[0]); acc[1] = fmaf(in[j], w0.y, acc[1]);
+      acc[2] = fmaf(in[j], w0.z, acc[2]); acc[3] = fmaf(in[j], w0.w, acc[3]);
+      acc[4] = fmaf(in[j], w1.x, acc[4]); acc[5] = fmaf(in[j], w1.y, acc[5]);
+      acc[6] = fmaf(in[j], w1.z, acc[6]); acc[7] = fmaf(in[j], w1.w, acc[7]);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = fmaxf(acc[c], 0.f);
+    unsigned char* chunk = base + (size_t)(n0 / ACT_BK) * ACT_CHUNK_BYTES;
+    const int g = (n0 % ACT_BK) / 8;
+    const float4 v0 = make_float4(acc[0], acc[1], acc[2], acc[3]), v1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    if (F8) {
+      uint2 h0, h1, l8, x8;
+      tc::split4_f8(v0, h0, l8.x, x8.x);
+      tc::split4_f8(v1, h1, l8.y, x8.y);
+      *reinterpret_cast<uint4*>(chunk + g * 2048) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+      *reinterpret_cast<uint2*>(chunk + ACT_LO8 + (g >> 1) * 2048 + (g & 1) * 8) = l8;
+      *reinterpret_cast<uint2*>(chunk + ACT_X8 + (g >> 1) * 2048 + (g & 1) * 8) = x8;
+    } else {
+      uint4 hi, lo;
+      tc::split8(v0, v1, hi, lo);
+      *reinterpret_cast<uint4*>(chunk + g * 2048) = hi;
+      *reinterpret_cast<uint4*>(chunk + ACT_LO + g * 2048) = lo;
+    }
+  }
+}
+
 }  // namespace
+
+int launch_mlp16_image(const float* x, const float* wt, const float* bias, const float* rowbias, int rows_per_bias, int M,
+                       void* img, int f8, cudaStream_t st) {
+  if (M <= 0) return CPN_OK;
+  const unsigned tiles = (unsigned)((M + 127) / 128);
+  if (f8)
+    mlp16_image_kernel<true><<<tiles, 256, 0, st>>>(x, wt, bias, rowbias, rows_per_bias > 0 ? rows_per_bias : 1, M,
+                                                    reinterpret_cast<unsigned char*>(img));
+  else
+    mlp16_image_kernel<false><<<tiles, 256, 0, st>>>(x, wt, bias, rowbias, rows_per_bias > 0 ? rows_per_bias : 1, M,
+                                                     reinterpret_cast<unsigned char*>(img));
+  CPN_CHECK_LAUNCH("mlp16_image_kernel");
+  return CPN_OK;
+}
 
 int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias, const float* rowbias,
                      int rows_per_bias, float* C, int ldc, int M, int N, int K, int relu, cudaStream_t st, int remap256,

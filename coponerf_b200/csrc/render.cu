@@ -258,8 +258,8 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
         CPN_TRY(launch_gemm_tc(a.weights, 8, w.H1, 0, w.K1, 0, R, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 1, KC128, st));
       }
       // coordinate embedding, CoPoNeRF.py:446; written column-blocked so the two logit epilogues read it coalesced
-      CPN_TRY(dense_simt(a, w.local16, 16, pw::WQT, pw::BQ, w.Q1, CPN_HIDDEN, R, CPN_HIDDEN, 16, 1, st));
-      CPN_TRY(launch_gemm_tc(a.weights, 5, w.Q1, CPN_HIDDEN, w.Qe, 0, R, 0, sch | CPN_TC_OUT_CB16, 1, 1, st));
+      CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQT, W + pw::BQ, nullptr, 1, R, w.Q1, a_form(a) == 2, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 5, w.Q1, 0, w.Qe, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_CB16, 1, 1, st));
       // key_map_2 with the round-1 logits <K, Q> / 11.31 (CoPoNeRF.py:450) as its epilogue: K itself is never stored
       CPN_TRY(launch_gemm_tc(a.weights, 4, w.K1, 0, w.lg1, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_ROWDOT, 1, 1, st, w.Qe,
                              11.31f));
@@ -286,13 +286,16 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
     // channels are the same for every sample of a ray, so they enter as a per-ray bias.
     CPN_TRY(dense_simt(a, w.r1, CPN_LATENT, pw::WET, pw::BE, w.zemb, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_LATENT, 0, st));
     CPN_TRY(dense_simt(a, w.zemb, CPN_HIDDEN, pw::WQRA_T, pw::BQR, w.rbias, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_HIDDEN, 0, st));
-    CPN_TRY(launch_gemm_simt(w.local16, 16, W + pw::WQRB_T, nullptr, w.rbias, 2 * a.S, w.K1, CPN_HIDDEN, R, CPN_HIDDEN,
-                             16, 1, st));
-    if (use_tc(a))   // query_repeat_embed_2 with the round-2 logits <Q2, Q> / 11.31 (CoPoNeRF.py:474) as its epilogue
-      CPN_TRY(launch_gemm_tc(a.weights, 6, w.K1, CPN_HIDDEN, w.lg2, 0, R, 0, tc_scheme(a) | CPN_TC_OUT_ROWDOT, 1, 1, st, w.Qe,
-                             11.31f));
-    else
+    if (use_tc(a)) {   // query_repeat_embed_2 with the round-2 logits <Q2, Q> / 11.31 (CoPoNeRF.py:474) as its epilogue
+      CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQRB_T, nullptr, w.rbias, 2 * a.S, R, w.K1,
+                                 a_form(a) == 2, st));
+      CPN_TRY(launch_gemm_tc(a.weights, 6, w.K1, 0, w.lg2, 0, R, 0, CPN_TC_A_IMAGE | tc_scheme(a) | CPN_TC_OUT_ROWDOT, 1, 1, st,
+                             w.Qe, 11.31f));
+    } else {
+      CPN_TRY(launch_gemm_simt(w.local16, 16, W + pw::WQRB_T, nullptr, w.rbias, 2 * a.S, w.K1, CPN_HIDDEN, R, CPN_HIDDEN,
+                               16, 1, st));
       CPN_TRY(dense_simt(a, w.K1, CPN_HIDDEN, pw::WQR2T, pw::BQR2, w.Kk, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
+    }
     if (late_v) {
       CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, nullptr, w.r1, z_all, st, w.lg2, w.wt2));
       CPN_TRY(launch_readout_image(a, nr, w.H1, w.wt2, w.hbar, a_form(a) == 2, st));
