@@ -217,57 +217,74 @@ template <bool F8>
 __global__ void __launch_bounds__(256) mlp16_image_kernel(const float* __restrict__ x, const float* __restrict__ Wt,
                                                           const float* __restrict__ bias, const float* __restrict__ rowbias,
                                                           int rows_per_bias, int M, unsigned char* __restrict__ img) {
+  // CTA = two 128-row tiles; thread -> (row of each tile, half of the 128 outputs): every shared-memory weight load
+  // feeds two rows
   __shared__ __align__(16) float ws[16][CPN_HIDDEN];
   __shared__ __align__(16) float bs[CPN_HIDDEN];
   const int t = threadIdx.x, rloc = t & 127, half = t >> 7;
   for (int i = t; i < 16 * CPN_HIDDEN; i += 256) ws[i / CPN_HIDDEN][i % CPN_HIDDEN] = Wt[i];
   if (t < CPN_HIDDEN) bs[t] = bias ? bias[t] : 0.f;
   __syncthreads();
-  const size_t tile = blockIdx.x, row = tile * 128 + rloc;
-  if (row >= (size_t)M) return;
-  float in[16];
+  const size_t tile0 = (size_t)blockIdx.x * 2;
+  float in[2][16];
+  const float* rb[2];
+  bool ok[2];
 #pragma unroll
-  for (int j = 0; j < 16; j += 4) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * 16 + j));
-    in[j] = v.x; in[j + 1] = v.y; in[j + 2] = v.z; in[j + 3] = v.w;
+  for (int q = 0; q < 2; ++q) {
+    const size_t row = (tile0 + q) * 128 + rloc;
+    ok[q] = row < (size_t)M;
+    const size_t rr = ok[q] ? row : 0;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + rr * 16 + j));
+      in[q][j] = v.x; in[q][j + 1] = v.y; in[q][j + 2] = v.z; in[q][j + 3] = v.w;
+    }
+    rb[q] = rowbias ? rowbias + (rr / rows_per_bias) * CPN_HIDDEN : nullptr;
   }
-  const float* rb = rowbias ? rowbias + (row / rows_per_bias) * CPN_HIDDEN : nullptr;
-  unsigned char* base = img + tile * (size_t)(CPN_HIDDEN / ACT_BK) * ACT_CHUNK_BYTES + rloc * 16;
-#pragma unroll 2
+#pragma unroll 1
   for (int n0 = half * 64; n0 < half * 64 + 64; n0 += 8) {
-    float acc[8];
+    float acc[2][8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = bs[n0 + c];
-    if (rb) {
-      const float4 r0 = __ldg(reinterpret_cast<const float4*>(rb + n0)), r1 = __ldg(reinterpret_cast<const float4*>(rb + n0 + 4));
-      acc[0] += r0.x; acc[1] += r0.y; acc[2] += r0.z; acc[3] += r0.w;
-      acc[4] += r1.x; acc[5] += r1.y; acc[6] += r1.z; acc[7] += r1.w;
+    for (int q = 0; q < 2; ++q) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[q][c] = bs[n0 + c];
+      if (rb[q]) {
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rb[q] + n0)), r1 = __ldg(reinterpret_cast<const float4*>(rb[q] + n0 + 4));
+        acc[q][0] += r0.x; acc[q][1] += r0.y; acc[q][2] += r0.z; acc[q][3] += r0.w;
+        acc[q][4] += r1.x; acc[q][5] += r1.y; acc[q][6] += r1.z; acc[q][7] += r1.w;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float4 w0 = *reinterpret_cast<const float4*>(&ws[j][n0]), w1 = *reinterpret_cast<const float4*>(&ws[j][n0 + 4]);
-      acc[0] = fmaf(in[j], w0.x, acc[0]); acc[1] = fmaf(in[j], w0.y, acc[1]);
-      acc[2] = fmaf(in[j], w0.z, acc[2]); acc[3] = fmaf(in[j], w0.w, acc[3]);
-      acc[4] = fmaf(in[j], w1.x, acc[4]); acc[5] = fmaf(in[j], w1.y, acc[5]);
-      acc[6] = fmaf(in[j], w1.z, acc[6]); acc[7] = fmaf(in[j], w1.w, acc[7]);
-    }
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = fmaxf(acc[c], 0.f);
-    unsigned char* chunk = base + (size_t)(n0 / ACT_BK) * ACT_CHUNK_BYTES;
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[q][c] = fmaf(in[q][j], wv[c], acc[q][c]);
+    }
     const int g = (n0 % ACT_BK) / 8;
-    const float4 v0 = make_float4(acc[0], acc[1], acc[2], acc[3]), v1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    if (F8) {
-      uint2 h0, h1, l8, x8;
-      tc::split4_f8(v0, h0, l8.x, x8.x);
-      tc::split4_f8(v1, h1, l8.y, x8.y);
-      *reinterpret_cast<uint4*>(chunk + g * 2048) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-      *reinterpret_cast<uint2*>(chunk + ACT_LO8 + (g >> 1) * 2048 + (g & 1) * 8) = l8;
-      *reinterpret_cast<uint2*>(chunk + ACT_X8 + (g >> 1) * 2048 + (g & 1) * 8) = x8;
-    } else {
-      uint4 hi, lo;
-      tc::split8(v0, v1, hi, lo);
-      *reinterpret_cast<uint4*>(chunk + g * 2048) = hi;
-      *reinterpret_cast<uint4*>(chunk + ACT_LO + g * 2048) = lo;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (!ok[q]) continue;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[q][c] = fmaxf(acc[q][c], 0.f);
+      unsigned char* chunk = img + ((tile0 + q) * (size_t)(CPN_HIDDEN / ACT_BK) + n0 / ACT_BK) * ACT_CHUNK_BYTES + rloc * 16;
+      const float4 v0 = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+      const float4 v1 = make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]);
+      if (F8) {
+        uint2 h0, h1, l8, x8;
+        tc::split4_f8(v0, h0, l8.x, x8.x);
+        tc::split4_f8(v1, h1, l8.y, x8.y);
+        *reinterpret_cast<uint4*>(chunk + g * 2048) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+        *reinterpret_cast<uint2*>(chunk + ACT_LO8 + (g >> 1) * 2048 + (g & 1) * 8) = l8;
+        *reinterpret_cast<uint2*>(chunk + ACT_X8 + (g >> 1) * 2048 + (g & 1) * 8) = x8;
+      } else {
+        uint4 hi, lo;
+        tc::split8(v0, v1, hi, lo);
+        *reinterpret_cast<uint4*>(chunk + g * 2048) = hi;
+        *reinterpret_cast<uint4*>(chunk + ACT_LO + g * 2048) = lo;
+      }
     }
   }
 }
@@ -277,7 +294,7 @@ __global__ void __launch_bounds__(256) mlp16_image_kernel(const float* __restric
 int launch_mlp16_image(const float* x, const float* wt, const float* bias, const float* rowbias, int rows_per_bias, int M,
                        void* img, int f8, cudaStream_t st) {
   if (M <= 0) return CPN_OK;
-  const unsigned tiles = (unsigned)((M + 127) / 128);
+  const unsigned tiles = (unsigned)((M + 255) / 256);   // two 128-row tiles per CTA
   if (f8)
     mlp16_image_kernel<true><<<tiles, 256, 0, st>>>(x, wt, bias, rowbias, rows_per_bias > 0 ? rows_per_bias : 1, M,
                                                     reinterpret_cast<unsigned char*>(img));
