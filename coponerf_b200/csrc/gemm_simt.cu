@@ -129,9 +129,13 @@ constexpr int SBM = 64, SBN = 64;
 __global__ void __launch_bounds__(NT, 2)
 gemm_simt_small_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Wt, const float* __restrict__ bias,
                        const float* __restrict__ rowbias, int rows_per_bias, float* __restrict__ C, int ldc, int M, int N,
-                       int K, int relu, int remap256, float out_div) {
+                       int K, int relu, int remap256, float out_div, float* __restrict__ part, int ksplit) {
+  // part != nullptr: split-K. CTA z covers k in [z * ksplit, min(K, (z + 1) * ksplit)) and writes its raw partial
+  // sums to part[z][M][N]; splitk_finish_kernel adds them in ascending z and applies bias / activation.
   __shared__ __align__(16) float As[2][BK][SBM];
   __shared__ __align__(16) float Bs[2][BK][SBN];
+  const int kbeg = part ? blockIdx.z * ksplit : 0;
+  if (part) K = min(K, kbeg + ksplit);
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
   const int a_row = tid & (SBM - 1), a_k = (tid >> 6) * 4;          // 64 rows x 4 groups of 4 k
@@ -158,11 +162,11 @@ gemm_simt_small_kernel(const float* __restrict__ A, int lda, const float* __rest
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  load_tiles(0);
+  load_tiles(kbeg);
   store_tiles(0);
   __syncthreads();
   int buf = 0;
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  for (int k0 = kbeg; k0 < K; k0 += BK) {
     const bool more = (k0 + BK) < K;
     if (more) load_tiles(k0 + BK);
 #pragma unroll
@@ -186,6 +190,10 @@ gemm_simt_small_kernel(const float* __restrict__ A, int lda, const float* __rest
     const int m = m0 + ty * 4 + i, n = n0 + tx * 4;
     if (m >= M || n >= N) continue;
     float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    if (part) {
+      *reinterpret_cast<float4*>(part + ((size_t)blockIdx.z * M + m) * N + n) = v;
+      continue;
+    }
     if (bias) {
       float4 bb = *reinterpret_cast<const float4*>(bias + n);
       v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
@@ -289,6 +297,42 @@ __global__ void __launch_bounds__(256) mlp16_image_kernel(const float* __restric
   }
 }
 
+// second stage of the split-K GEMM: C[m][n] = act(sum_z part[z][m][n] + bias[n]), z ascending
+__global__ void splitk_finish_kernel(const float* __restrict__ part, int nsplit, int M, int N, const float* __restrict__ bias,
+                                     int act, float* __restrict__ C, int ldc) {
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (idx >= M * N) return;
+  const int m = idx / N, n = idx % N;
+  float4 s = *reinterpret_cast<const float4*>(part + idx);
+  for (int z = 1; z < nsplit; ++z) {
+    const float4 p = *reinterpret_cast<const float4*>(part + (size_t)z * M * N + idx);
+    s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+  }
+  if (bias) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + n);
+    s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+  }
+  if (act == 1) {
+    s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
+  } else if (act == 2) {
+    s.x = gelu_erf(s.x); s.y = gelu_erf(s.y); s.z = gelu_erf(s.z); s.w = gelu_erf(s.w);
+  }
+  *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) = s;
+}
+
+// split count for the 64 x 64 tiling: enough CTAs for about two per SM, at least 128 k per split
+int simt_splits(int M, int N, int K, int* ksplit) {
+  const long long tiles = (long long)((N + SBN - 1) / SBN) * ((M + SBM - 1) / SBM);
+  int want = (int)((296 + tiles - 1) / tiles);
+  const int maxs = K / 128;
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  int ks = (K + want - 1) / want;
+  ks = (ks + BK - 1) / BK * BK;
+  *ksplit = ks;
+  return (K + ks - 1) / ks;
+}
+
 }  // namespace
 
 int launch_mlp16_image(const float* x, const float* wt, const float* bias, const float* rowbias, int rows_per_bias, int M,
@@ -317,7 +361,7 @@ int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias
   if ((long long)grid.x * grid.y < 96) {   // too few large tiles to fill the 148 SMs
     dim3 g2((N + SBN - 1) / SBN, (M + SBM - 1) / SBM);
     gemm_simt_small_kernel<<<g2, NT, 0, st>>>(A, lda, wt, bias, rowbias, rows_per_bias > 0 ? rows_per_bias : 1, C, ldc, M,
-                                              N, K, relu, remap256, out_div);
+                                              N, K, relu, remap256, out_div, nullptr, 0);
     CPN_CHECK_LAUNCH("gemm_simt_small_kernel");
     return CPN_OK;
   }
@@ -338,4 +382,41 @@ extern "C" int cpn_gemm_simt(const float* A, int lda, const float* wt, const flo
     return CPN_ERR_ARG;
   }
   return launch_gemm_simt(A, lda, wt, bias, nullptr, 1, C, ldc, M, N, K, relu, (cudaStream_t)stream, 0, 0.f);
+}
+
+// Split-K variant for GEMMs whose 64 x 64 tiling leaves most SMs idle (the token layers of the cost aggregation at
+// 256 / 1024 tokens with K up to 2304): the k range is split over blockIdx.z and reduced in a fixed order.
+extern "C" size_t cpn_gemm_simt_splitk_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  int ks;
+  const int ns = simt_splits(M, N, K, &ks);
+  return ns > 1 ? (size_t)ns * M * N * sizeof(float) : 0;
+}
+
+extern "C" int cpn_gemm_simt_splitk(const float* A, int lda, const float* wt, const float* bias, float* C, int ldc, int M,
+                                    int N, int K, int act, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!A || !wt || !C) {
+    cpn_set_error("cpn_gemm_simt_splitk: null pointer");
+    return CPN_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int ks;
+  const int ns = M > 0 && N > 0 && K > 0 ? simt_splits(M, N, K, &ks) : 1;
+  if (ns <= 1) return launch_gemm_simt(A, lda, wt, bias, nullptr, 1, C, ldc, M, N, K, act, st, 0, 0.f);
+  if ((K & 3) || (N & 3) || (lda & 3) || (ldc & 3)) {
+    cpn_set_error("gemm_simt_splitk: K, N, lda and ldc must be multiples of 4 (K=%d N=%d lda=%d ldc=%d)", K, N, lda, ldc);
+    return CPN_ERR_ARG;
+  }
+  const size_t need = (size_t)ns * M * N * sizeof(float);
+  if (!workspace || workspace_bytes < need) {
+    cpn_set_error("cpn_gemm_simt_splitk: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+    return CPN_ERR_WORKSPACE;
+  }
+  dim3 grid((N + SBN - 1) / SBN, (M + SBM - 1) / SBM, ns);
+  gemm_simt_small_kernel<<<grid, NT, 0, st>>>(A, lda, wt, nullptr, nullptr, 1, nullptr, 0, M, N, K, 0, 0, 0.f,
+                                              (float*)workspace, ks);
+  CPN_CHECK_LAUNCH("gemm_simt_small_kernel");
+  splitk_finish_kernel<<<(M * N / 4 + 255) / 256, 256, 0, st>>>((const float*)workspace, ns, M, N, bias, act, C, ldc);
+  CPN_CHECK_LAUNCH("splitk_finish_kernel");
+  return CPN_OK;
 }

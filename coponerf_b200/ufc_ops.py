@@ -64,6 +64,13 @@ class CudaOps:
         M = x.numel() // K
         wt, bias = self._transposed(w), _c(b)
         y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
+        nbytes = self.lib.cpn_gemm_simt_splitk_workspace_bytes(M, N, K) if M * N <= 148 * 64 * 64 else 0
+        if nbytes:     # few output tiles, long K: split the k range over CTAs (fixed-order reduction)
+            ws = self._scratch(nbytes, x.device)
+            self.launches += 2
+            _lib.check(self.lib.cpn_gemm_simt_splitk(_p(x), K, _p(wt), _p(bias), _p(y), N, M, N, K, _ACT[act], _p(ws),
+                                                     ws.numel(), _st()), "cpn_gemm_simt_splitk")
+            return y
         self.launches += 1
         _lib.check(self.lib.cpn_gemm_simt(_p(x), K, _p(wt), _p(bias), _p(y), N, M, N, K, _ACT[act], _st()),
                    "cpn_gemm_simt")

@@ -243,6 +243,12 @@ int cpn_prof_end(float* total_ms, int* launches);
 int cpn_gemm_simt(const float* A, int lda, const float* wt, const float* bias, float* C, int ldc,
                   int M, int N, int K, int relu /* 0 none, 1 ReLU, 2 exact GELU */, void* stream);
 
+/* The same GEMM with the k range split over CTAs and reduced in a fixed order, for shapes whose 64 x 64 tiling would leave
+ * most SMs idle (token layers of the cost aggregation: M = 256 / 1024 tokens, K up to 2304). act: 0 none, 1 ReLU, 2 GELU. */
+size_t cpn_gemm_simt_splitk_workspace_bytes(int M, int N, int K);
+int cpn_gemm_simt_splitk(const float* A, int lda, const float* wt, const float* bias, float* C, int ldc, int M, int N,
+                         int K, int act, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Tensor-core GEMM of one packed layer (0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value,
  * 3 key_map, 4 key_map_2, 5 query_embed_2, 6 query_repeat_embed_2, 7 latent_value o query_encode_latent_2,
  * 8 key_map o query_encode_latent_2, both with K = 1664): C[M, N_layer] = act(A[M, K_layer] * W^T + b),
