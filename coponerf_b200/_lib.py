@@ -17,6 +17,7 @@ FLAG_SIMT_ONLY = 1
 FLAG_F16X3 = 2
 FLAG_NO_FOLD = 4
 FLAG_EARLY_V = 8
+FLAG_NO_BILINEAR = 16
 TC_F16X3 = 4
 TC_CLUSTER = 8
 TC_PAIR = 16

@@ -221,22 +221,38 @@ gemm_simt_small_kernel(const float* __restrict__ A, int lda, const float* __rest
 // a per-ray bias): out[row][n] = relu(sum_j x[row][j] * Wt[j][n] + bias[n] + rowbias[row / rows_per_bias][n]).
 // With fp32 output the consumer GEMM has to convert its A operand itself (producer warps, DRAM-latency bound); the
 // image form lets it bulk-copy 16 KB blocks. CTA = one 128-row tile, thread -> (row, half of the 128 outputs).
+struct Mlp16Extra {
+  const float* sdot1;   // [128] vector + [128] constant: s1[row] = <out, vec> + const   (nullable)
+  float* s1;
+  const float* sdot2;
+  float* s2;
+  const float* dotv;    // CB16 fp32 (M, 128): lg[row] = (<out, dotv[row]> + rowadd[row]) / div   (nullable)
+  const float* rowadd;
+  float div;
+  float* lg;
+};
+
 template <bool F8>
-__global__ void __launch_bounds__(256) mlp16_image_kernel(const float* __restrict__ x, const float* __restrict__ Wt,
+__global__ void __launch_bounds__(128) mlp16_image_kernel(const float* __restrict__ x, const float* __restrict__ Wt,
                                                           const float* __restrict__ bias, const float* __restrict__ rowbias,
-                                                          int rows_per_bias, int M, unsigned char* __restrict__ img) {
-  // CTA = two 128-row tiles; thread -> (row of each tile, half of the 128 outputs): every shared-memory weight load
-  // feeds two rows
+                                                          int rows_per_bias, int M, unsigned char* __restrict__ img,
+                                                          Mlp16Extra e) {
+  // CTA = two 128-row tiles, thread -> the same row of each tile with all 128 outputs: every shared-memory weight load
+  // feeds two rows, and the optional per-row dot products stay inside one thread
   __shared__ __align__(16) float ws[16][CPN_HIDDEN];
   __shared__ __align__(16) float bs[CPN_HIDDEN];
-  const int t = threadIdx.x, rloc = t & 127, half = t >> 7;
-  for (int i = t; i < 16 * CPN_HIDDEN; i += 256) ws[i / CPN_HIDDEN][i % CPN_HIDDEN] = Wt[i];
-  if (t < CPN_HIDDEN) bs[t] = bias ? bias[t] : 0.f;
+  __shared__ __align__(16) float sd[2][CPN_HIDDEN];
+  const int t = threadIdx.x, rloc = t;
+  for (int i = t; i < 16 * CPN_HIDDEN; i += 128) ws[i / CPN_HIDDEN][i % CPN_HIDDEN] = Wt[i];
+  bs[t] = bias ? bias[t] : 0.f;
+  sd[0][t] = e.sdot1 ? e.sdot1[t] : 0.f;
+  sd[1][t] = e.sdot2 ? e.sdot2[t] : 0.f;
   __syncthreads();
   const size_t tile0 = (size_t)blockIdx.x * 2;
   float in[2][16];
   const float* rb[2];
   bool ok[2];
+  float d1[2] = {0.f, 0.f}, d2[2] = {0.f, 0.f}, dl[2] = {0.f, 0.f};
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     const size_t row = (tile0 + q) * 128 + rloc;
@@ -250,7 +266,7 @@ __global__ void __launch_bounds__(256) mlp16_image_kernel(const float* __restric
     rb[q] = rowbias ? rowbias + (rr / rows_per_bias) * CPN_HIDDEN : nullptr;
   }
 #pragma unroll 1
-  for (int n0 = half * 64; n0 < half * 64 + 64; n0 += 8) {
+  for (int n0 = 0; n0 < CPN_HIDDEN; n0 += 8) {
     float acc[2][8];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -277,6 +293,20 @@ __global__ void __launch_bounds__(256) mlp16_image_kernel(const float* __restric
       if (!ok[q]) continue;
 #pragma unroll
       for (int c = 0; c < 8; ++c) acc[q][c] = fmaxf(acc[q][c], 0.f);
+      if (e.s1) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          d1[q] = fmaf(acc[q][c], sd[0][n0 + c], d1[q]);
+          d2[q] = fmaf(acc[q][c], sd[1][n0 + c], d2[q]);
+        }
+      }
+      if (e.dotv) {   // CB16: [row tile][16-column block][128 rows][16]
+        const float* dv = e.dotv + (((tile0 + q) * (CPN_HIDDEN / 16) + n0 / 16) * 128 + rloc) * 16 + (n0 & 8);
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(dv)), a1 = __ldg(reinterpret_cast<const float4*>(dv + 4));
+        dl[q] = fmaf(acc[q][3], a0.w, fmaf(acc[q][2], a0.z, fmaf(acc[q][1], a0.y, fmaf(acc[q][0], a0.x, dl[q]))));
+        dl[q] = fmaf(acc[q][7], a1.w, fmaf(acc[q][6], a1.z, fmaf(acc[q][5], a1.y, fmaf(acc[q][4], a1.x, dl[q]))));
+      }
+      if (!img) continue;
       unsigned char* chunk = img + ((tile0 + q) * (size_t)(CPN_HIDDEN / ACT_BK) + n0 / ACT_BK) * ACT_CHUNK_BYTES + rloc * 16;
       const float4 v0 = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
       const float4 v1 = make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]);
@@ -294,6 +324,16 @@ __global__ void __launch_bounds__(256) mlp16_image_kernel(const float* __restric
         *reinterpret_cast<uint4*>(chunk + ACT_LO + g * 2048) = lo;
       }
     }
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (!ok[q]) continue;
+    const size_t row = (tile0 + q) * 128 + rloc;
+    if (e.s1) {
+      e.s1[row] = d1[q] + e.sdot1[CPN_HIDDEN];
+      if (e.s2) e.s2[row] = d2[q] + e.sdot2[CPN_HIDDEN];
+    }
+    if (e.dotv) e.lg[row] = (dl[q] + (e.rowadd ? e.rowadd[row] : 0.f)) / e.div;
   }
 }
 
@@ -336,15 +376,21 @@ int simt_splits(int M, int N, int K, int* ksplit) {
 }  // namespace
 
 int launch_mlp16_image(const float* x, const float* wt, const float* bias, const float* rowbias, int rows_per_bias, int M,
-                       void* img, int f8, cudaStream_t st) {
+                       void* img, int f8, cudaStream_t st, const float* sdot1, float* s1, const float* sdot2, float* s2,
+                       const float* dotv, const float* rowadd, float div, float* lg) {
   if (M <= 0) return CPN_OK;
-  const unsigned tiles = (unsigned)((M + 255) / 256);   // two 128-row tiles per CTA
+  if ((!img && !dotv) || (dotv && !lg) || (s1 && !sdot1) || (s2 && (!sdot2 || !s1))) {
+    cpn_set_error("mlp16_image: inconsistent outputs");
+    return CPN_ERR_ARG;
+  }
+  const unsigned ctas = (unsigned)((M + 255) / 256);   // two 128-row tiles per CTA
+  const Mlp16Extra e{sdot1, s1, sdot2, s2, dotv, rowadd, div, lg};
   if (f8)
-    mlp16_image_kernel<true><<<tiles, 256, 0, st>>>(x, wt, bias, rowbias, rows_per_bias > 0 ? rows_per_bias : 1, M,
-                                                    reinterpret_cast<unsigned char*>(img));
+    mlp16_image_kernel<true><<<ctas, 128, 0, st>>>(x, wt, bias, rowbias, rows_per_bias > 0 ? rows_per_bias : 1, M,
+                                                   reinterpret_cast<unsigned char*>(img), e);
   else
-    mlp16_image_kernel<false><<<tiles, 256, 0, st>>>(x, wt, bias, rowbias, rows_per_bias > 0 ? rows_per_bias : 1, M,
-                                                     reinterpret_cast<unsigned char*>(img));
+    mlp16_image_kernel<false><<<ctas, 128, 0, st>>>(x, wt, bias, rowbias, rows_per_bias > 0 ? rows_per_bias : 1, M,
+                                                    reinterpret_cast<unsigned char*>(img), e);
   CPN_CHECK_LAUNCH("mlp16_image_kernel");
   return CPN_OK;
 }

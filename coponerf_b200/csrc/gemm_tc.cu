@@ -69,6 +69,8 @@ const TcLayer kLayers[CPN_TC_LAYERS] = {
     {128, 128, 128, 128, RAW_WQR2, pw::BQR2, false},  // 6 query_repeat_embed_2
     {416, 1664, 1664, 208, pw::WVF, pw::BVF, true},   // 7 latent_value o query_encode_latent_2 (both branches)
     {128, 1664, 1664, 128, pw::WKF, pw::BKF, true},   // 8 key_map o query_encode_latent_2
+    {128, 128, 128, 128, pw::WM1, pw::BM1, true},     // 9 key_map_2^T query_embed_2 (round-1 logits as a bilinear form)
+    {128, 128, 128, 128, pw::WM2, pw::BM2, true},     // 10 query_repeat_embed_2^T query_embed_2 (round 2)
 };
 constexpr size_t TC_HEADER_BYTES = 256;   // floats [0..15] 1/scale per layer, [16..31] scale, uints [32..47] absmax bits
 static_assert(CPN_TC_LAYERS <= 16, "header slots");
@@ -164,6 +166,7 @@ struct GemmArgs {
   int out_kind;                  // fp32 output: 0 row-major, 2 column-blocked (CB16), 3 per-row dot with `dotv`
   const float* dotv;             // CB16 matrix the rows are dotted with (out_kind 3); C then holds one float per row
   float dot_div;
+  const float* dot_rowadd;       // optional per-row term added to the dot product before the division
 };
 
 // Drain one 128-row accumulator sub-tile: TMEM -> registers -> scale, bias, ReLU -> fp32 rows or the operand image
@@ -247,7 +250,8 @@ __device__ __forceinline__ void drain_subtile(const GemmArgs& g, uint32_t tmem, 
       for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
   }
-  if (!OUT_IMAGE && g.out_kind == 3 && row < g.M) reinterpret_cast<float*>(g.C)[row] = dot / g.dot_div;
+  if (!OUT_IMAGE && g.out_kind == 3 && row < g.M)
+    reinterpret_cast<float*>(g.C)[row] = (g.dot_rowadd ? dot + g.dot_rowadd[row] : dot) / g.dot_div;
 }
 
 // CLUSTER (> 1, operand-image A only): the CTAs of the N tiles of one 256-row tile form a cluster; each loads
@@ -560,7 +564,7 @@ int cpn_pack_tc_weights(const float* raw, const float* packed_fp32, void* dst_v,
 }
 
 int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,
-                   int out_div, int out_kchunks, cudaStream_t st, const float* dotv, float dot_div) {
+                   int out_div, int out_kchunks, cudaStream_t st, const float* dotv, float dot_div, const float* dot_rowadd) {
   const bool a_img = mode & CPN_TC_A_IMAGE, o_img = mode & CPN_TC_OUT_IMAGE;
   if (!packed || !A || !C || layer < 0 || layer >= CPN_TC_LAYERS || M < 0 || (!a_img && (lda & 3)) || (!o_img && !(mode & (CPN_TC_OUT_ROWDOT | CPN_TC_OUT_CB16)) && (ldc & 3)) ||
       (o_img && (out_div < 1 || out_kchunks < 1))) {
@@ -589,6 +593,7 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
   g.out_kind = (mode & CPN_TC_OUT_ROWDOT) ? 3 : ((mode & CPN_TC_OUT_CB16) ? 2 : 0);
   g.dotv = dotv;
   g.dot_div = dot_div;
+  g.dot_rowadd = dot_rowadd;
   if (g.out_kind && (o_img || L.out != L.nt || (g.out_kind == 3 && !dotv))) {
     cpn_set_error("gemm_tc: CB16 / row-dot outputs need a single-N-tile layer and fp32 output");
     return CPN_ERR_ARG;
@@ -647,11 +652,12 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
 
 extern "C" int cpn_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu,
                            int mode, int out_div, int out_kchunks, void* stream) {
-  return launch_gemm_tc(packed, layer, A, lda, C, ldc, M, relu, mode, out_div, out_kchunks, (cudaStream_t)stream, nullptr, 1.f);
+  return launch_gemm_tc(packed, layer, A, lda, C, ldc, M, relu, mode, out_div, out_kchunks, (cudaStream_t)stream, nullptr, 1.f,
+                        nullptr);
 }
 
 extern "C" int cpn_gemm_tc_rowdot(const void* packed, int layer, const void* A, int lda, const float* dotv_cb16, float* out,
                                   int M, int relu, int mode, float div, void* stream) {
   return launch_gemm_tc(packed, layer, A, lda, out, 0, M, relu, mode | CPN_TC_OUT_ROWDOT, 1, 1, (cudaStream_t)stream, dotv_cb16,
-                        div);
+                        div, nullptr);
 }

@@ -76,7 +76,7 @@ struct ProfScope {  // records an event pair around the enclosed launches when a
 // Workspace carve-up for one chunk of `nr` rays of each of B pairs (R = B * nr * 2 * S sample rows).
 struct Workspace {
   float *seg, *rowaux, *local16, *A, *H1, *E, *V, *K1, *Kk, *Q1, *Qe, *r1, *wp, *zemb, *rbias, *lg1, *lg2, *wt1, *wt2,
-      *hbar, *r2;
+      *hbar, *r2, *s1, *s2;
   size_t bytes;
 };
 
@@ -110,6 +110,8 @@ Workspace carve(void* base, int B, int nr, int S) {
   w.wt2 = take(R);
   w.hbar = take((rays + 127) / 128 * 128 * 2 * CPN_FEAT_DIM);   // operand image, whole 128-ray tiles
   w.r2 = take(rays * CPN_LATENT);
+  w.s1 = take(R);    // bilinear logits: per-row scalar terms of round 1 / round 2
+  w.s2 = take(R);
   w.bytes = off;
   return w;
 }
@@ -218,7 +220,8 @@ extern "C" int cpn_render_launch_count(const cpn_render_args* a) {
   if (!a || a->chunk_rays <= 0) return 0;
   int chunks = (a->N + a->chunk_rays - 1) / a->chunk_rays;
   const bool unfolded = (a->flags & CPN_FLAG_NO_FOLD) || (a->flags & CPN_FLAG_SIMT_ONLY);
-  const int per_chunk = unfolded ? 17 : ((a->flags & CPN_FLAG_EARLY_V) ? 16 : 20);
+  int per_chunk = unfolded ? 17 : ((a->flags & CPN_FLAG_EARLY_V) ? 16 : 20);
+  if (!unfolded && !(a->flags & CPN_FLAG_NO_BILINEAR)) per_chunk -= 1;   // one 128 x 128 layer fewer
   return chunks * per_chunk + 1;
 }
 
@@ -235,6 +238,7 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
     const int sch = tc_scheme(a);
     // late readout (attention.cu): the attention reads out the hidden layer and the folded latent_value runs per ray
     const bool late_v = use_tc(a) && !(a.flags & (CPN_FLAG_NO_FOLD | CPN_FLAG_EARLY_V));
+    const bool bilinear = use_tc(a) && !(a.flags & (CPN_FLAG_NO_FOLD | CPN_FLAG_NO_BILINEAR));
     if (use_tc(a)) {
       // per-sample encoder, CoPoNeRF.py:387-397: (835 -> 832 ReLU -> 416) for the primary and the secondary rows.
       // Activations travel between the tensor-core layers as fp16 hi/lo operand images (cpn_common.cuh).
@@ -255,14 +259,28 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
         // 21 % fewer MACs than the three layers, and the E image is never written or read.
         if (!late_v)
           CPN_TRY(launch_gemm_tc(a.weights, 7, w.H1, 0, w.V, CPN_LATENT, R, 0, CPN_TC_A_IMAGE | sch, 1, 1, st));
-        CPN_TRY(launch_gemm_tc(a.weights, 8, w.H1, 0, w.K1, 0, R, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 1, KC128, st));
       }
-      // coordinate embedding, CoPoNeRF.py:446; written column-blocked so the two logit epilogues read it coalesced
-      CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQT, W + pw::BQ, nullptr, 1, R, w.Q1, a_form(a) == 2, st));
-      CPN_TRY(launch_gemm_tc(a.weights, 5, w.Q1, 0, w.Qe, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_CB16, 1, 1, st));
-      // key_map_2 with the round-1 logits <K, Q> / 11.31 (CoPoNeRF.py:450) as its epilogue: K itself is never stored
-      CPN_TRY(launch_gemm_tc(a.weights, 4, w.K1, 0, w.lg1, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_ROWDOT, 1, 1, st, w.Qe,
-                             11.31f));
+      if (bilinear) {
+        // key_map_2, query_embed_2 and query_repeat_embed_2 have no activation, so both logits are bilinear forms of the
+        // 128-wide hidden vectors (cpn_common.cuh, pw::WM1): one 128 x 128 layer on the coordinate embedding per round
+        // instead of one on it and one on each key / repeat-query, and the key hidden layer is dotted in the epilogue
+        // of the folded key_map GEMM without ever being stored.
+        CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQT, W + pw::BQ, nullptr, 1, R, w.Q1, a_form(a) == 2, st, W + pw::WS1,
+                                   w.s1, W + pw::WS2, w.s2));
+        CPN_TRY(launch_gemm_tc(a.weights, 9, w.Q1, 0, w.Qe, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_CB16, 1, 1, st));
+        CPN_TRY(launch_gemm_tc(a.weights, 10, w.Q1, 0, w.Kk, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_CB16, 1, 1, st));
+        CPN_TRY(launch_gemm_tc(a.weights, 8, w.H1, 0, w.lg1, 0, R, 1, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_ROWDOT, 1, 1, st, w.Qe,
+                               11.31f, w.s1));
+      } else {
+        if (!(a.flags & CPN_FLAG_NO_FOLD))
+          CPN_TRY(launch_gemm_tc(a.weights, 8, w.H1, 0, w.K1, 0, R, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 1, KC128, st));
+        // coordinate embedding, CoPoNeRF.py:446; written column-blocked so the two logit epilogues read it coalesced
+        CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQT, W + pw::BQ, nullptr, 1, R, w.Q1, a_form(a) == 2, st));
+        CPN_TRY(launch_gemm_tc(a.weights, 5, w.Q1, 0, w.Qe, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_CB16, 1, 1, st));
+        // key_map_2 with the round-1 logits <K, Q> / 11.31 (CoPoNeRF.py:450) as its epilogue: K itself is never stored
+        CPN_TRY(launch_gemm_tc(a.weights, 4, w.K1, 0, w.lg1, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_ROWDOT, 1, 1, st, w.Qe,
+                               11.31f));
+      }
     } else {
       {
         ProfScope prof(st);
@@ -287,10 +305,14 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
     CPN_TRY(dense_simt(a, w.r1, CPN_LATENT, pw::WET, pw::BE, w.zemb, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_LATENT, 0, st));
     CPN_TRY(dense_simt(a, w.zemb, CPN_HIDDEN, pw::WQRA_T, pw::BQR, w.rbias, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_HIDDEN, 0, st));
     if (use_tc(a)) {   // query_repeat_embed_2 with the round-2 logits <Q2, Q> / 11.31 (CoPoNeRF.py:474) as its epilogue
-      CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQRB_T, nullptr, w.rbias, 2 * a.S, R, w.K1,
-                                 a_form(a) == 2, st));
-      CPN_TRY(launch_gemm_tc(a.weights, 6, w.K1, 0, w.lg2, 0, R, 0, CPN_TC_A_IMAGE | tc_scheme(a) | CPN_TC_OUT_ROWDOT, 1, 1, st,
-                             w.Qe, 11.31f));
+      if (bilinear) {   // the repeat-query hidden layer is dotted with WM2 q + BM2 (w.Kk, CB16) where it is produced
+        CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQRB_T, nullptr, w.rbias, 2 * a.S, R, nullptr, a_form(a) == 2, st,
+                                   nullptr, nullptr, nullptr, nullptr, w.Kk, w.s2, 11.31f, w.lg2));
+      } else {
+        CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQRB_T, nullptr, w.rbias, 2 * a.S, R, w.K1, a_form(a) == 2, st));
+        CPN_TRY(launch_gemm_tc(a.weights, 6, w.K1, 0, w.lg2, 0, R, 0, CPN_TC_A_IMAGE | tc_scheme(a) | CPN_TC_OUT_ROWDOT, 1, 1,
+                               st, w.Qe, 11.31f));
+      }
     } else {
       CPN_TRY(launch_gemm_simt(w.local16, 16, W + pw::WQRB_T, nullptr, w.rbias, 2 * a.S, w.K1, CPN_HIDDEN, R, CPN_HIDDEN,
                                16, 1, st));

@@ -69,6 +69,33 @@ __global__ void fold_kernel(const float* __restrict__ Wx, const float* __restric
   }
 }
 
+// Bilinear form of a logit <Wa x + ba, Wq q + bq> = x^T (WM q + BM) + (WS . q + CS):
+// WM[n][k] = sum_j Wa[j][n] Wq[j][k], BM[n] = sum_j Wa[j][n] bq[j], WS[k] = sum_j ba[j] Wq[j][k], CS = ba . bq (double).
+__global__ void bilinear_fold_kernel(const float* __restrict__ Wa, const float* __restrict__ ba, const float* __restrict__ Wq,
+                                     const float* __restrict__ bq, float* __restrict__ WM, float* __restrict__ BM,
+                                     float* __restrict__ WS) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 128 * 128) {
+    const int n = i / 128, k = i % 128;
+    double acc = 0.0;
+    for (int j = 0; j < 128; ++j) acc += (double)Wa[j * 128 + n] * (double)Wq[j * 128 + k];
+    WM[i] = (float)acc;
+  } else if (i < 128 * 128 + 128) {
+    const int n = i - 128 * 128;
+    double acc = 0.0, acc2 = 0.0;
+    for (int j = 0; j < 128; ++j) {
+      acc += (double)Wa[j * 128 + n] * (double)bq[j];
+      acc2 += (double)ba[j] * (double)Wq[j * 128 + n];
+    }
+    BM[n] = (float)acc;
+    WS[n] = (float)acc2;
+  } else if (i == 128 * 128 + 128) {
+    double acc = 0.0;
+    for (int j = 0; j < 128; ++j) acc += (double)ba[j] * (double)bq[j];
+    WS[128] = (float)acc;
+  }
+}
+
 struct Job {
   int tensor, col0, K, Kpad;  // K == 0: plain copy of the whole tensor
   size_t dst;
@@ -137,5 +164,13 @@ extern "C" int cpn_pack_weights(const float* src, void* dst_v, void* stream) {
   fold_kernel<<<(128 * 1664 + 255) / 256, 256, 0, st>>>(src + tensor_offset(6), src + tensor_offset(7), W2, b2, 128,
                                                         dst + pw::WKF, dst + pw::BKF);
   CPN_CHECK_LAUNCH("fold_kernel");
+  // attention logits as bilinear forms: key_map_2 (tensors 8, 9) and query_repeat_embed_2 (16, 17) against query_embed_2 (12, 13)
+  const float *Wq2 = src + tensor_offset(12), *bq2 = src + tensor_offset(13);
+  bilinear_fold_kernel<<<(128 * 128 + 129 + 255) / 256, 256, 0, st>>>(src + tensor_offset(8), src + tensor_offset(9), Wq2, bq2,
+                                                                      dst + pw::WM1, dst + pw::BM1, dst + pw::WS1);
+  CPN_CHECK_LAUNCH("bilinear_fold_kernel");
+  bilinear_fold_kernel<<<(128 * 128 + 129 + 255) / 256, 256, 0, st>>>(src + tensor_offset(16), src + tensor_offset(17), Wq2, bq2,
+                                                                      dst + pw::WM2, dst + pw::BM2, dst + pw::WS2);
+  CPN_CHECK_LAUNCH("bilinear_fold_kernel");
   return cpn_pack_tc_weights(src, dst, reinterpret_cast<char*>(dst_v) + cpn_packed_fp32_floats() * sizeof(float), st);
 }

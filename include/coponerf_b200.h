@@ -34,6 +34,8 @@ typedef enum {
 #define CPN_FLAG_EARLY_V 8    /* form V = latent_value(...) per sample (one GEMM over all sample rows) and let the attention
                                * read it; default: the attention reads out the hidden layer and the (linear) folded
                                * latent_value runs once per ray ("late readout") */
+#define CPN_FLAG_NO_BILINEAR 16 /* keep key_map_2 / query_embed_2 / query_repeat_embed_2 as three 128 x 128 layers (default:
+                                 * both attention logits are evaluated as bilinear forms, one layer per round) */
 #define CPN_N_LEVELS 4      /* feature maps per view: 3 refined ResNet levels + conv_map */
 #define CPN_FEAT_DIM 832    /* 256*3 + 64, models/CoPoNeRF.py:68 */
 #define CPN_LATENT 416      /* latent_dim // 2, models/CoPoNeRF.py:74 */
@@ -251,7 +253,8 @@ int cpn_gemm_simt_splitk(const float* A, int lda, const float* wt, const float* 
 
 /* Tensor-core GEMM of one packed layer (0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value,
  * 3 key_map, 4 key_map_2, 5 query_embed_2, 6 query_repeat_embed_2, 7 latent_value o query_encode_latent_2,
- * 8 key_map o query_encode_latent_2, both with K = 1664): C[M, N_layer] = act(A[M, K_layer] * W^T + b),
+ * 8 key_map o query_encode_latent_2, both with K = 1664, 9 key_map_2^T query_embed_2, 10 query_repeat_embed_2^T
+ * query_embed_2): C[M, N_layer] = act(A[M, K_layer] * W^T + b),
  * operands split into an fp16 head plus corrections (e4m3 on the fp8 path by default, fp16 with CPN_TC_F16X3)
  * and accumulated in fp32 on tcgen05.
  * `packed` is the blob from cpn_pack_weights. mode bit CPN_TC_A_IMAGE: A is an "operand image" (128-row tiles,

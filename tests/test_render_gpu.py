@@ -341,3 +341,13 @@ def test_late_readout_with_f16x3_images(case):
     H, W, n_rays, S, seed, val = [int(v) for v in g["meta"]]
     out = run_cuda(H, W, n_rays, S, seed, val, flags=2)
     check_against(out, g, case + "/late-f16x3")
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_three_layer_logit_path_matches_reference_golden(case):
+    """CPN_FLAG_NO_BILINEAR: key_map_2, query_embed_2 and query_repeat_embed_2 as three 128 x 128 layers (the default
+    evaluates both attention logits as bilinear forms of the hidden vectors, one layer per round)."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, case + ".npz")))
+    H, W, n_rays, S, seed, val = [int(v) for v in g["meta"]]
+    out = run_cuda(H, W, n_rays, S, seed, val, flags=16)
+    check_against(out, g, case + "/no-bilinear")
