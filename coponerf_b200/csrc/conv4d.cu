@@ -13,35 +13,127 @@
 
 namespace {
 
-constexpr int C4_THREADS = 64;   // 16^4 outputs -> 1024 CTAs: ~7 per SM so loads of several CTAs overlap
+constexpr int C4_POS = 32;        // output positions per CTA (one per lane: consecutive ws -> coalesced taps and stores)
+constexpr int C4_WARPS = 8;       // the (ci, branch, dy) tap rows of a position are dealt round-robin to 8 warps
+constexpr int C4_THREADS = C4_POS * C4_WARPS;
+constexpr int C4_GROUPS = 4;      // position groups per CTA
+constexpr int C4_CTA_POS = C4_POS * C4_GROUPS;
 
 // K, S: kernel size and stride as compile-time constants (0 = take them from the arguments), so that the tap and
 // pooling loops unroll for the three geometries UFC uses: (3, 1), (3, 2), (5, 4).
+//
+// The volumes are small (16^4 = 65 536 output positions), so one thread per position left the SMs at 20 % occupancy
+// with every thread walking Ci x 2 x k x k dependent tap loads (80 us for 75 MFMA). Here a position is shared by 8
+// warps, each taking whole tap rows (ci, branch, dy); the partial sums meet in shared memory and are added in warp
+// order (fixed, so the result does not depend on the launch).
 template <int CO, int K, int S>
 __global__ void __launch_bounds__(C4_THREADS) conv4d_kernel(cpn_conv4d_args a, int oq, int os, double* __restrict__ partials) {
-  extern __shared__ float wsm[];   // [2 branches][Ci][k*k][CO]
+  extern __shared__ __align__(16) float wsm[];   // [2 branches][Ci][k*k][CO], then the partial sums [8 warps][CO][32 positions]
   const int k = K ? K : a.k, kk = k * k, s = S ? S : a.stride, p = a.pad, Ci = a.Ci, Hq = a.Hq, Hs = a.Hs;
-  for (int i = threadIdx.x; i < 2 * Ci * kk * CO; i += C4_THREADS) {
-    int co = i % CO, tap = (i / CO) % kk, ci = (i / (CO * kk)) % Ci, br = i / (CO * kk * Ci);
-    const float* w = br ? a.ws : a.wq;   // (Co, Ci, k, k)
-    wsm[i] = w[((size_t)co * Ci + ci) * kk + tap];
+  {  // weights: coalesced reads of the (Co, Ci, k, k) tensors, scattered into the [ci][tap][co] shared layout
+    const int per = Ci * kk * CO;
+    for (int j = threadIdx.x; j < 2 * per; j += C4_THREADS) {
+      const int br = j >= per, jj = j - br * per, tap = jj % kk, ci = (jj / kk) % Ci, co = jj / (kk * Ci);
+      wsm[((size_t)(br * Ci + ci) * kk + tap) * CO + co] = (br ? a.ws : a.wq)[jj];
+    }
   }
-  __syncthreads();
+  float* red = wsm + 2 * Ci * kk * CO;
   const int P = oq * oq * os * os;
-  const int pos = blockIdx.x * C4_THREADS + threadIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  double sum = 0.0, sq = 0.0;
+  // C4_GROUPS groups of 32 positions per CTA: the weight staging and the CTA launch are paid once per 128 positions
+  for (int grp = 0; grp < C4_GROUPS; ++grp) {
+  const int pos0 = (blockIdx.x * C4_GROUPS + grp) * C4_POS, pos = pos0 + lane;
+  __syncthreads();   // weights staged (first group) / partial sums of the previous group consumed
+  if (pos0 >= P) break;
   float acc[CO];
 #pragma unroll
   for (int co = 0; co < CO; ++co) acc[co] = 0.f;
-  const bool live = pos < P;
-  if (live) {
+  if (pos < P) {
     const int ws_ = pos % os, hs = (pos / os) % os, wq = (pos / (os * os)) % oq, hq = pos / (os * os * oq);
     const size_t sHs = (size_t)Hs, plane = (size_t)Hq * Hq * Hs * Hs;
     const float* xb = a.x + (size_t)b * Ci * plane;
-    for (int ci = 0; ci < Ci; ++ci) {
-      const float* xc = xb + (size_t)ci * plane;
-      // query branch: conv over (Hq, Wq) of the input max-pooled over the support window of this output position
+    if (K > 0 && Ci >= C4_WARPS) {
+      // Tap table of this position, shared by all input channels: element offset of every tap (of its pooling window)
+      // inside one channel plane, or -1 outside the padded volume. A warp then owns whole (ci, branch) pairs, so a
+      // tap costs one load (per pooled element), two 16-byte weight loads per 8 outputs and the FMAs.
+      constexpr int KK = K > 0 ? K * K : 1, SS = S > 0 ? S : 1;
+      int qoff[KK], soff[KK];
 #pragma unroll
-      for (int dy = 0; dy < k; ++dy) {
+      for (int dy = 0; dy < (K > 0 ? K : 1); ++dy)
+#pragma unroll
+        for (int dx = 0; dx < (K > 0 ? K : 1); ++dx) {
+          const int qy = hq * SS + dy - p, qx = wq * SS + dx - p, sy = hs * SS + dy - p, sx = ws_ * SS + dx - p;
+          qoff[dy * K + dx] = (qy < 0 || qy >= Hq || qx < 0 || qx >= Hq) ? -1 : ((qy * Hq + qx) * Hs + hs * SS) * Hs + ws_ * SS;
+          soff[dy * K + dx] = (sy < 0 || sy >= Hs || sx < 0 || sx >= Hs) ? -1 : ((hq * SS * Hq + wq * SS) * Hs + sy) * Hs + sx;
+        }
+      const int nqi = min(SS, Hs - hs * SS), nqj = min(SS, Hs - ws_ * SS), nsi = min(SS, Hq - hq * SS), nsj = min(SS, Hq - wq * SS);
+      const int sstep = Hs * Hs;
+      for (int it = warp; it < 2 * Ci; it += C4_WARPS) {
+        const int br = it & 1, ci = it >> 1;
+        const float* xc = xb + (size_t)ci * plane;
+        const float* wrow = wsm + (size_t)(br * Ci + ci) * KK * CO;
+        if (br == 0) {
+#pragma unroll
+          for (int tp = 0; tp < KK; ++tp) {
+            float v;
+            if (S == 1) {   // no pooling: a padded tap is a zero, no branch
+              v = qoff[tp] >= 0 ? __ldg(xc + qoff[tp]) : 0.f;
+            } else {
+              if (qoff[tp] < 0) continue;
+              const float* base = xc + qoff[tp];
+              v = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < SS; ++i)
+#pragma unroll
+                for (int j = 0; j < SS; ++j)
+                  if (i < nqi && j < nqj) v = fmaxf(v, __ldg(base + i * Hs + j));
+            }
+#pragma unroll
+            for (int co = 0; co < CO; co += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wrow + tp * CO + co);
+              acc[co] = fmaf(v, w4.x, acc[co]);
+              acc[co + 1] = fmaf(v, w4.y, acc[co + 1]);
+              acc[co + 2] = fmaf(v, w4.z, acc[co + 2]);
+              acc[co + 3] = fmaf(v, w4.w, acc[co + 3]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int tp = 0; tp < KK; ++tp) {
+            float v;
+            if (S == 1) {
+              v = soff[tp] >= 0 ? __ldg(xc + soff[tp]) : 0.f;
+            } else {
+              if (soff[tp] < 0) continue;
+              const float* base = xc + soff[tp];
+              v = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < SS; ++i)
+#pragma unroll
+                for (int j = 0; j < SS; ++j)
+                  if (i < nsi && j < nsj) v = fmaxf(v, __ldg(base + (size_t)(i * Hq + j) * sstep));
+            }
+#pragma unroll
+            for (int co = 0; co < CO; co += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wrow + tp * CO + co);
+              acc[co] = fmaf(v, w4.x, acc[co]);
+              acc[co + 1] = fmaf(v, w4.y, acc[co + 1]);
+              acc[co + 2] = fmaf(v, w4.z, acc[co + 2]);
+              acc[co + 3] = fmaf(v, w4.w, acc[co + 3]);
+            }
+          }
+        }
+      }
+    } else {
+    const int items = Ci * 2 * k;
+    for (int it = warp; it < items; it += C4_WARPS) {
+      const int dy = it % k, br = (it / k) & 1, ci = it / (2 * k);
+      const float* xc = xb + (size_t)ci * plane;
+      const float* wrow = wsm + ((size_t)(br * Ci + ci) * kk + dy * k) * CO;
+      if (br == 0) {
+        // query branch: conv over (Hq, Wq) of the input max-pooled over the support window of this output position
         const int qy = hq * s + dy - p;
         if (qy < 0 || qy >= Hq) continue;
 #pragma unroll
@@ -61,14 +153,12 @@ __global__ void __launch_bounds__(C4_THREADS) conv4d_kernel(cpn_conv4d_args a, i
               v = fmaxf(v, __ldg(base + (size_t)y * Hs + x));
             }
           }
-          const float* w = wsm + ((size_t)(0 * Ci + ci) * kk + dy * k + dx) * CO;
+          const float* w = wrow + dx * CO;
 #pragma unroll
           for (int co = 0; co < CO; ++co) acc[co] = fmaf(v, w[co], acc[co]);
         }
-      }
-      // support branch: conv over (Hs, Ws) of the input max-pooled over the query window
-#pragma unroll
-      for (int dy = 0; dy < k; ++dy) {
+      } else {
+        // support branch: conv over (Hs, Ws) of the input max-pooled over the query window
         const int sy = hs * s + dy - p;
         if (sy < 0 || sy >= Hs) continue;
 #pragma unroll
@@ -87,41 +177,47 @@ __global__ void __launch_bounds__(C4_THREADS) conv4d_kernel(cpn_conv4d_args a, i
               v = fmaxf(v, __ldg(xc + (((size_t)y * Hq + x) * sHs + sy) * sHs + sx));
             }
           }
-          const float* w = wsm + ((size_t)(1 * Ci + ci) * kk + dy * k + dx) * CO;
+          const float* w = wrow + dx * CO;
 #pragma unroll
           for (int co = 0; co < CO; ++co) acc[co] = fmaf(v, w[co], acc[co]);
         }
       }
     }
+    }   // generic path
   }
-  double sum = 0.0, sq = 0.0;
-  if (live) {
-    float* yb = a.y + (size_t)b * CO * P + pos;
 #pragma unroll
-    for (int co = 0; co < CO; ++co) {
-      float v = acc[co] + (a.bq[co] + a.bs[co]);
-      yb[(size_t)co * P] = v;
-      sum += (double)v;
-      sq += (double)v * (double)v;
-    }
+  for (int co = 0; co < CO; ++co) red[(warp * CO + co) * C4_POS + lane] = acc[co];
+  __syncthreads();
+  // (co, position) pairs: add the 8 partial sums in warp order, add the biases, store, GroupNorm partial sums
+  for (int i = threadIdx.x; i < CO * C4_POS; i += C4_THREADS) {
+    const int co = i / C4_POS, l = i % C4_POS, ppos = pos0 + l;
+    if (ppos >= P) continue;
+    float v = red[co * C4_POS + l];
+#pragma unroll
+    for (int w = 1; w < C4_WARPS; ++w) v += red[(w * CO + co) * C4_POS + l];
+    v += a.bq[co] + a.bs[co];
+    a.y[((size_t)b * CO + co) * P + ppos] = v;
+    sum += (double)v;
+    sq += (double)v * (double)v;
   }
+  }  // position groups
   // per-CTA partial sums for GroupNorm (fixed order: warp tree, then warps in order)
-  __shared__ double red[2][C4_THREADS / 32];
+  __shared__ double red2[2][C4_WARPS];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     sum += __shfl_xor_sync(0xffffffffu, sum, o);
     sq += __shfl_xor_sync(0xffffffffu, sq, o);
   }
-  if ((threadIdx.x & 31) == 0) {
-    red[0][threadIdx.x >> 5] = sum;
-    red[1][threadIdx.x >> 5] = sq;
+  if (lane == 0) {
+    red2[0][warp] = sum;
+    red2[1][warp] = sq;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     double t0 = 0.0, t1 = 0.0;
-    for (int i = 0; i < C4_THREADS / 32; ++i) {
-      t0 += red[0][i];
-      t1 += red[1][i];
+    for (int i = 0; i < C4_WARPS; ++i) {
+      t0 += red2[0][i];
+      t1 += red2[1][i];
     }
     partials[((size_t)b * gridDim.x + blockIdx.x) * 2 + 0] = t0;
     partials[((size_t)b * gridDim.x + blockIdx.x) * 2 + 1] = t1;
@@ -179,7 +275,7 @@ extern "C" size_t cpn_conv4d_workspace_bytes(int B, int Hq, int Hs, int k, int s
   if (B <= 0 || Hq <= 0 || Hs <= 0 || k <= 0 || stride <= 0) return 0;
   int oq = out_size(Hq, k, stride, pad), os = out_size(Hs, k, stride, pad);
   size_t P = (size_t)oq * oq * os * os;
-  return (size_t)B * ((P + C4_THREADS - 1) / C4_THREADS) * 2 * sizeof(double);
+  return (size_t)B * ((P + C4_CTA_POS - 1) / C4_CTA_POS) * 2 * sizeof(double);
 }
 
 extern "C" int cpn_conv4d(const cpn_conv4d_args* args, void* stream) {
@@ -205,10 +301,10 @@ extern "C" int cpn_conv4d(const cpn_conv4d_args* args, void* stream) {
     cpn_set_error("cpn_conv4d: workspace of %zu bytes needed, %zu given", need, a.workspace_bytes);
     return CPN_ERR_WORKSPACE;
   }
-  const int P = oq * oq * os * os, nblk = (P + C4_THREADS - 1) / C4_THREADS;
-  const size_t smem = (size_t)2 * a.Ci * a.k * a.k * a.Co * sizeof(float);
+  const int P = oq * oq * os * os, nblk = (P + C4_CTA_POS - 1) / C4_CTA_POS;
+  const size_t smem = ((size_t)2 * a.Ci * a.k * a.k * a.Co + (size_t)C4_WARPS * a.Co * C4_POS) * sizeof(float);
   if (smem > 96 * 1024) {
-    cpn_set_error("cpn_conv4d: weights of %zu bytes do not fit in shared memory", smem);
+    cpn_set_error("cpn_conv4d: weights + partial sums of %zu bytes do not fit in shared memory", smem);
     return CPN_ERR_ARG;
   }
   double* partials = reinterpret_cast<double*>(a.workspace);
