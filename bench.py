@@ -406,7 +406,11 @@ def main():
                      "measured": f"CUDA events around every launch in a {prof_steps}-step pass with lanes=1 "
                                  f"({ms_prof / prof_steps:.1f} ms/step)",
                      "flop_per_launch": flop_per_launch,
-                     "whole_path_tflops": value * FLOP_PER_RAY / 1e12 / world},
+                     "whole_path_tflops": value * FLOP_PER_RAY / 1e12 / world,
+                     # fp32 parity costs 2.0 tensor passes per product (fp16 head + two e4m3 corrections at twice the fp16
+                     # rate), so the reachable ceiling of this kernel is peak / 2
+                     "tensor_passes_per_product": 2.0,
+                     "frac_of_parity_ceiling": achieved / (peak / 2.0)},
         "clocks": clk,
     }
 
