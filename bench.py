@@ -409,8 +409,8 @@ def main():
                      "whole_path_tflops": value * FLOP_PER_RAY / 1e12 / world,
                      # fp32 parity costs 2.0 tensor passes per product (fp16 head + two e4m3 corrections at twice the fp16
                      # rate), so the reachable ceiling of this kernel is peak / 2
-                     "tensor_passes_per_product": 2.0,
-                     "frac_of_parity_ceiling": achieved / (peak / 2.0)},
+                     "tensor_passes_per_product": None if args.simt else 2.0,
+                     "frac_of_parity_ceiling": None if args.simt else achieved / (peak / 2.0)},
         "clocks": clk,
     }
 

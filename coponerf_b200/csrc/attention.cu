@@ -196,7 +196,7 @@ __global__ void attn2_kernel(cpn_render_args a, int ray0, int nr, const float* _
 template <bool F8>
 __global__ void __launch_bounds__(128) readout_image_kernel(const unsigned char* __restrict__ img,
                                                             const float* __restrict__ wts, int S2,
-                                                            float* __restrict__ hbar) {
+                                                            float* __restrict__ hbar, int nr, int out_N, int out_ray0) {
   extern __shared__ float sm[];   // [2S] weights of this ray, [832] weighted sums of this branch
   float* hb = sm + S2;
   const int ray = blockIdx.x, br = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -271,8 +271,10 @@ __global__ void __launch_bounds__(128) readout_image_kernel(const unsigned char*
   // 8 values are exactly one 16-byte fp16 group plus half a 16-byte group in each correction plane
   const int kc = t >> 2, g = t & 3;
   const float4 v0 = *reinterpret_cast<const float4*>(hb + t * 8), v1 = *reinterpret_cast<const float4*>(hb + t * 8 + 4);
+  // output row: the chunk-local ray (out_N == nr, out_ray0 == 0) or the ray's index in the whole image b * N + n
+  const size_t oray = (size_t)(ray / nr) * out_N + out_ray0 + ray % nr;
   unsigned char* oblk = reinterpret_cast<unsigned char*>(hbar) +
-                        (((size_t)(ray >> 7) * (2 * KC) + br * KC + kc) * (size_t)ACT_CHUNK_BYTES) + (ray & 127) * 16;
+                        (((oray >> 7) * (2 * KC) + br * KC + kc) * (size_t)ACT_CHUNK_BYTES) + (oray & 127) * 16;
   if (F8) {
     uint2 h0, h1, l8, x8;
     tc::split4_f8(v0, h0, l8.x, x8.x);
@@ -288,14 +290,20 @@ __global__ void __launch_bounds__(128) readout_image_kernel(const unsigned char*
   }
 }
 
-// z = sum_v (R2 + R1) = R2 + 2 R1 (CoPoNeRF.py:481-485), R2 = WVF hbar2 + b from the late readout of round 2
-__global__ void combine_z_kernel(cpn_render_args a, int ray0, int nr, const float* __restrict__ r2,
-                                 const float* __restrict__ r1, float* __restrict__ z_all) {
+// z = sum_v (R2 + R1) = R2 + 2 R1 (CoPoNeRF.py:481-485), R2 = WVF hbar2 + b from the late readout of round 2.
+// Per chunk R1 is parked in z_all at the ray's image index; once every chunk is done, one GEMM over all rays of the
+// image gives R2 and finish_z_kernel adds it (one 65 536-row GEMM instead of 32 of 2048 rows).
+__global__ void park_r1_kernel(cpn_render_args a, int ray0, int nr, const float* __restrict__ r1, float* __restrict__ z_all) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.B * nr * CPN_LATENT) return;
   const int ray = i / CPN_LATENT, c = i % CPN_LATENT, b = ray / nr, n = ray0 + ray % nr;
-  const float r = r1[i];
-  z_all[((size_t)b * a.N + n) * CPN_LATENT + c] = (r2[i] + r) + r;
+  z_all[((size_t)b * a.N + n) * CPN_LATENT + c] = r1[i];
+}
+__global__ void finish_z_kernel(const float* __restrict__ r2, float* __restrict__ z_all, size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float r = z_all[i];
+  z_all[i] = (r2[i] + r) + r;
 }
 
 // phi. One CTA of 128 threads renders PHI_RAYS = 16 rays. Thread (cq = t % 32, rg = t / 32) owns a 4-channel x
@@ -429,27 +437,38 @@ int launch_attn2(const cpn_render_args& a, int ray0, int nr, const float* q2, co
 }
 
 int launch_readout_image(const cpn_render_args& a, int nr, const void* h1_image, const float* wts, float* hbar, int f8,
-                         cudaStream_t st) {
+                         cudaStream_t st, int out_N, int out_ray0) {
   const int S2 = 2 * a.S;
   if (S2 % 64) {
     cpn_set_error("readout_image: S=%d unsupported (S must be a multiple of 32)", a.S);
     return CPN_ERR_ARG;
   }
+  if (out_N <= 0) {   // chunk-local output rows
+    out_N = nr;
+    out_ray0 = 0;
+  }
+  const size_t smem = (S2 + CPN_FEAT_DIM) * sizeof(float);
   if (f8)
-    readout_image_kernel<true><<<dim3(a.B * nr, 2), 128, (S2 + CPN_FEAT_DIM) * sizeof(float), st>>>(reinterpret_cast<const unsigned char*>(h1_image),
-                                                                           wts, S2, hbar);
+    readout_image_kernel<true><<<dim3(a.B * nr, 2), 128, smem, st>>>(reinterpret_cast<const unsigned char*>(h1_image), wts, S2,
+                                                                     hbar, nr, out_N, out_ray0);
   else
-    readout_image_kernel<false><<<dim3(a.B * nr, 2), 128, (S2 + CPN_FEAT_DIM) * sizeof(float), st>>>(reinterpret_cast<const unsigned char*>(h1_image),
-                                                                            wts, S2, hbar);
+    readout_image_kernel<false><<<dim3(a.B * nr, 2), 128, smem, st>>>(reinterpret_cast<const unsigned char*>(h1_image), wts, S2,
+                                                                      hbar, nr, out_N, out_ray0);
   CPN_CHECK_LAUNCH("readout_image_kernel");
   return CPN_OK;
 }
 
-int launch_combine_z(const cpn_render_args& a, int ray0, int nr, const float* r2, const float* r1, float* z_all,
-                     cudaStream_t st) {
+int launch_park_r1(const cpn_render_args& a, int ray0, int nr, const float* r1, float* z_all, cudaStream_t st) {
   const int total = a.B * nr * CPN_LATENT;
-  combine_z_kernel<<<(total + 255) / 256, 256, 0, st>>>(a, ray0, nr, r2, r1, z_all);
-  CPN_CHECK_LAUNCH("combine_z_kernel");
+  park_r1_kernel<<<(total + 255) / 256, 256, 0, st>>>(a, ray0, nr, r1, z_all);
+  CPN_CHECK_LAUNCH("park_r1_kernel");
+  return CPN_OK;
+}
+
+int launch_finish_z(const cpn_render_args& a, const float* r2_all, float* z_all, cudaStream_t st) {
+  const size_t total = (size_t)a.B * a.N * CPN_LATENT;
+  finish_z_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r2_all, z_all, total);
+  CPN_CHECK_LAUNCH("finish_z_kernel");
   return CPN_OK;
 }
 

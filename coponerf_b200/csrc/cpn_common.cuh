@@ -138,10 +138,11 @@ int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, c
 int launch_attn2(const cpn_render_args& a, int ray0, int nr, const float* q2, const float* qemb, const float* value,
                  const float* r1, float* z_all, cudaStream_t st, const float* logits = nullptr, float* wts_out = nullptr);
 // late readout: hbar (rays, 1664) = sum over a ray's rows of w * [h_p ; h_s] read from the hidden-layer operand image
+// out_N > 0: output rows are indexed by the ray's position in the whole image (b * out_N + out_ray0 + n) instead of the chunk
 int launch_readout_image(const cpn_render_args& a, int nr, const void* h1_image, const float* wts, float* hbar, int f8,
-                         cudaStream_t st);
-int launch_combine_z(const cpn_render_args& a, int ray0, int nr, const float* r2, const float* r1, float* z_all,
-                     cudaStream_t st);
+                         cudaStream_t st, int out_N = 0, int out_ray0 = 0);
+int launch_park_r1(const cpn_render_args& a, int ray0, int nr, const float* r1, float* z_all, cudaStream_t st);
+int launch_finish_z(const cpn_render_args& a, const float* r2_all, float* z_all, cudaStream_t st);
 int launch_phi(const cpn_render_args& a, const float* z_all, cudaStream_t st);
 int launch_ray_epilogue(const cpn_render_args& a, int ray0, int nr, const float* wp, const float* seg, cudaStream_t st);
 

@@ -208,7 +208,13 @@ int dense_simt(const cpn_render_args& a, const float* A, int lda, size_t wt, siz
 }  // namespace
 
 // image-level part of the workspace: the per-ray latent z of every ray (phi runs once over the whole image)
-size_t image_bytes(int B, int N) { return ((size_t)B * N * CPN_LATENT * sizeof(float) + 255) / 256 * 256; }
+// image-level buffers: z of every ray; for the late readout also the round-2 readout of every ray as an operand image
+// (whole 128-ray tiles x 52 k-chunks) and the result of the one GEMM that turns it into R2
+size_t z_bytes(int B, int N) { return ((size_t)B * N * CPN_LATENT * sizeof(float) + 255) / 256 * 256; }
+size_t hbar_all_bytes(int B, int N) {
+  return ((size_t)B * N + 127) / 128 * (2 * CPN_FEAT_DIM / ACT_BK) * (size_t)ACT_CHUNK_BYTES;
+}
+size_t image_bytes(int B, int N) { return 2 * z_bytes(B, N) + hbar_all_bytes(B, N); }
 
 extern "C" size_t cpn_render_workspace_bytes(int B, int N, int chunk_rays, int S, int lanes) {
   if (B <= 0 || N < 0 || chunk_rays <= 0 || S <= 0 || lanes < 1 || lanes > MAX_LANES) return 0;
@@ -220,13 +226,15 @@ extern "C" int cpn_render_launch_count(const cpn_render_args* a) {
   if (!a || a->chunk_rays <= 0) return 0;
   int chunks = (a->N + a->chunk_rays - 1) / a->chunk_rays;
   const bool unfolded = (a->flags & CPN_FLAG_NO_FOLD) || (a->flags & CPN_FLAG_SIMT_ONLY);
-  int per_chunk = unfolded ? 17 : ((a->flags & CPN_FLAG_EARLY_V) ? 16 : 20);
+  const bool late = !unfolded && !(a->flags & CPN_FLAG_EARLY_V);
+  int per_chunk = unfolded ? 17 : (late ? 19 : 16);
   if (!unfolded && !(a->flags & CPN_FLAG_NO_BILINEAR)) per_chunk -= 1;   // one 128 x 128 layer fewer
-  return chunks * per_chunk + 1;
+  return chunks * per_chunk + (late ? 3 : 1);
 }
 
 namespace {
-int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int ray0, int nr, cudaStream_t st) {
+int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, float* hbar_all, int ray0, int nr,
+                 cudaStream_t st) {
     const float* W = reinterpret_cast<const float*>(a.weights);
     int rays = a.B * nr;
     int R = rays * 2 * a.S;
@@ -320,9 +328,9 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, int
     }
     if (late_v) {
       CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, nullptr, w.r1, z_all, st, w.lg2, w.wt2));
-      CPN_TRY(launch_readout_image(a, nr, w.H1, w.wt2, w.hbar, a_form(a) == 2, st));
-      CPN_TRY(launch_gemm_tc(a.weights, 7, w.hbar, 0, w.r2, CPN_LATENT, rays, 0, CPN_TC_A_IMAGE | sch, 1, 1, st));
-      CPN_TRY(launch_combine_z(a, ray0, nr, w.r2, w.r1, z_all, st));
+      // the round-2 readout lands in the image-level operand image; its GEMM runs once per image (finish_image)
+      CPN_TRY(launch_readout_image(a, nr, w.H1, w.wt2, hbar_all, a_form(a) == 2, st, a.N, ray0));
+      CPN_TRY(launch_park_r1(a, ray0, nr, w.r1, z_all, st));
     } else {
       CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, w.V, w.r1, z_all, st, use_tc(a) ? w.lg2 : nullptr));
     }
@@ -348,12 +356,23 @@ extern "C" int cpn_render_rays(const cpn_render_args* args, void* stream) {
     return CPN_ERR_WORKSPACE;
   }
   float* z_all = reinterpret_cast<float*>(a.workspace);
+  float* r2_all = reinterpret_cast<float*>(reinterpret_cast<char*>(a.workspace) + z_bytes(a.B, a.N));
+  float* hbar_all = reinterpret_cast<float*>(reinterpret_cast<char*>(a.workspace) + 2 * z_bytes(a.B, a.N));
+  const bool late_v = use_tc(a) && !(a.flags & (CPN_FLAG_NO_FOLD | CPN_FLAG_EARLY_V));
+  // late readout: R2 of every ray from one GEMM over the image, z = (R2 + R1) + R1, then the light-field decoder
+  auto finish_image = [&]() -> int {
+    if (late_v) {
+      CPN_TRY(launch_gemm_tc(a.weights, 7, hbar_all, 0, r2_all, CPN_LATENT, a.B * a.N, 0, CPN_TC_A_IMAGE | tc_scheme(a), 1, 1, st));
+      CPN_TRY(launch_finish_z(a, r2_all, z_all, st));
+    }
+    return launch_phi(a, z_all, st);
+  };
   char* lane_base = reinterpret_cast<char*>(a.workspace) + img_bytes;
   if (lanes == 1) {
     Workspace w = carve(lane_base, a.B, chunk, a.S);
     for (int ray0 = 0; ray0 < a.N; ray0 += chunk)
-      CPN_TRY(render_chunk(a, w, z_all, ray0, (a.N - ray0) < chunk ? (a.N - ray0) : chunk, st));
-    return launch_phi(a, z_all, st);
+      CPN_TRY(render_chunk(a, w, z_all, hbar_all, ray0, (a.N - ray0) < chunk ? (a.N - ray0) : chunk, st));
+    return finish_image();
   }
   LanePool* pool = nullptr;
   CPN_TRY(get_pool(&pool));
@@ -366,12 +385,13 @@ extern "C" int cpn_render_rays(const cpn_render_args* args, void* stream) {
   int status = CPN_OK;
   for (int c = 0; c < nchunks && status == CPN_OK; ++c) {
     int ray0 = c * chunk;
-    status = render_chunk(a, w[c % lanes], z_all, ray0, (a.N - ray0) < chunk ? (a.N - ray0) : chunk, pool->stream[c % lanes]);
+    status = render_chunk(a, w[c % lanes], z_all, hbar_all, ray0, (a.N - ray0) < chunk ? (a.N - ray0) : chunk,
+                          pool->stream[c % lanes]);
   }
   for (int l = 0; l < lanes; ++l) {   // always join, also after an error, so the caller's stream stays ordered
     cudaEventRecord(pool->done[l], pool->stream[l]);
     cudaStreamWaitEvent(st, pool->done[l], 0);
   }
   if (status != CPN_OK) return status;
-  return launch_phi(a, z_all, st);   // the light-field decoder runs once over every ray of the image
+  return finish_image();   // the light-field decoder runs once over every ray of the image
 }
