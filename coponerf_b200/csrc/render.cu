@@ -76,7 +76,7 @@ struct ProfScope {  // records an event pair around the enclosed launches when a
 // Workspace carve-up for one chunk of `nr` rays of each of B pairs (R = B * nr * 2 * S sample rows).
 struct Workspace {
   float *seg, *rowaux, *local16, *A, *H1, *E, *V, *K1, *Kk, *Q1, *Qe, *r1, *wp, *zemb, *rbias, *lg1, *lg2, *wt1, *wt2,
-      *hbar, *r2, *s1, *s2;
+      *hbar, *s1, *s2;
   size_t bytes;
 };
 
@@ -106,10 +106,9 @@ Workspace carve(void* base, int B, int nr, int S) {
   w.rbias = take(rays * CPN_HIDDEN);
   w.lg1 = take(R);   // attention logits of round 1 / round 2, one per sample row
   w.lg2 = take(R);
-  w.wt1 = take(R);   // late readout: softmax weights of round 1 / round 2, weighted hidden layer, round-2 latent
+  w.wt1 = take(R);   // late readout: softmax weights of round 1 / round 2, weighted hidden layer of round 1
   w.wt2 = take(R);
   w.hbar = take((rays + 127) / 128 * 128 * 2 * CPN_FEAT_DIM);   // operand image, whole 128-ray tiles
-  w.r2 = take(rays * CPN_LATENT);
   w.s1 = take(R);    // bilinear logits: per-row scalar terms of round 1 / round 2
   w.s2 = take(R);
   w.bytes = off;

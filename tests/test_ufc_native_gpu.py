@@ -92,3 +92,21 @@ def test_native_ufc_forward_at_512_sizes():
     for a, b in zip(got_flows, ref_flows):
         assert a.shape == b.shape
         assert float((a.cpu() - b).abs().max()) <= 2e-3 * 128
+
+
+def test_split_k_linear_matches_fp64_and_plain_kernel():
+    """cpn_gemm_simt_splitk (CudaOps.linear picks it for few-tile / long-K layers) against fp64, for the token-layer
+    shapes of the cost aggregation and ragged ones; deterministic from run to run."""
+    cu, _ = _ops()
+    g = torch.Generator().manual_seed(3)
+    for M, N, K, act in ((256, 512, 2304, None), (1024, 512, 2304, None), (256, 256, 1024, None), (1024, 256, 1024, "relu"),
+                         (200, 132, 520, "gelu"), (256, 1024, 256, "gelu")):
+        x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g) * 0.1
+        ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+        ref = ref.relu() if act == "relu" else torch.nn.functional.gelu(ref) if act == "gelu" else ref
+        n0 = cu.launches
+        got = cu.linear(x.cuda(), w.cuda(), b.cuda(), act=act)
+        _close(got, ref.float(), tol=3e-6)
+        assert torch.equal(got, cu.linear(x.cuda(), w.cuda(), b.cuda(), act=act))
+        if K >= 512:
+            assert cu.launches - n0 == 4, "expected the split-K path (GEMM + finish per call)"
