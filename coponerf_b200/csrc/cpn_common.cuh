@@ -49,14 +49,13 @@ constexpr size_t BVF = WVF + 416 * 1664;         // [416]
 constexpr size_t WKF = BVF + 416;                // [128][1664]
 constexpr size_t BKF = WKF + 128 * 1664;         // [128]
 // attention logits as bilinear forms (key_map_2, query_embed_2 and query_repeat_embed_2 have no activation,
-// CoPoNeRF.py:408,446,473): <Wk2 k + bk2, Wq2 q + bq2> = k^T (WM1 q + BM1) + (WS1 . q + CS1), with
-// WM1 = Wk2^T Wq2, BM1 = Wk2^T bq2, WS1 = Wq2^T bk2, CS1 = bk2 . bq2; the same with query_repeat_embed_2 for round 2.
-constexpr size_t WM1 = BKF + 128;                // [128][128] row-major (N, K)
-constexpr size_t BM1 = WM1 + 128 * 128;          // [128]
-constexpr size_t WS1 = BM1 + 128;                // [128] + CS1 at [128] (+3 pad)
-constexpr size_t WM2 = WS1 + 132;
-constexpr size_t BM2 = WM2 + 128 * 128;
-constexpr size_t WS2 = BM2 + 128;
+// CoPoNeRF.py:408,446,473): <Wk2 k + bk2, Wq2 q + bq2> = k^T (WM q + BM) + (WS . q + CS), with
+// WM = Wk2^T Wq2, BM = Wk2^T bq2, WS = Wq2^T bk2, CS = bk2 . bq2; the same with query_repeat_embed_2 for round 2. Both
+// WM / BM pairs are stacked into one 256-row layer, so one GEMM over the coordinate embedding serves both rounds.
+constexpr size_t WM12 = BKF + 128;               // [256][128] row-major (N, K): rows 0-127 round 1, 128-255 round 2
+constexpr size_t BM12 = WM12 + 256 * 128;        // [256]
+constexpr size_t WS1 = BM12 + 256;               // [128] + CS1 at [128] (+3 pad)
+constexpr size_t WS2 = WS1 + 132;
 constexpr size_t FP32_END = WS2 + 132;
 }  // namespace pw
 
@@ -129,7 +128,8 @@ int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias
 int launch_mlp16_image(const float* x, const float* wt, const float* bias, const float* rowbias, int rows_per_bias, int M,
                        void* img, int f8, cudaStream_t st, const float* sdot1 = nullptr, float* s1 = nullptr,
                        const float* sdot2 = nullptr, float* s2 = nullptr, const float* dotv = nullptr,
-                       const float* rowadd = nullptr, float div = 1.f, float* lg = nullptr);
+                       const float* rowadd = nullptr, float div = 1.f, float* lg = nullptr, int dot_blocks = CPN_HIDDEN / 16,
+                       int dot_block0 = 0);   // dotv rows are [row tile][dot_blocks][128][16]; this layer's columns start at dot_block0
 // logits != nullptr: one precomputed logit per sample row (key / qemb unused); else <key, qemb> / 11.31 is computed here
 int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, const float* qemb, const float* value,
                  const float* rowaux, float* r1, float* wp, cudaStream_t st, const float* logits = nullptr,
@@ -158,7 +158,7 @@ constexpr int ACT_CHUNK_BYTES = 2 * (ACT_BK / 8) * 128 * 16;
 constexpr int ACT_LO = 8192;      // f16x3: fp16 lo plane
 constexpr int ACT_LO8 = 8192;     // f8: e4m3 remainder plane
 constexpr int ACT_X8 = 12288;     // f8: e4m3 value plane
-constexpr int CPN_TC_LAYERS = 11;
+constexpr int CPN_TC_LAYERS = 10;
 size_t cpn_packed_fp32_floats();
 size_t cpn_tc_weights_bytes();
 int cpn_pack_tc_weights(const float* raw, const float* packed_fp32, void* dst, cudaStream_t st);
@@ -169,4 +169,4 @@ int cpn_pack_tc_weights(const float* raw, const float* packed_fp32, void* dst, c
 // CPN_TC_OUT_CB16: fp32 output as [row tile][16-col block][128][16]; CPN_TC_OUT_ROWDOT: C[row] = <out row, dotv row> / dot_div
 int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,
                    int out_div, int out_kchunks, cudaStream_t st, const float* dotv = nullptr, float dot_div = 1.f,
-                   const float* dot_rowadd = nullptr);   // row-dot output: C[row] = (<out row, dotv row> + dot_rowadd[row]) / dot_div
+                   const float* dot_rowadd = nullptr, int dot_blocks = 0, int dot_block0 = 0);   // row-dot output: C[row] = (<out row, dotv row> + dot_rowadd[row]) / dot_div

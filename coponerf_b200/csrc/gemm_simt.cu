@@ -230,6 +230,7 @@ struct Mlp16Extra {
   const float* rowadd;
   float div;
   float* lg;
+  int dot_blocks, dot_block0;   // dotv rows: [row tile][dot_blocks][128][16], this layer's 8 blocks start at dot_block0
 };
 
 template <bool F8>
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(128) mlp16_image_kernel(const float* __restric
         }
       }
       if (e.dotv) {   // CB16: [row tile][16-column block][128 rows][16]
-        const float* dv = e.dotv + (((tile0 + q) * (CPN_HIDDEN / 16) + n0 / 16) * 128 + rloc) * 16 + (n0 & 8);
+        const float* dv = e.dotv + (((tile0 + q) * e.dot_blocks + e.dot_block0 + n0 / 16) * 128 + rloc) * 16 + (n0 & 8);
         const float4 a0 = __ldg(reinterpret_cast<const float4*>(dv)), a1 = __ldg(reinterpret_cast<const float4*>(dv + 4));
         dl[q] = fmaf(acc[q][3], a0.w, fmaf(acc[q][2], a0.z, fmaf(acc[q][1], a0.y, fmaf(acc[q][0], a0.x, dl[q]))));
         dl[q] = fmaf(acc[q][7], a1.w, fmaf(acc[q][6], a1.z, fmaf(acc[q][5], a1.y, fmaf(acc[q][4], a1.x, dl[q]))));
@@ -377,14 +378,14 @@ int simt_splits(int M, int N, int K, int* ksplit) {
 
 int launch_mlp16_image(const float* x, const float* wt, const float* bias, const float* rowbias, int rows_per_bias, int M,
                        void* img, int f8, cudaStream_t st, const float* sdot1, float* s1, const float* sdot2, float* s2,
-                       const float* dotv, const float* rowadd, float div, float* lg) {
+                       const float* dotv, const float* rowadd, float div, float* lg, int dot_blocks, int dot_block0) {
   if (M <= 0) return CPN_OK;
   if ((!img && !dotv) || (dotv && !lg) || (s1 && !sdot1) || (s2 && (!sdot2 || !s1))) {
     cpn_set_error("mlp16_image: inconsistent outputs");
     return CPN_ERR_ARG;
   }
   const unsigned ctas = (unsigned)((M + 255) / 256);   // two 128-row tiles per CTA
-  const Mlp16Extra e{sdot1, s1, sdot2, s2, dotv, rowadd, div, lg};
+  const Mlp16Extra e{sdot1, s1, sdot2, s2, dotv, rowadd, div, lg, dot_blocks, dot_block0};
   if (f8)
     mlp16_image_kernel<true><<<ctas, 128, 0, st>>>(x, wt, bias, rowbias, rows_per_bias > 0 ? rows_per_bias : 1, M,
                                                    reinterpret_cast<unsigned char*>(img), e);

@@ -69,8 +69,7 @@ const TcLayer kLayers[CPN_TC_LAYERS] = {
     {128, 128, 128, 128, RAW_WQR2, pw::BQR2, false},  // 6 query_repeat_embed_2
     {416, 1664, 1664, 208, pw::WVF, pw::BVF, true},   // 7 latent_value o query_encode_latent_2 (both branches)
     {128, 1664, 1664, 128, pw::WKF, pw::BKF, true},   // 8 key_map o query_encode_latent_2
-    {128, 128, 128, 128, pw::WM1, pw::BM1, true},     // 9 key_map_2^T query_embed_2 (round-1 logits as a bilinear form)
-    {128, 128, 128, 128, pw::WM2, pw::BM2, true},     // 10 query_repeat_embed_2^T query_embed_2 (round 2)
+    {256, 128, 128, 128, pw::WM12, pw::BM12, true},   // 9 [key_map_2 ; query_repeat_embed_2]^T query_embed_2 (bilinear logits)
 };
 constexpr size_t TC_HEADER_BYTES = 256;   // floats [0..15] 1/scale per layer, [16..31] scale, uints [32..47] absmax bits
 static_assert(CPN_TC_LAYERS <= 16, "header slots");
@@ -167,6 +166,7 @@ struct GemmArgs {
   const float* dotv;             // CB16 matrix the rows are dotted with (out_kind 3); C then holds one float per row
   float dot_div;
   const float* dot_rowadd;       // optional per-row term added to the dot product before the division
+  int dot_blocks, dot_block0;    // dotv is [row tile][dot_blocks 16-column blocks][128][16]; this layer starts at dot_block0
 };
 
 // Drain one 128-row accumulator sub-tile: TMEM -> registers -> scale, bias, ReLU -> fp32 rows or the operand image
@@ -238,7 +238,8 @@ __device__ __forceinline__ void drain_subtile(const GemmArgs& g, uint32_t tmem, 
 #pragma unroll
       for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     } else if (g.out_kind == 3) {
-      const float4* qv = reinterpret_cast<const float4*>(g.dotv + cb_row + (size_t)((n0 + c0) / 16) * 128 * 16);
+      const float4* qv = reinterpret_cast<const float4*>(
+          g.dotv + (((size_t)(m0 / 128 + esub) * g.dot_blocks + g.dot_block0 + (n0 + c0) / 16) * 128 + rloc) * 16);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 x = __ldg(qv + j);
@@ -564,7 +565,8 @@ int cpn_pack_tc_weights(const float* raw, const float* packed_fp32, void* dst_v,
 }
 
 int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,
-                   int out_div, int out_kchunks, cudaStream_t st, const float* dotv, float dot_div, const float* dot_rowadd) {
+                   int out_div, int out_kchunks, cudaStream_t st, const float* dotv, float dot_div, const float* dot_rowadd, int dot_blocks,
+                   int dot_block0) {
   const bool a_img = mode & CPN_TC_A_IMAGE, o_img = mode & CPN_TC_OUT_IMAGE;
   if (!packed || !A || !C || layer < 0 || layer >= CPN_TC_LAYERS || M < 0 || (!a_img && (lda & 3)) || (!o_img && !(mode & (CPN_TC_OUT_ROWDOT | CPN_TC_OUT_CB16)) && (ldc & 3)) ||
       (o_img && (out_div < 1 || out_kchunks < 1))) {
@@ -594,8 +596,10 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
   g.dotv = dotv;
   g.dot_div = dot_div;
   g.dot_rowadd = dot_rowadd;
-  if (g.out_kind && (o_img || L.out != L.nt || (g.out_kind == 3 && !dotv))) {
-    cpn_set_error("gemm_tc: CB16 / row-dot outputs need a single-N-tile layer and fp32 output");
+  g.dot_blocks = dot_blocks > 0 ? dot_blocks : L.out / 16;
+  g.dot_block0 = dot_block0;
+  if (g.out_kind && (o_img || (g.out_kind == 3 && (L.out != L.nt || !dotv)))) {
+    cpn_set_error("gemm_tc: CB16 / row-dot outputs are fp32; the row-dot needs a single-N-tile layer");
     return CPN_ERR_ARG;
   }
   g.wtiles = tcw + layer_offset(layer, g.f8);
@@ -653,11 +657,11 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
 extern "C" int cpn_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu,
                            int mode, int out_div, int out_kchunks, void* stream) {
   return launch_gemm_tc(packed, layer, A, lda, C, ldc, M, relu, mode, out_div, out_kchunks, (cudaStream_t)stream, nullptr, 1.f,
-                        nullptr);
+                        nullptr, 0, 0);
 }
 
 extern "C" int cpn_gemm_tc_rowdot(const void* packed, int layer, const void* A, int lda, const float* dotv_cb16, float* out,
                                   int M, int relu, int mode, float div, void* stream) {
   return launch_gemm_tc(packed, layer, A, lda, out, 0, M, relu, mode | CPN_TC_OUT_ROWDOT, 1, 1, (cudaStream_t)stream, dotv_cb16,
-                        div, nullptr);
+                        div, nullptr, 0, 0);
 }

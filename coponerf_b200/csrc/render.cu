@@ -76,7 +76,7 @@ struct ProfScope {  // records an event pair around the enclosed launches when a
 // Workspace carve-up for one chunk of `nr` rays of each of B pairs (R = B * nr * 2 * S sample rows).
 struct Workspace {
   float *seg, *rowaux, *local16, *A, *H1, *E, *V, *K1, *Kk, *Q1, *Qe, *r1, *wp, *zemb, *rbias, *lg1, *lg2, *wt1, *wt2,
-      *hbar, *s1, *s2;
+      *hbar, *s1, *s2, *Qm;
   size_t bytes;
 };
 
@@ -111,6 +111,7 @@ Workspace carve(void* base, int B, int nr, int S) {
   w.hbar = take((rays + 127) / 128 * 128 * 2 * CPN_FEAT_DIM);   // operand image, whole 128-ray tiles
   w.s1 = take(R);    // bilinear logits: per-row scalar terms of round 1 / round 2
   w.s2 = take(R);
+  w.Qm = take(R * 2 * CPN_HIDDEN);   // [WM q + BM] of both rounds, column-blocked: [row tile][16 blocks][128][16]
   w.bytes = off;
   return w;
 }
@@ -227,7 +228,7 @@ extern "C" int cpn_render_launch_count(const cpn_render_args* a) {
   const bool unfolded = (a->flags & CPN_FLAG_NO_FOLD) || (a->flags & CPN_FLAG_SIMT_ONLY);
   const bool late = !unfolded && !(a->flags & CPN_FLAG_EARLY_V);
   int per_chunk = unfolded ? 17 : (late ? 19 : 16);
-  if (!unfolded && !(a->flags & CPN_FLAG_NO_BILINEAR)) per_chunk -= 1;   // one 128 x 128 layer fewer
+  if (!unfolded && !(a->flags & CPN_FLAG_NO_BILINEAR)) per_chunk -= 2;   // one GEMM over the coordinate embedding instead of three 128 x 128 layers
   return chunks * per_chunk + (late ? 3 : 1);
 }
 
@@ -269,15 +270,14 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, flo
       }
       if (bilinear) {
         // key_map_2, query_embed_2 and query_repeat_embed_2 have no activation, so both logits are bilinear forms of the
-        // 128-wide hidden vectors (cpn_common.cuh, pw::WM1): one 128 x 128 layer on the coordinate embedding per round
+        // 128-wide hidden vectors (cpn_common.cuh, pw::WM12): one 128 -> 256 layer on the coordinate embedding for both rounds
         // instead of one on it and one on each key / repeat-query, and the key hidden layer is dotted in the epilogue
         // of the folded key_map GEMM without ever being stored.
         CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQT, W + pw::BQ, nullptr, 1, R, w.Q1, a_form(a) == 2, st, W + pw::WS1,
                                    w.s1, W + pw::WS2, w.s2));
-        CPN_TRY(launch_gemm_tc(a.weights, 9, w.Q1, 0, w.Qe, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_CB16, 1, 1, st));
-        CPN_TRY(launch_gemm_tc(a.weights, 10, w.Q1, 0, w.Kk, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_CB16, 1, 1, st));
-        CPN_TRY(launch_gemm_tc(a.weights, 8, w.H1, 0, w.lg1, 0, R, 1, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_ROWDOT, 1, 1, st, w.Qe,
-                               11.31f, w.s1));
+        CPN_TRY(launch_gemm_tc(a.weights, 9, w.Q1, 0, w.Qm, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_CB16, 1, 1, st));
+        CPN_TRY(launch_gemm_tc(a.weights, 8, w.H1, 0, w.lg1, 0, R, 1, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_ROWDOT, 1, 1, st, w.Qm,
+                               11.31f, w.s1, 2 * CPN_HIDDEN / 16, 0));
       } else {
         if (!(a.flags & CPN_FLAG_NO_FOLD))
           CPN_TRY(launch_gemm_tc(a.weights, 8, w.H1, 0, w.K1, 0, R, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 1, KC128, st));
@@ -312,9 +312,10 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, flo
     CPN_TRY(dense_simt(a, w.r1, CPN_LATENT, pw::WET, pw::BE, w.zemb, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_LATENT, 0, st));
     CPN_TRY(dense_simt(a, w.zemb, CPN_HIDDEN, pw::WQRA_T, pw::BQR, w.rbias, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_HIDDEN, 0, st));
     if (use_tc(a)) {   // query_repeat_embed_2 with the round-2 logits <Q2, Q> / 11.31 (CoPoNeRF.py:474) as its epilogue
-      if (bilinear) {   // the repeat-query hidden layer is dotted with WM2 q + BM2 (w.Kk, CB16) where it is produced
+      if (bilinear) {   // the repeat-query hidden layer is dotted with WM2 q + BM2 (second half of w.Qm) where it is produced
         CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQRB_T, nullptr, w.rbias, 2 * a.S, R, nullptr, a_form(a) == 2, st,
-                                   nullptr, nullptr, nullptr, nullptr, w.Kk, w.s2, 11.31f, w.lg2));
+                                   nullptr, nullptr, nullptr, nullptr, w.Qm, w.s2, 11.31f, w.lg2, 2 * CPN_HIDDEN / 16,
+                                   CPN_HIDDEN / 16));
       } else {
         CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQRB_T, nullptr, w.rbias, 2 * a.S, R, w.K1, a_form(a) == 2, st));
         CPN_TRY(launch_gemm_tc(a.weights, 6, w.K1, 0, w.lg2, 0, R, 0, CPN_TC_A_IMAGE | tc_scheme(a) | CPN_TC_OUT_ROWDOT, 1, 1,

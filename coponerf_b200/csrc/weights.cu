@@ -167,10 +167,10 @@ extern "C" int cpn_pack_weights(const float* src, void* dst_v, void* stream) {
   // attention logits as bilinear forms: key_map_2 (tensors 8, 9) and query_repeat_embed_2 (16, 17) against query_embed_2 (12, 13)
   const float *Wq2 = src + tensor_offset(12), *bq2 = src + tensor_offset(13);
   bilinear_fold_kernel<<<(128 * 128 + 129 + 255) / 256, 256, 0, st>>>(src + tensor_offset(8), src + tensor_offset(9), Wq2, bq2,
-                                                                      dst + pw::WM1, dst + pw::BM1, dst + pw::WS1);
+                                                                      dst + pw::WM12, dst + pw::BM12, dst + pw::WS1);
   CPN_CHECK_LAUNCH("bilinear_fold_kernel");
   bilinear_fold_kernel<<<(128 * 128 + 129 + 255) / 256, 256, 0, st>>>(src + tensor_offset(16), src + tensor_offset(17), Wq2, bq2,
-                                                                      dst + pw::WM2, dst + pw::BM2, dst + pw::WS2);
+                                                                      dst + pw::WM12 + 128 * 128, dst + pw::BM12 + 128, dst + pw::WS2);
   CPN_CHECK_LAUNCH("bilinear_fold_kernel");
   return cpn_pack_tc_weights(src, dst, reinterpret_cast<char*>(dst_v) + cpn_packed_fp32_floats() * sizeof(float), st);
 }

@@ -253,8 +253,8 @@ int cpn_gemm_simt_splitk(const float* A, int lda, const float* wt, const float* 
 
 /* Tensor-core GEMM of one packed layer (0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value,
  * 3 key_map, 4 key_map_2, 5 query_embed_2, 6 query_repeat_embed_2, 7 latent_value o query_encode_latent_2,
- * 8 key_map o query_encode_latent_2, both with K = 1664, 9 key_map_2^T query_embed_2, 10 query_repeat_embed_2^T
- * query_embed_2): C[M, N_layer] = act(A[M, K_layer] * W^T + b),
+ * 8 key_map o query_encode_latent_2, both with K = 1664, 9 [key_map_2 ; query_repeat_embed_2]^T query_embed_2 with
+ * N = 256): C[M, N_layer] = act(A[M, K_layer] * W^T + b),
  * operands split into an fp16 head plus corrections (e4m3 on the fp8 path by default, fp16 with CPN_TC_F16X3)
  * and accumulated in fp32 on tcgen05.
  * `packed` is the blob from cpn_pack_weights. mode bit CPN_TC_A_IMAGE: A is an "operand image" (128-row tiles,
