@@ -116,7 +116,9 @@ int launch_ray_setup(const cpn_render_args& a, int ray0, int nr, float* seg, cud
 // a_image: 0 fp32 rows of CPN_KA; 1 operand image (K = CPN_KA_IMG), f16x3 scheme; 2 operand image, f8 scheme
 int launch_sample(const cpn_render_args& a, int ray0, int nr, const float* seg, float* rowaux, float* local16,
                   float* A, int a_image, cudaStream_t st);
-int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowaux, float* A, int a_image, cudaStream_t st);
+// taps: (rows, 2 branches, 4 levels, 8) floats of scratch for the precomputed bilinear taps (operand-image forms only)
+int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowaux, float* A, int a_image, cudaStream_t st,
+                  float* taps = nullptr);
 // remap256: output row m goes to row (m / 256) * 128 + m % 128 at column offset ((m / 128) & 1) * N (undoes enc_row)
 int launch_gemm_simt(const float* A, int lda, const float* wt, const float* bias, const float* rowbias,
                      int rows_per_bias, float* C, int ldc, int M, int N, int K, int relu, cudaStream_t st,

@@ -94,8 +94,33 @@ __device__ __forceinline__ Taps make_taps_safe(float gx, float gy, int h, int w,
   return t;
 }
 
+// Bilinear taps of every (sample row, branch, level), one thread each: 4 element offsets + 4 weights = 32 bytes.
+// In gather_image_kernel the 32 lanes of a warp share a row, so computing the taps there repeats the same ~100
+// instructions per level in every lane (40 % of that issue-bound kernel's instructions); here they are computed once
+// and the gather fetches them with two uniform 16-byte loads per level. Same arithmetic, same bits.
+__global__ void __launch_bounds__(256) taps_kernel(cpn_render_args a, int nr, const float* __restrict__ rowaux,
+                                                   int4* __restrict__ taps) {
+  const unsigned nrows = (unsigned)(a.B * nr * 2 * a.S);
+  const unsigned i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= nrows * 2 * CPN_N_LEVELS) return;
+  const int l = i % CPN_N_LEVELS, branch = (i / CPN_N_LEVELS) & 1;
+  const unsigned row = i / (2 * CPN_N_LEVELS);
+  const float2 g = *reinterpret_cast<const float2*>(rowaux + (size_t)row * CPN_ROWAUX + branch * 2);
+  int h = a.feat_h[0], w = a.feat_w[0], C = a.feat_c[0];
+#pragma unroll
+  for (int k = 1; k < CPN_N_LEVELS; ++k)
+    if (l == k) {
+      h = a.feat_h[k];
+      w = a.feat_w[k];
+      C = a.feat_c[k];
+    }
+  const Taps t = make_taps_safe(g.x, g.y, h, w, C, branch == 0);
+  taps[(size_t)i * 2] = make_int4(t.off[0], t.off[1], t.off[2], t.off[3]);
+  taps[(size_t)i * 2 + 1] = make_int4(__float_as_int(t.w[0]), __float_as_int(t.w[1]), __float_as_int(t.w[2]), __float_as_int(t.w[3]));
+}
+
 template <bool F8>
-__global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, int nr, const float* __restrict__ rowaux,
+__global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, int nr, const int4* __restrict__ taps,
                                                            unsigned char* __restrict__ img) {
   // f16x3: [hi | lo][row][channel] fp16. f8: plane 0 = fp16 hi; plane 1 holds the two byte planes back to back,
   // e4m3(lo * 2^8) in bytes [0, 832) and e4m3(x * 2^-6) in bytes [848, 1680) of each row.
@@ -109,14 +134,19 @@ __global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, in
     const int v = (int)((row / S) & 1u);
     const int b = (int)(row / (2u * S * (unsigned)nr));
     const int im = b * 2 + (branch ? 1 - v : v);
-    const float2 g = *reinterpret_cast<const float2*>(rowaux + (size_t)row * CPN_ROWAUX + branch * 2);
+    const int4* trow = taps + ((size_t)row * 2 + branch) * CPN_N_LEVELS * 2;
     __half* sh_hi = &sh[0][warp][0];
     unsigned char* sh_b = reinterpret_cast<unsigned char*>(&sh[1][warp][0]);
     int col = 0;
 #pragma unroll
     for (int l = 0; l < CPN_N_LEVELS; ++l) {
       const int h = a.feat_h[l], w = a.feat_w[l], C = a.feat_c[l];
-      const Taps t = make_taps_safe(g.x, g.y, h, w, C, branch == 0);
+      Taps t;   // precomputed by taps_kernel; the address is the same in every lane (one broadcast transaction)
+      {
+        const int4 o = __ldg(trow + 2 * l), wv = __ldg(trow + 2 * l + 1);
+        t.off[0] = o.x; t.off[1] = o.y; t.off[2] = o.z; t.off[3] = o.w;
+        t.w[0] = __int_as_float(wv.x); t.w[1] = __int_as_float(wv.y); t.w[2] = __int_as_float(wv.z); t.w[3] = __int_as_float(wv.w);
+      }
       const float* base = a.feat[l] + (size_t)im * h * w * C + lane * 4;
       for (int c = lane * 4; c < C; c += 128, base += 128) {
         const float4 f0 = __ldg(reinterpret_cast<const float4*>(base + t.off[0]));
@@ -208,7 +238,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __rest
 
 }  // namespace
 
-int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowaux, float* A, int a_image, cudaStream_t st) {
+int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowaux, float* A, int a_image, cudaStream_t st,
+                  float* taps) {
   (void)ray0;
   long long warps = (long long)a.B * nr * 2 * a.S * 2;
   long long blocks = (warps * 32 + 255) / 256;
@@ -218,11 +249,18 @@ int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowau
       cpn_set_error("gather: %lld sample rows per chunk / S=%d unsupported (S must be a multiple of 8)", rows, a.S);
       return CPN_ERR_ARG;
     }
+    if (!taps) {
+      cpn_set_error("gather: the operand-image gather needs the tap buffer");
+      return CPN_ERR_ARG;
+    }
+    int4* tp = reinterpret_cast<int4*>(taps);
+    taps_kernel<<<(unsigned)((rows * 2 * CPN_N_LEVELS + 255) / 256), 256, 0, st>>>(a, nr, rowaux, tp);
+    CPN_CHECK_LAUNCH("taps_kernel");
     dim3 grid((unsigned)((rows + GI_ROWS - 1) / GI_ROWS), 2);
     if (a_image == 2)
-      gather_image_kernel<true><<<grid, 256, 0, st>>>(a, nr, rowaux, reinterpret_cast<unsigned char*>(A));
+      gather_image_kernel<true><<<grid, 256, 0, st>>>(a, nr, tp, reinterpret_cast<unsigned char*>(A));
     else
-      gather_image_kernel<false><<<grid, 256, 0, st>>>(a, nr, rowaux, reinterpret_cast<unsigned char*>(A));
+      gather_image_kernel<false><<<grid, 256, 0, st>>>(a, nr, tp, reinterpret_cast<unsigned char*>(A));
   } else {
     gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, nr, rowaux, A);
   }

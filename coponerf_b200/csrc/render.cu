@@ -76,7 +76,7 @@ struct ProfScope {  // records an event pair around the enclosed launches when a
 // Workspace carve-up for one chunk of `nr` rays of each of B pairs (R = B * nr * 2 * S sample rows).
 struct Workspace {
   float *seg, *rowaux, *local16, *A, *H1, *E, *V, *K1, *Kk, *Q1, *Qe, *r1, *wp, *zemb, *rbias, *lg1, *lg2, *wt1, *wt2,
-      *hbar, *s1, *s2, *Qm;
+      *hbar, *s1, *s2, *Qm, *taps;
   size_t bytes;
 };
 
@@ -92,6 +92,7 @@ Workspace carve(void* base, int B, int nr, int S) {
   w.seg = take(rays * 2 * 6);
   w.rowaux = take(R * CPN_ROWAUX);
   w.local16 = take(R * 16);
+  w.taps = take(R * 2 * CPN_N_LEVELS * 8);   // bilinear taps of every (row, branch, level)
   w.A = take(R * 2 * CPN_KA_IMG);   // fp32 rows of CPN_KA, or the operand image with K = CPN_KA_IMG
   w.H1 = take(R * 2 * CPN_FEAT_DIM);
   w.E = take(R * CPN_FEAT_DIM);
@@ -227,7 +228,7 @@ extern "C" int cpn_render_launch_count(const cpn_render_args* a) {
   int chunks = (a->N + a->chunk_rays - 1) / a->chunk_rays;
   const bool unfolded = (a->flags & CPN_FLAG_NO_FOLD) || (a->flags & CPN_FLAG_SIMT_ONLY);
   const bool late = !unfolded && !(a->flags & CPN_FLAG_EARLY_V);
-  int per_chunk = unfolded ? 17 : (late ? 19 : 16);
+  int per_chunk = (unfolded ? 17 : (late ? 19 : 16)) + ((a->flags & CPN_FLAG_SIMT_ONLY) ? 0 : 1);   // + taps_kernel
   if (!unfolded && !(a->flags & CPN_FLAG_NO_BILINEAR)) per_chunk -= 2;   // one GEMM over the coordinate embedding instead of three 128 x 128 layers
   return chunks * per_chunk + (late ? 3 : 1);
 }
@@ -240,7 +241,7 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, flo
     int R = rays * 2 * a.S;
     CPN_TRY(launch_ray_setup(a, ray0, nr, w.seg, st));
     CPN_TRY(launch_sample(a, ray0, nr, w.seg, w.rowaux, w.local16, w.A, a_form(a), st));
-    CPN_TRY(launch_gather(a, ray0, nr, w.rowaux, w.A, a_form(a), st));
+    CPN_TRY(launch_gather(a, ray0, nr, w.rowaux, w.A, a_form(a), st, w.taps));
     const int Rp = (R + 127) / 128 * 128;
     const int KC832 = CPN_FEAT_DIM / ACT_BK, KC128 = CPN_HIDDEN / ACT_BK;
     const int sch = tc_scheme(a);
