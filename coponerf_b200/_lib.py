@@ -150,6 +150,15 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH) and os.environ.get("CPN_NO_AUTOBUILD") != "1":
+        # the library is built in-tree by __graft_entry__.build(); if a checkout arrives without it and nvcc is there,
+        # build it now (about a minute) instead of failing every caller
+        try:
+            from .build import build_library
+            print(f"coponerf_b200: {LIB_PATH} is missing, building it with nvcc ...", flush=True)
+            build_library()
+        except Exception as e:      # no nvcc, compile error: fall through to the loud failure below
+            print(f"coponerf_b200: automatic build failed: {e}", flush=True)
     if not os.path.exists(LIB_PATH):
         raise CpnError(f"{LIB_PATH} is missing: run `python -m coponerf_b200.build` (or __graft_entry__.build()); "
                        "there is no CPU or PyTorch fallback for the render path")
