@@ -92,8 +92,28 @@ class CoPoNeRF(nn.Module):
         self.H = self.W = None
 
     # ------------------------------------------------------------------ engine management
+    def _param_list(self):
+        """All parameters, cached: walking the module tree costs ~1 ms per call, the version check itself 0.2 ms.
+        The cache is dropped by load_state_dict() and by .to() / .cuda(); call refresh_parameters() after replacing a
+        Parameter OBJECT by hand (in-place updates are seen through the tensors' version counters)."""
+        pl = self.__dict__.get("_plist")
+        if pl is None:
+            pl = self.__dict__["_plist"] = list(self.parameters())
+        return pl
+
+    def refresh_parameters(self):
+        self.__dict__["_plist"] = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self.refresh_parameters()
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.refresh_parameters()
+        return super().load_state_dict(*args, **kwargs)
+
     def _weights_version(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return tuple((p.data_ptr(), p._version) for p in self._param_list())
 
     def engine(self):
         """RenderEngine holding the packed weights; repacked when parameters change or move."""

@@ -181,7 +181,8 @@ def _sub_state(model, prefix):
 
 def _state_cache(model):
     cache = model.__dict__.setdefault("_sd_cache", {})
-    ver = tuple((p.data_ptr(), p._version) for p in model.parameters())
+    ver = model._weights_version() if hasattr(model, "_weights_version") else \
+        tuple((p.data_ptr(), p._version) for p in model.parameters())
     if cache.get("ver") != ver:
         cache.clear()
         cache["ver"] = ver
