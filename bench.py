@@ -69,8 +69,7 @@ WORKLOADS = {
 def cpu_pair_stage(stage, seed, timings=None):
     """Seconds the CPU restatement needs for the per-pair work of one image (reference formulation, incl. the
     Python positional-encoding loop of backbone.py:269-273), and its outputs (z, rel_pose, flow) for `full`."""
-    from coponerf_b200 import synth, ufc_native
-    from oracle.ufc_ops_torch import TorchOps
+    from coponerf_b200 import synth
     if stage == "full":
         from oracle import pair_oracle
         sd = synth.full_state_dict(0)
@@ -80,10 +79,11 @@ def cpu_pair_stage(stage, seed, timings=None):
         res = pair_oracle.get_z(sd, inp, fast_pos=False, timings=timings)
         return time.perf_counter() - t0, res
     if stage == "pair":
+        from oracle import ufc_forward_oracle
         sdc, pyc = synth.ufc_state_dict(0), synth.ufc_inputs(seed)
-        ufc_native.ufc_forward(sdc, pyc, 2, TorchOps())
+        ufc_forward_oracle.ufc_forward(sdc, pyc, 2)
         t0 = time.perf_counter()
-        ufc_native.ufc_forward(sdc, pyc, 2, TorchOps())
+        ufc_forward_oracle.ufc_forward(sdc, pyc, 2)
         return time.perf_counter() - t0, None
     return 0.0, None
 

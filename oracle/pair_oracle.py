@@ -10,15 +10,16 @@ Follows the reference's own formulation line by line (not the re-associated one 
   CrossAttention.forward     models/backbone.py:279-330 (both dual softmaxes, (v^T A) v association)
   CrossBlock.forward         models/backbone.py:400-420
   pose head, r6d2mat         models/CoPoNeRF.py:33-52,106-128,194-204
-The cost aggregation (models/aggregation.py:509-562) is the state_dict-driven restatement with the PyTorch operator
-set (oracle/ufc_ops_torch.py), which tests/test_ufc_orchestration_cpu.py pins to the unmodified reference module.
+The cost aggregation (models/aggregation.py:509-562) is oracle/ufc_forward_oracle.py, a restatement in the reference's own
+formulation that tests/test_ufc_orchestration_cpu.py pins to the unmodified reference module. Nothing here imports
+coponerf_b200/.
 
 Pinned by tests/golden/pair_256.npz (outputs of the unmodified reference's get_z, tests/golden/make_goldens_pair.py).
 """
 import torch
 import torch.nn.functional as F
 
-from .ufc_ops_torch import TorchOps
+from . import ufc_forward_oracle
 
 
 def _encoder(sd, x):
@@ -105,11 +106,29 @@ def cross_block(sd, x, corr, intr, fast_pos=False):
     return ln(fund + h, "norm")
 
 
+def pose_head(h0, sd):
+    """CoPoNeRF.py:33-52,106-128,198-204 after the first Linear + ReLU: h0 = relu(pose_regressor[0](pose_feat))."""
+    h = F.relu(F.linear(h0, sd["pose_regressor.2.weight"], sd["pose_regressor.2.bias"]))
+    h = F.relu(F.linear(h, sd["pose_regressor.4.weight"], sd["pose_regressor.4.bias"]))[:, :128]
+
+    def head(name):
+        y = F.relu(h)
+        y = F.relu(F.linear(y, sd[name + ".1.weight"], sd[name + ".1.bias"]))
+        y = F.relu(F.linear(y, sd[name + ".3.weight"], sd[name + ".3.bias"]))
+        return F.linear(y, sd[name + ".5.weight"], sd[name + ".5.bias"])
+    d6, tr = head("rotation_regressor"), head("translation_regressor")
+    a1, a2 = d6[..., :3], d6[..., 3:]
+    b1 = F.normalize(a1, dim=-1)
+    b2 = F.normalize(a2 - (b1 * a2).sum(-1, keepdim=True) * b1, dim=-1)
+    R = torch.stack((b1, b2, torch.cross(b1, b2, dim=-1)), dim=-2)
+    bottom = torch.tensor([0.0, 0.0, 0.0, 1.0]).expand(h0.shape[0], 1, -1)
+    return torch.cat((torch.cat((R, tr.unsqueeze(-1)), dim=-1), bottom), dim=1)
+
+
 @torch.no_grad()
 def get_z(sd, inp, fast_pos=False, timings=None):
     """sd: full model state_dict (CPU tensors). Returns (z list, rel_pose, flows) like CoPoNeRF.get_z."""
     import time
-    from coponerf_b200 import ufc_native   # the orchestration only; every operator comes from TorchOps below
     t0 = time.perf_counter()
     rgb = inp["context"]["rgb"]
     B, n_ctxt, H, W, _ = rgb.shape
@@ -123,14 +142,14 @@ def get_z(sd, inp, fast_pos=False, timings=None):
     t1 = time.perf_counter()
     pre = "feature_cost_aggregation."
     ufc_sd = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
-    feats, flows, c = ufc_native.ufc_forward(ufc_sd, z, 2, TorchOps())
+    feats, flows, c = ufc_forward_oracle.ufc_forward(ufc_sd, z, 2)
     t2 = time.perf_counter()
     k = inp["context"]["intrinsics"].clone()
     k[:, :, :2, :] = k[:, :, :2, :] / H
     intr = [k[:, 0, 0, 0].reshape(B, 1), k[:, 0, 1, 1].reshape(B, 1), k[:, 0, 0, 2].reshape(B, 1), k[:, 0, 1, 2].reshape(B, 1)]
     feat = cross_block(sd, feats[-1].flatten(-2, -1).transpose(-1, -2), c, intr, fast_pos).reshape([B, -1])
     h0 = F.relu(F.linear(feat, sd["pose_regressor.0.weight"], sd["pose_regressor.0.bias"]))
-    rel_pose = TorchOps().pose_head(h0, sd)
+    rel_pose = pose_head(h0, sd)
     t3 = time.perf_counter()
     if timings is not None:
         timings.update(encoder=t1 - t0, ufc=t2 - t1, pose=t3 - t2)
