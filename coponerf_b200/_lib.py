@@ -18,13 +18,17 @@ FLAG_F16X3 = 2
 FLAG_NO_FOLD = 4
 FLAG_EARLY_V = 8
 FLAG_NO_BILINEAR = 16
+FLAG_NO_GFOLD = 32
 TC_F16X3 = 4
 TC_CLUSTER = 8
 TC_PAIR = 16
 TC_OUT_CB16 = 32
+TC_OUT_KG = 128
+TC_NO_PERSIST = 256
 TC_A_IMAGE = 1
 TC_OUT_IMAGE = 2
 ACT_CHUNK_BYTES = 16384
+ABI_VERSION = 200        # cpn_version() of the library this binding was written against
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
 
@@ -76,6 +80,7 @@ class PoseHeadArgs(ctypes.Structure):
 # symbol -> (restype, argtypes); every entry point include/coponerf_b200.h declares
 SIGNATURES = {
     "cpn_version": (ctypes.c_int, []),
+    "cpn_shutdown": (ctypes.c_int, []),
     "cpn_last_error": (ctypes.c_char_p, []),
     "cpn_sizeof_render_args": (ctypes.c_size_t, []),
     "cpn_prof_begin": (ctypes.c_int, [ctypes.c_int]),
@@ -97,6 +102,13 @@ SIGNATURES = {
     "cpn_gemm_tc_rowdot": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                           ctypes.c_void_p]),
+    "cpn_gather_rows_taps_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "cpn_gather_rows": (ctypes.c_int, [ctypes.POINTER(RenderArgs), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_void_p]),
+    "cpn_gemm_tc_trace": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "cpn_gemm_tc_kg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                      ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_void_p]),
     "cpn_ufc_tail_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                        ctypes.POINTER(ctypes.c_int32)]),
     "cpn_ufc_tail": (ctypes.c_int, [ctypes.POINTER(UfcTailArgs), ctypes.c_void_p]),
@@ -154,9 +166,9 @@ def load():
         # the library is built in-tree by __graft_entry__.build(); if a checkout arrives without it and nvcc is there,
         # build it now (about a minute) instead of failing every caller
         try:
-            from .build import build_library
+            from .build import build_library_locked
             print(f"coponerf_b200: {LIB_PATH} is missing, building it with nvcc ...", flush=True)
-            build_library()
+            build_library_locked()      # inter-process lock + atomic rename: safe under torchrun
         except Exception as e:      # no nvcc, compile error: fall through to the loud failure below
             print(f"coponerf_b200: automatic build failed: {e}", flush=True)
     if not os.path.exists(LIB_PATH):
@@ -167,8 +179,9 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.cpn_sizeof_render_args() != ctypes.sizeof(RenderArgs):
-        raise CpnError("cpn_render_args layout mismatch between _lib.py and the built library: rebuild")
+    if lib.cpn_sizeof_render_args() != ctypes.sizeof(RenderArgs) or lib.cpn_version() != ABI_VERSION:
+        raise CpnError(f"{LIB_PATH} is stale (ABI version {lib.cpn_version()}, this binding expects {ABI_VERSION}): "
+                       "rebuild with `python -m coponerf_b200.build`")
     _lib = lib
     return lib
 

@@ -73,11 +73,25 @@ def build_library(force=False, verbose=False):
         if verbose and out.strip():
             print(out)
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs
+        tmp = f"{LIB}.{os.getpid()}.tmp"      # link aside and rename: a concurrent dlopen never sees a partial file
+        cmd = [nvcc, "-shared", "-o", tmp] + objs
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}")
+        os.replace(tmp, LIB)
     return LIB
+
+
+def build_library_locked(**kw):
+    """build_library under an inter-process file lock (several ranks of a torchrun job may find the library missing)."""
+    import fcntl
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    with open(os.path.join(OBJ_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return build_library(**kw)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":

@@ -72,7 +72,8 @@ __device__ __forceinline__ float block_softmax(float logit, float* red, int warp
 __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* __restrict__ key,
                              const float* __restrict__ qemb, const float* __restrict__ value,
                              const float* __restrict__ rowaux, float* __restrict__ r1, float* __restrict__ wp,
-                             const float* __restrict__ logits, float* __restrict__ wts_out) {
+                             const float* __restrict__ logits, float* __restrict__ wts_out, const float* __restrict__ gh,
+                             float* __restrict__ rbias) {
   extern __shared__ float sm[];
   const int S = a.S, S2 = 2 * S;
   float* w = sm;            // [2S]
@@ -140,6 +141,20 @@ __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* _
     for (int i = 0; i < wpv; ++i) acc1 += red[16 + (wpv + i) * 3 + c];
     wp[(size_t)ray * 4 + c] = acc0 + acc1;
   }
+  if (gh) {
+    // per-ray bias of query_repeat_embed (CoPoNeRF.py:463-472) = sum_rows w1 (G h + g0), rows in ascending order:
+    // thread c owns one of the 128 channels, a warp reads 128 contiguous bytes per row
+    // gh is column-blocked: [row tile of 128][8 blocks of 16 channels][128 rows][16] (the layer-10 epilogue, gemm_tc.cu)
+    for (int c = t; c < CPN_HIDDEN; c += S2) {
+      float acc = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < S2; ++r) {
+        const size_t row = row0 + r;
+        acc = fmaf(w[r], __ldg(gh + (((row >> 7) * (CPN_HIDDEN / 16) + (c >> 4)) * 128 + (row & 127)) * 16 + (c & 15)), acc);
+      }
+      rbias[(size_t)ray * CPN_HIDDEN + c] = acc;
+    }
+  }
   if (!value) return;
   for (int c = t; c < CPN_LATENT; c += S2) {
     const float* vp = value + row0 * CPN_LATENT + c;
@@ -156,7 +171,7 @@ __global__ void attn1_kernel(cpn_render_args a, int ray0, int nr, const float* _
 __global__ void attn2_kernel(cpn_render_args a, int ray0, int nr, const float* __restrict__ q2,
                              const float* __restrict__ qemb, const float* __restrict__ value,
                              const float* __restrict__ r1, float* __restrict__ z_all, const float* __restrict__ logits,
-                             float* __restrict__ wts_out) {
+                             float* __restrict__ wts_out, const float* __restrict__ w1) {
   extern __shared__ float sm[];
   const int S = a.S, S2 = 2 * S;
   float* w = sm;
@@ -166,7 +181,8 @@ __global__ void attn2_kernel(cpn_render_args a, int ray0, int nr, const float* _
   const size_t row0 = (size_t)ray * S2;
   float logit = logits ? logits[row0 + t] : warp_row_logits(q2, qemb, row0, warp, lane);
   w[t] = block_softmax(logit, red, warp, lane, nwarps);
-  if (wts_out) wts_out[row0 + t] = w[t];
+  // w1 given: z = R2 + 2 R1 = WVF (sum_rows (w2 + 2 w1) h) + 3 b, so one readout with the combined weight serves both rounds
+  if (wts_out) wts_out[row0 + t] = w1 ? fmaf(2.f, w1[row0 + t], w[t]) : w[t];
   if (!value) return;
   __syncthreads();
   for (int c = t; c < CPN_LATENT; c += S2) {
@@ -227,10 +243,9 @@ __global__ void __launch_bounds__(128) readout_image_kernel(const unsigned char*
         const uint32_t lw[2] = {lo.x, lo.y};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const __half2_raw h2 = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((lw[j >> 1] >> ((j & 1) * 16)) & 0xffffu), __NV_E4M3);
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2));
-          x[2 * j] = fmaf(f.x, 1.f / 256.f, x[2 * j]);          // e4m3((x - hi) * 2^8), tc_common.cuh
-          x[2 * j + 1] = fmaf(f.y, 1.f / 256.f, x[2 * j + 1]);
+          const float2 f = tc::lo8_to_float2(lw[j >> 1] >> ((j & 1) * 16));   // e5m2((x - hi) * 2^10), tc_common.cuh
+          x[2 * j] += f.x;
+          x[2 * j + 1] += f.y;
         }
       } else {
         const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p + ACT_LO + g * 2048));
@@ -304,6 +319,14 @@ __global__ void finish_z_kernel(const float* __restrict__ r2, float* __restrict_
   if (i >= total) return;
   const float r = z_all[i];
   z_all[i] = (r2[i] + r) + r;
+}
+
+// combined readout: r2 = WVF sum_rows (w2 + 2 w1) h + b (one GEMM over the image) -> z = r2 + 2 b
+__global__ void finish_z_bias_kernel(const float* __restrict__ r2, const float* __restrict__ bias, float* __restrict__ z_all,
+                                     size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  z_all[i] = fmaf(2.f, bias[i % CPN_LATENT], r2[i]);
 }
 
 // phi. One CTA of 128 threads renders PHI_RAYS = 16 rays. Thread (cq = t % 32, rg = t / 32) owns a 4-channel x
@@ -420,18 +443,19 @@ __global__ void __launch_bounds__(128) phi_kernel(cpn_render_args a, const float
 }  // namespace
 
 int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, const float* qemb, const float* value,
-                 const float* rowaux, float* r1, float* wp, cudaStream_t st, const float* logits, float* wts_out) {
+                 const float* rowaux, float* r1, float* wp, cudaStream_t st, const float* logits, float* wts_out,
+                 const float* gh, float* rbias) {
   int S2 = 2 * a.S;
   attn1_kernel<<<a.B * nr, S2, (S2 + 48) * sizeof(float), st>>>(a, ray0, nr, key, qemb, value, rowaux, r1, wp, logits,
-                                                                wts_out);
+                                                                wts_out, gh, rbias);
   CPN_CHECK_LAUNCH("attn1_kernel");
   return CPN_OK;
 }
 
 int launch_attn2(const cpn_render_args& a, int ray0, int nr, const float* q2, const float* qemb, const float* value,
-                 const float* r1, float* z_all, cudaStream_t st, const float* logits, float* wts_out) {
+                 const float* r1, float* z_all, cudaStream_t st, const float* logits, float* wts_out, const float* w1) {
   int S2 = 2 * a.S;
-  attn2_kernel<<<a.B * nr, S2, (S2 + 8) * sizeof(float), st>>>(a, ray0, nr, q2, qemb, value, r1, z_all, logits, wts_out);
+  attn2_kernel<<<a.B * nr, S2, (S2 + 8) * sizeof(float), st>>>(a, ray0, nr, q2, qemb, value, r1, z_all, logits, wts_out, w1);
   CPN_CHECK_LAUNCH("attn2_kernel");
   return CPN_OK;
 }
@@ -469,6 +493,13 @@ int launch_finish_z(const cpn_render_args& a, const float* r2_all, float* z_all,
   const size_t total = (size_t)a.B * a.N * CPN_LATENT;
   finish_z_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r2_all, z_all, total);
   CPN_CHECK_LAUNCH("finish_z_kernel");
+  return CPN_OK;
+}
+
+int launch_finish_z_bias(const cpn_render_args& a, const float* r2_all, const float* bias, float* z_all, cudaStream_t st) {
+  const size_t total = (size_t)a.B * a.N * CPN_LATENT;
+  finish_z_bias_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r2_all, bias, z_all, total);
+  CPN_CHECK_LAUNCH("finish_z_bias_kernel");
   return CPN_OK;
 }
 

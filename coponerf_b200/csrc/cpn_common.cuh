@@ -47,16 +47,23 @@ constexpr size_t PHI_BOUT = PHI_OUT + 3 * 128;   // [3] (+1 pad)
 constexpr size_t WVF = PHI_BOUT + 4;             // [416][1664]
 constexpr size_t BVF = WVF + 416 * 1664;         // [416]
 constexpr size_t WKF = BVF + 416;                // [128][1664]
-constexpr size_t BKF = WKF + 128 * 1664;         // [128]
+// Round-2 query bias as a linear function of the round-1 readout (no activation between latent_value, encode_latent and the
+// z_embed half of query_repeat_embed, CoPoNeRF.py:463-473):  rbias = G hbar1 + g0 with G = Wqr[:, :128] We WVF (128 x 1664),
+// g0 = Wqr[:, :128] (We bVF + be) + bqr.  The softmax weights of a ray sum to one, so  rbias = sum_rows w1 (G h + g0):
+// G is stacked under WKF (one 256-row layer over the hidden image) and the 1664-wide round-1 readout is never formed.
+constexpr size_t WG = WKF + 128 * 1664;          // [128][1664], directly after WKF: [WKF ; G] is one (256, 1664) matrix
+constexpr size_t BKF = WG + 128 * 1664;          // [128]
+constexpr size_t BG = BKF + 128;                 // [128] = g0, directly after BKF
 // attention logits as bilinear forms (key_map_2, query_embed_2 and query_repeat_embed_2 have no activation,
 // CoPoNeRF.py:408,446,473): <Wk2 k + bk2, Wq2 q + bq2> = k^T (WM q + BM) + (WS . q + CS), with
 // WM = Wk2^T Wq2, BM = Wk2^T bq2, WS = Wq2^T bk2, CS = bk2 . bq2; the same with query_repeat_embed_2 for round 2. Both
 // WM / BM pairs are stacked into one 256-row layer, so one GEMM over the coordinate embedding serves both rounds.
-constexpr size_t WM12 = BKF + 128;               // [256][128] row-major (N, K): rows 0-127 round 1, 128-255 round 2
+constexpr size_t WM12 = BG + 128;                // [256][128] row-major (N, K): rows 0-127 round 1, 128-255 round 2
 constexpr size_t BM12 = WM12 + 256 * 128;        // [256]
 constexpr size_t WS1 = BM12 + 256;               // [128] + CS1 at [128] (+3 pad)
 constexpr size_t WS2 = WS1 + 132;
-constexpr size_t FP32_END = WS2 + 132;
+constexpr size_t M1D = (WS2 + 132 + 1) / 2 * 2;               // scratch of the G fold: Wqr[:, :128] We as (128, 416) doubles
+constexpr size_t FP32_END = M1D + 2 * 128 * 416;
 }  // namespace pw
 
 // ---- per-pair constants (floats), written by cpn_pair_setup ---------------------------------
@@ -135,16 +142,19 @@ int launch_mlp16_image(const float* x, const float* wt, const float* bias, const
 // logits != nullptr: one precomputed logit per sample row (key / qemb unused); else <key, qemb> / 11.31 is computed here
 int launch_attn1(const cpn_render_args& a, int ray0, int nr, const float* key, const float* qemb, const float* value,
                  const float* rowaux, float* r1, float* wp, cudaStream_t st, const float* logits = nullptr,
-                 float* wts_out = nullptr);   // value == nullptr: no readout here, the weights go to wts_out
+                 float* wts_out = nullptr,    // value == nullptr: no readout here, the weights go to wts_out
+                 const float* gh = nullptr, float* rbias = nullptr);   // gh (R, 128): rbias[ray] = sum_rows w1 gh[row]
 // z_all: (B, N, 416) latent of every ray of the image
 int launch_attn2(const cpn_render_args& a, int ray0, int nr, const float* q2, const float* qemb, const float* value,
-                 const float* r1, float* z_all, cudaStream_t st, const float* logits = nullptr, float* wts_out = nullptr);
+                 const float* r1, float* z_all, cudaStream_t st, const float* logits = nullptr, float* wts_out = nullptr,
+                 const float* w1 = nullptr);   // w1: wts_out = w2 + 2 w1 (combined readout weight)
 // late readout: hbar (rays, 1664) = sum over a ray's rows of w * [h_p ; h_s] read from the hidden-layer operand image
 // out_N > 0: output rows are indexed by the ray's position in the whole image (b * out_N + out_ray0 + n) instead of the chunk
 int launch_readout_image(const cpn_render_args& a, int nr, const void* h1_image, const float* wts, float* hbar, int f8,
                          cudaStream_t st, int out_N = 0, int out_ray0 = 0);
 int launch_park_r1(const cpn_render_args& a, int ray0, int nr, const float* r1, float* z_all, cudaStream_t st);
 int launch_finish_z(const cpn_render_args& a, const float* r2_all, float* z_all, cudaStream_t st);
+int launch_finish_z_bias(const cpn_render_args& a, const float* r2_all, const float* bias, float* z_all, cudaStream_t st);
 int launch_phi(const cpn_render_args& a, const float* z_all, cudaStream_t st);
 int launch_ray_epilogue(const cpn_render_args& a, int ray0, int nr, const float* wp, const float* seg, cudaStream_t st);
 
@@ -160,7 +170,7 @@ constexpr int ACT_CHUNK_BYTES = 2 * (ACT_BK / 8) * 128 * 16;
 constexpr int ACT_LO = 8192;      // f16x3: fp16 lo plane
 constexpr int ACT_LO8 = 8192;     // f8: e4m3 remainder plane
 constexpr int ACT_X8 = 12288;     // f8: e4m3 value plane
-constexpr int CPN_TC_LAYERS = 10;
+constexpr int CPN_TC_LAYERS = 11;
 size_t cpn_packed_fp32_floats();
 size_t cpn_tc_weights_bytes();
 int cpn_pack_tc_weights(const float* raw, const float* packed_fp32, void* dst, cudaStream_t st);
@@ -171,4 +181,4 @@ int cpn_pack_tc_weights(const float* raw, const float* packed_fp32, void* dst, c
 // CPN_TC_OUT_CB16: fp32 output as [row tile][16-col block][128][16]; CPN_TC_OUT_ROWDOT: C[row] = <out row, dotv row> / dot_div
 int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,
                    int out_div, int out_kchunks, cudaStream_t st, const float* dotv = nullptr, float dot_div = 1.f,
-                   const float* dot_rowadd = nullptr, int dot_blocks = 0, int dot_block0 = 0);   // row-dot output: C[row] = (<out row, dotv row> + dot_rowadd[row]) / dot_div
+                   const float* dot_rowadd = nullptr, int dot_blocks = 0, int dot_block0 = 0, float* c2 = nullptr);   // row-dot output: C[row] = (<out row, dotv row> + dot_rowadd[row]) / dot_div

@@ -278,3 +278,20 @@ extern "C" int cpn_pack_features(const float* nchw, float* nhwc, int n_img, int 
   CPN_CHECK_LAUNCH("nchw_to_nhwc_kernel");
   return CPN_OK;
 }
+
+extern "C" size_t cpn_gather_rows_taps_bytes(int rows) { return (size_t)rows * 2 * CPN_N_LEVELS * 8 * sizeof(float); }
+
+extern "C" int cpn_gather_rows(const cpn_render_args* a, int nr, const float* rowaux, void* out, int form, void* taps,
+                               void* stream) {
+  if (!a || !rowaux || !out || nr <= 0 || a->B <= 0 || a->S <= 0 || form < 0 || form > 2) {
+    cpn_set_error("cpn_gather_rows: bad argument");
+    return CPN_ERR_ARG;
+  }
+  for (int l = 0; l < CPN_N_LEVELS; ++l)
+    if (!a->feat[l] || a->feat_h[l] <= 0 || a->feat_w[l] <= 0 || a->feat_c[l] <= 0 || (a->feat_c[l] & 3)) {
+      cpn_set_error("cpn_gather_rows: bad feature level %d", l);
+      return CPN_ERR_ARG;
+    }
+  return launch_gather(*a, 0, nr, rowaux, reinterpret_cast<float*>(out), form, (cudaStream_t)stream,
+                       reinterpret_cast<float*>(taps));
+}

@@ -20,6 +20,7 @@
 //   warp 1   allocates TMEM; lane 0 issues the MMAs and commits stage-free / accumulator-ready barriers
 //   warp 2-9 fp32-A mode: produce the A operand (32 rows per warp, two k-chunks of loads in flight), then
 //            the epilogue: TMEM -> registers -> scale, bias, ReLU -> global (fp32 or hi/lo image)
+#include <stdlib.h>
 #include "cpn_common.cuh"
 #include "tc_common.cuh"
 
@@ -30,7 +31,7 @@ using namespace tc;
 constexpr int BM = 256;            // rows per CTA: 2 sub-tiles of UMMA M = 128
 constexpr int BK = ACT_BK;         // k per stage (32): 2 MMA k-steps of 16
 constexpr int STAGES = 3;
-constexpr int NT_MAX = 208;        // widest N tile (832 = 4 x 208, 416 = 2 x 208)
+constexpr int NT_MAX = 256;        // widest N tile (832 = 4 x 208, 416 = 2 x 208; 256 for layer 10: both accumulators fill TMEM)
 constexpr int A_LBO = 128 * 16;                 // bytes between 8-wide k-chunks of a 128-row A sub-tile
 constexpr int A_HALF = (BK / 8) * A_LBO;        // hi (or lo) half of one sub-tile stage = 8 KB
 constexpr int A_SUB = 2 * A_HALF;               // one sub-tile stage = ACT_CHUNK_BYTES
@@ -70,6 +71,8 @@ const TcLayer kLayers[CPN_TC_LAYERS] = {
     {416, 1664, 1664, 208, pw::WVF, pw::BVF, true},   // 7 latent_value o query_encode_latent_2 (both branches)
     {128, 1664, 1664, 128, pw::WKF, pw::BKF, true},   // 8 key_map o query_encode_latent_2
     {256, 128, 128, 128, pw::WM12, pw::BM12, true},   // 9 [key_map_2 ; query_repeat_embed_2]^T query_embed_2 (bilinear logits)
+    {256, 1664, 1664, 256, pw::WKF, pw::BKF, true},   // 10 [key_map ; G] o query_encode_latent_2: key hidden layer and the
+                                                      //    per-row term of the round-2 query bias (cpn_common.cuh, pw::WG)
 };
 constexpr size_t TC_HEADER_BYTES = 256;   // floats [0..15] 1/scale per layer, [16..31] scale, uints [32..47] absmax bits
 static_assert(CPN_TC_LAYERS <= 16, "header slots");
@@ -97,13 +100,13 @@ __global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned in
   if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
-// power-of-two scale that brings max|w| to about 2^10
+// power-of-two scale that brings max|w| into [2^14, 2^15) (tc_common.cuh: TC_WEIGHT_LOG2)
 __device__ __forceinline__ float layer_scale(unsigned int absmax_bits) {
   float m = __uint_as_float(absmax_bits);
   if (!(m > 0.f) || isinf(m)) return 1.f;
   int e;
   frexpf(m, &e);              // m = f * 2^e, f in [0.5, 1)
-  return ldexpf(1.f, 10 - e);
+  return ldexpf(1.f, TC_WEIGHT_LOG2 - e);
 }
 
 // dst tile (nt, kc), 128 * NT bytes: f16x3 [hi | lo] x [4 k-groups][NT rows][8 halves];
@@ -136,7 +139,7 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, int out, int in, int
   const float lo_exact = x - __half2float(hi);
   size_t off8 = ((size_t)((k % BK) / 16) * NT + nl) * 16 + (k % 16);
   const unsigned char w8 = __nv_cvt_float_to_fp8(__half2float(hi) * F8_W_SCALE, __NV_SATFINITE, __NV_E4M3);
-  const unsigned char wl8 = __nv_cvt_float_to_fp8(lo_exact * F8_WLO_SCALE, __NV_SATFINITE, __NV_E4M3);
+  const unsigned char wl8 = __nv_cvt_float_to_fp8(lo_exact, __NV_SATFINITE, __NV_E4M3);
   t8[half_elems * 2 + off8] = w8;
   t8[half_elems * 3 + off8] = wl8;
   // pair tiles: (nt, half, kc) with NH = NT / 2 rows: [hi: 4 groups x NH x 16 B | w8: 2 x NH x 16 | w_lo8: 2 x NH x 16]
@@ -162,7 +165,11 @@ struct GemmArgs {
   int kchunks, NT;
   uint32_t idesc;
   int f8;                        // 1: fp16 + two e4m3 correction MMAs, 0: three fp16 MMAs
-  int out_kind;                  // fp32 output: 0 row-major, 2 column-blocked (CB16), 3 per-row dot with `dotv`
+  int out_kind;                  // fp32 output: 0 row-major, 2 column-blocked (CB16), 3 per-row dot with `dotv`,
+                                 // 4 N tile 0 as kind 3 (with ReLU), the other N tiles row-major into C2 without ReLU
+  float* C2;                     // out_kind 4: fp32 (M, N - NT) row-major
+  unsigned long long* dbg;       // phase timestamps of the first `dbg_cap` CTAs (cpn_gemm_tc_trace), else null
+  int dbg_cap;
   const float* dotv;             // CB16 matrix the rows are dotted with (out_kind 3); C then holds one float per row
   float dot_div;
   const float* dot_rowadd;       // optional per-row term added to the dot product before the division
@@ -171,14 +178,21 @@ struct GemmArgs {
 
 // Drain one 128-row accumulator sub-tile: TMEM -> registers -> scale, bias, ReLU -> fp32 rows or the operand image
 // of the next layer. Warp quadrant q owns TMEM lanes 32 q .. 32 q + 31.
+// Columns [c_lo, c_hi) of the tile (multiples of 16); returns this thread's partial row-dot (kinds 3 / 4) and, with
+// finish_dot, also writes the finished logit (callers that split the columns over several warps combine the partials).
 template <bool OUT_IMAGE>
-__device__ __forceinline__ void drain_subtile(const GemmArgs& g, uint32_t tmem, int m0, int n_tile, int esub, int q,
-                                              int lane) {
+__device__ __forceinline__ float drain_subtile(const GemmArgs& g, uint32_t tmem, int m0, int n_tile, int esub, int q,
+                                               int lane, int c_lo, int c_hi, bool finish_dot) {
   const int NT = g.NT;
   const int rloc = q * 32 + lane;                  // row inside the 128-row sub-tile
   const int row = m0 + esub * 128 + rloc;
   const float inv = *g.inv_scale;
   const int n0 = n_tile * NT;
+  // out_kind 4 (layer 10, one 256-column tile): columns 0-127 (key hidden layer) are dotted like kind 3, columns 128-255
+  // (G h + g0) leave column-blocked (8 blocks of 16 per 128-row tile)
+  const bool kg = g.out_kind == 4;
+  float* const crow = reinterpret_cast<float*>(g.C);
+  const int ldc = g.ldc, ccol0 = n0;
   const uint32_t tsrc = tmem + esub * 256 + ((uint32_t)(q * 32) << 16);
   unsigned char* img = nullptr;   // this thread's row inside the output image tile
   int kbase = 0;                  // k of the next layer that column n0 of this tile maps to
@@ -191,7 +205,9 @@ __device__ __forceinline__ void drain_subtile(const GemmArgs& g, uint32_t tmem, 
   // 32 rows of a warp 2 KB: coalesced for this epilogue and for a consumer that owns one row per thread
   const size_t cb_row = ((size_t)(m0 / 128 + esub) * (g.N / 16)) * 128 * 16 + (size_t)rloc * 16;
   float dot = 0.f;
-  for (int c0 = 0; c0 < NT; c0 += 16) {
+  for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+    const int kind = kg ? (c0 < CPN_HIDDEN ? 3 : 0) : g.out_kind;
+    const bool relu = kg ? (c0 < CPN_HIDDEN) : (g.relu != 0);
     float v[16];
     tmem_ld16(tsrc + c0, v);
 #pragma unroll
@@ -202,7 +218,7 @@ __device__ __forceinline__ void drain_subtile(const GemmArgs& g, uint32_t tmem, 
       v[j + 2] = v[j + 2] * inv + b.z;
       v[j + 3] = v[j + 3] * inv + b.w;
     }
-    if (g.relu) {
+    if (relu) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
     }
@@ -233,11 +249,11 @@ __device__ __forceinline__ void drain_subtile(const GemmArgs& g, uint32_t tmem, 
           *reinterpret_cast<uint4*>(p + A_HALF) = lo;
         }
       }
-    } else if (g.out_kind == 2) {
+    } else if (kind == 2) {
       float* out = reinterpret_cast<float*>(g.C) + cb_row + (size_t)((n0 + c0) / 16) * 128 * 16;
 #pragma unroll
       for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else if (g.out_kind == 3) {
+    } else if (kind == 3) {
       const float4* qv = reinterpret_cast<const float4*>(
           g.dotv + (((size_t)(m0 / 128 + esub) * g.dot_blocks + g.dot_block0 + (n0 + c0) / 16) * 128 + rloc) * 16);
 #pragma unroll
@@ -245,14 +261,20 @@ __device__ __forceinline__ void drain_subtile(const GemmArgs& g, uint32_t tmem, 
         const float4 x = __ldg(qv + j);
         dot = fmaf(v[4 * j + 3], x.w, fmaf(v[4 * j + 2], x.z, fmaf(v[4 * j + 1], x.y, fmaf(v[4 * j], x.x, dot))));
       }
+    } else if (kg) {
+      // G h + g0 leaves column-blocked like CB16 with 8 blocks per row tile: 64 contiguous bytes per thread, 2 KB per warp
+      float* out = g.C2 + (((size_t)(m0 / 128 + esub) * (CPN_HIDDEN / 16) + (c0 - CPN_HIDDEN) / 16) * 128 + rloc) * 16;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     } else if (row < g.M) {
-      float* out = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + n0 + c0;
+      float* out = crow + (size_t)row * ldc + ccol0 + c0;
 #pragma unroll
       for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
   }
-  if (!OUT_IMAGE && g.out_kind == 3 && row < g.M)
+  if (finish_dot && !OUT_IMAGE && (kg || g.out_kind == 3) && row < g.M)
     reinterpret_cast<float*>(g.C)[row] = (g.dot_rowadd ? dot + g.dot_rowadd[row] : dot) / g.dot_div;
+  return dot;
 }
 
 // CLUSTER (> 1, operand-image A only): the CTAs of the N tiles of one 256-row tile form a cluster; each loads
@@ -271,6 +293,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
   const int NT = g.NT;
   const uint32_t w_half = (uint32_t)(BK / 8) * NT * 16;      // bytes of the hi (or lo) part of a weight tile
   const bool sub1_valid = (m0 + 128) < g.M;                  // does the second 128-row sub-tile hold any row?
+  // optional phase trace: [0] CTA start, [1] setup done, [2] first stage landed, [3] last MMA issued, [4] accumulators
+  // ready (seen by an epilogue warp), [5] epilogue warp done, [6] CTA end, [7] smid
+  const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+  unsigned long long* const dbg = (g.dbg && cta_lin < g.dbg_cap) ? g.dbg + (size_t)cta_lin * 8 : nullptr;
+  auto stamp = [&](int i) {
+    if (dbg) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      dbg[i] = t;
+    }
+  };
+  if (threadIdx.x == 0) stamp(0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -287,6 +321,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
   if (CLUSTER > 1) cluster_sync();   // every CTA's barriers are initialised before any remote arrive / copy
   tcgen05_fence_after();
   const uint32_t tmem = tmem_base_s;
+  if (threadIdx.x == 0) {
+    stamp(1);
+    if (dbg) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      dbg[7] = smid;
+    }
+  }
   const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0;
   constexpr uint16_t cmask = (uint16_t)((1u << CLUSTER) - 1);
 
@@ -324,6 +366,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
         uint32_t u = i / STAGES;
         if (!A_IMAGE) mbar_wait(full_a + 8 * s, u & 1);
         mbar_wait(full_w + 8 * s, u & 1);
+        if (i == 0) stamp(2);
         tcgen05_fence_after();
         uint32_t stage = smem0 + s * STAGE_BYTES;
         uint32_t b_hi = stage + 2 * A_SUB, b_lo = b_hi + w_half;
@@ -338,9 +381,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
               mma_f16_ss(d, make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128), make_desc(b_hi + j * 2 * NT * 16, NT * 16, 128),
                          g.idesc, (i | j) != 0);
             // e4m3 planes: K = 32 per instruction = two 16-byte core matrices along k
-            mma_f8_ss(d, make_desc(a_hi + ACT_LO8, A_LBO, 128), make_desc(b_hi + w_half, NT * 16, 128), g.idesc, 1);
+            mma_f8_ss(d, make_desc(a_hi + ACT_LO8, A_LBO, 128), make_desc(b_hi + w_half, NT * 16, 128), g.idesc | IDESC_A_E5M2, 1);
             mma_f8_ss(d, make_desc(a_hi + ACT_X8, A_LBO, 128), make_desc(b_hi + w_half + w_half / 2, NT * 16, 128),
-                      g.idesc, 1);
+                      g.idesc | IDESC_A_E5M2, 1);
           } else {
 #pragma unroll
             for (int j = 0; j < BK / 16; ++j) {
@@ -358,6 +401,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
         if (CLUSTER > 1) mma_commit_multicast(empty + 8 * s, cmask); else mma_commit(empty + 8 * s);
       }
       mma_commit(accum);
+      stamp(3);
     }
   } else {
     const int pwarp = warp - 2;               // 0..7: rows [32 * pwarp, 32 * pwarp + 32) of the CTA tile
@@ -425,14 +469,182 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
     const int esub = pwarp >> 2, q = warp & 3;
     if (esub == 0 || sub1_valid) {
       mbar_wait(accum, 0);
+      if (threadIdx.x == 64) stamp(4);
       tcgen05_fence_after();
-      drain_subtile<OUT_IMAGE>(g, tmem, m0, n_tile, esub, q, lane);
+      drain_subtile<OUT_IMAGE>(g, tmem, m0, n_tile, esub, q, lane, 0, g.NT, true);
+      if (threadIdx.x == 64) stamp(5);
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   if (CLUSTER > 1) cluster_sync();   // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+  if (threadIdx.x == 32) stamp(6);
+}
+
+// ---- persistent version (operand-image A) -----------------------------------------------------------------------
+// One CTA per SM walks the (row tile, N tile) list with a stride of gridDim.x. The operand ring runs across tiles, so
+// the copies of tile j + 1 are in flight while tile j is drained, and TMEM / barriers are set up once per launch. A phase
+// trace of the one-tile-per-CTA kernel (profiles/r2_gemm1_trace.json) showed 15.9 us of MMA issue per tile against 6.5 us
+// of drain by 8 warps (instruction-latency bound), 1.3 us waiting for the first stage and 0.7 us between CTAs: 36 % of an
+// SM's time. Here 24 epilogue warps (three per 128-row sub-tile and TMEM lane quadrant, each a third of the columns) drain
+// a tile, and the MMA warp restarts as soon as they have read the accumulators (accum_empty).
+// EPI_WARPS = 8 * PARTS: 16 leaves registers for a co-resident CTA of another kernel (the gather / readout of the other chunk
+// lane: a persistent grid does not block the dispatch of later kernels the way a long CTA queue does).
+template <bool OUT_IMAGE, int P_EPI_WARPS>
+__global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_kernel(GemmArgs g, int ntiles_n, int ntiles) {
+  constexpr int PARTS = P_EPI_WARPS / 8;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sdot[2][PARTS][128];     // row-dot partials of the column parts
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t full = smem_u32(&bars[0]), empty = smem_u32(&bars[STAGES]), accum_full = smem_u32(&bars[2 * STAGES]),
+                 accum_empty = smem_u32(&bars[2 * STAGES + 1]);
+  const int NT = g.NT;
+  const uint32_t w_half = (uint32_t)(BK / 8) * NT * 16;
+  auto stamp = [&](int tile_no, int i) {   // optional phase trace, 8 x u64 per (CTA, tile) slot
+    if (g.dbg) {
+      const int slot = tile_no * gridDim.x + blockIdx.x;
+      if (slot < g.dbg_cap) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g.dbg[(size_t)slot * 8 + i] = t;
+      }
+    }
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + 8 * s, 1);
+      mbar_init(empty + 8 * s, 1);
+    }
+    mbar_init(accum_full, 1);
+    mbar_init(accum_empty, P_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const unsigned char* asrc = reinterpret_cast<const unsigned char*>(g.A);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int n_tile = t % ntiles_n, m0 = (t / ntiles_n) * BM;
+        const bool sub1_valid = (m0 + 128) < g.M;
+        const unsigned char* wsrc = g.wtiles + (size_t)n_tile * g.kchunks * 2 * w_half;
+        const size_t tile0 = (size_t)(m0 / 128);
+        for (int i = 0; i < g.kchunks; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t u = it / STAGES;
+          mbar_wait(empty + 8 * s, (u & 1) ^ 1);
+          const uint32_t stage = smem0 + s * STAGE_BYTES;
+          mbar_arrive_expect_tx(full + 8 * s, 2 * w_half + (sub1_valid ? 2 : 1) * A_SUB);
+          bulk_g2s(stage + 2 * A_SUB, wsrc + (size_t)i * 2 * w_half, 2 * w_half, full + 8 * s);
+          bulk_g2s(stage, asrc + (tile0 * g.kchunks + i) * ACT_CHUNK_BYTES, A_SUB, full + 8 * s);
+          if (sub1_valid)
+            bulk_g2s(stage + A_SUB, asrc + ((tile0 + 1) * g.kchunks + i) * ACT_CHUNK_BYTES, A_SUB, full + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
+        const int m0 = (t / ntiles_n) * BM;
+        const bool sub1_valid = (m0 + 128) < g.M;
+        mbar_wait(accum_empty, (tcount & 1) ^ 1);     // the epilogue warps have read the previous tile out of TMEM
+        tcgen05_fence_after();
+        stamp(tcount, 0);
+        for (int i = 0; i < g.kchunks; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t u = it / STAGES;
+          mbar_wait(full + 8 * s, u & 1);
+          if (i == 0) stamp(tcount, 1);
+          tcgen05_fence_after();
+          const uint32_t stage = smem0 + s * STAGE_BYTES;
+          const uint32_t b_hi = stage + 2 * A_SUB, b_lo = b_hi + w_half;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            if (sub == 1 && !sub1_valid) break;
+            const uint32_t a_hi = stage + sub * A_SUB, a_lo = a_hi + A_HALF;
+            const uint32_t d = tmem + sub * 256;
+            if (g.f8) {
+#pragma unroll
+              for (int j = 0; j < BK / 16; ++j)
+                mma_f16_ss(d, make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128), make_desc(b_hi + j * 2 * NT * 16, NT * 16, 128),
+                           g.idesc, (i | j) != 0);
+              mma_f8_ss(d, make_desc(a_hi + ACT_LO8, A_LBO, 128), make_desc(b_hi + w_half, NT * 16, 128), g.idesc | IDESC_A_E5M2, 1);
+              mma_f8_ss(d, make_desc(a_hi + ACT_X8, A_LBO, 128), make_desc(b_hi + w_half + w_half / 2, NT * 16, 128),
+                        g.idesc | IDESC_A_E5M2, 1);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BK / 16; ++j) {
+                const uint64_t da_hi = make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128);
+                const uint64_t da_lo = make_desc(a_lo + j * 2 * A_LBO, A_LBO, 128);
+                const uint64_t db_hi = make_desc(b_hi + j * 2 * NT * 16, NT * 16, 128);
+                const uint64_t db_lo = make_desc(b_lo + j * 2 * NT * 16, NT * 16, 128);
+                mma_f16_ss(d, da_hi, db_hi, g.idesc, (i | j) != 0);
+                mma_f16_ss(d, da_hi, db_lo, g.idesc, 1);
+                mma_f16_ss(d, da_lo, db_hi, g.idesc, 1);
+              }
+            }
+          }
+          mma_commit(empty + 8 * s);
+        }
+        mma_commit(accum_full);
+        stamp(tcount, 2);
+      }
+    }
+  } else {
+    // epilogue warp -> (TMEM lane quadrant q = warp % 4, sub-tile, column part): warps 2.. give every quadrant
+    // 2 * PARTS warps, r = (warp - 2) / 4 -> sub = r / PARTS, part = r % PARTS
+    const int q = warp & 3, r = (warp - 2) >> 2, esub = r / PARTS, part = r % PARTS;
+    const int niter = NT / 16, c_lo = (part * niter / PARTS) * 16, c_hi = ((part + 1) * niter / PARTS) * 16;
+    const bool dotkind = !OUT_IMAGE && (g.out_kind == 3 || g.out_kind == 4);
+    uint32_t tcount = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
+      const int n_tile = t % ntiles_n, m0 = (t / ntiles_n) * BM;
+      const bool valid = esub == 0 || (m0 + 128) < g.M;
+      mbar_wait(accum_full, tcount & 1);
+      tcgen05_fence_after();
+      if (threadIdx.x == 64) stamp(tcount, 3);
+      float dot = 0.f;
+      if (valid) dot = drain_subtile<OUT_IMAGE>(g, tmem, m0, n_tile, esub, q, lane, c_lo, c_hi, false);
+      // every TMEM read of this warp has completed (tcgen05.wait::ld inside tmem_ld16): hand the accumulators back
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accum_empty);
+      if (dotkind) {   // the three column parts of a row meet in shared memory, summed in part order
+        const int rloc = q * 32 + lane;
+        sdot[esub][part][rloc] = dot;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + esub * 4 + q), "n"(32 * PARTS) : "memory");
+        if (part == 0 && valid) {
+          const int row = m0 + esub * 128 + rloc;
+          if (row < g.M) {
+            float tot = sdot[esub][0][rloc];
+#pragma unroll
+            for (int pp = 1; pp < PARTS; ++pp) tot += sdot[esub][pp][rloc];
+            reinterpret_cast<float*>(g.C)[row] = (g.dot_rowadd ? tot + g.dot_rowadd[row] : tot) / g.dot_div;
+          }
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + esub * 4 + q), "n"(32 * PARTS) : "memory");   // sdot is free for the next tile
+      }
+      if (threadIdx.x == 64) stamp(tcount, 4);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+  if (g.dbg && threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if ((int)blockIdx.x < g.dbg_cap) g.dbg[(size_t)blockIdx.x * 8 + 7] = smid;
+  }
 }
 
 // ---- CTA-pair version (cta_group::2, operand-image A, f8 scheme) -------------------------------------------------
@@ -442,6 +654,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
 // this GEMM), and the smaller stage allows a 4-deep ring. The leader CTA's MMA thread issues for the pair; the
 // peer relays "my stage has landed" to the leader with a remote mbarrier arrive; tcgen05.commit multicasts
 // "stage free" / "accumulators ready" to both CTAs.
+// All waits are plain (CTA-scope) mbarrier waits: the operands travel through the async proxy (bulk copies in, tensor-core
+// reads) and are ordered by the barrier completions themselves. The first version spun on try_wait.acquire.cluster, which
+// ptxas lowers to a loop around CCTL.IVALL (an L1 invalidate per spin): 61 % of that kernel's issue samples
+// (profiles/r2_ncu_pair_kernel_sass_hotspots.txt) and the reason it measured slower than independent CTAs.
 constexpr int PSTAGES = 4;
 constexpr int PW_STAGE_MAX = (NT_MAX / 2) * 128;                 // bytes of half a weight tile per k-chunk
 constexpr int PSTAGE_BYTES = 2 * A_SUB + PW_STAGE_MAX;
@@ -486,7 +702,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_pair_kernel(GemmArgs g
       for (int i = 0; i < g.kchunks; ++i) {
         int s = i % PSTAGES;
         uint32_t u = i / PSTAGES;
-        mbar_wait_cluster(empty + 8 * s, (u & 1) ^ 1);
+        mbar_wait(empty + 8 * s, (u & 1) ^ 1);
         uint32_t stage = smem0 + s * PSTAGE_BYTES;
         mbar_arrive_expect_tx(full + 8 * s, 2 * wh + 2 * A_SUB);
         bulk_g2s(stage + 2 * A_SUB, wsrc + (size_t)i * 2 * wh, 2 * wh, full + 8 * s);
@@ -509,7 +725,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_pair_kernel(GemmArgs g
         int s = i % PSTAGES;
         uint32_t u = i / PSTAGES;
         mbar_wait(full + 8 * s, u & 1);
-        mbar_wait_cluster(peer_full + 8 * s, u & 1);
+        mbar_wait(peer_full + 8 * s, u & 1);
         tcgen05_fence_after();
         uint32_t stage = smem0 + s * PSTAGE_BYTES;
         uint32_t b_hi = stage + 2 * A_SUB;
@@ -521,8 +737,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_pair_kernel(GemmArgs g
           for (int j = 0; j < BK / 16; ++j)
             mma_f16_ss_pair(d, make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128), make_desc(b_hi + j * 2 * NH * 16, NH * 16, 128),
                             idesc, (i | j) != 0);
-          mma_f8_ss_pair(d, make_desc(a_hi + ACT_LO8, A_LBO, 128), make_desc(b_hi + wh, NH * 16, 128), idesc, 1);
-          mma_f8_ss_pair(d, make_desc(a_hi + ACT_X8, A_LBO, 128), make_desc(b_hi + wh + wh / 2, NH * 16, 128), idesc, 1);
+          mma_f8_ss_pair(d, make_desc(a_hi + ACT_LO8, A_LBO, 128), make_desc(b_hi + wh, NH * 16, 128), idesc | IDESC_A_E5M2, 1);
+          mma_f8_ss_pair(d, make_desc(a_hi + ACT_X8, A_LBO, 128), make_desc(b_hi + wh + wh / 2, NH * 16, 128), idesc | IDESC_A_E5M2, 1);
         }
         mma_commit_pair(empty + 8 * s, 3);   // both CTAs may refill the stage once these MMAs have read it
       }
@@ -530,9 +746,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_pair_kernel(GemmArgs g
     }
   } else {
     const int pwarp = warp - 2, esub = pwarp >> 2, q = warp & 3;
-    mbar_wait_cluster(accum, 0);
+    mbar_wait(accum, 0);
     tcgen05_fence_after();
-    drain_subtile<OUT_IMAGE>(g, tmem, m0, n_tile, esub, q, lane);
+    drain_subtile<OUT_IMAGE>(g, tmem, m0, n_tile, esub, q, lane, 0, g.NT, true);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -541,6 +757,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_pair_kernel(GemmArgs g
 }
 
 }  // namespace
+
+// phase trace of the single-CTA kernel (profiling hook like cpn_prof_begin; not thread-safe): while set, every
+// gemm_tc_kernel launch writes 8 x u64 per CTA for its first `cap` CTAs
+static unsigned long long* g_tc_dbg = nullptr;
+static int g_tc_dbg_cap = 0;
+extern "C" int cpn_gemm_tc_trace(unsigned long long* device_buf, int cap_ctas) {
+  g_tc_dbg = device_buf;
+  g_tc_dbg_cap = device_buf ? cap_ctas : 0;
+  return CPN_OK;
+}
 
 size_t cpn_tc_weights_bytes() { return TC_HEADER_BYTES + 3 * scheme_bytes(); }
 
@@ -566,9 +792,9 @@ int cpn_pack_tc_weights(const float* raw, const float* packed_fp32, void* dst_v,
 
 int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,
                    int out_div, int out_kchunks, cudaStream_t st, const float* dotv, float dot_div, const float* dot_rowadd, int dot_blocks,
-                   int dot_block0) {
+                   int dot_block0, float* c2) {
   const bool a_img = mode & CPN_TC_A_IMAGE, o_img = mode & CPN_TC_OUT_IMAGE;
-  if (!packed || !A || !C || layer < 0 || layer >= CPN_TC_LAYERS || M < 0 || (!a_img && (lda & 3)) || (!o_img && !(mode & (CPN_TC_OUT_ROWDOT | CPN_TC_OUT_CB16)) && (ldc & 3)) ||
+  if (!packed || !A || !C || layer < 0 || layer >= CPN_TC_LAYERS || M < 0 || (!a_img && (lda & 3)) || (!o_img && !(mode & (CPN_TC_OUT_ROWDOT | CPN_TC_OUT_CB16 | CPN_TC_OUT_KG)) && (ldc & 3)) ||
       (o_img && (out_div < 1 || out_kchunks < 1))) {
     cpn_set_error("gemm_tc: bad argument (layer=%d M=%d lda=%d ldc=%d mode=%d)", layer, M, lda, ldc, mode);
     return CPN_ERR_ARG;
@@ -592,14 +818,18 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
   g.out_div = out_div;
   g.out_kchunks = out_kchunks;
   g.f8 = (mode & CPN_TC_F16X3) ? 0 : 1;
-  g.out_kind = (mode & CPN_TC_OUT_ROWDOT) ? 3 : ((mode & CPN_TC_OUT_CB16) ? 2 : 0);
+  g.out_kind = (mode & CPN_TC_OUT_KG) ? 4 : ((mode & CPN_TC_OUT_ROWDOT) ? 3 : ((mode & CPN_TC_OUT_CB16) ? 2 : 0));
+  g.C2 = c2;
+  g.dbg = g_tc_dbg;
+  g.dbg_cap = g_tc_dbg_cap;
   g.dotv = dotv;
   g.dot_div = dot_div;
   g.dot_rowadd = dot_rowadd;
   g.dot_blocks = dot_blocks > 0 ? dot_blocks : L.out / 16;
   g.dot_block0 = dot_block0;
-  if (g.out_kind && (o_img || (g.out_kind == 3 && (L.out != L.nt || !dotv)))) {
-    cpn_set_error("gemm_tc: CB16 / row-dot outputs are fp32; the row-dot needs a single-N-tile layer");
+  if (g.out_kind && (o_img || (g.out_kind == 3 && (L.out != L.nt || !dotv)) ||
+                     (g.out_kind == 4 && (L.out != L.nt || L.nt != 2 * CPN_HIDDEN || !dotv || !c2)))) {
+    cpn_set_error("gemm_tc: CB16 / row-dot outputs are fp32; the row-dot needs a single-N-tile layer (two for the KG form)");
     return CPN_ERR_ARG;
   }
   g.wtiles = tcw + layer_offset(layer, g.f8);
@@ -631,6 +861,27 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
     CPN_CHECK_CUDA(cudaLaunchKernelEx(&pc, pk, g));
     return CPN_OK;
   }
+  if (a_img && !(mode & (CPN_TC_CLUSTER | CPN_TC_NO_PERSIST))) {
+    static int n_sm = 0;   // SMs of the current device (all devices of a box are the same part)
+    if (n_sm == 0) {
+      int dev = 0;
+      CPN_CHECK_CUDA(cudaGetDevice(&dev));
+      CPN_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    static int epi_warps = 0;   // CPN_TC_EPI_WARPS = 16 | 24 (A/B runs)
+    if (epi_warps == 0) {
+      const char* e = getenv("CPN_TC_EPI_WARPS");
+      epi_warps = (e && atoi(e) == 24) ? 24 : 16;
+    }
+    void (*pk)(GemmArgs, int, int) =
+        epi_warps == 24 ? (o_img ? gemm_tc_persist_kernel<true, 24> : gemm_tc_persist_kernel<false, 24>)
+                        : (o_img ? gemm_tc_persist_kernel<true, 16> : gemm_tc_persist_kernel<false, 16>);
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const int total = ntiles * (int)grid.y;
+    pk<<<total < n_sm ? total : n_sm, (2 + epi_warps) * 32, SMEM_BYTES, st>>>(g, ntiles, total);
+    CPN_CHECK_LAUNCH("gemm_tc_persist_kernel");
+    return CPN_OK;
+  }
   const int cluster = (a_img && (mode & CPN_TC_CLUSTER)) ? ntiles : 1;   // 4, 2 or 1; opt-in: measured slower
   void (*kern)(GemmArgs);
   if (cluster == 4) kern = o_img ? gemm_tc_kernel<true, true, 4> : gemm_tc_kernel<true, false, 4>;
@@ -656,12 +907,18 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
 
 extern "C" int cpn_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu,
                            int mode, int out_div, int out_kchunks, void* stream) {
-  return launch_gemm_tc(packed, layer, A, lda, C, ldc, M, relu, mode, out_div, out_kchunks, (cudaStream_t)stream, nullptr, 1.f,
-                        nullptr, 0, 0);
+  return launch_gemm_tc(packed, layer, A, lda, C, ldc, M, relu, mode & ~(CPN_TC_OUT_ROWDOT | CPN_TC_OUT_KG), out_div, out_kchunks,
+                        (cudaStream_t)stream, nullptr, 1.f, nullptr, 0, 0);
 }
 
 extern "C" int cpn_gemm_tc_rowdot(const void* packed, int layer, const void* A, int lda, const float* dotv_cb16, float* out,
                                   int M, int relu, int mode, float div, void* stream) {
-  return launch_gemm_tc(packed, layer, A, lda, out, 0, M, relu, mode | CPN_TC_OUT_ROWDOT, 1, 1, (cudaStream_t)stream, dotv_cb16,
-                        div, nullptr, 0, 0);
+  return launch_gemm_tc(packed, layer, A, lda, out, 0, M, relu, (mode & ~CPN_TC_OUT_KG) | CPN_TC_OUT_ROWDOT, 1, 1,
+                        (cudaStream_t)stream, dotv_cb16, div, nullptr, 0, 0);
+}
+
+extern "C" int cpn_gemm_tc_kg(const void* packed, const void* h1_image, const float* dotv_cb16, int dot_blocks,
+                              const float* rowadd, float div, float* logits, float* gh, int M, int mode, void* stream) {
+  return launch_gemm_tc(packed, 10, h1_image, 0, logits, 0, M, 1, (mode & CPN_TC_F16X3) | CPN_TC_A_IMAGE | CPN_TC_OUT_KG, 1, 1,
+                        (cudaStream_t)stream, dotv_cb16, div, rowadd, dot_blocks, 0, gh);
 }

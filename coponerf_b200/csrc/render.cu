@@ -2,6 +2,7 @@
 // asynchronous sequence of kernels per chunk of rays. Also the library's error string and version.
 #include <stdarg.h>
 #include <string.h>
+#include <mutex>
 #include "cpn_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -14,7 +15,7 @@ void cpn_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* cpn_last_error(void) { return g_err; }
-extern "C" int cpn_version(void) { return 100; }
+extern "C" int cpn_version(void) { return 200; }   // bumped whenever an entry point or struct changes (_lib.ABI_VERSION)
 extern "C" size_t cpn_sizeof_render_args(void) { return sizeof(cpn_render_args); }
 
 // ---- optional device timing of the dominant kernel (bench.py's roofline) -------------------
@@ -173,6 +174,7 @@ struct LanePool {
   cudaEvent_t fork;
 };
 LanePool g_pool[MAX_DEVICES];
+std::mutex g_pool_mutex;   // creation / destruction only; a device's pool is used by one host thread at a time (header)
 
 int get_pool(LanePool** out) {
   int dev = 0;
@@ -182,6 +184,7 @@ int get_pool(LanePool** out) {
     return CPN_ERR_ARG;
   }
   LanePool& p = g_pool[dev];
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
   if (!p.ready) {
     for (int i = 0; i < MAX_LANES; ++i) {
       CPN_CHECK_CUDA(cudaStreamCreateWithFlags(&p.stream[i], cudaStreamNonBlocking));
@@ -193,6 +196,32 @@ int get_pool(LanePool** out) {
   *out = &p;
   return CPN_OK;
 }
+
+}  // namespace
+
+// Releases the library's only persistent resources: the per-device lane streams / events (created by the first
+// cpn_render_rays call with lanes > 1). Safe to call at any time no render is in flight; they are re-created on demand.
+extern "C" int cpn_shutdown(void) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < MAX_DEVICES; ++d) {
+    LanePool& p = g_pool[d];
+    if (!p.ready) continue;
+    cudaSetDevice(d);
+    for (int i = 0; i < MAX_LANES; ++i) {
+      cudaStreamSynchronize(p.stream[i]);
+      cudaStreamDestroy(p.stream[i]);
+      cudaEventDestroy(p.done[i]);
+    }
+    cudaEventDestroy(p.fork);
+    p.ready = false;
+  }
+  cudaSetDevice(cur);
+  return CPN_OK;
+}
+
+namespace {
 
 bool use_tc(const cpn_render_args& a) { return !(a.flags & CPN_FLAG_SIMT_ONLY); }
 // encoder-input form for sample / gather: 0 fp32 rows, 1 operand image (f16x3), 2 operand image (f8 scheme)
@@ -230,6 +259,7 @@ extern "C" int cpn_render_launch_count(const cpn_render_args* a) {
   const bool late = !unfolded && !(a->flags & CPN_FLAG_EARLY_V);
   int per_chunk = (unfolded ? 17 : (late ? 19 : 16)) + ((a->flags & CPN_FLAG_SIMT_ONLY) ? 0 : 1);   // + taps_kernel
   if (!unfolded && !(a->flags & CPN_FLAG_NO_BILINEAR)) per_chunk -= 2;   // one GEMM over the coordinate embedding instead of three 128 x 128 layers
+  if (late && !(a->flags & (CPN_FLAG_NO_BILINEAR | CPN_FLAG_NO_GFOLD))) per_chunk -= 5;   // no round-1 readout + per-ray GEMM, encode_latent, z half of query_repeat_embed, park
   return chunks * per_chunk + (late ? 3 : 1);
 }
 
@@ -248,6 +278,9 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, flo
     // late readout (attention.cu): the attention reads out the hidden layer and the folded latent_value runs per ray
     const bool late_v = use_tc(a) && !(a.flags & (CPN_FLAG_NO_FOLD | CPN_FLAG_EARLY_V));
     const bool bilinear = use_tc(a) && !(a.flags & (CPN_FLAG_NO_FOLD | CPN_FLAG_NO_BILINEAR));
+    // G fold (cpn_common.cuh, pw::WG): the per-ray bias of round 2 comes from a 128-wide per-row term next to the key
+    // hidden layer, so there is no round-1 readout, and one readout with weights w2 + 2 w1 gives z
+    const bool gfold = late_v && bilinear && !(a.flags & CPN_FLAG_NO_GFOLD);
     if (use_tc(a)) {
       // per-sample encoder, CoPoNeRF.py:387-397: (835 -> 832 ReLU -> 416) for the primary and the secondary rows.
       // Activations travel between the tensor-core layers as fp16 hi/lo operand images (cpn_common.cuh).
@@ -277,8 +310,12 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, flo
         CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQT, W + pw::BQ, nullptr, 1, R, w.Q1, a_form(a) == 2, st, W + pw::WS1,
                                    w.s1, W + pw::WS2, w.s2));
         CPN_TRY(launch_gemm_tc(a.weights, 9, w.Q1, 0, w.Qm, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_CB16, 1, 1, st));
-        CPN_TRY(launch_gemm_tc(a.weights, 8, w.H1, 0, w.lg1, 0, R, 1, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_ROWDOT, 1, 1, st, w.Qm,
-                               11.31f, w.s1, 2 * CPN_HIDDEN / 16, 0));
+        if (gfold)   // w.K1 (R, 128) receives G h + g0
+          CPN_TRY(launch_gemm_tc(a.weights, 10, w.H1, 0, w.lg1, 0, R, 1, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_KG, 1, 1, st, w.Qm,
+                                 11.31f, w.s1, 2 * CPN_HIDDEN / 16, 0, w.K1));
+        else
+          CPN_TRY(launch_gemm_tc(a.weights, 8, w.H1, 0, w.lg1, 0, R, 1, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_ROWDOT, 1, 1, st, w.Qm,
+                                 11.31f, w.s1, 2 * CPN_HIDDEN / 16, 0));
       } else {
         if (!(a.flags & CPN_FLAG_NO_FOLD))
           CPN_TRY(launch_gemm_tc(a.weights, 8, w.H1, 0, w.K1, 0, R, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 1, KC128, st));
@@ -301,7 +338,9 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, flo
       CPN_TRY(dense_simt(a, w.local16, 16, pw::WQT, pw::BQ, w.Q1, CPN_HIDDEN, R, CPN_HIDDEN, 16, 1, st));
       CPN_TRY(dense_simt(a, w.Q1, CPN_HIDDEN, pw::WQ2T, pw::BQ2, w.Qe, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
     }
-    if (late_v) {
+    if (gfold) {
+      CPN_TRY(launch_attn1(a, ray0, nr, w.Kk, w.Qe, nullptr, w.rowaux, w.r1, w.wp, st, w.lg1, w.wt1, w.K1, w.rbias));
+    } else if (late_v) {
       CPN_TRY(launch_attn1(a, ray0, nr, w.Kk, w.Qe, nullptr, w.rowaux, w.r1, w.wp, st, w.lg1, w.wt1));
       CPN_TRY(launch_readout_image(a, nr, w.H1, w.wt1, w.hbar, a_form(a) == 2, st));
       CPN_TRY(launch_gemm_tc(a.weights, 7, w.hbar, 0, w.r1, CPN_LATENT, rays, 0, CPN_TC_A_IMAGE | sch, 1, 1, st));
@@ -310,8 +349,10 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, flo
     }
     // round 2, CoPoNeRF.py:467-473: query_repeat_embed(cat(encode_latent(R1), local_coords)); the z_embed
     // channels are the same for every sample of a ray, so they enter as a per-ray bias.
-    CPN_TRY(dense_simt(a, w.r1, CPN_LATENT, pw::WET, pw::BE, w.zemb, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_LATENT, 0, st));
-    CPN_TRY(dense_simt(a, w.zemb, CPN_HIDDEN, pw::WQRA_T, pw::BQR, w.rbias, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_HIDDEN, 0, st));
+    if (!gfold) {
+      CPN_TRY(dense_simt(a, w.r1, CPN_LATENT, pw::WET, pw::BE, w.zemb, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_LATENT, 0, st));
+      CPN_TRY(dense_simt(a, w.zemb, CPN_HIDDEN, pw::WQRA_T, pw::BQR, w.rbias, CPN_HIDDEN, rays, CPN_HIDDEN, CPN_HIDDEN, 0, st));
+    }
     if (use_tc(a)) {   // query_repeat_embed_2 with the round-2 logits <Q2, Q> / 11.31 (CoPoNeRF.py:474) as its epilogue
       if (bilinear) {   // the repeat-query hidden layer is dotted with WM2 q + BM2 (second half of w.Qm) where it is produced
         CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQRB_T, nullptr, w.rbias, 2 * a.S, R, nullptr, a_form(a) == 2, st,
@@ -327,7 +368,11 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, flo
                                16, 1, st));
       CPN_TRY(dense_simt(a, w.K1, CPN_HIDDEN, pw::WQR2T, pw::BQR2, w.Kk, CPN_HIDDEN, R, CPN_HIDDEN, CPN_HIDDEN, 0, st));
     }
-    if (late_v) {
+    if (gfold) {
+      // combined weight w2 + 2 w1 -> one readout into the image-level operand image; z is finished per image
+      CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, nullptr, w.r1, z_all, st, w.lg2, w.wt2, w.wt1));
+      CPN_TRY(launch_readout_image(a, nr, w.H1, w.wt2, hbar_all, a_form(a) == 2, st, a.N, ray0));
+    } else if (late_v) {
       CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, nullptr, w.r1, z_all, st, w.lg2, w.wt2));
       // the round-2 readout lands in the image-level operand image; its GEMM runs once per image (finish_image)
       CPN_TRY(launch_readout_image(a, nr, w.H1, w.wt2, hbar_all, a_form(a) == 2, st, a.N, ray0));
@@ -360,11 +405,15 @@ extern "C" int cpn_render_rays(const cpn_render_args* args, void* stream) {
   float* r2_all = reinterpret_cast<float*>(reinterpret_cast<char*>(a.workspace) + z_bytes(a.B, a.N));
   float* hbar_all = reinterpret_cast<float*>(reinterpret_cast<char*>(a.workspace) + 2 * z_bytes(a.B, a.N));
   const bool late_v = use_tc(a) && !(a.flags & (CPN_FLAG_NO_FOLD | CPN_FLAG_EARLY_V));
+  const bool gfold = late_v && !(a.flags & (CPN_FLAG_NO_BILINEAR | CPN_FLAG_NO_GFOLD));
   // late readout: R2 of every ray from one GEMM over the image, z = (R2 + R1) + R1, then the light-field decoder
   auto finish_image = [&]() -> int {
     if (late_v) {
       CPN_TRY(launch_gemm_tc(a.weights, 7, hbar_all, 0, r2_all, CPN_LATENT, a.B * a.N, 0, CPN_TC_A_IMAGE | tc_scheme(a), 1, 1, st));
-      CPN_TRY(launch_finish_z(a, r2_all, z_all, st));
+      if (gfold)   // the operand image held sum (w2 + 2 w1) h: z = WVF hbar + 3 b
+        CPN_TRY(launch_finish_z_bias(a, r2_all, reinterpret_cast<const float*>(a.weights) + pw::BVF, z_all, st));
+      else
+        CPN_TRY(launch_finish_z(a, r2_all, z_all, st));
     }
     return launch_phi(a, z_all, st);
   };

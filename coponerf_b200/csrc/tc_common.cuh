@@ -218,27 +218,42 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
 }
 
 // ---- fp16 + fp8-correction split ("f8 scheme") ----------------------------------------------------------------
-// x*w = x_hi*w_hi                         fp16 MMA, exact products, fp32 accumulation
-//     + e4m3(x_lo * 2^8) * e4m3(w_hi * 2^-8)    x_lo = x - x_hi, |x_lo| <= 2^-11 |x|
-//     + e4m3(x * 2^-6)   * e4m3(w_lo * 2^6)     w_lo = w - w_hi
-// The two correction terms only need ~4 significant bits (they are 2^-11 of the product), so they run on the
-// fp8 tensor path at twice the fp16 rate: 2.0 MMA passes per product instead of 3.0. Measured on the reference
-// goldens (scripts/emulate_fp8_scheme.py): rgb max error on well-conditioned rays 1-2e-5 (fp16 alone: 3e-4).
-constexpr float F8_XLO_SCALE = 256.f, F8_W_SCALE = 1.f / 256.f, F8_X_SCALE = 1.f / 64.f, F8_WLO_SCALE = 64.f;
+// x*w = x_hi*w_hi                               fp16 MMA, exact products, fp32 accumulation
+//     + e5m2(x_lo * 2^10) * e4m3(w_hi * 2^-10)   x_lo = x - x_hi, |x_lo| <= 2^-11 |x|
+//     + e5m2(x_hi)        * e4m3(w_lo)           w_lo = w - w_hi
+// The two correction terms are 2^-11 of the product, so 3-4 significant bits suffice and they run on the fp8 tensor path at
+// twice the fp16 rate: 2.0 MMA passes per product instead of 3.0. The ACTIVATION planes are e5m2: its five exponent bits
+// give them the dynamic range of fp16 itself (normal from |x| ~ 1e-4 up to 65504), so the accuracy does not depend on the
+// scale of the activations; the first version used e4m3 there too, whose 15 binades only cover |x| in about [0.25, 7000]:
+// post-ReLU rows of magnitude 0.03 or inputs scaled by 1e-3 fell to plain fp16 accuracy (3e-4). The WEIGHT planes stay e4m3
+// (4 significant bits): weights are pre-scaled per layer to max |w| in [2^14, 2^15), a known range.
+// Emulated on the reference goldens and on scaled inputs (scripts/emulate_fp8_scheme.py): 2.5e-5 worst row of a K = 832
+// layer for input scales 1e-3 ... 3e4, rgb max error on well-conditioned rays 0.8-1.3e-5 (fp16 alone: 3e-4).
+constexpr float F8_XLO_SCALE = 1024.f, F8_W_SCALE = 1.f / 1024.f;
+constexpr int TC_WEIGHT_LOG2 = 15;              // per-layer weight scale: max |w| -> [2^14, 2^15)
+constexpr uint32_t IDESC_A_E5M2 = 1u << 7;      // kind::f8f6f4 instruction descriptor: A format E5M2 (B stays E4M3)
 
-__device__ __forceinline__ uint32_t f8x4(float a, float b, float c, float d) {
-  uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
-  uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+__device__ __forceinline__ uint32_t e5m2x4(float a, float b, float c, float d) {
+  uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E5M2);
+  uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E5M2);
   return lo | (hi << 16);
 }
-// 4 values -> 4 fp16 hi (uint2), 4 e4m3 of the scaled remainder, 4 e4m3 of the scaled value
+// 4 values -> 4 fp16 hi (uint2), 4 e5m2 of the scaled remainder, 4 e5m2 of the fp16 value
 __device__ __forceinline__ void split4_f8(const float4& x, uint2& hi, uint32_t& lo8, uint32_t& x8) {
   __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
   float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
   hi.x = *reinterpret_cast<uint32_t*>(&h0);
   hi.y = *reinterpret_cast<uint32_t*>(&h1);
-  lo8 = f8x4((x.x - f0.x) * F8_XLO_SCALE, (x.y - f0.y) * F8_XLO_SCALE, (x.z - f1.x) * F8_XLO_SCALE, (x.w - f1.y) * F8_XLO_SCALE);
-  x8 = f8x4(x.x * F8_X_SCALE, x.y * F8_X_SCALE, x.z * F8_X_SCALE, x.w * F8_X_SCALE);
+  lo8 = e5m2x4((x.x - f0.x) * F8_XLO_SCALE, (x.y - f0.y) * F8_XLO_SCALE, (x.z - f1.x) * F8_XLO_SCALE, (x.w - f1.y) * F8_XLO_SCALE);
+  const uint32_t a = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<__half2_raw*>(&h0), __NV_SATFINITE, __NV_E5M2);
+  const uint32_t b = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<__half2_raw*>(&h1), __NV_SATFINITE, __NV_E5M2);
+  x8 = a | (b << 16);
+}
+// the remainder plane back to fp32: 2 packed e5m2 -> (x - x_hi) of the two elements
+__device__ __forceinline__ float2 lo8_to_float2(uint32_t two_bytes) {
+  const __half2_raw h2 = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(two_bytes & 0xffffu), __NV_E5M2);
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+  return make_float2(f.x * (1.f / F8_XLO_SCALE), f.y * (1.f / F8_XLO_SCALE));
 }
 
 }  // namespace tc

@@ -96,6 +96,34 @@ __global__ void bilinear_fold_kernel(const float* __restrict__ Wa, const float* 
   }
 }
 
+// G fold, stage 1: M1 = Wqr[:, :128] We (128 x 416) in double.  Wqr (128, 144) = query_repeat_embed.weight, whose first
+// 128 input channels see encode_latent's output (CoPoNeRF.py:467-472); We (128, 416) = encode_latent.weight.
+__global__ void gfold_m1_kernel(const float* __restrict__ Wqr, const float* __restrict__ We, double* __restrict__ M1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128 * 416) return;
+  const int n = i / 416, j = i % 416;
+  double acc = 0.0;
+  for (int m = 0; m < 128; ++m) acc += (double)Wqr[n * 144 + m] * (double)We[m * 416 + j];
+  M1[i] = acc;
+}
+// stage 2: G = M1 WVF (128 x 1664), g0 = M1 bVF + Wqr[:, :128] be + bqr, with WVF / bVF the folded latent_value.
+__global__ void gfold_kernel(const double* __restrict__ M1, const float* __restrict__ WVF, const float* __restrict__ bVF,
+                             const float* __restrict__ Wqr, const float* __restrict__ be, const float* __restrict__ bqr,
+                             float* __restrict__ G, float* __restrict__ g0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128 * 1664) return;
+  const int n = i / 1664, col = i % 1664;
+  double acc = 0.0;
+  for (int j = 0; j < 416; ++j) acc += M1[n * 416 + j] * (double)WVF[(size_t)j * 1664 + col];
+  G[i] = (float)acc;
+  if (col == 0) {
+    double b = (double)bqr[n];
+    for (int j = 0; j < 416; ++j) b += M1[n * 416 + j] * (double)bVF[j];
+    for (int m = 0; m < 128; ++m) b += (double)Wqr[n * 144 + m] * (double)be[m];
+    g0[n] = (float)b;
+  }
+}
+
 struct Job {
   int tensor, col0, K, Kpad;  // K == 0: plain copy of the whole tensor
   size_t dst;
@@ -164,6 +192,16 @@ extern "C" int cpn_pack_weights(const float* src, void* dst_v, void* stream) {
   fold_kernel<<<(128 * 1664 + 255) / 256, 256, 0, st>>>(src + tensor_offset(6), src + tensor_offset(7), W2, b2, 128,
                                                         dst + pw::WKF, dst + pw::BKF);
   CPN_CHECK_LAUNCH("fold_kernel");
+  // round-2 query bias as a linear map of the hidden layer (cpn_common.cuh, pw::WG): needs WVF / BVF from above
+  {
+    double* M1 = reinterpret_cast<double*>(dst + pw::M1D);
+    gfold_m1_kernel<<<(128 * 416 + 255) / 256, 256, 0, st>>>(src + tensor_offset(14), src + tensor_offset(18), M1);
+    CPN_CHECK_LAUNCH("gfold_m1_kernel");
+    gfold_kernel<<<(128 * 1664 + 255) / 256, 256, 0, st>>>(M1, dst + pw::WVF, dst + pw::BVF, src + tensor_offset(14),
+                                                           src + tensor_offset(19), src + tensor_offset(15), dst + pw::WG,
+                                                           dst + pw::BG);
+    CPN_CHECK_LAUNCH("gfold_kernel");
+  }
   // attention logits as bilinear forms: key_map_2 (tensors 8, 9) and query_repeat_embed_2 (16, 17) against query_embed_2 (12, 13)
   const float *Wq2 = src + tensor_offset(12), *bq2 = src + tensor_offset(13);
   bilinear_fold_kernel<<<(128 * 128 + 129 + 255) / 256, 256, 0, st>>>(src + tensor_offset(8), src + tensor_offset(9), Wq2, bq2,

@@ -6,7 +6,6 @@ get_z() is standalone too (coponerf_b200/pair_stage.py): the ResNet-34 image enc
 (BASELINE.json: "models/backbone.py and the train/test drivers stay"), the cost aggregation and the pose
 features / pose head run on the sm_100a operators. The module carries all 744 state_dict keys of the reference
 model, so `load_state_dict(torch.load(ckpt)['model'], strict=False)` (test.py:143) works unchanged.
-`attach_pair_stage(reference_model)` is kept for A/B runs against the reference's own get_z().
 """
 import torch
 import torch.nn as nn
@@ -81,14 +80,12 @@ class CoPoNeRF(nn.Module):
         self.phi = _ResnetFC(n_view * 9, half * n_view, hidden)
         self.chunk_rays = chunk_rays
         self.lanes = lanes
-        self.native_ufc = True          # get_z(): cost aggregation (UFC) on the sm_100a operators
         self.graph_get_z = True         # get_z(): replay the per-pair stage (~800 short kernels) from a CUDA graph: same
                                         # kernels, same bits; keeps the stage at its GPU time when the host is slow
         self._ufc_ops = None
         self.pixel_val_on_host = True   # the reference returns out['pixel_val'] as a CPU tensor (CoPoNeRF.py:490)
         self._engine = None
         self._engine_version = None
-        self._pair_stage = None
         self.H = self.W = None
 
     # ------------------------------------------------------------------ engine management
@@ -98,7 +95,8 @@ class CoPoNeRF(nn.Module):
         Parameter OBJECT by hand (in-place updates are seen through the tensors' version counters)."""
         pl = self.__dict__.get("_plist")
         if pl is None:
-            pl = self.__dict__["_plist"] = list(self.parameters())
+            # buffers too: fold_encoder reads the BatchNorm running statistics (pair_stage.py)
+            pl = self.__dict__["_plist"] = list(self.parameters()) + list(self.buffers())
         return pl
 
     def refresh_parameters(self):
@@ -126,42 +124,17 @@ class CoPoNeRF(nn.Module):
             self._engine_version = ver
         return self._engine
 
-    def attach_pair_stage(self, ref_model):
-        """Use a reference CoPoNeRF instance's encoder / aggregation / pose head for get_z()."""
-        object.__setattr__(self, "_pair_stage", ref_model)
-
     # ------------------------------------------------------------------ reference API
     def get_z(self, input, val=False):
         """models/CoPoNeRF.py:159-206: image features, estimated relative pose, correspondence fields."""
-        if self._pair_stage is None:
-            dev = next(self.parameters()).device
-            if dev.type != "cuda":
-                raise RuntimeError("coponerf_b200.CoPoNeRF.get_z() runs on CUDA only: call .cuda() first (no CPU fallback)")
-            if self._ufc_ops is None:
-                from .ufc_ops import CudaOps
-                self._ufc_ops = CudaOps()
-            with torch.cuda.device(dev):
-                return pair_stage.get_z(self, input, self._ufc_ops, use_graph=self.graph_get_z)
-        ref = self._pair_stage
-        fca = ref.feature_cost_aggregation
-        if not self.native_ufc:
-            out = ref.get_z(input)
-        else:
-            # same call, with the cost aggregation (UFC.forward, aggregation.py:509-562) running on the sm_100a
-            # operators: only the module's parameters are used, none of its Python code
-            from . import ufc_native
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("coponerf_b200.CoPoNeRF.get_z() runs on CUDA only: call .cuda() first (no CPU fallback)")
+        if self._ufc_ops is None:
             from .ufc_ops import CudaOps
-            if self._ufc_ops is None:
-                self._ufc_ops = CudaOps()
-            sd = dict(fca.state_dict())
-            orig = fca.forward
-            fca.forward = lambda feat, nview: ufc_native.ufc_forward(sd, feat, nview, self._ufc_ops)
-            try:
-                out = ref.get_z(input)
-            finally:
-                fca.forward = orig
-        self.H, self.W = ref.H, ref.W
-        return out
+            self._ufc_ops = CudaOps()
+        with torch.cuda.device(dev):
+            return pair_stage.get_z(self, input, self._ufc_ops, use_graph=self.graph_get_z)
 
     @torch.no_grad()
     def forward(self, input, z=None, rel_pose=None, val=False, flow=None, debug=False):
@@ -187,7 +160,7 @@ class CoPoNeRF(nn.Module):
         if self.pixel_val_on_host:   # pinned staging (torch's caching host allocator) instead of a pageable .cpu()
             pv = torch.empty(o["pixel_val"].shape, dtype=torch.float32, pin_memory=True)
             pv.copy_(o["pixel_val"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            torch.cuda.current_stream(o["pixel_val"].device).synchronize()   # the stream of the model's device, not of the current one
             out["pixel_val"] = pv
         else:
             out["pixel_val"] = o["pixel_val"]

@@ -182,9 +182,12 @@ def _sub_state(model, prefix):
 def _state_cache(model):
     cache = model.__dict__.setdefault("_sd_cache", {})
     ver = model._weights_version() if hasattr(model, "_weights_version") else \
-        tuple((p.data_ptr(), p._version) for p in model.parameters())
+        tuple((p.data_ptr(), p._version) for p in list(model.parameters()) + list(model.buffers()))
     if cache.get("ver") != ver:
         cache.clear()
+        ops = model.__dict__.get("_ufc_ops")
+        if ops is not None:         # the transposed weight copies belong to the old parameter versions
+            ops._wt.clear()
         cache["ver"] = ver
         cache["ufc"] = _sub_state(model, "feature_cost_aggregation")
         cache["encoder"] = fold_encoder(model.encoder)

@@ -129,10 +129,42 @@ def pose_head(sd, pose_feat, ops):
     return ops.pose_head(h0, sd)
 
 
+_POS_ID_CACHE = OrderedDict()
+
+
+def _positional_encodings_device(k, n_tokens, H, device):
+    """The same table computed on the device from device intrinsics, stream-ordered, without reading them back: K is
+    [[a, 0, c], [0, b, d], [0, 0, 1]], so K^-1 [x, y, 1] = [(x - c) / a, (y - d) / b, 1] in closed form (square token
+    grids only; agrees with the host path to 1e-6, tests/test_pair_oracle_golden.py)."""
+    side = int(round(n_tokens ** 0.5))
+    B = k.shape[0]
+    fx, fy, cx, cy = k[:, 0, 0] / H, k[:, 1, 1] / H, k[:, 0, 2] / H, k[:, 1, 2] / H
+    a, b = (fx / (cx * 2)) * 2, (fy / (cy * 2)) * 2
+    c, d = (cx / (cx * 2)) * 2 - 1, (cy / (cy * 2)) * 2 - 1
+    lin = torch.linspace(-1, 1, steps=side).to(k.device)
+    p4 = (lin[None, :] * (1 / a)[:, None] + (-c / a)[:, None])[:, :, None].expand(B, side, side).reshape(B, n_tokens)   # x'
+    p3 = (lin[None, :] * (1 / b)[:, None] + (-d / b)[:, None])[:, None, :].expand(B, side, side).reshape(B, n_tokens)   # y'
+    pos = torch.stack((p3 * p3, p4 * p4, p3 * p4, p3, p4, torch.ones_like(p3)), dim=2)
+    return pos.to(device) if device is not None else pos
+
+
 def positional_encodings_for(intrinsics, n_tokens, H, device=None):
     """The table for context['intrinsics'] (B, n_ctxt, 4, 4) as get_z prepares them (CoPoNeRF.py:188-191: rows 0-1
-    divided by H, view 0's fx, fy, cx, cy)."""
+    divided by H, view 0's fx, fy, cx, cy). Host intrinsics: memoised by value. Device intrinsics: memoised by tensor
+    identity, otherwise computed on the device with no host synchronisation."""
     B = intrinsics.shape[0]
+    if intrinsics.is_cuda:
+        side = int(round(n_tokens ** 0.5))
+        if side * side == n_tokens and n_tokens != 48 * 64:
+            key = (intrinsics.data_ptr(), intrinsics._version, tuple(intrinsics.shape), str(intrinsics.device), n_tokens, H,
+                   str(device))
+            hit = _POS_ID_CACHE.get(key)
+            if hit is None:
+                pos = _positional_encodings_device(intrinsics[:, 0].detach().to(torch.float32), n_tokens, H, device)
+                hit = _POS_ID_CACHE[key] = (pos, intrinsics)      # the tensor is kept alive so its address stays unique
+                while len(_POS_ID_CACHE) > 4:
+                    _POS_ID_CACHE.popitem(last=False)
+            return hit[0]
     k = intrinsics[:, 0].detach().to(torch.float32)
     intr = [(k[:, 0, 0] / H).reshape(B, 1), (k[:, 1, 1] / H).reshape(B, 1),
             (k[:, 0, 2] / H).reshape(B, 1), (k[:, 1, 2] / H).reshape(B, 1)]

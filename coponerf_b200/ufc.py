@@ -1,6 +1,7 @@
-"""Host side of the per-pair cost-aggregation kernels (models/aggregation.py). Built so far: the closing stage of
-UFC.forward() -- correlation of the refined features of the three levels, 4-D upsampling, their mean `c`, the two
-soft-argmax flow fields and the conversion to pixel flow (aggregation.py:527,539,549-561) -- as `ufc_tail`."""
+"""Thin host wrappers of three cost-aggregation entry points (models/aggregation.py, models/conv4d.py) used by the operator
+tests and benches: the closing stage of UFC.forward() (`ufc_tail`: aggregation.py:527,539,549-561), one Encoder4D block
+(`conv4d_block`: conv4d.py:149-153) and LinearAttention (`linear_attention`: aggregation.py:84-117). The whole
+UFC.forward runs through coponerf_b200/ufc_native.py over coponerf_b200/ufc_ops.py::CudaOps."""
 import ctypes
 
 import torch
@@ -107,97 +108,3 @@ def linear_attention(queries, keys, values):
                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
                    "cpn_linear_attention")
     return out
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# UFC.forward with the native closing stage. The coarse-to-fine refinement (proj_feat, embedding, the five UFCLayer
-# blocks: aggregation.py:509-549) is not native yet and is delegated to the attached reference module's own
-# submodules; what is replaced is everything after the last UFCLayer.
-def _tokens_to_map(x, n):
-    return x.transpose(1, 2).reshape(x.shape[0], x.shape[2], n, n)
-
-
-def _correlation(src_tok, trg_tok, n, eps=1e-5):
-    """aggregation.py:70-74 on token features."""
-    s, t = _tokens_to_map(src_tok, n), _tokens_to_map(trg_tok, n)
-    s = s / (s.norm(dim=1, p=2, keepdim=True) + eps)
-    t = t / (t.norm(dim=1, p=2, keepdim=True) + eps)
-    return torch.einsum("bchw,bcxy->bhwxy", s, t)[:, None]
-
-
-def _upsample_tokens(x, n_out):
-    """aggregation.py:58-63 (interpolate2d_token)."""
-    n = int(round(x.shape[1] ** 0.5))
-    y = torch.nn.functional.interpolate(_tokens_to_map(x, n), size=(n_out, n_out), mode="bilinear", align_corners=True)
-    return y.flatten(2).transpose(1, 2)
-
-
-def _encoder4d_forward(enc, block_fn):
-    """forward() for a reference Encoder4D module (conv4d.py:156-163) that runs every
-    Conv4d -> GroupNorm -> ReLU block through `block_fn` (conv4d_block on CUDA)."""
-    def forward(x):
-        for blk in enc.conv4d:
-            c4, gn = blk[0], blk[1]
-            x = block_fn(x, c4.query_conv.weight, c4.query_conv.bias, c4.supp_conv.weight, c4.supp_conv.bias,
-                         gn.weight, gn.bias, c4.stride[0], c4.padding[0])
-        return x
-    return forward
-
-
-class _patched_modules:
-    """Context manager: for the duration of a call, route every Encoder4D inside `root` through `block_fn` and
-    every LinearAttention through `attention_fn`."""
-
-    def __init__(self, root, block_fn, attention_fn):
-        self.enc = [m for m in root.modules() if type(m).__name__ == "Encoder4D"]
-        self.att = [m for m in root.modules() if type(m).__name__ == "LinearAttention"]
-        self.block_fn, self.attention_fn = block_fn, attention_fn
-
-    def __enter__(self):
-        for m in self.enc:
-            m.forward = _encoder4d_forward(m, self.block_fn)
-        for m in self.att:
-            m.forward = lambda q, k, v, q_mask=None, kv_mask=None, _f=self.attention_fn: _f(q, k, v)
-
-    def __exit__(self, *exc):
-        for m in self.enc + self.att:
-            del m.forward          # back to the class's own forward
-        return False
-
-
-def ufc_forward(fca, feat, nview, tail=None, conv_block=None, attention=None):
-    """Drop-in for UFC.forward(feat, nview) (aggregation.py:509-562) of the attached reference module `fca`.
-
-    Returns (feat_list, (flow, flow_flip, flow_t_to_s, flow_s_to_t), c) like the reference. Native so far: every
-    Encoder4D block (63 Conv4d + GroupNorm + ReLU per pair, `conv_block`, default conv4d_block), every
-    LinearAttention (20 per pair, `attention`, default linear_attention) and the closing stage (`tail`, default
-    ufc_tail). Tests pass the CPU oracles for all three to check the orchestration without a GPU.
-    """
-    tail = tail or ufc_tail
-    with _patched_modules(fca, conv_block or conv4d_block, attention or linear_attention):
-        return _ufc_forward(fca, feat, nview, tail)
-
-
-def _ufc_forward(fca, feat, nview, tail):
-    B = feat[0].shape[0]
-    sizes = [f.shape[-1] for f in feat]
-
-    def side(i, v):
-        x = feat[i].view(B // nview, nview, -1, sizes[i], sizes[i])[:, v]
-        return fca.proj_feat[i](x.flatten(2).transpose(1, 2))
-
-    src = [side(i, 0) for i in range(3)]
-    trg = [side(i, 1) for i in range(3)]
-    feat_list, refined = [], []
-    corr, s, t = None, None, None
-    for lvl in range(3):
-        raw = fca.embedding[lvl](_correlation(src[lvl], trg[lvl], sizes[lvl]))
-        corr = raw if lvl == 0 else corr + raw
-        s = src[lvl] if lvl == 0 else _upsample_tokens(s, sizes[lvl]) + src[lvl]
-        t = trg[lvl] if lvl == 0 else _upsample_tokens(t, sizes[lvl]) + trg[lvl]
-        corr, s, t = fca.layers[lvl](corr, s, t)
-        both = torch.stack((s, t), dim=1).flatten(0, 1)
-        feat_list.append(_tokens_to_map(both, sizes[lvl]))
-        refined.append((s, t))
-    flows, c = tail([r[0] for r in refined], [r[1] for r in refined], tuple(sizes), sizes[-1])
-    return feat_list, flows, c

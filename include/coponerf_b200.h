@@ -8,7 +8,11 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer to a caller-owned, contiguous buffer (fp32 unless
- *     the name says otherwise); the library allocates nothing and keeps no global state;
+ *     the name says otherwise); the library allocates no device memory. Its only process-wide state: a per-device
+ *     pool of internal streams / events for the chunk lanes of cpn_render_rays (created on first use with lanes > 1,
+ *     released by cpn_shutdown) and the optional profiling hooks (cpn_prof_*, cpn_gemm_tc_trace). cpn_render_rays is
+ *     therefore single-threaded per device: one host thread (and one caller stream) at a time, as the reference's
+ *     callers are;
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*): no host
  *     sync, no host copies;
  *   - return value: 0 on success, a negative cpn_status otherwise; cpn_last_error()
@@ -43,10 +47,14 @@ typedef enum {
 #define CPN_PAIR_CONSTS_FLOATS 320
 #define CPN_FLAG_SIMT_ONLY 1  /* run the big 1x1 convs on the fp32 CUDA-core GEMM (cross-check path) */
 #define CPN_FLAG_F16X3 2      /* tensor-core GEMMs with three fp16 MMAs per product (default: fp16 + 2 fp8) */
+#define CPN_FLAG_NO_GFOLD 32  /* keep latent_value -> encode_latent -> query_repeat_embed as a per-ray chain behind a separate
+                               * round-1 readout (default: folded into one 128 x 1664 map applied per sample row next to
+                               * key_map, one combined readout with weights w2 + 2 w1 for z = R2 + 2 R1) */
 #define CPN_FLAG_NO_FOLD 4    /* keep query_encode_latent_2, latent_value and key_map as three GEMMs (default: the
                                * activation-free query_encode_latent_2 is folded into the other two at pack time) */
 
 int cpn_version(void);
+int cpn_shutdown(void);                /* destroys the lane streams / events of every device; re-created on demand */
 const char* cpn_last_error(void);
 size_t cpn_sizeof_render_args(void);   /* ABI check for FFI bindings */
 
@@ -239,6 +247,21 @@ int cpn_pose_head(const cpn_pose_head_args* args, void* stream);
 int cpn_prof_begin(int max_launches);
 int cpn_prof_end(float* total_ms, int* launches);
 
+/* The epipolar feature gather alone (for unit tests): F.grid_sample(bilinear, align_corners=False) of the four channels-last
+ * maps in a->feat at the coordinates of `rowaux` (rows, 8) = [gx, gy of the primary branch ('border' padding, view v of the
+ * row), gx, gy of the secondary branch ('zeros' padding, view 1 - v), 4 unused], rows = B * nr * 2 * S ordered
+ * ((b * nr + n) * 2 + v) * S + s  (models/CoPoNeRF.py:312,370). Only B, S and the feat* fields of `a` are read.
+ * form 0: out = fp32 rows of 848 (835 used; row index enc_row = (row / 128) * 256 + branch * 128 + row % 128);
+ * form 1 / 2: out = the operand image (K = 864) of the f16x3 / f16+f8 scheme; `taps` = cpn_gather_rows_taps_bytes(rows)
+ * bytes of scratch (forms 1, 2). Columns 832.. (tanh of the 3-D point, written by the sampling kernel) are left untouched. */
+size_t cpn_gather_rows_taps_bytes(int rows);
+int cpn_gather_rows(const cpn_render_args* a, int nr, const float* rowaux, void* out, int form, void* taps, void* stream);
+
+/* Phase trace of the tensor-core GEMM (profiling only): while a buffer is set, every launch of the single-CTA kernel
+ * writes 8 x uint64 per CTA for its first cap_ctas CTAs: globaltimer ns at CTA start, setup done, first operand stage
+ * landed, last MMA issued, accumulators ready, epilogue done, CTA end, and the SM id. Pass NULL to switch it off. */
+int cpn_gemm_tc_trace(unsigned long long* device_buf, int cap_ctas);
+
 /* ---- building blocks exported for unit tests ------------------------------------------
  * C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]); fp32 row-major, lda/ldc in floats.
  * `wt` is W transposed to [K,N] (fp32, as produced by cpn_pack_weights for SIMT layers). */
@@ -268,6 +291,8 @@ int cpn_gemm_simt_splitk(const float* A, int lda, const float* wt, const float* 
                           * M % 512 == 0); correct, but measured 20-28 % slower than independent CTAs on B200 */
 #define CPN_TC_OUT_CB16 32  /* fp32 output column-blocked: [row tile of 128][16-column block][row][16] (N = 128 layers) */
 #define CPN_TC_OUT_ROWDOT 64 /* set by cpn_gemm_tc_rowdot */
+#define CPN_TC_NO_PERSIST 256 /* operand-image GEMMs: one tile per CTA (the first kernel) instead of the persistent kernel */
+#define CPN_TC_OUT_KG 128    /* set by cpn_gemm_tc_kg */
 #define CPN_TC_CLUSTER 8 /* experiment: the N-tile CTAs of a row tile form a cluster and multicast the A operand
                           * (halves L2 reads, but measured 8-18 % slower than independent CTAs on B200) */
 int cpn_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, int ldc, int M, int relu, int mode,
@@ -277,6 +302,16 @@ int cpn_gemm_tc(const void* packed, int layer, const void* A, int lda, void* C, 
  * key_map_2 / query_repeat_embed_2 followed by the einsum('bijk,bijk->bjk') / 11.31 of models/CoPoNeRF.py:450,474. */
 int cpn_gemm_tc_rowdot(const void* packed, int layer, const void* A, int lda, const float* dotv_cb16, float* out, int M,
                        int relu, int mode, float div, void* stream);
+
+/* Layer 10 = [key_map ; G] o query_encode_latent_2 over the hidden-layer operand image (K = 1664, N = 256), M sample rows:
+ *   logits[m] = (<relu(WKF h_m + bKF), dotv[m, :]> + rowadd[m]) / div      round-1 logit (models/CoPoNeRF.py:408,450)
+ *   gh[m, :]  = G h_m + g0   (M rounded up to 128, 128) fp32 column-blocked [row tile of 128][8 blocks][128 rows][16]:
+ *               the per-row term of the round-2 query bias. G folds latent_value,
+ *               encode_latent and the z_embed columns of query_repeat_embed (models/CoPoNeRF.py:404,463-472, all linear),
+ *               so that query_repeat_embed's per-ray bias is sum_rows w1[m] gh[m, :] and the round-1 readout is never formed.
+ * dotv is CB16 with `dot_blocks` 16-column blocks per row tile, of which blocks 0..7 are used. */
+int cpn_gemm_tc_kg(const void* packed, const void* h1_image, const float* dotv_cb16, int dot_blocks, const float* rowadd,
+                   float div, float* logits, float* gh, int M, int mode, void* stream);
 
 #ifdef __cplusplus
 }

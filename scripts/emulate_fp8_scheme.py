@@ -1,6 +1,11 @@
 """CPU emulation of candidate tensor-core precision schemes inside the oracle, against the reference goldens.
    scheme 'f16x3' : a_hi*w_hi + a_hi*w_lo + a_lo*w_hi   (what gemm_tc does today)
-   scheme 'f16+f8': a_hi*w_hi (fp16) + e4m3(a_lo 2^p)*e4m3(w_hi 2^-p) + e4m3(a_hi 2^-q)*e4m3(w_lo 2^q)
+   scheme 'f16+f8': a_hi*w_hi (fp16) + e5m2(a_lo 2^p)*e4m3(w_hi 2^-p) + e5m2(a_hi 2^-q)*e4m3(w_lo 2^q)   (the default: p = 10, q = 0,
+                    weights scaled to max |w| in [2^14, 2^15))
+   scheme 'e4m3'  : the first version of that scheme, e4m3 activation planes (p = 8, q = 6, weights to 2^10): narrow range
+Also prints the worst-row error of one K = 832 layer for inputs scaled by 1e-3 ... 3e4 (the robustness case of ADVICE.md).
+
+    python scripts/emulate_fp8_scheme.py [f16+f8 | e4m3 | f16x3 | f16] [p] [q] [log2 weight scale]
 """
 import glob, os, sys
 import numpy as np, torch
@@ -12,16 +17,19 @@ from oracle import render_oracle
 
 BIG = {"query_encode_latent", "query_encode_latent_2", "latent_value", "key_map", "key_map_2", "query_embed_2", "query_repeat_embed_2"}
 f8 = lambda t: t.to(torch.float8_e4m3fn).to(torch.float32)
+e5 = lambda t: t.clamp(-57344, 57344).to(torch.float8_e5m2).to(torch.float32)
 SCHEME = sys.argv[1] if len(sys.argv) > 1 else "f16+f8"
-P = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-Q = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+OLD = SCHEME == "e4m3"
+P = int(sys.argv[2]) if len(sys.argv) > 2 else (8 if OLD else 10)
+Q = int(sys.argv[3]) if len(sys.argv) > 3 else (6 if OLD else 0)
+WLOG = int(sys.argv[4]) if len(sys.argv) > 4 else (10 if OLD else 15)
 
 def emu(sd, name, x):
     w = sd[name + ".weight"]; w = w.reshape(w.shape[0], -1); b = sd[name + ".bias"]
     if name not in BIG:
         return torch.nn.functional.linear(x, w, b)
     m = w.abs().max().item(); e = int(np.floor(np.log2(m))) + 1
-    s = 2.0 ** (10 - e)
+    s = 2.0 ** (WLOG - e)
     ws = w * s
     w_hi = ws.half().float(); w_lo = ws - w_hi
     a_hi = x.half().float(); a_lo = x - a_hi
@@ -31,8 +39,20 @@ def emu(sd, name, x):
     elif SCHEME == "f16":
         y = mm(a_hi, w_hi)
     else:
-        y = mm(a_hi, w_hi) + mm(f8(a_lo * 2.0 ** P), f8(w_hi * 2.0 ** -P)) + mm(f8(a_hi * 2.0 ** -Q), f8(w_lo * 2.0 ** Q))
+        fa = f8 if OLD else e5
+        y = mm(a_hi, w_hi) + mm(fa(a_lo * 2.0 ** P), f8(w_hi * 2.0 ** -P)) + mm(fa(a_hi * 2.0 ** -Q), f8(w_lo * 2.0 ** Q))
     return y / s + b
+
+
+_sd = synth.render_state_dict(0)
+torch.manual_seed(21)
+_base = torch.randn(512, 832)
+_bias0 = dict(_sd); _bias0["query_encode_latent_2.bias"] = torch.zeros(416)
+for tag, A in (("x1", _base), ("x1e-3", _base * 1e-3), ("x1e3", _base * 1e3), ("rows 1e-2..1e2", _base * torch.logspace(-2, 2, 512)[:, None]),
+               ("relu x0.03", _base.relu() * 0.03), ("x3e4", _base.clamp(-2, 2) * 3e4)):
+    ref = A.double() @ _sd["query_encode_latent_2.weight"].reshape(416, 832).double().T
+    err = (emu(_bias0, "query_encode_latent_2", A).double() - ref).abs().amax(1) / ref.abs().amax(1)
+    print(f"K=832 layer, input {tag}: worst row rel err {float(err.max()):.1e}, median {float(err.median()):.1e}")
 
 render_oracle._conv = emu
 for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "render_*.npz"))):

@@ -1,0 +1,69 @@
+"""Per-tile phase trace of a tensor-core GEMM at bench size (cpn_gemm_tc_trace): where an SM's time goes.
+
+    python scripts/gemm1_trace.py [rows] [layer: 0 | 8 | 10] [persist: 1 | 0]
+"""
+import ctypes, json, os, sys
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from cases import cuda_model
+from coponerf_b200 import _lib
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 524288       # encoder rows (layer 0); layers 8 / 10 see M / 2 sample rows
+layer = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+persist = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+lib = _lib.load(); eng = cuda_model().engine()
+tiles = M // 128
+kin = {0: 27, 8: 52, 10: 52}[layer]
+A = torch.zeros((tiles // (2 if layer else 1)) * kin * 16384, dtype=torch.uint8, device="cuda")
+Av = A.view(-1, 16384)
+Av[:, :8192] = (torch.rand(Av.shape[0], 4096, device="cuda") * 4 - 2).half().view(torch.uint8)
+C = torch.empty(tiles * 26 * 16384, dtype=torch.uint8, device="cuda")
+dv = torch.randn(M // 2 * 256, device="cuda")
+gh = torch.empty(M // 2 * 128, device="cuda")
+p = lambda t: ctypes.c_void_p(t.data_ptr()); st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+rows = M if layer == 0 else M // 2
+ntn = 4 if layer == 0 else 1
+ntiles = ntn * (rows // 256)
+extra = 0 if persist else _lib.TC_NO_PERSIST
+buf = torch.zeros(ntiles * 8, dtype=torch.int64, device="cuda")
+def run():
+    if layer == 0:
+        _lib.check(lib.cpn_gemm_tc(p(eng.weights), 0, p(A), 0, p(C), 0, M, 1, _lib.TC_A_IMAGE | _lib.TC_OUT_IMAGE | extra, 1, 26, st), "gemm_tc")
+    elif layer == 10:
+        _lib.check(lib.cpn_gemm_tc_kg(p(eng.weights), p(A), p(dv), 16, None, 11.31, p(C), p(gh), rows, extra, st), "gemm_tc_kg")
+    else:
+        _lib.check(lib.cpn_gemm_tc(p(eng.weights), layer, p(A), 0, p(C), 128, rows, 1, _lib.TC_A_IMAGE | extra, 1, 1, st), "gemm_tc")
+run(); run(); torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+ev[0].record(); run(); ev[1].record(); torch.cuda.synchronize()
+lib.cpn_gemm_tc_trace(p(buf), ntiles)
+run(); torch.cuda.synchronize()
+lib.cpn_gemm_tc_trace(None, 0)
+t = buf.cpu().numpy().reshape(ntiles, 8).astype(np.float64)
+st_ = lambda v: {"mean": float(v.mean() / 1e3), "p10": float(np.quantile(v, .1) / 1e3), "p50": float(np.median(v) / 1e3), "p90": float(np.quantile(v, .9) / 1e3)}
+out = {"layer": layer, "rows": rows, "tiles": ntiles, "persistent": bool(persist), "untraced_launch_ms": ev[0].elapsed_time(ev[1])}
+if persist:
+    ncta = min(148, ntiles)
+    per = ntiles // ncta                      # complete rounds of tiles
+    tt = t[:per * ncta].reshape(per, ncta, 8)
+    out["kernel_span_us"] = float((t[:, 4].max() - tt[0, :, 0].min()) / 1e3)
+    out["ring_wait_at_tile_start_us"] = st_(tt[:, :, 1] - tt[:, :, 0])
+    out["mainloop_issue_us"] = st_(tt[:, :, 2] - tt[:, :, 1])
+    out["accum_ready_after_last_issue_us"] = st_(tt[:, :, 3] - tt[:, :, 2])
+    out["drain_us"] = st_(tt[:, :, 4] - tt[:, :, 3])
+    out["tile_period_us"] = st_(tt[1:, :, 0] - tt[:-1, :, 0])
+    out["mma_idle_between_tiles_us"] = st_(tt[1:, :, 0] - tt[:-1, :, 2])
+else:
+    t0 = t[:, 0].min()
+    out["kernel_span_us"] = float((t[:, 6].max() - t0) / 1e3)
+    for k, (a, b) in {"setup": (0, 1), "first_stage_wait": (1, 2), "mainloop_issue": (2, 3), "accum_ready_after_last_issue": (3, 4),
+                      "drain": (4, 5), "exit": (5, 6), "cta_total": (0, 6)}.items():
+        out[k + "_us"] = st_(t[:, b] - t[:, a])
+    sm = t[:, 7].astype(int)
+    gaps = []
+    for s in np.unique(sm):
+        a = t[sm == s]; a = a[np.argsort(a[:, 0])]
+        gaps += list(a[1:, 0] - a[:-1, 6])
+    out["gap_between_ctas_us"] = st_(np.array(gaps))
+print(json.dumps(out, indent=1))

@@ -42,8 +42,9 @@ def to_device(obj, dev):
 
 
 SENS_KEYS = ("rgb", "at_wt", "depth_ray", "T_to_C1_pts", "T_to_C2_pts", "C2_pts_to_C1")
-SENS_FACTOR = 8.0      # four 1-ulp perturbation samples understate the worst case by a few x (measured: <= 4)
+SENS_FACTOR = 4.0      # four perturbation samples understate the worst case by a few x (measured on B200: <= 4)
 SENS_FLOOR = 1e-6      # rays whose reference output moves less than this (relative) get the plain gate
+PARITY_LOG = []        # one line per (case, key) with the raw error statistics; printed by conftest.py at the end of a run
 
 
 def per_ray(d, key):
@@ -106,7 +107,7 @@ def run_cuda(H, W, n_rays, S, seed, val, chunk_rays=2048, pose=None, batch=1, fl
     return {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
 
 
-def check_against(out, ref, tag, tol=GPU_TOL):
+def check_against(out, ref, tag, tol=GPU_TOL, min_stable=0.5):
     """Float outputs within `tol` (relative to max|ref|); integer / boolean outputs exact up to float-noise ties.
 
     The reference is ill-conditioned on a minority of rays: triangulating near-parallel rays amplifies
@@ -124,13 +125,23 @@ def check_against(out, ref, tag, tol=GPU_TOL):
             err = per_ray(a.astype(np.float64) - b.astype(np.float64), k)
             allowed = t * scale + SENS_FACTOR * np.maximum(0.0, sens - SENS_FLOOR * scale)
             bad = err > allowed
+            # raw statistics next to the gate: how large the error really is, how many rays sit on a widened gate and how
+            # many of them needed it (error above the plain gate)
+            widened = allowed > 2.0 * t * scale
+            needed = err > t * scale
+            PARITY_LOG.append(f"{tag}:{k} max {(err / scale).max():.2e} p99 {np.quantile(err / scale, 0.99):.2e} "
+                              f"median {np.median(err / scale):.2e} (gate {t:.0e}); rays with gate > 2x plain "
+                              f"{widened.mean():.4f}, rays above the plain gate {needed.mean():.4f}")
             assert not bad.any(), (f"{tag}:{k} {int(bad.sum())} rays over the gate; worst err/scale "
                                    f"{(err / scale).max():.3e}, worst excess {(err - allowed).max() / scale:.3e}")
-            if k == "rgb":   # the plain gate must cover most of the image, or the case is a poor test
+            # the widening is an allowance for a minority: at most 5 % of the rays may need it at all
+            assert needed.mean() <= 0.05, f"{tag}:{k} {needed.mean():.3f} of the rays are above the plain gate {t}"
+            if k == "rgb" and min_stable is not None:   # the plain gate must cover most of the image, or the case is a poor test
                 stable = sens <= SENS_FLOOR * scale
-                assert stable.mean() > 0.4, f"{tag}: only {stable.mean():.2f} of the rays are well-conditioned"
+                assert stable.mean() >= min_stable, f"{tag}: only {stable.mean():.2f} of the rays are well-conditioned"
         else:
             e = rel_err(a, b)
+            PARITY_LOG.append(f"{tag}:{k} max {e:.2e} (gate {t:.0e})")
             assert e <= t, f"{tag}:{k} rel err {e:.3e} > {t}"
     # argmax of the round-1 weights: may differ only where the top two reference weights tie within noise
     am, gm, w = get(out, "at_wt_max"), get(ref, "at_wt_max"), get(ref, "at_wt")

@@ -15,3 +15,15 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Raw parity statistics of every check_against call of the run (tests/cases.py), next to the pass/fail line."""
+    try:
+        from cases import PARITY_LOG
+    except ImportError:
+        return
+    if PARITY_LOG:
+        terminalreporter.section("parity statistics (error / max|reference|)")
+        for line in PARITY_LOG:
+            terminalreporter.write_line(line)

@@ -56,3 +56,33 @@ def test_bilinear_logits_equal_the_two_layer_dot_product():
         WM, BM, WS, CS = Wa.T @ Wq, Wa.T @ bq, Wq.T @ ba, ba @ bq        # bilinear_fold_kernel
         got = (k * (q @ WM.T + BM)).sum(-1) + q @ WS + CS
         assert torch.allclose(ref, got, rtol=1e-12, atol=1e-12)
+
+
+def test_round2_query_bias_is_a_linear_map_of_the_hidden_layer_and_one_readout_gives_z():
+    """latent_value, encode_latent and the z_embed columns of query_repeat_embed have no activation between them
+    (CoPoNeRF.py:404,463-472), so the per-ray bias of round 2 is sum_rows w1 (G h + g0) with G = Wqr[:, :128] We WVF
+    (weights.cu: gfold_kernel), and z = R2 + 2 R1 = WVF sum_rows (w2 + 2 w1) h + 3 b."""
+    sd = synth.render_state_dict(0)
+    W2, b2 = _w(sd, "query_encode_latent_2")
+    Wv, bv = _w(sd, "latent_value")
+    We, be = _w(sd, "encode_latent")
+    Wqr, bqr = _w(sd, "query_repeat_embed")
+    WVF = torch.cat((Wv[:, :416] @ W2, Wv[:, 416:] @ W2), dim=1)
+    bVF = bv + Wv[:, :416] @ b2 + Wv[:, 416:] @ b2
+    g = torch.Generator().manual_seed(3)
+    h = torch.rand(128, 1664, generator=g, dtype=torch.float64)
+    w1 = torch.softmax(torch.randn(128, generator=g, dtype=torch.float64) * 4, 0)
+    w2 = torch.softmax(torch.randn(128, generator=g, dtype=torch.float64) * 4, 0)
+    local = torch.rand(128, 16, generator=g, dtype=torch.float64)
+    V = h @ WVF.T + bVF
+    R1 = w1 @ V                                                             # CoPoNeRF.py:456-461
+    z_embed = We @ R1 + be                                                  # :467
+    q2_ref = torch.relu(torch.cat((z_embed.expand(128, 128), local), dim=1) @ Wqr.T + bqr)   # :468-473
+    G = Wqr[:, :128] @ We @ WVF
+    g0 = Wqr[:, :128] @ (We @ bVF + be) + bqr
+    rbias = w1 @ (h @ G.T + g0)
+    q2 = torch.relu(local @ Wqr[:, 128:].T + rbias)
+    assert torch.allclose(q2_ref, q2, rtol=1e-11, atol=1e-11)
+    R2 = w2 @ V
+    z = ((w2 + 2 * w1) @ h) @ WVF.T + 3 * bVF
+    assert torch.allclose(R2 + 2 * R1, z, rtol=1e-11, atol=1e-11)

@@ -97,13 +97,13 @@ def test_get_z_matches_reference_golden_and_cpu_restatement(model, golden):
     inp = _inp()
     z, rel_pose, flow = model.get_z(to_device(inp, "cuda:0"))
     torch.cuda.synchronize()
-    check_pair_outputs(z, rel_pose, flow, golden, tol_z=5e-5, tol_pose=5e-5)
+    check_pair_outputs(z, rel_pose, flow, golden, tol_z=1e-5, tol_pose=1.5e-5, tol_flow_px=1e-3)   # measured 2e-6 / 2-4e-6 / 5e-5 px
     zr, pr, fr = pair_oracle.get_z(synth.full_state_dict(CASE["weights_seed"]), inp, fast_pos=True)
     for a, b in zip(z, zr):         # every element, not only the golden's strided sample
-        _close(a, b, tol=5e-5)
-    assert (rel_pose.cpu() - pr).abs().max() <= 5e-5
+        _close(a, b, tol=1e-5)
+    assert (rel_pose.cpu() - pr).abs().max() <= 1.5e-5
     for i, (a, b) in enumerate(zip(flow, fr)):
-        assert (a.cpu() - b).abs().max() <= 2e-3 * (64.0 if i < 2 else 2.0)
+        assert (a.cpu() - b).abs().max() <= 1e-3 * (1.0 if i < 2 else 1.0 / 32.0), (i, float((a.cpu() - b).abs().max()))
     assert model._ufc_ops.launches > 400          # the native operators ran (no library / eager fallback)
 
 
@@ -118,7 +118,7 @@ def test_get_z_accepts_host_input_and_batches(model):
         _close(a[2:4], b.cpu(), tol=2e-5)
     assert (p2[1] - p1[0]).abs().max() <= 2e-5
     for i, (a, b) in enumerate(zip(f2, f1)):
-        assert (a[1] - b[0]).abs().max() <= 2e-3 * (64.0 if i < 2 else 2.0)
+        assert (a[1] - b[0]).abs().max() <= 1e-3 * (1.0 if i < 2 else 1.0 / 32.0)
 
 
 def test_full_forward_matches_reference_golden(model, golden):
@@ -126,12 +126,14 @@ def test_full_forward_matches_reference_golden(model, golden):
     out = model(_inp(), val=True)
     torch.cuda.synchronize()
     assert tuple(out["rgb"].shape) == golden["rgb"].shape
-    scale = np.abs(golden["rgb"]).max()
-    err = np.abs(out["rgb"].cpu().numpy() - golden["rgb"]).max(axis=-1)[0, 0] / scale
-    # the reference is ill-conditioned on a minority of rays: gate the bulk at 1e-4
-    assert np.median(err) <= 5e-5 and np.quantile(err, 0.9) <= 3e-4, (np.median(err), np.quantile(err, 0.9), err.max())
+    # every ray gated: 1e-4 where the reference is stable against get_z-level input noise, widened by its own measured
+    # per-ray sensitivity elsewhere (tests/golden/add_pair_sens.py); exact masks, integer outputs exact up to ties
+    from cases import GPU_TOL, check_against
+    host = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+    tol = dict(GPU_TOL, rel_pose_flip=1e-5, pixel_val=1e-4, coords=1e-5)   # view 2 uses the ESTIMATED pose (4e-6 abs)
+    check_against(host, golden, "pair_256/full-forward", tol=tol, min_stable=None)
     assert np.array_equal(out["valid_mask"].cpu().numpy(), golden["valid_mask"])
-    assert np.abs(out["rel_pose"].cpu().numpy() - golden["rel_pose"]).max() <= 5e-5
+    assert np.abs(out["rel_pose"].cpu().numpy() - golden["rel_pose"]).max() <= 1e-5
     assert len(out["z"]) == 4 and len(out["flow"]) == 4
 
 

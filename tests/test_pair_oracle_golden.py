@@ -26,16 +26,17 @@ def case():
     return sd, inp
 
 
-def check_pair_outputs(z, rel_pose, flow, golden, tol_z=2e-5, tol_pose=2e-5, tol_flow=2e-3):
-    """z relative to max|ref|, rel_pose absolute, flows in units of the 64-pixel grid (flow[0:2]) / [-1, 1] (flow[2:4])."""
+def check_pair_outputs(z, rel_pose, flow, golden, tol_z=2e-6, tol_pose=1e-5, tol_flow_px=1e-4):
+    """z relative to max|ref|, rel_pose absolute, flows in pixels of the 64-pixel grid (flow[2:4] live in [-1, 1]: 1 px = 1/32).
+    Defaults are for CPU restatements (measured 4e-7 / 2e-6 / 1.3e-5 px); the CUDA path passes its own (tests/test_pair_gpu.py)."""
     for i, (t, (sc, sy, sx)) in enumerate(zip(z, Z_STRIDE)):
         a, b = t[:, ::sc, ::sy, ::sx].cpu().numpy(), golden[f"z{i}"]
         assert a.shape == b.shape
         assert np.abs(a - b).max() <= tol_z * np.abs(b).max(), (i, np.abs(a - b).max(), np.abs(b).max())
     assert np.abs(rel_pose.cpu().numpy() - golden["rel_pose"]).max() <= tol_pose
     for i, f in enumerate(flow):
-        scale = 64.0 if i < 2 else 2.0
-        assert np.abs(f.cpu().numpy() - golden[f"flow{i}"]).max() <= tol_flow * scale, i
+        px = 1.0 if i < 2 else 1.0 / 32.0
+        assert np.abs(f.cpu().numpy() - golden[f"flow{i}"]).max() <= tol_flow_px * px, (i, np.abs(f.cpu().numpy() - golden[f"flow{i}"]).max())
 
 
 def test_pair_oracle_matches_reference_golden(case, golden):
@@ -56,6 +57,11 @@ def test_positional_encodings_loop_equals_batched():
     assert torch.allclose(slow, fast, atol=1e-6, rtol=1e-6)
     assert torch.allclose(slow, ours, atol=1e-6, rtol=1e-6)
     assert pose_native.positional_encodings(1, 4096, intr) is ours      # memoised by value
+    # the closed-form variant that runs on the device without reading the intrinsics back (same formula, CPU tensors here)
+    K = synth.make_input(256, 256, 8, seed=7, pose_set="mild", batch=2)["context"]["intrinsics"]
+    host = pose_native.positional_encodings_for(K, 4096, 256)
+    closed = pose_native._positional_encodings_device(K[:, 0].float(), 4096, 256, None)
+    assert torch.allclose(host, closed, atol=1e-6, rtol=1e-6)
 
 
 def test_product_orchestration_on_torch_ops_matches_golden(case, golden):
@@ -67,7 +73,7 @@ def test_product_orchestration_on_torch_ops_matches_golden(case, golden):
     m = CoPoNeRF(n_view=2).eval()
     m.load_state_dict(sd, strict=True)          # every one of the 744 reference keys, nothing else
     z, rel_pose, flow = pair_stage.get_z(m, inp, TorchOps())
-    check_pair_outputs(z, rel_pose, flow, golden)
+    check_pair_outputs(z, rel_pose, flow, golden, tol_z=6e-6)     # folded BatchNorm + a different op order: 2.1e-6 measured
     assert (m.H, m.W) == (256, 256)
 
 
@@ -87,5 +93,7 @@ def test_pipeline_oracle_matches_reference_golden(case, golden):
     out = render_oracle.render_forward(sd, inp, z, rel_pose, flow, CASE["H"], CASE["W"], 64, True)
     scale = np.abs(golden["rgb"]).max()
     err = np.abs(out["rgb"].numpy() - golden["rgb"]).max(axis=-1)[0, 0] / scale
-    assert np.median(err) <= 2e-5 and np.quantile(err, 0.9) <= 1e-3, (np.median(err), np.quantile(err, 0.9), err.max())
+    # every ray gated by the reference's own measured sensitivity to get_z-level input noise (tests/golden/add_pair_sens.py)
+    allowed = 1e-4 + 4.0 * golden["rgb_sens"][0] / scale
+    assert (err <= allowed).all() and np.median(err) <= 2e-5, (np.median(err), err.max(), (err / allowed).max())
     assert np.array_equal(out["valid_mask"].numpy(), golden["valid_mask"])

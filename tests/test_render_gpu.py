@@ -351,3 +351,86 @@ def test_three_layer_logit_path_matches_reference_golden(case):
     H, W, n_rays, S, seed, val = [int(v) for v in g["meta"]]
     out = run_cuda(H, W, n_rays, S, seed, val, flags=16)
     check_against(out, g, case + "/no-bilinear")
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_per_ray_chain_path_matches_reference_golden(case):
+    """CPN_FLAG_NO_GFOLD: round-1 readout, latent_value per ray, encode_latent and the z half of query_repeat_embed as
+    separate steps (the default folds them into a 128-wide per-row term next to the key hidden layer and reads the hidden
+    layer out once with the weights w2 + 2 w1)."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, case + ".npz")))
+    H, W, n_rays, S, seed, val = [int(v) for v in g["meta"]]
+    out = run_cuda(H, W, n_rays, S, seed, val, flags=32)
+    check_against(out, g, case + "/no-gfold")
+
+
+@pytest.mark.parametrize("scheme", [0, 4], ids=["f16+f8", "f16x3"])
+def test_gemm_tc_key_and_round2_bias_layer(scheme):
+    """Layer 10 = [key_map ; G] o query_encode_latent_2 over the hidden image (cpn_gemm_tc_kg): the key tile leaves as the
+    round-1 logit, the G tile as fp32 rows G h + g0, against the layer-by-layer chain of CoPoNeRF.py:393-408,463-472 in
+    fp64 (G h + g0 = query_repeat_embed's z_embed columns applied to encode_latent(latent_value(.)))."""
+    from coponerf_b200 import _lib
+    lib, eng, W1, b1 = _tc_setup("query_encode_latent")
+    _, _, W2, b2 = _tc_setup("query_encode_latent_2")
+    _, _, WV, bV = _tc_setup("latent_value")
+    _, _, WK, bK = _tc_setup("key_map")
+    _, _, WE, bE = _tc_setup("encode_latent")
+    _, _, WQR, bQR = _tc_setup("query_repeat_embed")
+    torch.manual_seed(13)
+    R = 700
+    Rp = (R + 127) // 128 * 128
+    x = torch.randn(2, R, 835, device="cuda")
+    A = torch.zeros(2 * Rp, 848, device="cuda")
+    rows = torch.arange(R, device="cuda")
+    for br in range(2):
+        A[(rows // 128) * 256 + br * 128 + rows % 128, :835] = x[br]
+    chunk = _lib.ACT_CHUNK_BYTES
+    H1 = torch.empty(2 * Rp // 128 * 26 * chunk, dtype=torch.uint8, device="cuda")
+    w = _p(eng.weights)
+    _lib.check(lib.cpn_gemm_tc(w, 0, _p(A), 848, _p(H1), 0, 2 * Rp, 1, _lib.TC_OUT_IMAGE | scheme, 1, 26, _st()), "gemm1")
+    # dotv: CB16 with 16 blocks per row tile (as the bilinear-logit layer writes it), blocks 0-7 used
+    dv = torch.randn(Rp, 256, device="cuda")
+    dv_cb = dv.view(Rp // 128, 128, 16, 16).permute(0, 2, 1, 3).contiguous()
+    rowadd = torch.randn(Rp, device="cuda")
+    lg = torch.full((Rp,), float("nan"), device="cuda")
+    gh = torch.full((Rp, 128), float("nan"), device="cuda")
+    _lib.check(lib.cpn_gemm_tc_kg(w, _p(H1), _p(dv_cb), 16, _p(rowadd), 11.31, _p(lg), _p(gh), R, scheme, _st()), "kg")
+    lin = torch.nn.functional.linear
+    h = lin(x.double(), W1.double(), b1.double()).relu()
+    e = lin(h, W2.double(), b2.double())
+    cat = torch.cat((e[0], e[1]), dim=-1)
+    k1 = lin(cat, WK.double(), bK.double()).relu()
+    ref_lg = ((k1 * dv[:R, :128].double()).sum(-1) + rowadd[:R].double()) / 11.31
+    v = lin(cat, WV.double(), bV.double())
+    ref_gh = lin(lin(v, WE.double(), bE.double()), WQR[:, :128].double(), bQR.double())
+    gh_rows = gh.view(Rp // 128, 8, 128, 16).permute(0, 2, 1, 3).reshape(Rp, 128)      # column-blocked -> rows
+    e1, e2 = rel_err(lg[:R].cpu().numpy(), ref_lg.cpu().numpy()), rel_err(gh_rows[:R].cpu().numpy(), ref_gh.cpu().numpy())
+    print(f"layer 10 scheme={scheme}: logit rel err {e1:.2e}, G h + g0 rel err {e2:.2e}")
+    assert e1 < (2e-5 if scheme == 4 else 1e-4) and e2 < (2e-5 if scheme == 4 else 1e-4), (e1, e2)
+
+
+@pytest.mark.parametrize("scheme", [0, 4], ids=["f16+f8", "f16x3"])
+def test_gemm_tc_activation_scale_robustness(scheme):
+    """The split-precision schemes must hold fp32-level accuracy over the dynamic range a trained checkpoint can produce, not
+    only for O(1) activations: whole input scaled by 1e-3 and 1e3, and one matrix whose rows span 1e4 in magnitude. The error
+    of a row is judged against that row's own output scale."""
+    from coponerf_b200 import _lib
+    lib, eng, Wm, bias = _tc_setup("query_encode_latent_2")
+    N, K = Wm.shape
+    torch.manual_seed(21)
+    M = 512
+    base = torch.randn(M, K, device="cuda")
+    ramp = torch.logspace(-2, 2, M, device="cuda")[:, None]
+    worst = {}
+    for tag, A in (("x1", base), ("x1e-3", base * 1e-3), ("x1e3", base * 1e3), ("rows 1e-2..1e2", base * ramp),
+                   ("relu x0.03", base.relu() * 0.03)):
+        A = A.contiguous()
+        C = torch.full((M, N), float("nan"), device="cuda")
+        _lib.check(lib.cpn_gemm_tc(_p(eng.weights), 1, _p(A), K, _p(C), N, M, 0, scheme, 1, 1, _st()), "cpn_gemm_tc")
+        ref = A.double() @ Wm.double().t()          # without the bias: it would mask the error of small rows
+        got = C.double() - bias.double()
+        err = (got - ref).abs().amax(dim=1) / ref.abs().amax(dim=1)
+        worst[tag] = float(err.max())
+        print(f"gemm_tc scheme={scheme} {tag}: worst row rel err {worst[tag]:.2e}, median {float(err.median()):.2e}")
+    for tag, e in worst.items():
+        assert e < 6e-5, (tag, e, worst)      # measured / emulated: 2.5e-5 (f16+f8), 3e-5 at x1e-3 (f16x3: fp16 subnormal remainders)

@@ -1,5 +1,5 @@
-"""ufc_forward (the host orchestration around the native closing stage) against the unmodified reference
-UFC.forward, on CPU with the oracle standing in for the CUDA tail. Needs /root/reference (build container only)."""
+"""The state_dict-driven orchestration of the cost aggregation (coponerf_b200/ufc_native.py, with the PyTorch operator set)
+and the independent oracle against the unmodified reference UFC.forward on CPU. Needs /root/reference (build container only)."""
 import os
 import sys
 
@@ -7,34 +7,6 @@ import pytest
 import torch
 
 REF = os.environ.get("COPONERF_REFERENCE", "/root/reference")
-
-
-@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
-def test_ufc_forward_matches_reference_module():
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
-    from make_goldens import import_reference
-    import_reference()
-    from models.aggregation import UFC
-    from coponerf_b200.ufc import ufc_forward
-    from oracle import conv4d_oracle, ufc_oracle
-
-    def conv_block(x, wq, bq, ws, bs, gamma, beta, stride, pad):
-        return conv4d_oracle.encoder4d_layer(x, dict(wq=wq, bq=bq, ws=ws, bs=bs, gamma=gamma, beta=beta), stride, pad)
-    torch.manual_seed(0)
-    fca = UFC().eval()
-    g = torch.Generator().manual_seed(3)
-    feat = [torch.randn(2, 512, 16, 16, generator=g), torch.randn(2, 256, 32, 32, generator=g),
-            torch.randn(2, 128, 64, 64, generator=g)]
-    with torch.no_grad():
-        ref_feats, ref_flows, ref_c = fca(feat, 2)
-        got_feats, got_flows, got_c = ufc_forward(fca, feat, 2, tail=ufc_oracle.ufc_tail, conv_block=conv_block,
-                                                      attention=ufc_oracle.linear_attention)
-    assert all('forward' not in m.__dict__ for m in fca.modules())   # patches removed
-    for a, b in zip(got_feats, ref_feats):
-        assert a.shape == b.shape and torch.allclose(a, b, atol=1e-5, rtol=1e-5)
-    assert got_c.shape == ref_c.shape and (got_c - ref_c).abs().max() <= 1e-5
-    for a, b in zip(got_flows, ref_flows):
-        assert a.shape == b.shape and (a - b).abs().max() <= 1e-3 * 64
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
