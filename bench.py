@@ -1,26 +1,33 @@
 #!/usr/bin/env python
 """Rendered rays/s of the CoPoNeRF render path (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--config 2|4]
 
-Workload (BASELINE.json configs[1]): one RealEstate10K-shape 256x256 stereo pair, all 65 536 target rays,
-S = 64 samples per epipolar line; at N > 1 one such pair per rank (configs[2]: pairs shard across ranks,
-one NCCL gather of the final pixels to rank 0, weak scaling). A "step" (default `--stage full`) is the whole
-drop-in call on one pair, images in, pixels out: get_z() (ResNet-34 encoder + conv_map in PyTorch/cuDNN, which
-BASELINE.json says stays; cost aggregation, pose features and pose head on the sm_100a operators) followed by
-forward(val=True) over every ray with the estimated pose. `--stage pair` starts from the encoder's feature pyramid
-(cost aggregation + render), `--stage render` times the render half alone (z, rel_pose, flow given).
+Workloads (BASELINE.json `configs`):
+  N = 1   configs[1]: one RealEstate10K-shape 256x256 stereo pair, all 65 536 target rays, S = 64 samples per line.
+  N > 1   configs[2]: a batch of 8 such pairs sharded over the ranks (8 / N pairs per rank, no data-path collective), one
+          NCCL gather of the final pixels to rank 0. The total work is fixed, so the line says "scaling": "strong"; the rate
+          (rays/s) is directly comparable with the N = 1 line. The line also carries "strong": ONE pair with its rays
+          sharded over the N ranks (coponerf_b200/dist.py: get_z on rank 0, one broadcast of its outputs, one all-gather of
+          rgb), the curve that can bend (SURVEY.md section 8(e) case 2), with a bit-exact check against the 1-GPU render.
+  --config 4   configs[3]: 512x512 pair, S = 128, 262 144 rays, cost aggregation at feature sizes 32 / 64 / 128 with a
+          128^4 correlation volume (`--stage pair`: the encoder / pose head of get_z are hard-wired to 256x256 in the reference).
+A "step" (default `--stage full`) is the whole drop-in call on one batch, images in, pixels out: get_z() (ResNet-34 encoder
++ conv_map in PyTorch/cuDNN, which BASELINE.json says stays; cost aggregation, pose features and pose head on the sm_100a
+operators) followed by forward(val=True) over every ray with the estimated pose. `--stage pair` starts from the encoder's
+feature pyramid (cost aggregation + render), `--stage render` times the render half alone (z, rel_pose, flow given).
 
 `value`  : inputs resident in HBM, timed on the device with CUDA events, L2 flushed between steps.
-`e2e`    : the same through the drop-in forward() with HOST inputs: pinned host -> device copies of the
-           feature maps / poses / uv and the device -> host read of rgb (+ the reference's pixel_val.cpu())
-           are inside the timed region.
-`--impl reference`: the CPU oracle port of the reference path (oracle/render_oracle.py, torch CPU, all host
-           threads) on a bounded sample of the same workload; rank 0 only.
+`e2e`    : the same through the drop-in forward() with HOST inputs: pinned host -> device copies of the images / poses / uv
+           and the device -> host read of rgb (+ the reference's pixel_val.cpu()) are inside the timed region.
+`--impl reference`: the reference path on the host cores, rank 0 only: the unmodified reference when a checkout is present
+           (COPONERF_REFERENCE or baseline/_ref: models/CoPoNeRF.py driven through the three import shims), else the CPU
+           oracle port (oracle/render_oracle.py + oracle/pair_oracle.py), on a bounded sample of the same workload.
 """
 import argparse
 import ctypes
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -37,6 +44,25 @@ N_RAYS = H * W
 FLOP_PER_RAY = 667.9e6                    # reference formulation, S = 64
 DOMINANT_MACS_PER_ROW = 835 * 832         # query_encode_latent, one encoder row
 CPU_SAMPLE_RAYS = 1024
+BATCH_PAIRS = 8                           # BASELINE config 3: batch-8 pairs over the GPUs of one box
+UFC_SIZES = (16, 32, 64)                  # feature sizes of the cost aggregation at 256 x 256
+UFC_MIN_BYTES = 135e6                     # weights + features in + c + features out per pair at 256 x 256
+CONFIG = 2
+
+
+def set_config(cfg):
+    """BASELINE config 2 (default: 256 x 256, S = 64, 65 536 rays) or config 4 (512 x 512, S = 128, 262 144 rays,
+    cost aggregation at feature sizes 32 / 64 / 128 with a 128^4 correlation volume)."""
+    global H, W, S, N_RAYS, FLOP_PER_RAY, CPU_SAMPLE_RAYS, UFC_SIZES, UFC_MIN_BYTES, CONFIG
+    CONFIG = cfg
+    if cfg == 4:
+        H = W = 512
+        S = 128
+        N_RAYS = H * W
+        FLOP_PER_RAY = 1334.8e6           # SURVEY.md 8(d), S = 128
+        CPU_SAMPLE_RAYS = 256
+        UFC_SIZES = (32, 64, 128)
+        UFC_MIN_BYTES = 1.2e9             # SURVEY.md 8(d): c alone is 1.07 GB
 
 
 def parse():
@@ -45,25 +71,55 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4], help="BASELINE config: 2 = 256x256 / S=64 (default), "
+                    "4 = 512x512 / S=128 / 128^4 cost volume (implies --stage pair)")
     ap.add_argument("--chunk-rays", type=int, default=2048)
     ap.add_argument("--lanes", type=int, default=2, help="chunks in flight on internal streams")
     ap.add_argument("--simt", action="store_true", help="fp32 CUDA-core GEMMs only (cross-check path)")
     ap.add_argument("--no-fold", action="store_true", help="keep query_encode_latent_2 / latent_value / key_map as three GEMMs")
     ap.add_argument("--early-v", action="store_true", help="form V per sample (GEMM over all sample rows) instead of the late readout")
+    ap.add_argument("--no-gfold", action="store_true", help="per-ray chain for the round-2 query bias + two readouts")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the one-pair ray-sharded measurement")
     ap.add_argument("--eager-get-z", action="store_true", help="launch get_z()'s kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--stage", default="full", choices=["full", "pair", "render"],
                     help="full: get_z (encoder, cost aggregation, pose) + render per step; pair: cost aggregation "
                          "(UFC) + render from a given feature pyramid; render: render half only (z given)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    set_config(a.config)
+    if a.config == 4 and a.stage == "full":
+        a.stage = "pair"
+    return a
 
 
-WORKLOADS = {
-    "full": "256x256 stereo pair, 65536 rays, S=64: get_z (ResNet-34 encoder, cost aggregation, pose features + pose "
-            "head) + forward(val=True), images in, pixels out",
-    "pair": "256x256 stereo pair, 65536 rays, S=64: cost aggregation (UFC) + render; encoder and pose head outputs are inputs",
-    "render": "256x256 stereo pair, 65536 rays, S=64 (render half: forward with z given)",
-}
+def workload_name(stage):
+    head = f"{H}x{W} stereo pair, {N_RAYS} rays, S={S}"
+    return {
+        "full": head + ": get_z (ResNet-34 encoder, cost aggregation, pose features + pose head) + forward(val=True), "
+                       "images in, pixels out",
+        "pair": head + f": cost aggregation (UFC, feature sizes {'/'.join(map(str, UFC_SIZES))}) + render; encoder and pose "
+                       "head outputs are inputs",
+        "render": head + " (render half: forward with z given)",
+    }[stage]
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def reference_root():
+    """A checkout of the unmodified reference, if one is reachable (never the case on a gpurun box unless the driver put one
+    under baseline/_ref)."""
+    for p in (os.environ.get("COPONERF_REFERENCE"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if p and os.path.exists(os.path.join(p, "models", "CoPoNeRF.py")):
+            return p
+    return None
 
 
 def cpu_pair_stage(stage, seed, timings=None):
@@ -80,8 +136,9 @@ def cpu_pair_stage(stage, seed, timings=None):
         return time.perf_counter() - t0, res
     if stage == "pair":
         from oracle import ufc_forward_oracle
-        sdc, pyc = synth.ufc_state_dict(0), synth.ufc_inputs(seed)
-        ufc_forward_oracle.ufc_forward(sdc, pyc, 2)
+        sdc, pyc = synth.ufc_state_dict(0, UFC_SIZES), synth.ufc_inputs(seed, 1, UFC_SIZES)
+        if CONFIG != 4:
+            ufc_forward_oracle.ufc_forward(sdc, pyc, 2)      # warm-up (skipped at 512 x 512: one pass takes tens of seconds)
         t0 = time.perf_counter()
         ufc_forward_oracle.ufc_forward(sdc, pyc, 2)
         return time.perf_counter() - t0, None
@@ -99,8 +156,9 @@ def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "measured (bf16 dense, sustained)"
-    return 1400.0, "fallback (B200_PROFILING.md sustained)"
+        return (d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "measured (bf16 dense, sustained)",
+                d.get("hbm_gbs", 6650.0))
+    return 1400.0, "fallback (B200_PROFILING.md sustained)", 6650.0
 
 
 class ClockSampler:
@@ -151,44 +209,83 @@ class ClockSampler:
         return out
 
 
+def strided_sample(inp):
+    import torch
+    idx = torch.arange(0, N_RAYS, N_RAYS // CPU_SAMPLE_RAYS)[:CPU_SAMPLE_RAYS]
+    sub = {"context": inp["context"], "query": dict(inp["query"])}
+    sub["query"]["uv"] = inp["query"]["uv"][:, :, idx].contiguous()
+    sub["query"]["rgb"] = inp["query"]["rgb"][:, :, idx].contiguous()
+    return sub, idx
+
+
 def run_reference(args, rank):
-    """The reference arm: CPU oracle port on a bounded sample of the workload, all host threads."""
+    """The reference arm: the reference's own CPU path on a bounded sample of the workload, all host threads."""
     if rank != 0:
         return
     import torch
-    from oracle import render_oracle
     from coponerf_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     inp, z, rel_pose, flow = workload(10)
-    sd = synth.render_state_dict(0)
-    t_pair, res = cpu_pair_stage(args.stage, 10)
-    if res is not None:       # render from the restatement's own features / estimated pose / flows
-        z, rel_pose, flow = res
-    sub = {"context": inp["context"], "query": dict(inp["query"])}
-    idx = torch.arange(0, N_RAYS, N_RAYS // CPU_SAMPLE_RAYS)[:CPU_SAMPLE_RAYS]
-    sub["query"]["uv"] = inp["query"]["uv"][:, :, idx].contiguous()
-    sub["query"]["rgb"] = inp["query"]["rgb"][:, :, idx].contiguous()
+    sub, _ = strided_sample(inp)
+    ref_root = reference_root() if (args.stage == "full" and CONFIG == 2) else None
+    if ref_root is not None:
+        # the UNMODIFIED reference (models/CoPoNeRF.py) through the three import shims of SURVEY.md section 8(c)
+        os.environ["COPONERF_REFERENCE"] = ref_root
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        from make_goldens import import_reference
+        model = import_reference().CoPoNeRF(n_view=2).eval()
+        model.load_state_dict(synth.full_state_dict(0), strict=True)
+        with torch.no_grad():
+            model.get_z(inp)                                  # warm-up
+            t0 = time.perf_counter()
+            zr, pr, fr = model.get_z(inp)
+            t_pair = time.perf_counter() - t0
 
-    def step():
-        return render_oracle.render_forward(sd, sub, z, rel_pose, flow, H, W, S, True, chunk=512)
+            def step():
+                return model(sub, z=zr, rel_pose=pr, flow=fr, val=True)
+            for _ in range(args.warmup):
+                step()
+            times = []
+            for _ in range(args.steps):
+                t0 = time.perf_counter()
+                step()
+                times.append(time.perf_counter() - t0)
+        kind = "reference"
+        what = f"unmodified reference ({ref_root}: models/CoPoNeRF.py get_z + forward(val=True)), torch CPU fp32"
+    else:
+        from oracle import render_oracle
+        sd = synth.render_state_dict(0)
+        t_pair, res = cpu_pair_stage(args.stage, 10)
+        if res is not None:       # render from the restatement's own features / estimated pose / flows
+            z, rel_pose, flow = res
 
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    # whole-image rate: the per-pair work once + 65536 rays at the sampled per-ray cost
-    v = N_RAYS / (t_pair + (N_RAYS / CPU_SAMPLE_RAYS) * dt / args.steps)
-    sample = (f"{CPU_SAMPLE_RAYS} evenly strided rays of the 65536-ray image per step (chunks of 512), torch CPU fp32, "
-              f"extrapolated to the image; per-pair stage ({args.stage}) timed once ({t_pair * 1e3:.0f} ms)")
+        def step():
+            return render_oracle.render_forward(sd, sub, z, rel_pose, flow, H, W, S, True, chunk=512)
+        for _ in range(args.warmup):
+            step()
+        times = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            step()
+            times.append(time.perf_counter() - t0)
+        kind = "port"
+        what = "CPU oracle port of the reference path (oracle/), torch CPU fp32"
+    dt = sum(times) / len(times)
+    best = min(times)
+    # whole-image rate: the per-pair work once + all rays at the sampled per-ray cost
+    v = N_RAYS / (t_pair + (N_RAYS / CPU_SAMPLE_RAYS) * dt)
+    sample = (f"{what}: {CPU_SAMPLE_RAYS} evenly strided rays of the {N_RAYS}-ray image per step, mean of "
+              f"{args.steps} steps (best {best * 1e3:.0f} ms), extrapolated to the image; per-pair stage ({args.stage}) timed "
+              f"once ({t_pair * 1e3:.0f} ms)")
     line = {
         "impl": "reference", "metric": "rendered rays/sec at 256x256 stereo", "value": v, "unit": "rays/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.stage], "stage": args.stage, "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt,
+        "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.stage), "stage": args.stage, "baseline_config": CONFIG, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "cpu_model": cpu_model(), "kind": kind,
+                         "sample": sample, "best_of_steps_value": N_RAYS / (t_pair + (N_RAYS / CPU_SAMPLE_RAYS) * best)},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -209,6 +306,7 @@ def main():
     import torch
     import torch.distributed as dist
     from coponerf_b200 import _lib, synth
+    from coponerf_b200.dist import gather_rays, shard_range
     from coponerf_b200.model import CoPoNeRF
 
     if not torch.cuda.is_available():
@@ -230,8 +328,13 @@ def main():
     model.H, model.W = H, W
     eng = model.engine()
     eng.flags = (_lib.FLAG_SIMT_ONLY if args.simt else 0) | (_lib.FLAG_NO_FOLD if args.no_fold else 0) | \
-        (_lib.FLAG_EARLY_V if args.early_v else 0)
+        (_lib.FLAG_EARLY_V if args.early_v else 0) | (_lib.FLAG_NO_GFOLD if args.no_gfold else 0)
     lib = _lib.load()
+
+    # BASELINE config 3 at N > 1: a batch of 8 pairs over the ranks; config 2 / 4 at N = 1: one pair
+    ppr = max(1, BATCH_PAIRS // world) if world > 1 else 1
+    total_pairs = ppr * world
+    seeds = [10 + rank * ppr + i for i in range(ppr)]
 
     # ---- cost aggregation (per-pair stage): seeded UFC parameters and encoder pyramid
     with_ufc = args.stage == "pair"
@@ -239,80 +342,100 @@ def main():
         from coponerf_b200 import ufc_native
         from coponerf_b200.ufc_ops import CudaOps
         ufc_ops = CudaOps()
-        ufc_sd = {k: v.to(dev) for k, v in synth.ufc_state_dict(0).items()}
-        pyr_host = [t.contiguous().pin_memory() for t in synth.ufc_inputs(10 + rank)]
-        pyr_d = [t.to(dev) for t in pyr_host]
+        ufc_sd = {k: v.to(dev) for k, v in synth.ufc_state_dict(0, UFC_SIZES).items()}
+        pyr_host = [[t.contiguous().pin_memory() for t in synth.ufc_inputs(sd_, 1, UFC_SIZES)] for sd_ in seeds]
+        pyr_d = [[t.to(dev) for t in p] for p in pyr_host]
 
-    # ---- this rank's pair: host (pinned) and device copies
-    inp_h, z_h, rel_h, flow_h = workload(10 + rank)
+    # ---- this rank's pairs: host (pinned) and device copies
     pin = lambda t: t.contiguous().pin_memory()
-    host = {
-        "context": {k: pin(v) for k, v in inp_h["context"].items()},
-        "query": {k: pin(v) for k, v in inp_h["query"].items() if k != "rgb"},
-    }
-    z_host = [pin(t) for t in z_h]
-    flow_host = tuple(pin(t) for t in flow_h)
-    rel_host = pin(rel_h)
     todev = lambda t: t.to(dev, non_blocking=True)
-    inp_d = {"context": {k: todev(v) for k, v in host["context"].items()},
-             "query": {k: todev(v) for k, v in host["query"].items()}}
-    z_d = [todev(t) for t in z_host]
-    flow_d = tuple(todev(t) for t in flow_host)
-    rel_d = todev(rel_host)
-    uv_d = inp_d["query"]["uv"].reshape(1, N_RAYS, 2)
+    host, z_host, flow_host, rel_host, inp_d, z_d, flow_d, rel_d, uv_d, cpu_case = [], [], [], [], [], [], [], [], [], []
+    for sd_ in seeds:
+        inp_h, z_h, rel_h, flow_h = workload(sd_)
+        cpu_case.append((inp_h, z_h, rel_h, flow_h))
+        host.append({"context": {k: pin(v) for k, v in inp_h["context"].items()},
+                     "query": {k: pin(v) for k, v in inp_h["query"].items() if k != "rgb"}})
+        z_host.append([pin(t) for t in z_h])
+        flow_host.append(tuple(pin(t) for t in flow_h))
+        rel_host.append(pin(rel_h))
+        inp_d.append({"context": {k: todev(v) for k, v in host[-1]["context"].items()},
+                      "query": {k: todev(v) for k, v in host[-1]["query"].items()}})
+        z_d.append([todev(t) for t in z_host[-1]])
+        flow_d.append(tuple(todev(t) for t in flow_host[-1]))
+        rel_d.append(todev(rel_host[-1]))
+        uv_d.append(inp_d[-1]["query"]["uv"].reshape(1, N_RAYS, 2))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-    gather_buf = [torch.empty((1, 1, N_RAYS, 3), device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    rgb_rank = torch.empty((ppr, 1, N_RAYS, 3), device=dev)            # this rank's pixels, gathered with ONE collective
+    gather_buf = [torch.empty((ppr, 1, N_RAYS, 3), device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
     state = {}
+    ufc_events = []
+
+    def render_pair(i, inp, host_side):
+        """One pair: per-pair stage + render. Returns the output dict (device tensors)."""
+        if full:       # images -> features, estimated pose, flows -> pixels
+            if host_side:   # the call a user makes: forward(input, val=True) with z=None
+                return model(inp, val=True)
+            z, rel, flows = model.get_z(inp)
+            state["z"], state["flow"], state["rel"] = z, flows, rel
+            st = eng.prepare_pair(inp, z, rel, flows, H, W, True)
+            return eng.render_rays(st, uv_d[i], S)
+        if with_ufc:   # refined features + flows of this pair; conv_map (z[3]) comes from the encoder side
+            pyr = [todev(t) for t in pyr_host[i]] if host_side else pyr_d[i]
+            timing = state.get("time_ufc") and not host_side
+            if timing:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            feats, flows, _c = ufc_native.ufc_forward(ufc_sd, pyr, 2, ufc_ops)
+            if timing:
+                e1.record()
+                ufc_events.append((e0, e1))
+            z = feats + [todev(z_host[i][3]) if host_side else z_d[i][3]]
+            rel = todev(rel_host[i]) if host_side else rel_d[i]
+            state["z"], state["flow"] = z, flows
+            if host_side:
+                return model(inp, z=z, rel_pose=rel, val=True, flow=flows)
+            st = eng.prepare_pair(inp, z, rel, flows, H, W, True)
+            return eng.render_rays(st, uv_d[i], S)
+        if host_side:
+            return model(inp, z=[todev(t) for t in z_host[i]], rel_pose=todev(rel_host[i]), val=True,
+                         flow=tuple(todev(t) for t in flow_host[i]))
+        st = eng.prepare_pair(inp, z_d[i], rel_d[i], flow_d[i], H, W, True)
+        return eng.render_rays(st, uv_d[i], S)
 
     def device_step():
-        # feature re-layout included every step (the cache would hide it): new pair state each image
-        eng._feat_cache.clear()
-        if full:       # images -> features, estimated pose, flows -> pixels
-            z, rel, flows = model.get_z(inp_d)
-            state["z"], state["flow"], state["rel"] = z, flows, rel
-            st = eng.prepare_pair(inp_d, z, rel, flows, H, W, True)
-        elif with_ufc:   # refined features + flows of this pair; conv_map (z[3]) comes from the encoder side
-            feats, flows, _c = ufc_native.ufc_forward(ufc_sd, pyr_d, 2, ufc_ops)
-            state["z"], state["flow"] = feats + [z_d[3]], flows
-            st = eng.prepare_pair(inp_d, state["z"], rel_d, flows, H, W, True)
-        else:
-            st = eng.prepare_pair(inp_d, z_d, rel_d, flow_d, H, W, True)
-        o = eng.render_rays(st, uv_d, S)
+        o = None
+        for i in range(ppr):
+            eng._feat_cache.clear()     # feature re-layout included every step (the cache would hide it): new pair state each image
+            o = render_pair(i, inp_d[i], False)
+            if world > 1:
+                rgb_rank[i].copy_(o["rgb"][0])
         if world > 1:
-            dist.gather(o["rgb"], gather_buf, dst=0)
+            dist.gather(rgb_rank, gather_buf, dst=0)
         state["out"] = o
         return o
 
-    rgb_pinned = torch.empty((1, 1, N_RAYS, 3)).pin_memory()
+    rgb_pinned = torch.empty((ppr, 1, N_RAYS, 3)).pin_memory()
 
     def e2e_step():
-        eng._feat_cache.clear()
-        inp = {"context": {k: todev(v) for k, v in host["context"].items()},
-               "query": {k: todev(v) for k, v in host["query"].items()}}
-        if full:       # the call a user makes: forward(input, val=True) with z=None
-            out = model(inp, val=True)
-            if world > 1:
-                dist.gather(out["rgb"], gather_buf, dst=0)
-            rgb_pinned.copy_(out["rgb"], non_blocking=True)
-            return out
-        if with_ufc:
-            feats, fl, _c = ufc_native.ufc_forward(ufc_sd, [todev(t) for t in pyr_host], 2, ufc_ops)
-            z = feats + [todev(z_host[3])]
-        else:
-            z = [todev(t) for t in z_host]
-            fl = tuple(todev(t) for t in flow_host)
-        out = model(inp, z=z, rel_pose=todev(rel_host), val=True, flow=fl)
+        out = None
+        for i in range(ppr):
+            eng._feat_cache.clear()
+            inp = {"context": {k: todev(v) for k, v in host[i]["context"].items()},
+                   "query": {k: todev(v) for k, v in host[i]["query"].items()}}
+            out = render_pair(i, inp, True)
+            rgb_rank[i].copy_(out["rgb"][0])
         if world > 1:
-            dist.gather(out["rgb"], gather_buf, dst=0)
-        rgb_pinned.copy_(out["rgb"], non_blocking=True)
+            dist.gather(rgb_rank, gather_buf, dst=0)
+        rgb_pinned.copy_(rgb_rank, non_blocking=True)
         return out
 
-    h2d = sum(t.numel() * t.element_size() for d in host.values() for t in d.values())
     nbytes = lambda ts: sum(t.numel() * t.element_size() for t in ts)
+    h2d = sum(nbytes(d.values()) for d in host[0].values())
     if not full:
-        h2d += (nbytes(pyr_host) + nbytes([z_host[3]])) if with_ufc else (nbytes(z_host) + nbytes(flow_host))
-        h2d += rel_host.numel() * 4
-    d2h = N_RAYS * 3 * 4 + 2 * N_RAYS * S * 2 * 4    # rgb + the reference's out['pixel_val'].cpu()
+        h2d += (nbytes(pyr_host[0]) + nbytes([z_host[0][3]])) if with_ufc else (nbytes(z_host[0]) + nbytes(flow_host[0]))
+        h2d += rel_host[0].numel() * 4
+    h2d *= ppr
+    d2h = ppr * (N_RAYS * 3 * 4 + 2 * N_RAYS * S * 2 * 4)    # rgb + the reference's out['pixel_val'].cpu()
 
     def barrier():
         if world > 1:
@@ -353,21 +476,81 @@ def main():
     eng.lanes = 1
     device_step()
     torch.cuda.synchronize()
-    _lib.check(lib.cpn_prof_begin(chunks * prof_steps), "cpn_prof_begin")
+    _lib.check(lib.cpn_prof_begin(chunks * prof_steps * ppr), "cpn_prof_begin")
+    state["time_ufc"] = with_ufc
     ms_prof = timed(device_step, prof_steps, 0)
+    state["time_ufc"] = False
     dom_ms, dom_n = ctypes.c_float(0), ctypes.c_int(0)
     _lib.check(lib.cpn_prof_end(ctypes.byref(dom_ms), ctypes.byref(dom_n)), "cpn_prof_end")
+    ufc_ms = [a.elapsed_time(b) for a, b in ufc_events]
     eng.lanes = args.lanes
-    launches = args.steps * (eng.last_launch_count + 6)   # + 4 feature re-layouts, pair_setup, pair_prologue
+    launches = args.steps * ppr * (eng.last_launch_count + 6)   # + 4 feature re-layouts, pair_setup, pair_prologue
     if with_ufc:
-        launches += args.steps * ufc_ops.launches_per_forward
+        launches += args.steps * ppr * ufc_ops.launches_per_forward
     if full:       # cost aggregation + pose operators of one get_z (the cuDNN encoder kernels are not ours: not counted)
         model.graph_get_z = False     # counted on one eager call; the timed steps replay the same kernels from a graph
         n0 = model._ufc_ops.launches
-        model.get_z(inp_d)
-        launches += args.steps * (model._ufc_ops.launches - n0)
+        model.get_z(inp_d[0])
+        launches += args.steps * ppr * (model._ufc_ops.launches - n0)
         model.graph_get_z = not args.eager_get_z
     ms_e2e = timed(e2e_step, args.steps, 2)
+
+    # ---- N > 1: ONE pair, rays sharded over the ranks (SURVEY.md 8(e) case 2). Rank 0 runs get_z, one broadcast of a
+    # flat buffer carries z / rel_pose / flows to the others, every rank renders its slice, one all-gather of rgb.
+    strong = None
+    if world > 1 and full and not args.no_strong:
+        inp0_h, _, _, _ = workload(10)
+        inp0 = {"context": {k: v.to(dev) for k, v in inp0_h["context"].items()},
+                "query": {k: v.to(dev) for k, v in inp0_h["query"].items() if k != "rgb"}}
+        uv0 = inp0["query"]["uv"].reshape(1, N_RAYS, 2)
+        zt, relt, flt = model.get_z(inp0)                # shapes of the per-pair outputs (every rank, once)
+        shapes = [tuple(t.shape) for t in zt] + [tuple(relt.shape)] + [tuple(t.shape) for t in flt]
+        sizes = [math.prod(s) for s in shapes]
+        flat = torch.empty(sum(sizes), device=dev)
+        lo, hi = shard_range(N_RAYS, world, rank)
+
+        def strong_step():
+            eng._feat_cache.clear()
+            if rank == 0:
+                z, rel, flows = model.get_z(inp0)
+                torch.cat([t.reshape(-1) for t in list(z) + [rel] + list(flows)], out=flat)
+            dist.broadcast(flat, src=0)
+            parts = [p.view(s) for p, s in zip(flat.split(sizes), shapes)]
+            z, rel, flows = parts[:4], parts[4], tuple(parts[5:])
+            st = eng.prepare_pair(inp0, z, rel, flows, H, W, True)
+            o = eng.render_rays(st, uv0[:, lo:hi], S)
+            state["strong_rgb"] = gather_rays(o["rgb"], N_RAYS, -2)
+            return o
+
+        ms_strong = timed(strong_step, args.steps, 2)
+
+        def strong_step_redundant():     # every rank runs get_z itself (no broadcast): what SURVEY.md 8(e) proposes
+            eng._feat_cache.clear()
+            z, rel, flows = model.get_z(inp0)
+            st = eng.prepare_pair(inp0, z, rel, flows, H, W, True)
+            o = eng.render_rays(st, uv0[:, lo:hi], S)
+            state["strong_rgb_r"] = gather_rays(o["rgb"], N_RAYS, -2)
+            return o
+        ms_strong_r = timed(strong_step_redundant, args.steps, 2)
+        torch.cuda.synchronize()
+        # parity: the gathered image against a single-GPU render of the same pair on this rank, bit for bit
+        z, rel, flows = model.get_z(inp0)
+        st = eng.prepare_pair(inp0, z, rel, flows, H, W, True)
+        single = eng.render_rays(st, uv0, S)["rgb"]
+        same = torch.tensor([int(torch.equal(single, state["strong_rgb_r"]))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        # the broadcast variant renders from rank 0's get_z: equal to rank 0's single-GPU render
+        same_b = torch.tensor([int(torch.equal(single, state["strong_rgb"])) if rank == 0 else 1], device=dev)
+        dist.all_reduce(same_b, op=dist.ReduceOp.MIN)
+        strong = {"workload": "ONE 256x256 pair, 65536 rays sharded over the ranks: get_z on rank 0 + one broadcast of z / "
+                              "rel_pose / flow (%.1f MB), each rank renders its contiguous ray slice, one all-gather of rgb"
+                              % (flat.numel() * 4 / 1e6),
+                  "value": N_RAYS * args.steps / (ms_strong * 1e-3), "unit": "rays/s", "ms_per_step": ms_strong / args.steps,
+                  "redundant_get_z": {"value": N_RAYS * args.steps / (ms_strong_r * 1e-3), "ms_per_step": ms_strong_r / args.steps,
+                                      "note": "every rank runs get_z itself, no broadcast"},
+                  "bit_exact_vs_single_gpu_render": bool(same.item()) and bool(same_b.item()),
+                  "what_is_left": "get_z (encoder, cost aggregation, pose) is not sharded and sits on the critical path of "
+                                  "every step (Amdahl), plus tile quantisation of the last chunk per rank"}
     clk = clocks.stop() if clocks else None
 
     if rank != 0:
@@ -375,31 +558,39 @@ def main():
             dist.destroy_process_group()
         return
 
-    total_rays = world * N_RAYS * args.steps
+    total_rays = total_pairs * N_RAYS * args.steps
     value = total_rays / (ms_dev * 1e-3)
     e2e_value = total_rays / (ms_e2e * 1e-3)
-    peak, peak_src = peaks()
+    peak, peak_src, hbm_peak = peaks()
     rows_per_launch = 2 * 2 * S * min(args.chunk_rays, N_RAYS)       # encoder rows: 2 branches x 2 views x S per ray
     flop_per_launch = 2.0 * DOMINANT_MACS_PER_ROW * rows_per_launch
     achieved = flop_per_launch * dom_n.value / (dom_ms.value * 1e-3) / 1e12 if dom_ms.value > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("simt" if args.simt else "tc")
+    if os.path.exists(tpath) and S == 64 and args.chunk_rays == 2048:
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get("simt" if args.simt else "tc"), tj.get("source")
     line = {
         "metric": "rendered rays/sec at 256x256 stereo", "value": value, "unit": "rays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.stage], "stage": args.stage, "get_z": "eager launches" if args.eager_get_z else "CUDA graph replay", "pairs_per_gpu": 1, "chunk_rays": args.chunk_rays, "lanes": args.lanes, "l2": "flushed between timed steps (256 MB write)",
-                   "gemm_path": "simt-fp32" if args.simt else "tcgen05: fp16 head + two e4m3 correction MMAs per product (fp32 accumulate)"
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.stage), "baseline_config": CONFIG if world == 1 else 3, "stage": args.stage,
+                   "get_z": "eager launches" if args.eager_get_z else "CUDA graph replay",
+                   "pairs_per_step": total_pairs, "pairs_per_gpu": ppr, "chunk_rays": args.chunk_rays, "lanes": args.lanes,
+                   "l2": "flushed between timed steps (256 MB write)",
+                   "gemm_path": "simt-fp32" if args.simt else "tcgen05: fp16 head + two fp8 correction MMAs per product (e5m2 "
+                                "activation planes, e4m3 weight planes, fp32 accumulate), persistent kernel"
                                 + ("" if args.no_fold else "; query_encode_latent_2 folded into latent_value / key_map")
-                                + ("" if (args.no_fold or args.early_v or args.simt) else "; attention reads out the hidden layer, latent_value per ray"),
-                   "parallelism": f"pairs sharded over {world} GPU(s), one NCCL gather of rgb" if world > 1 else "1 GPU"},
+                                + ("" if (args.no_fold or args.early_v or args.simt) else "; attention reads out the hidden layer, latent_value per ray")
+                                + ("" if (args.no_fold or args.early_v or args.simt or args.no_gfold) else "; round-2 query bias as a per-row linear map, one combined readout"),
+                   "parallelism": (f"batch of {total_pairs} pairs sharded over {world} GPUs ({ppr} per rank), one NCCL gather of rgb"
+                                   if world > 1 else "1 GPU")},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "query_encode_latent GEMM (835->832, ReLU)", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": traffic_src,
                      "peak_source": peak_src, "launches": dom_n.value,
                      "avg_launch_ms": dom_ms.value / max(dom_n.value, 1),
                      "share_of_step": dom_ms.value / ms_prof,
@@ -407,21 +598,28 @@ def main():
                                  f"({ms_prof / prof_steps:.1f} ms/step)",
                      "flop_per_launch": flop_per_launch,
                      "whole_path_tflops": value * FLOP_PER_RAY / 1e12 / world,
-                     # fp32 parity costs 2.0 tensor passes per product (fp16 head + two e4m3 corrections at twice the fp16
+                     # fp32 parity costs 2.0 tensor passes per product (fp16 head + two fp8 corrections at twice the fp16
                      # rate), so the reachable ceiling of this kernel is peak / 2
                      "tensor_passes_per_product": None if args.simt else 2.0,
                      "frac_of_parity_ceiling": None if args.simt else achieved / (peak / 2.0)},
         "clocks": clk,
     }
+    if strong is not None:
+        line["strong"] = strong
+    if ufc_ms:      # cost aggregation timed on the device inside the roofline pass: an HBM-bound stage
+        t_ufc = statistics.median(ufc_ms) * 1e-3
+        line["roofline_ufc"] = {"bound": "hbm", "kernel": "cost aggregation (UFC.forward), all kernels of one pair",
+                                "achieved": UFC_MIN_BYTES / t_ufc / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": UFC_MIN_BYTES / t_ufc / 1e9 / hbm_peak, "ms_per_pair": t_ufc * 1e3,
+                                "algorithmic_bytes": UFC_MIN_BYTES, "traffic": None,
+                                "launches_per_pair": ufc_ops.launches_per_forward}
 
     if world == 1 and not args.no_cpu_baseline:
         from oracle import render_oracle
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        idx = torch.arange(0, N_RAYS, N_RAYS // CPU_SAMPLE_RAYS)[:CPU_SAMPLE_RAYS]
-        sub = {"context": inp_h["context"], "query": dict(inp_h["query"])}
-        sub["query"]["uv"] = inp_h["query"]["uv"][:, :, idx].contiguous()
-        sub["query"]["rgb"] = inp_h["query"]["rgb"][:, :, idx].contiguous()
+        inp_h, z_h, rel_h, flow_h = cpu_case[0]
+        sub, idx = strided_sample(inp_h)
         sd = synth.render_state_dict(0)
         # the oracle renders from the same per-pair state the CUDA path used (the native UFC's outputs when the
         # cost aggregation is part of the step; its own parity is covered by tests/test_ufc_*_gpu.py)
@@ -429,21 +627,21 @@ def main():
         flow_cpu = tuple(t.detach().cpu() for t in state["flow"]) if (with_ufc or full) else flow_h
         rel_cpu = state["rel"].detach().cpu() if full else rel_h
         run = lambda: render_oracle.render_forward(sd, sub, z_cpu, rel_cpu, flow_cpu, H, W, S, True, chunk=512)
-        run()
-        t0 = time.perf_counter()
         ref = run()
-        t1 = time.perf_counter()
-        ref = run()
-        t2 = time.perf_counter()
-        dt = min(t1 - t0, t2 - t1)
+        ts = []
+        for _ in range(3 if CONFIG == 2 else 1):
+            t0 = time.perf_counter()
+            ref = run()
+            ts.append(time.perf_counter() - t0)
+        dt = min(ts)
         tm = {}
         t_pair, pair_res = cpu_pair_stage(args.stage, 10, tm)
-        sample = (f"{CPU_SAMPLE_RAYS} evenly strided rays of the same image (chunks of 512), best of 2, extrapolated to "
+        sample = (f"{CPU_SAMPLE_RAYS} evenly strided rays of the same image (chunks of 512), best of {len(ts)}, extrapolated to "
                   f"the image; per-pair stage ({args.stage}) timed once ({t_pair * 1e3:.0f} ms"
                   + (f": encoder {tm['encoder'] * 1e3:.0f}, cost aggregation {tm['ufc'] * 1e3:.0f}, pose {tm['pose'] * 1e3:.0f}"
                      if tm else "") + ")")
         line["cpu_baseline"] = {"value": N_RAYS / (t_pair + (N_RAYS / CPU_SAMPLE_RAYS) * dt), "unit": "rays/s",
-                                "cores": cores, "kind": "port", "sample": sample}
+                                "cores": cores, "cpu_model": cpu_model(), "kind": "port", "sample": sample}
         if pair_res is not None:     # get_z parity of this very step against the CPU restatement
             zc, pc, fc = pair_res
             line["pair_parity"] = {
@@ -455,7 +653,6 @@ def main():
         per_ray_err = (got - want).abs().max(dim=-1).values / want.abs().max()
         err = float(per_ray_err.max())
         mse = float(((got.clamp(-1, 1) - want.clamp(-1, 1)) ** 2).mean())
-        import math
         line["parity"] = {"rgb_max_rel_err_vs_oracle": err, "rgb_median_rel_err_vs_oracle": float(per_ray_err.median()),
                           "rgb_p99_rel_err_vs_oracle": float(per_ray_err.kthvalue(int(0.99 * len(per_ray_err))).values),
                           "note": "the max sits on rays where the reference itself is ill-conditioned (DESIGN.md section 2)",

@@ -1,6 +1,7 @@
 // Epipolar-line feature gather: F.grid_sample(bilinear, align_corners=False) of the four
 // channels-last feature maps, primary ('border' padding, models/CoPoNeRF.py:312) and secondary
 // ('zeros' padding at the reprojected coordinates, models/CoPoNeRF.py:370).
+#include <stdlib.h>
 #include "cpn_common.cuh"
 #include "tc_common.cuh"
 
@@ -219,6 +220,147 @@ __global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, in
   }
 }
 
+// Sequential-row variant of the operand-image gather (experiment, opt-in with CPN_GATHER_SEQ=1: it removes 58 % of the tap
+// loads and measured 590 us per chunk against 595 us -- the kernel is bound by instruction issue of the blend + split +
+// staging work, not by the tap loads). Consecutive samples of an epipolar line fall into the same texel cell
+// several times in a row at the coarse levels (a 16 x 16 map: 4-8 samples per cell; 32 x 32: 2-4; 64 x 64: 1-2), and the
+// kernel above re-fetches the four taps for every sample: 112 of its ~190 L1 wavefronts per (row, branch) are tap loads
+// (the L1 data pipe was its limit, 76 % of the LSU-wavefront peak). Here a CTA owns 16 consecutive rows of one branch and a
+// WARP owns a (level, half of the channels) unit for all of them: it walks the rows in order and keeps the four tap
+// vectors in registers, reloading one only when its texel changes. Same taps, same blend order, same bits. Level 3
+// (64 channels at full resolution: a new cell for every sample) is fetched directly, two rows per warp pass.
+constexpr int GS_ROWS = 16;
+constexpr int GS_SMEM = 2 * GS_ROWS * GI_PITCH * (int)sizeof(__half);
+
+template <bool F8>
+__device__ __forceinline__ void gs_store(float4 acc, __half* sh_hi, unsigned char* sh_b, int col) {
+  if (F8) {
+    uint2 hi;
+    uint32_t l8, x8;
+    tc::split4_f8(acc, hi, l8, x8);
+    *reinterpret_cast<uint2*>(sh_hi + col) = hi;
+    *reinterpret_cast<uint32_t*>(sh_b + col) = l8;
+    *reinterpret_cast<uint32_t*>(sh_b + GI_B8 + col) = x8;
+  } else {
+    uint2 hi, lo;
+    tc::split2(acc.x, acc.y, hi.x, lo.x);
+    tc::split2(acc.z, acc.w, hi.y, lo.y);
+    *reinterpret_cast<uint2*>(sh_hi + col) = hi;
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(sh_b) + col) = lo;
+  }
+}
+__device__ __forceinline__ float4 gs_blend(const float4& f0, const float4& f1, const float4& f2, const float4& f3, const int4& wv) {
+  const float w0 = __int_as_float(wv.x), w1 = __int_as_float(wv.y), w2 = __int_as_float(wv.z), w3 = __int_as_float(wv.w);
+  float4 acc;   // same order as the fp32 kernel: ((f0 w0 + f1 w1) + f2 w2) + f3 w3
+  acc.x = fmaf(f3.x, w3, fmaf(f2.x, w2, fmaf(f1.x, w1, f0.x * w0)));
+  acc.y = fmaf(f3.y, w3, fmaf(f2.y, w2, fmaf(f1.y, w1, f0.y * w0)));
+  acc.z = fmaf(f3.z, w3, fmaf(f2.z, w2, fmaf(f1.z, w1, f0.z * w0)));
+  acc.w = fmaf(f3.w, w3, fmaf(f2.w, w2, fmaf(f1.w, w1, f0.w * w0)));
+  return acc;
+}
+
+template <bool F8>
+__global__ void __launch_bounds__(256) gather_image_seq_kernel(cpn_render_args a, int nr, const int4* __restrict__ taps,
+                                                               unsigned char* __restrict__ img) {
+  extern __shared__ __align__(16) unsigned char gs_smem[];
+  __half(*sh)[GS_ROWS][GI_PITCH] = reinterpret_cast<__half(*)[GS_ROWS][GI_PITCH]>(gs_smem);   // [plane][row][channel]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int branch = blockIdx.y;
+  const unsigned nrows = (unsigned)(a.B * nr * 2 * a.S);
+  const unsigned row0 = blockIdx.x * GS_ROWS;
+  // the 16 rows share (pair, view): S is a multiple of 16 (checked by the launcher)
+  const unsigned S = (unsigned)a.S;
+  const int v = (int)((row0 / S) & 1u), b = (int)(row0 / (2u * S * (unsigned)nr));
+  const int im = b * 2 + (branch ? 1 - v : v);
+  if (warp < 6) {
+    const int l = warp >> 1, cbase = (warp & 1) * 128;          // levels 0-2 have 256 channels: two warps each
+    const int h = a.feat_h[l], w = a.feat_w[l], C = a.feat_c[l];
+    int col0 = 0;
+    for (int k = 0; k < l; ++k) col0 += a.feat_c[k];
+    const int col = col0 + cbase + lane * 4;
+    if (cbase + lane * 4 < C) {
+      const float* base = a.feat[l] + (size_t)im * h * w * C + cbase + lane * 4;
+      int oc0 = -1, oc1 = -1, oc2 = -1, oc3 = -1;
+      float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0, f2 = f0, f3 = f0;
+#pragma unroll 4
+      for (int r = 0; r < GS_ROWS; ++r) {
+        const unsigned row = row0 + r;
+        if (row >= nrows) break;
+        const int4* trow = taps + (((size_t)row * 2 + branch) * CPN_N_LEVELS + l) * 2;
+        const int4 o = __ldg(trow), wv = __ldg(trow + 1);
+        if (o.x != oc0) { f0 = __ldg(reinterpret_cast<const float4*>(base + o.x)); oc0 = o.x; }
+        if (o.y != oc1) { f1 = __ldg(reinterpret_cast<const float4*>(base + o.y)); oc1 = o.y; }
+        if (o.z != oc2) { f2 = __ldg(reinterpret_cast<const float4*>(base + o.z)); oc2 = o.z; }
+        if (o.w != oc3) { f3 = __ldg(reinterpret_cast<const float4*>(base + o.w)); oc3 = o.w; }
+        gs_store<F8>(gs_blend(f0, f1, f2, f3, wv), &sh[0][r][0], reinterpret_cast<unsigned char*>(&sh[1][r][0]), col);
+      }
+    }
+  } else {
+    // level 3: (warp - 6) takes rows 0-7 / 8-15, the two half-warps two rows at a time, lanes along the 64 channels
+    const int l = CPN_N_LEVELS - 1;
+    const int h = a.feat_h[l], w = a.feat_w[l], C = a.feat_c[l];
+    int col0 = 0;
+    for (int k = 0; k < l; ++k) col0 += a.feat_c[k];
+    const int half = lane >> 4, lc = (lane & 15) * 4;
+    for (int c = lc; c < C; c += 64) {
+      const float* base = a.feat[l] + (size_t)im * h * w * C + c;
+#pragma unroll
+      for (int it = 0; it < GS_ROWS / 4; ++it) {
+        const int r = (warp - 6) * (GS_ROWS / 2) + it * 2 + half;
+        const unsigned row = row0 + r;
+        if (row >= nrows) continue;
+        const int4* trow = taps + (((size_t)row * 2 + branch) * CPN_N_LEVELS + l) * 2;
+        const int4 o = __ldg(trow), wv = __ldg(trow + 1);
+        const float4 f0 = __ldg(reinterpret_cast<const float4*>(base + o.x));
+        const float4 f1 = __ldg(reinterpret_cast<const float4*>(base + o.y));
+        const float4 f2 = __ldg(reinterpret_cast<const float4*>(base + o.z));
+        const float4 f3 = __ldg(reinterpret_cast<const float4*>(base + o.w));
+        gs_store<F8>(gs_blend(f0, f1, f2, f3, wv), &sh[0][r][0], reinterpret_cast<unsigned char*>(&sh[1][r][0]), col0 + c);
+      }
+    }
+  }
+  __syncthreads();
+  // 208 16-byte groups per row; thread -> (group, row): 16 threads write 256 contiguous bytes of the image
+  const int rr = threadIdx.x & (GS_ROWS - 1);
+  if (row0 + rr < nrows) {
+    constexpr int NG8 = CPN_FEAT_DIM / 8, NG16 = CPN_FEAT_DIM / 16, GPI = 256 / GS_ROWS;   // groups per pass
+    unsigned char* tile = img + ((size_t)(row0 >> 7) * 2 + branch) * ((size_t)(CPN_KA_IMG / ACT_BK) * ACT_CHUNK_BYTES) +
+                          ((row0 & 127) + rr) * 16;
+    const unsigned char* s_hi = reinterpret_cast<const unsigned char*>(&sh[0][rr][0]);
+    const unsigned char* s_b = reinterpret_cast<const unsigned char*>(&sh[1][rr][0]);
+#pragma unroll
+    for (int it = 0; it < (NG8 + GPI - 1) / GPI; ++it) {   // plane 0: fp16 hi
+      const int gi = it * GPI + (threadIdx.x / GS_ROWS);
+      if (gi < NG8) {
+        const int k = gi * 8;
+        *reinterpret_cast<uint4*>(tile + (k >> 5) * ACT_CHUNK_BYTES + ((k & 31) >> 3) * 2048) =
+            *reinterpret_cast<const uint4*>(s_hi + gi * 16);
+      }
+    }
+    if (F8) {
+#pragma unroll
+      for (int it = 0; it < (2 * NG16 + GPI - 1) / GPI; ++it) {
+        const int item = it * GPI + (threadIdx.x / GS_ROWS);
+        if (item < 2 * NG16) {
+          const int pl = item >= NG16, gi = item - pl * NG16, k = gi * 16;
+          *reinterpret_cast<uint4*>(tile + (k >> 5) * ACT_CHUNK_BYTES + (pl ? ACT_X8 : ACT_LO8) + ((k & 31) >> 4) * 2048) =
+              *reinterpret_cast<const uint4*>(s_b + pl * GI_B8 + gi * 16);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < (NG8 + GPI - 1) / GPI; ++it) {
+        const int gi = it * GPI + (threadIdx.x / GS_ROWS);
+        if (gi < NG8) {
+          const int k = gi * 8;
+          *reinterpret_cast<uint4*>(tile + (k >> 5) * ACT_CHUNK_BYTES + ACT_LO + ((k & 31) >> 3) * 2048) =
+              *reinterpret_cast<const uint4*>(s_b + gi * 16);
+        }
+      }
+    }
+  }
+}
+
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
   __shared__ float tile[32][33];
   int img = blockIdx.z;
@@ -256,6 +398,22 @@ int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowau
     int4* tp = reinterpret_cast<int4*>(taps);
     taps_kernel<<<(unsigned)((rows * 2 * CPN_N_LEVELS + 255) / 256), 256, 0, st>>>(a, nr, rowaux, tp);
     CPN_CHECK_LAUNCH("taps_kernel");
+    static int per_row = -1;   // CPN_GATHER_SEQ=1 selects the sequential-row kernel (measured equal: 590 vs 595 us per chunk)
+    if (per_row < 0) {
+      const char* e = getenv("CPN_GATHER_SEQ");
+      per_row = (e && atoi(e) != 0) ? 0 : 1;
+    }
+    const bool seq_ok = !per_row && (a.S % GS_ROWS) == 0 && a.feat_c[0] == 256 && a.feat_c[1] == 256 && a.feat_c[2] == 256 &&
+                        a.feat_c[3] <= 64;
+    if (seq_ok) {
+      dim3 grid((unsigned)((rows + GS_ROWS - 1) / GS_ROWS), 2);
+      void (*k)(cpn_render_args, int, const int4*, unsigned char*) =
+          a_image == 2 ? gather_image_seq_kernel<true> : gather_image_seq_kernel<false>;
+      CPN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM));
+      k<<<grid, 256, GS_SMEM, st>>>(a, nr, tp, reinterpret_cast<unsigned char*>(A));
+      CPN_CHECK_LAUNCH("gather_image_seq_kernel");
+      return CPN_OK;
+    }
     dim3 grid((unsigned)((rows + GI_ROWS - 1) / GI_ROWS), 2);
     if (a_image == 2)
       gather_image_kernel<true><<<grid, 256, 0, st>>>(a, nr, tp, reinterpret_cast<unsigned char*>(A));

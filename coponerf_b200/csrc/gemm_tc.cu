@@ -170,6 +170,7 @@ struct GemmArgs {
   float* C2;                     // out_kind 4: fp32 (M, N - NT) row-major
   unsigned long long* dbg;       // phase timestamps of the first `dbg_cap` CTAs (cpn_gemm_tc_trace), else null
   int dbg_cap;
+  int dbg_skip;                  // trace runs only (CPN_TC_DBG_SKIP): 1 no image stores, 2 no split / conversions, 4 no TMEM loads
   const float* dotv;             // CB16 matrix the rows are dotted with (out_kind 3); C then holds one float per row
   float dot_div;
   const float* dot_rowadd;       // optional per-row term added to the dot product before the division
@@ -209,7 +210,12 @@ __device__ __forceinline__ float drain_subtile(const GemmArgs& g, uint32_t tmem,
     const int kind = kg ? (c0 < CPN_HIDDEN ? 3 : 0) : g.out_kind;
     const bool relu = kg ? (c0 < CPN_HIDDEN) : (g.relu != 0);
     float v[16];
-    tmem_ld16(tsrc + c0, v);
+    if (g.dbg_skip & 4) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = (float)(c0 + j);
+    } else {
+      tmem_ld16(tsrc + c0, v);
+    }
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
       float4 b = *reinterpret_cast<const float4*>(g.bias + n0 + c0 + j);
@@ -229,15 +235,26 @@ __device__ __forceinline__ float drain_subtile(const GemmArgs& g, uint32_t tmem,
       if (g.f8) {
         uint2 h[4];
         uint4 l8, x8;
-        split4_f8(make_float4(v[0], v[1], v[2], v[3]), h[0], l8.x, x8.x);
-        split4_f8(make_float4(v[4], v[5], v[6], v[7]), h[1], l8.y, x8.y);
-        split4_f8(make_float4(v[8], v[9], v[10], v[11]), h[2], l8.z, x8.z);
-        split4_f8(make_float4(v[12], v[13], v[14], v[15]), h[3], l8.w, x8.w);
+        if (g.dbg_skip & 2) {   // trace runs: raw bits instead of the split
+          h[0] = make_uint2(__float_as_uint(v[0]), __float_as_uint(v[1]));
+          h[1] = make_uint2(__float_as_uint(v[2]), __float_as_uint(v[3]));
+          h[2] = make_uint2(__float_as_uint(v[4]), __float_as_uint(v[5]));
+          h[3] = make_uint2(__float_as_uint(v[6]), __float_as_uint(v[7]));
+          l8 = make_uint4(__float_as_uint(v[8]), __float_as_uint(v[9]), __float_as_uint(v[10]), __float_as_uint(v[11]));
+          x8 = make_uint4(__float_as_uint(v[12]), __float_as_uint(v[13]), __float_as_uint(v[14]), __float_as_uint(v[15]));
+        } else {
+          split4_f8(make_float4(v[0], v[1], v[2], v[3]), h[0], l8.x, x8.x);
+          split4_f8(make_float4(v[4], v[5], v[6], v[7]), h[1], l8.y, x8.y);
+          split4_f8(make_float4(v[8], v[9], v[10], v[11]), h[2], l8.z, x8.z);
+          split4_f8(make_float4(v[12], v[13], v[14], v[15]), h[3], l8.w, x8.w);
+        }
         unsigned char* ph = chunk + ((k % BK) / 8) * A_LBO;
-        *reinterpret_cast<uint4*>(ph) = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
-        *reinterpret_cast<uint4*>(ph + A_LBO) = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
-        *reinterpret_cast<uint4*>(chunk + ACT_LO8 + ((k % BK) / 16) * A_LBO) = l8;
-        *reinterpret_cast<uint4*>(chunk + ACT_X8 + ((k % BK) / 16) * A_LBO) = x8;
+        if (!(g.dbg_skip & 1) || (h[0].x == 0x12345678u && l8.y == 0x9abcdef0u)) {
+          *reinterpret_cast<uint4*>(ph) = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
+          *reinterpret_cast<uint4*>(ph + A_LBO) = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
+          *reinterpret_cast<uint4*>(chunk + ACT_LO8 + ((k % BK) / 16) * A_LBO) = l8;
+          *reinterpret_cast<uint4*>(chunk + ACT_X8 + ((k % BK) / 16) * A_LBO) = x8;
+        }
       } else {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -482,6 +499,67 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
   if (threadIdx.x == 32) stamp(6);
 }
 
+// Row-dot epilogue of the persistent kernel for the 128-wide dot part (kinds 3 / 4), two column parts per row: the 4 x 16
+// values of `dotv` a thread needs are fetched BEFORE the accumulators are ready (they do not depend on them), so the drain is
+// register work only. The first version loaded them inside the column loop, behind tcgen05.wait::ld: one exposed L2 / HBM
+// round trip per 16 columns, 11-13 us of drain per tile for layer 10 (profiles/r2_kg_trace_*.json).
+struct DotPrefetch {
+  float4 v[4][4];
+};
+__device__ __forceinline__ void dot_prefetch(const GemmArgs& g, int m0, int esub, int rloc, int part, DotPrefetch& p) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4* qv = reinterpret_cast<const float4*>(
+        g.dotv + (((size_t)(m0 / 128 + esub) * g.dot_blocks + g.dot_block0 + part * 4 + i) * 128 + rloc) * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p.v[i][j] = __ldg(qv + j);
+  }
+}
+// columns [64 part, 64 part + 64) of the dot part; for kind 4 also columns 128 + [64 part, 64 part + 64) -> C2 (column-blocked)
+__device__ __forceinline__ float drain_dot2(const GemmArgs& g, uint32_t tmem, int m0, int esub, int q, int lane, int part,
+                                            const DotPrefetch& p) {
+  const int rloc = q * 32 + lane;
+  const float inv = *g.inv_scale;
+  const uint32_t tsrc = tmem + esub * 256 + ((uint32_t)(q * 32) << 16);
+  const float floor_ = (g.out_kind == 4 || g.relu) ? 0.f : -INFINITY;   // ReLU on the dot part, or none (key_map_2 / query_repeat_embed_2)
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c0 = (part * 4 + i) * 16;
+    float v[16];
+    tmem_ld16(tsrc + c0, v);
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(g.bias + c0 + j);
+      v[j] = fmaxf(v[j] * inv + b.x, floor_);
+      v[j + 1] = fmaxf(v[j + 1] * inv + b.y, floor_);
+      v[j + 2] = fmaxf(v[j + 2] * inv + b.z, floor_);
+      v[j + 3] = fmaxf(v[j + 3] * inv + b.w, floor_);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 x = p.v[i][j];
+      dot = fmaf(v[4 * j + 3], x.w, fmaf(v[4 * j + 2], x.z, fmaf(v[4 * j + 1], x.y, fmaf(v[4 * j], x.x, dot))));
+    }
+  }
+  if (g.out_kind == 4) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c0 = CPN_HIDDEN + (part * 4 + i) * 16;
+      float v[16];
+      tmem_ld16(tsrc + c0, v);
+      float* out = g.C2 + (((size_t)(m0 / 128 + esub) * (CPN_HIDDEN / 16) + part * 4 + i) * 128 + rloc) * 16;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(g.bias + c0 + j);
+        *reinterpret_cast<float4*>(out + j) =
+            make_float4(v[j] * inv + b.x, v[j + 1] * inv + b.y, v[j + 2] * inv + b.z, v[j + 3] * inv + b.w);
+      }
+    }
+  }
+  return dot;
+}
+
 // ---- persistent version (operand-image A) -----------------------------------------------------------------------
 // One CTA per SM walks the (row tile, N tile) list with a stride of gridDim.x. The operand ring runs across tiles, so
 // the copies of tile j + 1 are in flight while tile j is drained, and TMEM / barriers are set up once per launch. A phase
@@ -610,11 +688,17 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
       const int n_tile = t % ntiles_n, m0 = (t / ntiles_n) * BM;
       const bool valid = esub == 0 || (m0 + 128) < g.M;
+      constexpr bool PREFETCH = !OUT_IMAGE && PARTS == 2;   // dot kinds run on the 16-warp kernel (launcher)
+      DotPrefetch pf;
+      if (PREFETCH && dotkind && valid) dot_prefetch(g, m0, esub, q * 32 + lane, part, pf);
       mbar_wait(accum_full, tcount & 1);
       tcgen05_fence_after();
       if (threadIdx.x == 64) stamp(tcount, 3);
       float dot = 0.f;
-      if (valid) dot = drain_subtile<OUT_IMAGE>(g, tmem, m0, n_tile, esub, q, lane, c_lo, c_hi, false);
+      if (valid) {
+        if (PREFETCH && dotkind) dot = drain_dot2(g, tmem, m0, esub, q, lane, part, pf);
+        else dot = drain_subtile<OUT_IMAGE>(g, tmem, m0, n_tile, esub, q, lane, c_lo, c_hi, false);
+      }
       // every TMEM read of this warp has completed (tcgen05.wait::ld inside tmem_ld16): hand the accumulators back
       tcgen05_fence_before();
       __syncwarp();
@@ -676,6 +760,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_pair_kernel(GemmArgs g
                  accum = smem_u32(&bars[3 * PSTAGES]);
   const int NT = g.NT, NH = NT / 2;
   const uint32_t wh = (uint32_t)(BK / 8) * NH * 16;          // fp16 plane of this CTA's half tile; e4m3 planes wh / 2 each
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * 2 + blockIdx.x;
+  unsigned long long* const dbg = (g.dbg && cta_lin < g.dbg_cap) ? g.dbg + (size_t)cta_lin * 8 : nullptr;
+  auto stamp = [&](int i) {   // same slots as gemm_tc_kernel
+    if (dbg) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      dbg[i] = t;
+    }
+  };
+  if (threadIdx.x == 0) stamp(0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < PSTAGES; ++s) {
@@ -692,6 +786,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_pair_kernel(GemmArgs g
   cluster_sync();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_base_s;
+  if (threadIdx.x == 0) {
+    stamp(1);
+    if (dbg) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      dbg[7] = smid;
+    }
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -726,6 +828,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_pair_kernel(GemmArgs g
         uint32_t u = i / PSTAGES;
         mbar_wait(full + 8 * s, u & 1);
         mbar_wait(peer_full + 8 * s, u & 1);
+        if (i == 0) stamp(2);
         tcgen05_fence_after();
         uint32_t stage = smem0 + s * PSTAGE_BYTES;
         uint32_t b_hi = stage + 2 * A_SUB;
@@ -743,17 +846,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_pair_kernel(GemmArgs g
         mma_commit_pair(empty + 8 * s, 3);   // both CTAs may refill the stage once these MMAs have read it
       }
       mma_commit_pair(accum, 3);
+      stamp(3);
     }
   } else {
     const int pwarp = warp - 2, esub = pwarp >> 2, q = warp & 3;
     mbar_wait(accum, 0);
+    if (threadIdx.x == 64) stamp(4);
     tcgen05_fence_after();
     drain_subtile<OUT_IMAGE>(g, tmem, m0, n_tile, esub, q, lane, 0, g.NT, true);
+    if (threadIdx.x == 64) stamp(5);
   }
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync();
   if (warp == 1) tmem_dealloc_pair(tmem, TMEM_COLS);
+  if (threadIdx.x == 32) stamp(6);
 }
 
 }  // namespace
@@ -822,6 +929,11 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
   g.C2 = c2;
   g.dbg = g_tc_dbg;
   g.dbg_cap = g_tc_dbg_cap;
+  g.dbg_skip = 0;
+  if (g_tc_dbg) {   // cost attribution of the epilogue, trace runs only
+    const char* e = getenv("CPN_TC_DBG_SKIP");
+    if (e) g.dbg_skip = atoi(e);
+  }
   g.dotv = dotv;
   g.dot_div = dot_div;
   g.dot_rowadd = dot_rowadd;
@@ -873,12 +985,13 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
       const char* e = getenv("CPN_TC_EPI_WARPS");
       epi_warps = (e && atoi(e) == 24) ? 24 : 16;
     }
+    const bool dots = g.out_kind == 3 || g.out_kind == 4;   // their prefetching epilogue is written for two column parts
     void (*pk)(GemmArgs, int, int) =
-        epi_warps == 24 ? (o_img ? gemm_tc_persist_kernel<true, 24> : gemm_tc_persist_kernel<false, 24>)
+        (epi_warps == 24 && !dots) ? (o_img ? gemm_tc_persist_kernel<true, 24> : gemm_tc_persist_kernel<false, 24>)
                         : (o_img ? gemm_tc_persist_kernel<true, 16> : gemm_tc_persist_kernel<false, 16>);
     CPN_CHECK_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const int total = ntiles * (int)grid.y;
-    pk<<<total < n_sm ? total : n_sm, (2 + epi_warps) * 32, SMEM_BYTES, st>>>(g, ntiles, total);
+    pk<<<total < n_sm ? total : n_sm, (2 + ((epi_warps == 24 && !dots) ? 24 : 16)) * 32, SMEM_BYTES, st>>>(g, ntiles, total);
     CPN_CHECK_LAUNCH("gemm_tc_persist_kernel");
     return CPN_OK;
   }

@@ -57,9 +57,12 @@ def per_ray(d, key):
     return d.reshape(d.shape[0], d.shape[1], -1).max(axis=-1)
 
 
-def run_oracle(H, W, n_rays, S, seed, val, chunk=None, pose=None, batch=1, with_sens=False):
+def run_oracle(H, W, n_rays, S, seed, val, chunk=None, pose=None, batch=1, with_sens=False, ray_idx=None):
     from oracle import render_oracle
     inp, z, rel_pose, flow = make_case(H, W, n_rays, seed, pose, batch)
+    if ray_idx is not None:     # a subset of the rays of the case (rays are independent)
+        inp["query"]["uv"] = inp["query"]["uv"][:, :, ray_idx].contiguous()
+        inp["query"]["rgb"] = inp["query"]["rgb"][:, :, ray_idx].contiguous()
     sd = synth.render_state_dict(0)
     base = render_oracle.render_forward(sd, inp, z, rel_pose, flow, H, W, S, bool(val), chunk=chunk)
     if with_sens:   # the same 1-ulp pose perturbation the golden generator applies to the reference

@@ -71,6 +71,28 @@ def test_native_ufc_forward_matches_restatement():
         assert float((a.cpu() - b).abs().max()) <= 2e-3 * 64   # soft-argmax at temperature 0.02 amplifies c by 50
 
 
+def test_native_ufc_forward_matches_independent_oracle():
+    """The CUDA cost aggregation against oracle/ufc_forward_oracle.py, the restatement in the reference's own
+    rearrange-based formulation that shares no code with the product (pinned to the unmodified UFC module on CPU by
+    tests/test_ufc_orchestration_cpu.py)."""
+    from coponerf_b200 import ufc_native
+    from oracle import ufc_forward_oracle
+    cu, _ = _ops()
+    sd = synth.ufc_state_dict(0)
+    feat = synth.ufc_inputs(2)
+    ref_feats, ref_flows, ref_c = ufc_forward_oracle.ufc_forward(sd, feat, 2)
+    got_feats, got_flows, got_c = ufc_native.ufc_forward({k: v.cuda() for k, v in sd.items()}, [f.cuda() for f in feat], 2, cu)
+    torch.cuda.synchronize()
+    for a, b in zip(got_feats, ref_feats):
+        _close(a, b, tol=1e-4)
+    e_c = float((got_c.cpu() - ref_c).abs().max())
+    e_f = [float((a.cpu() - b).abs().max()) for a, b in zip(got_flows, ref_flows)]
+    print(f"CUDA UFC vs independent oracle: c {e_c:.2e}, flows (px, px, [-1,1], [-1,1]) {e_f}")
+    assert e_c <= 2e-5
+    for i, e in enumerate(e_f):
+        assert e <= 1e-3 * (1.0 if i < 2 else 1.0 / 32.0), (i, e)
+
+
 def test_native_ufc_forward_at_512_sizes():
     """BASELINE config 4: the cost aggregation at 512x512 (feature sizes 32 / 64 / 128, correlation size 32, a 128^4
     = 1.07 GB volume `c`). The reference UFC is hard-wired to 256x256, so the oracle here is the
