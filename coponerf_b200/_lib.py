@@ -25,6 +25,7 @@ TC_PAIR = 16
 TC_OUT_CB16 = 32
 TC_OUT_KG = 128
 TC_NO_PERSIST = 256
+TC_PPAIR = 512
 TC_A_IMAGE = 1
 TC_OUT_IMAGE = 2
 ACT_CHUNK_BYTES = 16384
@@ -97,11 +98,16 @@ SIGNATURES = {
     "cpn_pair_prologue": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 +
                           [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "cpn_render_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5),
+    "cpn_render_workspace_bytes_for": (ctypes.c_size_t, [ctypes.c_int] * 6),
     "cpn_render_rays": (ctypes.c_int, [ctypes.POINTER(RenderArgs), ctypes.c_void_p]),
     "cpn_render_launch_count": (ctypes.c_int, [ctypes.POINTER(RenderArgs)]),
     "cpn_gemm_tc_rowdot": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                           ctypes.c_void_p]),
+    "cpn_linear_tc_packed_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "cpn_linear_tc_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "cpn_linear_tc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "cpn_gather_rows_taps_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "cpn_gather_rows": (ctypes.c_int, [ctypes.POINTER(RenderArgs), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                        ctypes.c_void_p, ctypes.c_void_p]),

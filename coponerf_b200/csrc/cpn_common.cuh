@@ -174,6 +174,9 @@ constexpr int CPN_TC_LAYERS = 11;
 size_t cpn_packed_fp32_floats();
 size_t cpn_tc_weights_bytes();
 int cpn_pack_tc_weights(const float* raw, const float* packed_fp32, void* dst, cudaStream_t st);
+// generic Linear on the tensor-core kernel (include/coponerf_b200.h: cpn_linear_tc); the accumulators are scaled by out_mul
+int launch_linear_tc(const void* packed, int N, int K, const float* x, int ldx, const float* bias, float* y, int ldy, int M,
+                     int act, int mode, float out_mul, cudaStream_t stream);
 // layer: 0 query_encode_latent, 1 query_encode_latent_2, 2 latent_value, 3 key_map, 4 key_map_2,
 //        5 query_embed_2, 6 query_repeat_embed_2, 7 latent_value o query_encode_latent_2 (K = 1664: the hidden
 //        layer of the primary branch then of the secondary one), 8 key_map o query_encode_latent_2.  mode: CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE.

@@ -143,6 +143,7 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, int out, int in, int
   t8[half_elems * 2 + off8] = w8;
   t8[half_elems * 3 + off8] = wl8;
   // pair tiles: (nt, half, kc) with NH = NT / 2 rows: [hi: 4 groups x NH x 16 B | w8: 2 x NH x 16 | w_lo8: 2 x NH x 16]
+  if (!dstp) return;
   const int NH = NT / 2, hf = nl / NH, nh = nl % NH;
   unsigned char* tp = dstp + (((size_t)nt * 2 + hf) * kchunks + kc) * (size_t)NH * 128;
   reinterpret_cast<__half*>(tp)[((size_t)c * NH + nh) * 8 + e] = hi;
@@ -170,6 +171,7 @@ struct GemmArgs {
   float* C2;                     // out_kind 4: fp32 (M, N - NT) row-major
   unsigned long long* dbg;       // phase timestamps of the first `dbg_cap` CTAs (cpn_gemm_tc_trace), else null
   int dbg_cap;
+  float out_mul;                 // the accumulators are multiplied by inv_scale * out_mul before the bias (1 except the tail GEMM)
   int dbg_skip;                  // trace runs only (CPN_TC_DBG_SKIP): 1 no image stores, 2 no split / conversions, 4 no TMEM loads
   const float* dotv;             // CB16 matrix the rows are dotted with (out_kind 3); C then holds one float per row
   float dot_div;
@@ -187,7 +189,7 @@ __device__ __forceinline__ float drain_subtile(const GemmArgs& g, uint32_t tmem,
   const int NT = g.NT;
   const int rloc = q * 32 + lane;                  // row inside the 128-row sub-tile
   const int row = m0 + esub * 128 + rloc;
-  const float inv = *g.inv_scale;
+  const float inv = *g.inv_scale * g.out_mul;
   const int n0 = n_tile * NT;
   // out_kind 4 (layer 10, one 256-column tile): columns 0-127 (key hidden layer) are dotted like kind 3, columns 128-255
   // (G h + g0) leave column-blocked (8 blocks of 16 per 128-row tile)
@@ -208,7 +210,7 @@ __device__ __forceinline__ float drain_subtile(const GemmArgs& g, uint32_t tmem,
   float dot = 0.f;
   for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
     const int kind = kg ? (c0 < CPN_HIDDEN ? 3 : 0) : g.out_kind;
-    const bool relu = kg ? (c0 < CPN_HIDDEN) : (g.relu != 0);
+    const int act = kg ? (c0 < CPN_HIDDEN ? 1 : 0) : g.relu;   // 0 none, 1 ReLU, 2 exact GELU
     float v[16];
     if (g.dbg_skip & 4) {
 #pragma unroll
@@ -224,9 +226,12 @@ __device__ __forceinline__ float drain_subtile(const GemmArgs& g, uint32_t tmem,
       v[j + 2] = v[j + 2] * inv + b.z;
       v[j + 3] = v[j + 3] * inv + b.w;
     }
-    if (relu) {
+    if (act == 1) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == 2) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
     }
     if (OUT_IMAGE) {
       // 16 consecutive k of the next layer; lanes are consecutive rows -> every store instruction writes 512 B runs
@@ -519,7 +524,7 @@ __device__ __forceinline__ void dot_prefetch(const GemmArgs& g, int m0, int esub
 __device__ __forceinline__ float drain_dot2(const GemmArgs& g, uint32_t tmem, int m0, int esub, int q, int lane, int part,
                                             const DotPrefetch& p) {
   const int rloc = q * 32 + lane;
-  const float inv = *g.inv_scale;
+  const float inv = *g.inv_scale * g.out_mul;
   const uint32_t tsrc = tmem + esub * 256 + ((uint32_t)(q * 32) << 16);
   const float floor_ = (g.out_kind == 4 || g.relu) ? 0.f : -INFINITY;   // ReLU on the dot part, or none (key_map_2 / query_repeat_embed_2)
   float dot = 0.f;
@@ -567,6 +572,9 @@ __device__ __forceinline__ float drain_dot2(const GemmArgs& g, uint32_t tmem, in
 // of drain by 8 warps (instruction-latency bound), 1.3 us waiting for the first stage and 0.7 us between CTAs: 36 % of an
 // SM's time. Here 24 epilogue warps (three per 128-row sub-tile and TMEM lane quadrant, each a third of the columns) drain
 // a tile, and the MMA warp restarts as soon as they have read the accumulators (accum_empty).
+// A deeper operand ring does not help: with separate rings for the activation stages (4 x 32 KB) and the weight stages
+// (3 x 32 KB, a second producer warp) the query_encode_latent GEMM went from 1.33 to 1.44 ms (main loop 16.9 -> 18.1 us per
+// tile, profiles/r2_gemm1_trace_splitring.json): the loop is bound by L2 -> SM bandwidth, not by load latency.
 // EPI_WARPS = 8 * PARTS: 16 leaves registers for a co-resident CTA of another kernel (the gather / readout of the other chunk
 // lane: a persistent grid does not block the dispatch of later kernels the way a long CTA queue does).
 template <bool OUT_IMAGE, int P_EPI_WARPS>
@@ -863,6 +871,146 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_pair_kernel(GemmArgs g
   if (threadIdx.x == 32) stamp(6);
 }
 
+// ---- persistent CTA-pair version (cta_group::2, operand-image A, f8 scheme) --------------------------------------
+// The pair kernel above spends 9.95 us of its 31.6 us per tile in the MMA loop (profiles/r2_gemm1_trace_pair.json; the
+// independent-CTA kernel: 15.9 of 25.1 us): every MMA spans the two SMs, each stages half of the weight tile, so a k-chunk
+// costs 45.3 KB of L2 -> SM traffic per SM instead of 58.6 KB and the ring holds four stages. What made it slower overall was
+// the per-tile overhead of a cluster (TMEM allocation, three cluster barriers, 8 epilogue warps). Here a cluster of two CTAs
+// is persistent: it walks the (512-row tile, N tile) list, the rings run across tiles, 16 epilogue warps per CTA drain, and the
+// leader's MMA thread restarts when the epilogue warps of BOTH CTAs have read their accumulators (remote mbarrier arrives).
+constexpr int PP_EPI_WARPS = 16;
+constexpr int PP_THREADS = (2 + PP_EPI_WARPS) * 32;
+
+template <bool OUT_IMAGE>
+__global__ void __launch_bounds__(PP_THREADS, 1) gemm_tc_ppair_kernel(GemmArgs g, int ntiles_n, int nptiles) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[3 * PSTAGES + 2];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t full = smem_u32(&bars[0]), peer_full = smem_u32(&bars[PSTAGES]), empty = smem_u32(&bars[2 * PSTAGES]),
+                 accum_full = smem_u32(&bars[3 * PSTAGES]), accum_empty = smem_u32(&bars[3 * PSTAGES + 1]);
+  const int NT = g.NT, NH = NT / 2;
+  const uint32_t wh = (uint32_t)(BK / 8) * NH * 16;          // fp16 plane of this CTA's half tile; byte planes wh / 2 each
+  auto stamp = [&](int tile_no, int i) {
+    if (g.dbg) {
+      const int slot = tile_no * gridDim.x + blockIdx.x;
+      if (slot < g.dbg_cap) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g.dbg[(size_t)slot * 8 + i] = t;
+      }
+    }
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PSTAGES; ++s) {
+      mbar_init(full + 8 * s, 1);
+      mbar_init(peer_full + 8 * s, 1);
+      mbar_init(empty + 8 * s, 1);
+    }
+    mbar_init(accum_full, 1);
+    mbar_init(accum_empty, 2 * PP_EPI_WARPS);   // the leader's: every epilogue warp of both CTAs arrives on it
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(smem_u32(&tmem_base_s), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const unsigned char* asrc = reinterpret_cast<const unsigned char*>(g.A);
+      uint32_t it = 0;
+      for (int pt = cluster_id; pt < nptiles; pt += nclusters) {
+        const int n_tile = pt % ntiles_n, m0 = ((pt / ntiles_n) * 2 + (int)rank) * BM;
+        const unsigned char* wsrc = g.wtiles + ((size_t)n_tile * 2 + rank) * g.kchunks * 2 * wh;
+        const size_t tile0 = (size_t)(m0 / 128);
+        for (int i = 0; i < g.kchunks; ++i, ++it) {
+          const int s = it % PSTAGES;
+          const uint32_t u = it / PSTAGES;
+          mbar_wait(empty + 8 * s, (u & 1) ^ 1);
+          const uint32_t stage = smem0 + s * PSTAGE_BYTES;
+          mbar_arrive_expect_tx(full + 8 * s, 2 * wh + 2 * A_SUB);
+          bulk_g2s(stage + 2 * A_SUB, wsrc + (size_t)i * 2 * wh, 2 * wh, full + 8 * s);
+          bulk_g2s(stage, asrc + (tile0 * g.kchunks + i) * ACT_CHUNK_BYTES, A_SUB, full + 8 * s);
+          bulk_g2s(stage + A_SUB, asrc + ((tile0 + 1) * g.kchunks + i) * ACT_CHUNK_BYTES, A_SUB, full + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 1) {
+      // peer: tell the leader when a stage of this CTA has landed
+      uint32_t it = 0;
+      for (int pt = cluster_id; pt < nptiles; pt += nclusters)
+        for (int i = 0; i < g.kchunks; ++i, ++it) {
+          const int s = it % PSTAGES;
+          mbar_wait(full + 8 * s, (it / PSTAGES) & 1);
+          mbar_arrive_remote(peer_full + 8 * s, 0);
+        }
+    } else if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(256, NT);
+      uint32_t it = 0, tcount = 0;
+      for (int pt = cluster_id; pt < nptiles; pt += nclusters, ++tcount) {
+        mbar_wait(accum_empty, (tcount & 1) ^ 1);     // both CTAs' epilogue warps have read the previous tile out of TMEM
+        tcgen05_fence_after();
+        stamp(tcount, 0);
+        for (int i = 0; i < g.kchunks; ++i, ++it) {
+          const int s = it % PSTAGES;
+          const uint32_t u = it / PSTAGES;
+          mbar_wait(full + 8 * s, u & 1);
+          mbar_wait(peer_full + 8 * s, u & 1);
+          if (i == 0) stamp(tcount, 1);
+          tcgen05_fence_after();
+          const uint32_t stage = smem0 + s * PSTAGE_BYTES;
+          const uint32_t b_hi = stage + 2 * A_SUB;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const uint32_t a_hi = stage + sub * A_SUB;
+            const uint32_t d = tmem + sub * 256;
+#pragma unroll
+            for (int j = 0; j < BK / 16; ++j)
+              mma_f16_ss_pair(d, make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128), make_desc(b_hi + j * 2 * NH * 16, NH * 16, 128),
+                              idesc, (i | j) != 0);
+            mma_f8_ss_pair(d, make_desc(a_hi + ACT_LO8, A_LBO, 128), make_desc(b_hi + wh, NH * 16, 128), idesc | IDESC_A_E5M2, 1);
+            mma_f8_ss_pair(d, make_desc(a_hi + ACT_X8, A_LBO, 128), make_desc(b_hi + wh + wh / 2, NH * 16, 128),
+                           idesc | IDESC_A_E5M2, 1);
+          }
+          mma_commit_pair(empty + 8 * s, 3);   // both CTAs may refill the stage once these MMAs have read it
+        }
+        mma_commit_pair(accum_full, 3);
+        stamp(tcount, 2);
+      }
+    }
+  } else {
+    // epilogue warps 2..17: quadrant q = warp % 4, r = (warp - 2) / 4 -> sub-tile r / 2, column part r % 2
+    const int q = warp & 3, r = (warp - 2) >> 2, esub = r >> 1, part = r & 1;
+    const int niter = NT / 16, c_lo = (part * niter / 2) * 16, c_hi = ((part + 1) * niter / 2) * 16;
+    uint32_t tcount = 0;
+    for (int pt = cluster_id; pt < nptiles; pt += nclusters, ++tcount) {
+      const int n_tile = pt % ntiles_n, m0 = ((pt / ntiles_n) * 2 + (int)rank) * BM;
+      mbar_wait(accum_full, tcount & 1);
+      tcgen05_fence_after();
+      if (threadIdx.x == 64) stamp(tcount, 3);
+      drain_subtile<OUT_IMAGE>(g, tmem, m0, n_tile, esub, q, lane, c_lo, c_hi, false);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(accum_empty);
+        else mbar_arrive_remote(accum_empty, 0);
+      }
+      if (threadIdx.x == 64) stamp(tcount, 4);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 1) tmem_dealloc_pair(tmem, TMEM_COLS);
+}
+
 }  // namespace
 
 // phase trace of the single-CTA kernel (profiling hook like cpn_prof_begin; not thread-safe): while set, every
@@ -927,6 +1075,7 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
   g.f8 = (mode & CPN_TC_F16X3) ? 0 : 1;
   g.out_kind = (mode & CPN_TC_OUT_KG) ? 4 : ((mode & CPN_TC_OUT_ROWDOT) ? 3 : ((mode & CPN_TC_OUT_CB16) ? 2 : 0));
   g.C2 = c2;
+  g.out_mul = 1.f;
   g.dbg = g_tc_dbg;
   g.dbg_cap = g_tc_dbg_cap;
   g.dbg_skip = 0;
@@ -973,13 +1122,42 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
     CPN_CHECK_CUDA(cudaLaunchKernelEx(&pc, pk, g));
     return CPN_OK;
   }
+  static int n_sm = 0;   // SMs of the current device (all devices of a box are the same part)
+  if (n_sm == 0) {
+    int dev = 0;
+    CPN_CHECK_CUDA(cudaGetDevice(&dev));
+    CPN_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  static int ppair_env = -1;   // CPN_TC_PPAIR=1: persistent CTA pairs wherever they apply (A/B runs)
+  if (ppair_env < 0) {
+    const char* e = getenv("CPN_TC_PPAIR");
+    ppair_env = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  if (ppair_env) mode |= CPN_TC_PPAIR;
+  if (a_img && g.f8 && (mode & CPN_TC_PPAIR) && (M % (2 * BM)) == 0 && (g.out_kind == 0 || g.out_kind == 2) &&
+      !(mode & (CPN_TC_CLUSTER | CPN_TC_NO_PERSIST))) {
+    // persistent CTA pairs: one cluster of two per SM pair walks the (512-row tile, N tile) list
+    g.wtiles = tcw + layer_offset(layer, 2);
+    void (*pk)(GemmArgs, int, int) = o_img ? gemm_tc_ppair_kernel<true> : gemm_tc_ppair_kernel<false>;
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, PSMEM_BYTES));
+    const int nptiles = ntiles * (M / (2 * BM));
+    const int nclusters = nptiles < n_sm / 2 ? nptiles : n_sm / 2;
+    cudaLaunchConfig_t pc = {};
+    pc.gridDim = dim3(2 * nclusters);
+    pc.blockDim = dim3(PP_THREADS);
+    pc.dynamicSmemBytes = PSMEM_BYTES;
+    pc.stream = st;
+    cudaLaunchAttribute pa[1];
+    pa[0].id = cudaLaunchAttributeClusterDimension;
+    pa[0].val.clusterDim.x = 2;
+    pa[0].val.clusterDim.y = 1;
+    pa[0].val.clusterDim.z = 1;
+    pc.attrs = pa;
+    pc.numAttrs = 1;
+    CPN_CHECK_CUDA(cudaLaunchKernelEx(&pc, pk, g, ntiles, nptiles));
+    return CPN_OK;
+  }
   if (a_img && !(mode & (CPN_TC_CLUSTER | CPN_TC_NO_PERSIST))) {
-    static int n_sm = 0;   // SMs of the current device (all devices of a box are the same part)
-    if (n_sm == 0) {
-      int dev = 0;
-      CPN_CHECK_CUDA(cudaGetDevice(&dev));
-      CPN_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    }
     static int epi_warps = 0;   // CPN_TC_EPI_WARPS = 16 | 24 (A/B runs)
     if (epi_warps == 0) {
       const char* e = getenv("CPN_TC_EPI_WARPS");
@@ -1034,4 +1212,84 @@ extern "C" int cpn_gemm_tc_kg(const void* packed, const void* h1_image, const fl
                               const float* rowadd, float div, float* logits, float* gh, int M, int mode, void* stream) {
   return launch_gemm_tc(packed, 10, h1_image, 0, logits, 0, M, 1, (mode & CPN_TC_F16X3) | CPN_TC_A_IMAGE | CPN_TC_OUT_KG, 1, 1,
                         (cudaStream_t)stream, dotv_cb16, div, rowadd, dot_blocks, 0, gh);
+}
+
+
+// ---- generic Linear on the tensor-core kernel (token layers of the cost aggregation, models/aggregation.py:269-340) --------
+// y[M, N] = act(x[M, K] W[N, K]^T + b) for any weight with N a multiple of 128 and K a multiple of 8: the weight is packed once
+// (cpn_linear_tc_pack: per-layer power-of-two scale, split tiles of both schemes), activations stay fp32 row-major (producer
+// warps split them inside the kernel).
+namespace {
+size_t lin_bias_bytes(int N) { return ((size_t)N * 4 + 255) / 256 * 256; }
+size_t lin_tiles_bytes(int N, int K) { return (size_t)N * ((K + BK - 1) / BK * BK) * 4; }
+}  // namespace
+
+extern "C" size_t cpn_linear_tc_packed_bytes(int N, int K) {
+  if (N <= 0 || K <= 0 || (N % 128) != 0) return 0;
+  return TC_HEADER_BYTES + lin_bias_bytes(N) + 2 * lin_tiles_bytes(N, K);
+}
+
+extern "C" int cpn_linear_tc_pack(const float* w, int N, int K, void* packed, void* stream) {
+  if (!w || !packed || N <= 0 || K <= 0 || (N % 128) != 0) {
+    cpn_set_error("cpn_linear_tc_pack: N must be a positive multiple of 128 (N=%d K=%d)", N, K);
+    return CPN_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* dst = reinterpret_cast<unsigned char*>(packed);
+  CPN_CHECK_CUDA(cudaMemsetAsync(dst, 0, cpn_linear_tc_packed_bytes(N, K), st));
+  unsigned int* absmax = reinterpret_cast<unsigned int*>(dst) + 32;
+  const int kpad = (K + BK - 1) / BK * BK;
+  absmax_kernel<<<64, 256, 0, st>>>(w, (size_t)N * K, absmax);
+  CPN_CHECK_LAUNCH("absmax_kernel");
+  unsigned char* t0 = dst + TC_HEADER_BYTES + lin_bias_bytes(N);
+  const size_t total = (size_t)N * kpad;
+  pack_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, N, K, kpad, 128, absmax, reinterpret_cast<__half*>(t0),
+                                                                  t0 + lin_tiles_bytes(N, K), nullptr,
+                                                                  reinterpret_cast<float*>(dst), 0);
+  CPN_CHECK_LAUNCH("pack_tc_kernel");
+  return CPN_OK;
+}
+
+extern "C" int cpn_linear_tc(const void* packed, int N, int K, const float* x, int ldx, const float* bias, float* y, int ldy,
+                             int M, int act, int mode, void* stream) {
+  return launch_linear_tc(packed, N, K, x, ldx, bias, y, ldy, M, act, mode, 1.f, (cudaStream_t)stream);
+}
+
+int launch_linear_tc(const void* packed, int N, int K, const float* x, int ldx, const float* bias, float* y, int ldy, int M,
+                     int act, int mode, float out_mul, cudaStream_t stream) {
+  if (!packed || !x || !y || N <= 0 || K <= 0 || (N % 128) != 0 || (K & 7) || (ldx & 3) || (ldy & 3) || ldx < K || M < 0 ||
+      act < 0 || act > 2) {
+    cpn_set_error("cpn_linear_tc: bad argument (N=%d K=%d ldx=%d ldy=%d M=%d act=%d): N %% 128 == 0, K %% 8 == 0", N, K, ldx, ldy,
+                  M, act);
+    return CPN_ERR_ARG;
+  }
+  if (M == 0) return CPN_OK;
+  const unsigned char* p = reinterpret_cast<const unsigned char*>(packed);
+  GemmArgs g = {};
+  g.A = x;
+  g.lda = ldx;
+  g.kreal = K;
+  g.M = M;
+  g.C = y;
+  g.ldc = ldy;
+  g.N = N;
+  g.relu = act;
+  g.out_div = 1;
+  g.out_kchunks = 1;
+  g.f8 = (mode & CPN_TC_F16X3) ? 0 : 1;
+  g.out_kind = 0;
+  g.wtiles = p + TC_HEADER_BYTES + lin_bias_bytes(N) + (g.f8 ? lin_tiles_bytes(N, K) : 0);
+  g.bias = bias ? bias : reinterpret_cast<const float*>(p + TC_HEADER_BYTES);   // zeros
+  g.inv_scale = reinterpret_cast<const float*>(p);
+  g.kchunks = (K + BK - 1) / BK;
+  g.NT = 128;
+  g.idesc = make_idesc_f16(128, 128);
+  g.dot_div = 1.f;
+  g.out_mul = out_mul;
+  void (*kern)(GemmArgs) = gemm_tc_kernel<false, false, 1>;
+  CPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  dim3 grid(N / 128, (M + BM - 1) / BM);
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(g);
+  CPN_CHECK_LAUNCH("gemm_tc_kernel (linear)");
+  return CPN_OK;
 }

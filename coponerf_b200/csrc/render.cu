@@ -81,8 +81,12 @@ struct Workspace {
   size_t bytes;
 };
 
-Workspace carve(void* base, int B, int nr, int S) {
+// `flags` selects the code path (CPN_FLAG_*): buffers only an alternative path reads are not carved for the default one
+Workspace carve(void* base, int B, int nr, int S, int flags) {
   Workspace w;
+  const bool simt = flags & CPN_FLAG_SIMT_ONLY, nofold = simt || (flags & CPN_FLAG_NO_FOLD);
+  const bool early_v = nofold || (flags & CPN_FLAG_EARLY_V), nobil = nofold || (flags & CPN_FLAG_NO_BILINEAR);
+  const bool nogfold = early_v || nobil || (flags & CPN_FLAG_NO_GFOLD);
   size_t rays = (size_t)B * nr, R = (rays * 2 * S + 127) / 128 * 128;   // whole 128-row tiles
   size_t off = 0;
   auto take = [&](size_t floats) {
@@ -96,12 +100,12 @@ Workspace carve(void* base, int B, int nr, int S) {
   w.taps = take(R * 2 * CPN_N_LEVELS * 8);   // bilinear taps of every (row, branch, level)
   w.A = take(R * 2 * CPN_KA_IMG);   // fp32 rows of CPN_KA, or the operand image with K = CPN_KA_IMG
   w.H1 = take(R * 2 * CPN_FEAT_DIM);
-  w.E = take(R * CPN_FEAT_DIM);
-  w.V = take(R * CPN_LATENT);
-  w.K1 = take(R * CPN_HIDDEN);
-  w.Kk = take(R * CPN_HIDDEN);
+  w.E = take(nofold ? R * CPN_FEAT_DIM : 0);      // query_encode_latent_2 output: unfolded paths only
+  w.V = take(early_v ? R * CPN_LATENT : 0);       // per-sample values: early-V / unfolded paths only
+  w.K1 = take(R * CPN_HIDDEN);                    // key hidden layer image, or G h + g0 of the default path
+  w.Kk = take(nobil ? R * CPN_HIDDEN : 0);        // key_map_2 / query_repeat_embed_2 outputs: three-layer logits only
   w.Q1 = take(R * CPN_HIDDEN);
-  w.Qe = take(R * CPN_HIDDEN);
+  w.Qe = take(nobil ? R * CPN_HIDDEN : 0);
   w.r1 = take(rays * CPN_LATENT);
   w.wp = take(rays * 4);
   w.zemb = take(rays * CPN_HIDDEN);
@@ -110,7 +114,7 @@ Workspace carve(void* base, int B, int nr, int S) {
   w.lg2 = take(R);
   w.wt1 = take(R);   // late readout: softmax weights of round 1 / round 2, weighted hidden layer of round 1
   w.wt2 = take(R);
-  w.hbar = take((rays + 127) / 128 * 128 * 2 * CPN_FEAT_DIM);   // operand image, whole 128-ray tiles
+  w.hbar = take(nogfold ? (rays + 127) / 128 * 128 * 2 * CPN_FEAT_DIM : 0);   // round-1 readout image (per-ray chain path)
   w.s1 = take(R);    // bilinear logits: per-row scalar terms of round 1 / round 2
   w.s2 = take(R);
   w.Qm = take(R * 2 * CPN_HIDDEN);   // [WM q + BM] of both rounds, column-blocked: [row tile][16 blocks][128][16]
@@ -246,10 +250,14 @@ size_t hbar_all_bytes(int B, int N) {
 }
 size_t image_bytes(int B, int N) { return 2 * z_bytes(B, N) + hbar_all_bytes(B, N); }
 
-extern "C" size_t cpn_render_workspace_bytes(int B, int N, int chunk_rays, int S, int lanes) {
+extern "C" size_t cpn_render_workspace_bytes_for(int B, int N, int chunk_rays, int S, int lanes, int flags) {
   if (B <= 0 || N < 0 || chunk_rays <= 0 || S <= 0 || lanes < 1 || lanes > MAX_LANES) return 0;
   int chunk = chunk_rays < N ? chunk_rays : (N > 0 ? N : 1);
-  return image_bytes(B, N) + carve(nullptr, B, chunk, S).bytes * lanes;
+  return image_bytes(B, N) + carve(nullptr, B, chunk, S, flags).bytes * lanes;
+}
+// every path: the largest carve-up (all alternative-path buffers)
+extern "C" size_t cpn_render_workspace_bytes(int B, int N, int chunk_rays, int S, int lanes) {
+  return cpn_render_workspace_bytes_for(B, N, chunk_rays, S, lanes, CPN_FLAG_SIMT_ONLY);
 }
 
 extern "C" int cpn_render_launch_count(const cpn_render_args* a) {
@@ -395,7 +403,7 @@ extern "C" int cpn_render_rays(const cpn_render_args* args, void* stream) {
   int lanes = a.lanes < 1 ? 1 : a.lanes;
   if (lanes > MAX_LANES) lanes = MAX_LANES;
   if (lanes > nchunks) lanes = nchunks;
-  const size_t lane_bytes = carve(nullptr, a.B, chunk, a.S).bytes, img_bytes = image_bytes(a.B, a.N);
+  const size_t lane_bytes = carve(nullptr, a.B, chunk, a.S, a.flags).bytes, img_bytes = image_bytes(a.B, a.N);
   if (img_bytes + lane_bytes * lanes > a.workspace_bytes) {
     cpn_set_error("cpn_render_rays: workspace of %zu bytes needed (%d lanes), %zu given", img_bytes + lane_bytes * lanes,
                   lanes, a.workspace_bytes);
@@ -419,7 +427,7 @@ extern "C" int cpn_render_rays(const cpn_render_args* args, void* stream) {
   };
   char* lane_base = reinterpret_cast<char*>(a.workspace) + img_bytes;
   if (lanes == 1) {
-    Workspace w = carve(lane_base, a.B, chunk, a.S);
+    Workspace w = carve(lane_base, a.B, chunk, a.S, a.flags);
     for (int ray0 = 0; ray0 < a.N; ray0 += chunk)
       CPN_TRY(render_chunk(a, w, z_all, hbar_all, ray0, (a.N - ray0) < chunk ? (a.N - ray0) : chunk, st));
     return finish_image();
@@ -429,7 +437,7 @@ extern "C" int cpn_render_rays(const cpn_render_args* args, void* stream) {
   CPN_CHECK_CUDA(cudaEventRecord(pool->fork, st));
   Workspace w[MAX_LANES];
   for (int l = 0; l < lanes; ++l) {
-    w[l] = carve(lane_base + l * lane_bytes, a.B, chunk, a.S);
+    w[l] = carve(lane_base + l * lane_bytes, a.B, chunk, a.S, a.flags);
     CPN_CHECK_CUDA(cudaStreamWaitEvent(pool->stream[l], pool->fork, 0));
   }
   int status = CPN_OK;

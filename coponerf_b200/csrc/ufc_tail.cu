@@ -7,7 +7,9 @@
 // target vector, so   interp4d(corr_l)[s, t] = < up(src_l)[s], up(trg_l)[t] >   with `up` the 2-D bilinear
 // upsampling of the L2-normalised feature maps. Hence
 //     c = (1/3) * [up(S_0) | up(S_1) | up(S_2)] * [up(T_0) | up(T_1) | up(T_2)]^T ,
-// one (4096 x 768) x (768 x 4096) fp32 GEMM per pair: `c` is written once and nothing else of size 64^4 exists.
+// one (4096 x 768) x (768 x 4096) GEMM per pair: `c` is written once and nothing else of size 64^4 exists. It runs on the
+// tcgen05 kernel with three fp16 MMAs per product (4e-6 of fp64 at K = 768; the soft-argmax at temperature 0.02 amplifies
+// errors of c by 50, flows stay within 1e-4 px of the fp32 path): the target operand is packed per pair like a weight (cpn_linear_tc_pack), the source operand streams as fp32 rows.
 // The soft-argmax passes then read `c` row-wise (flow_t_to_s / flow) and column-wise (flow_s_to_t / flow_flip).
 #include <math.h>
 #include "cpn_common.cuh"
@@ -165,7 +167,7 @@ int launch_ufc_normalize(const float* in, float* out, int tokens, int C, cudaStr
 namespace {
 
 struct TailWs {
-  float *ntok[2][3], *S, *Tt;
+  float *ntok[2][3], *S, *Tt, *packed;
   size_t bytes;
 };
 
@@ -180,7 +182,8 @@ TailWs carve_tail(void* base, int B, int C, int out, const int* sizes) {
   for (int side = 0; side < 2; ++side)
     for (int l = 0; l < 3; ++l) w.ntok[side][l] = take((size_t)B * sizes[l] * sizes[l] * C);
   w.S = take((size_t)B * out * out * 3 * C);
-  w.Tt = take((size_t)B * out * out * 3 * C);
+  w.Tt = take((size_t)B * out * out * 3 * C);     // target operand, row-major (P, K) like S
+  w.packed = take((cpn_linear_tc_packed_bytes(out * out, 3 * C) + 3) / 4);   // its tensor-core tiles (one pair at a time; 0 if the shape does not qualify)
   w.bytes = off;
   return w;
 }
@@ -215,6 +218,7 @@ extern "C" int cpn_ufc_tail(const cpn_ufc_tail_args* args, void* stream) {
     return CPN_ERR_WORKSPACE;
   }
   const int P = a.out * a.out, K = 3 * a.C;
+  const bool use_tc = (P % 128) == 0 && (K % 8) == 0;   // the tensor-core kernel's shape rules; else the fp32 CUDA-core GEMM
   for (int l = 0; l < 3; ++l) {
     int tokens = a.B * a.sizes[l] * a.sizes[l];
     for (int side = 0; side < 2; ++side) {
@@ -224,12 +228,23 @@ extern "C" int cpn_ufc_tail(const cpn_ufc_tail_args* args, void* stream) {
     dim3 grid(P, a.B);
     ufc_upsample_pack_kernel<<<grid, 256, 0, st>>>(w.ntok[0][l], a.sizes[l], a.out, a.C, l * a.C, K, w.S, nullptr);
     CPN_CHECK_LAUNCH("ufc_upsample_pack_kernel");
-    ufc_upsample_pack_kernel<<<grid, 256, 0, st>>>(w.ntok[1][l], a.sizes[l], a.out, a.C, l * a.C, K, nullptr, w.Tt);
+    if (use_tc)   // target operand row-major (P, K), packed like a weight below
+      ufc_upsample_pack_kernel<<<grid, 256, 0, st>>>(w.ntok[1][l], a.sizes[l], a.out, a.C, l * a.C, K, w.Tt, nullptr);
+    else          // k-major for the fp32 CUDA-core GEMM
+      ufc_upsample_pack_kernel<<<grid, 256, 0, st>>>(w.ntok[1][l], a.sizes[l], a.out, a.C, l * a.C, K, nullptr, w.Tt);
     CPN_CHECK_LAUNCH("ufc_upsample_pack_kernel");
   }
-  for (int b = 0; b < a.B; ++b) {   // c[b] = S[b] * Tt[b] / 3 (fp32 CUDA cores: the soft-argmax amplifies errors of c by 1 / 0.02)
-    int rc = launch_gemm_simt(w.S + (size_t)b * P * K, K, w.Tt + (size_t)b * K * P, nullptr, nullptr, 1, a.c + (size_t)b * P * P,
-                              P, P, P, K, 0, st, 0, 3.0f);
+  for (int b = 0; b < a.B; ++b) {   // c[b] = S[b] * T[b]^T / 3
+    int rc;
+    if (use_tc) {
+      rc = cpn_linear_tc_pack(w.Tt + (size_t)b * P * K, P, K, w.packed, stream);
+      if (rc != CPN_OK) return rc;
+      rc = launch_linear_tc(w.packed, P, K, w.S + (size_t)b * P * K, K, nullptr, a.c + (size_t)b * P * P, P, P, 0, CPN_TC_F16X3,
+                            1.f / 3.f, st);
+    } else {
+      rc = launch_gemm_simt(w.S + (size_t)b * P * K, K, w.Tt + (size_t)b * K * P, nullptr, nullptr, 1, a.c + (size_t)b * P * P,
+                            P, P, P, K, 0, st, 0, 3.0f);
+    }
     if (rc != CPN_OK) return rc;
   }
   dim3 rows(P, a.B), cols((P + 31) / 32, a.B);

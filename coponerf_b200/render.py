@@ -156,7 +156,7 @@ class RenderEngine:
             if N == 0:
                 return o
             lanes = max(1, min(self.lanes, 4, -(-N // chunk)))
-            ws_bytes = self.lib.cpn_render_workspace_bytes(B, N, chunk, S, lanes)
+            ws_bytes = self.lib.cpn_render_workspace_bytes_for(B, N, chunk, S, lanes, self.flags)
             ws = self._get_workspace(ws_bytes)
             a = _lib.RenderArgs()
             a.B, a.N, a.S, a.H, a.W = B, N, S, st.H, st.W

@@ -25,6 +25,14 @@ def _enc_params(sd, prefix):
     return blocks
 
 
+def _cat_cached(sd, key, names):
+    """Concatenation of parameters along dim 0, made once per parameter view `sd` (rebuilt when the weights change), so that
+    the operator set sees one stable tensor and packs it once."""
+    if key not in sd:
+        sd[key] = torch.cat([sd[n] for n in names], dim=0)
+    return sd[key]
+
+
 def _mlp(ops, sd, p, x, n):
     """Linear -> DWConv 3x3 -> GELU -> Linear (aggregation.py:184-189)."""
     h = ops.linear(x, sd[p + ".0.weight"], sd[p + ".0.bias"])
@@ -37,8 +45,8 @@ def _forward_attention(ops, sd, p, corr, feat, n):
     B, L, C = feat.shape
     featn = ops.layernorm(feat, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"])
     cf = torch.cat((ops.corr_to_tokens(corr, n), featn), dim=-1)
-    qk = ops.linear(cf, torch.cat((sd[p + ".q_proj.weight"], sd[p + ".k_proj.weight"]), dim=0),
-                    torch.cat((sd[p + ".q_proj.bias"], sd[p + ".k_proj.bias"]), dim=0))
+    qk = ops.linear(cf, _cat_cached(sd, f"_{p}.qk_proj.weight", (p + ".q_proj.weight", p + ".k_proj.weight")),
+                    _cat_cached(sd, f"_{p}.qk_proj.bias", (p + ".q_proj.bias", p + ".k_proj.bias")))
     pos = sd[p + ".pos_embed"]
     query = qk[..., :C].reshape(B, L, NHEAD, HEAD_DIM) + pos
     key = qk[..., C:].reshape(B, L, NHEAD, HEAD_DIM) + pos

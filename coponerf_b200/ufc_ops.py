@@ -1,6 +1,7 @@
 """CUDA operator set for coponerf_b200.ufc_native.ufc_forward: every operator is one C-ABI call into
 libcoponerf_b200.so (include/coponerf_b200.h). PyTorch only provides device memory, views and elementwise adds."""
 import ctypes
+import os
 
 import torch
 
@@ -29,6 +30,9 @@ class CudaOps:
         self._ws = None    # scratch for the split reductions (stream-ordered reuse)
         self._ws_old = []
         self._wt = {}      # weight tensor -> transposed [K][N] copy for the GEMM (made once per weight)
+        # token Linears on the tcgen05 kernel (three fp16 MMAs per product: 1e-5 of fp64 at K = 2304); CPN_UFC_SIMT_LINEAR=1 keeps every Linear on the fp32 CUDA-core GEMM for A/B runs
+        self.tc_linear = os.environ.get("CPN_UFC_SIMT_LINEAR", "0") != "1"
+        self.tc_min_rows = int(os.environ.get("CPN_UFC_TC_MIN_ROWS", "2048"))
         self.launches = 0  # kernels launched so far (bench.py's gpu_launches)
         self.launches_per_forward = 0
 
@@ -57,11 +61,31 @@ class CudaOps:
                    "cpn_layernorm")
         return y
 
+    def _packed_tc(self, w):
+        """W (N, K) -> tensor-core tiles, once per weight tensor (cpn_linear_tc_pack)."""
+        key = ("tc", w.data_ptr(), tuple(w.shape), w._version)
+        hit = self._wt.get(key)
+        if hit is None:
+            w = _c(w)
+            N, K = w.shape
+            packed = torch.empty(self.lib.cpn_linear_tc_packed_bytes(N, K), dtype=torch.uint8, device=w.device)
+            _lib.check(self.lib.cpn_linear_tc_pack(_p(w), N, K, _p(packed), _st()), "cpn_linear_tc_pack")
+            hit = self._wt[key] = (packed, w)
+        return hit[0]
+
     def linear(self, x, w, b, act=None):
         x = _c(x)
         self._check_dev(x)
         N, K = w.shape
         M = x.numel() // K
+        # from 2048 rows on (the 64 x 64 level, every level at 512 x 512): below that the tensor-core kernel has too few CTAs
+        # (one 256-row tile each, serial over K) and the split-K CUDA-core GEMM over all SMs is as fast (measured)
+        if self.tc_linear and N % 128 == 0 and K % 8 == 0 and M >= self.tc_min_rows:
+            y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
+            self.launches += 1
+            _lib.check(self.lib.cpn_linear_tc(_p(self._packed_tc(w)), N, K, _p(x), K, _p(_c(b)) if b is not None else None,
+                                              _p(y), N, M, _ACT[act], _lib.TC_F16X3, _st()), "cpn_linear_tc")
+            return y
         wt, bias = self._transposed(w), _c(b)
         y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
         nbytes = self.lib.cpn_gemm_simt_splitk_workspace_bytes(M, N, K) if M * N <= 148 * 64 * 64 else 0

@@ -131,7 +131,9 @@ typedef struct {
   size_t workspace_bytes;
 } cpn_render_args;
 
-size_t cpn_render_workspace_bytes(int B, int N, int chunk_rays, int S, int lanes);
+size_t cpn_render_workspace_bytes(int B, int N, int chunk_rays, int S, int lanes);   /* enough for every flag combination */
+/* the same for one flag combination: the default path (flags 0) leaves out the buffers only the A/B paths read */
+size_t cpn_render_workspace_bytes_for(int B, int N, int chunk_rays, int S, int lanes, int flags);
 int cpn_render_rays(const cpn_render_args* args, void* stream);
 /* number of kernels one cpn_render_rays call launches (for bench.py's gpu_launches) */
 int cpn_render_launch_count(const cpn_render_args* args);
@@ -291,6 +293,7 @@ int cpn_gemm_simt_splitk(const float* A, int lda, const float* wt, const float* 
                           * M % 512 == 0); correct, but measured 20-28 % slower than independent CTAs on B200 */
 #define CPN_TC_OUT_CB16 32  /* fp32 output column-blocked: [row tile of 128][16-column block][row][16] (N = 128 layers) */
 #define CPN_TC_OUT_ROWDOT 64 /* set by cpn_gemm_tc_rowdot */
+#define CPN_TC_PPAIR 512     /* operand-image GEMMs, f8 scheme, M % 512 == 0: persistent cta_group::2 CTA pairs */
 #define CPN_TC_NO_PERSIST 256 /* operand-image GEMMs: one tile per CTA (the first kernel) instead of the persistent kernel */
 #define CPN_TC_OUT_KG 128    /* set by cpn_gemm_tc_kg */
 #define CPN_TC_CLUSTER 8 /* experiment: the N-tile CTAs of a row tile form a cluster and multicast the A operand
@@ -312,6 +315,17 @@ int cpn_gemm_tc_rowdot(const void* packed, int layer, const void* A, int lda, co
  * dotv is CB16 with `dot_blocks` 16-column blocks per row tile, of which blocks 0..7 are used. */
 int cpn_gemm_tc_kg(const void* packed, const void* h1_image, const float* dotv_cb16, int dot_blocks, const float* rowadd,
                    float div, float* logits, float* gh, int M, int mode, void* stream);
+
+/* ---- generic Linear on the tcgen05 kernel: the token layers of the cost aggregation (q / k / v projections, MLPs,
+ * proj_feat: models/aggregation.py:269-340,509-520) and any other nn.Linear with N % 128 == 0, K % 8 == 0.
+ *   cpn_linear_tc_pack   W (N, K) fp32 as stored in the state_dict -> split, pre-scaled tensor-core tiles (once per weight)
+ *   cpn_linear_tc        y[M, N] = act(x[M, K] W^T + bias), x / y fp32 row-major (ldx, ldy in floats), bias may be NULL;
+ *                        act 0 none, 1 ReLU, 2 exact GELU; mode 0 = fp16 + two fp8 corrections, CPN_TC_F16X3 = three fp16 MMAs
+ *                        (1e-5 of fp64 at K = 2304, against 4e-5 for the default scheme). */
+size_t cpn_linear_tc_packed_bytes(int N, int K);
+int cpn_linear_tc_pack(const float* w, int N, int K, void* packed, void* stream);
+int cpn_linear_tc(const void* packed, int N, int K, const float* x, int ldx, const float* bias, float* y, int ldy, int M,
+                  int act, int mode, void* stream);
 
 #ifdef __cplusplus
 }

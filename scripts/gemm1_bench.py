@@ -10,7 +10,7 @@ from cases import cuda_model
 from coponerf_b200 import _lib
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 524288
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-modes = [int(x) for x in sys.argv[3:]] or [0]
+modes = [int(x) for x in sys.argv[3:]] or [0]      # 0 persistent, 256 one tile per CTA, 16 CTA pairs, 512 persistent CTA pairs
 lib = _lib.load(); eng = cuda_model().engine()
 tiles = M // 128
 g = torch.Generator(device="cuda").manual_seed(0)

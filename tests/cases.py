@@ -119,6 +119,7 @@ def check_against(out, ref, tag, tol=GPU_TOL, min_stable=0.5):
     of a ray is tol + SENS_FACTOR * max(0, sens - floor): the plain gate wherever the reference is stable.
     """
     get = lambda d, k: np.asarray(d[k].numpy() if isinstance(d[k], torch.Tensor) else d[k])
+    allowed_by_key = {}
     for k, t in tol.items():
         a, b = get(out, k), get(ref, k)
         assert a.shape == b.shape, (tag, k, a.shape, b.shape)
@@ -128,6 +129,7 @@ def check_against(out, ref, tag, tol=GPU_TOL, min_stable=0.5):
             err = per_ray(a.astype(np.float64) - b.astype(np.float64), k)
             allowed = t * scale + SENS_FACTOR * np.maximum(0.0, sens - SENS_FLOOR * scale)
             bad = err > allowed
+            allowed_by_key[k] = allowed
             # raw statistics next to the gate: how large the error really is, how many rays sit on a widened gate and how
             # many of them needed it (error above the plain gate)
             widened = allowed > 2.0 * t * scale
@@ -152,7 +154,9 @@ def check_against(out, ref, tag, tol=GPU_TOL, min_stable=0.5):
     d = np.nonzero(am[..., 0] != gm[..., 0])
     if d[0].size:
         top2 = np.sort(w[d[0], d[1]], axis=-1)[:, -2:]
-        assert np.all((top2[:, 1] - top2[:, 0]) <= 2e-4 * top2[:, 1]), f"{tag}: at_wt_max differs off a tie"
+        # a tie within noise: 2e-4 relative, plus twice the weight error this ray is allowed (ill-conditioned rays only)
+        slack = 2.0 * allowed_by_key["at_wt"][d[0], d[1]] if "at_wt" in allowed_by_key else 0.0
+        assert np.all((top2[:, 1] - top2[:, 0]) <= 2e-4 * top2[:, 1] + slack), f"{tag}: at_wt_max differs off a tie"
         assert d[0].size <= max(2, 0.01 * am.size), f"{tag}: too many at_wt_max ties ({d[0].size})"
     # masks looked up at trunc(T_to_C2_pts): may differ only where that point sits on a pixel boundary
     c2 = get(ref, "T_to_C2_pts").astype(np.float64)

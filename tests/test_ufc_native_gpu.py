@@ -120,6 +120,7 @@ def test_split_k_linear_matches_fp64_and_plain_kernel():
     """cpn_gemm_simt_splitk (CudaOps.linear picks it for few-tile / long-K layers) against fp64, for the token-layer
     shapes of the cost aggregation and ragged ones; deterministic from run to run."""
     cu, _ = _ops()
+    cu.tc_linear = False          # this test is about the fp32 CUDA-core path (small token counts take it in the product too)
     g = torch.Generator().manual_seed(3)
     for M, N, K, act in ((256, 512, 2304, None), (1024, 512, 2304, None), (256, 256, 1024, None), (1024, 256, 1024, "relu"),
                          (200, 132, 520, "gelu"), (256, 1024, 256, "gelu")):
@@ -132,3 +133,31 @@ def test_split_k_linear_matches_fp64_and_plain_kernel():
         assert torch.equal(got, cu.linear(x.cuda(), w.cuda(), b.cuda(), act=act))
         if K >= 512:
             assert cu.launches - n0 == 4, "expected the split-K path (GEMM + finish per call)"
+
+
+@pytest.mark.parametrize("mode", [4, 0], ids=["f16x3", "f16+f8"])
+def test_linear_tc_matches_fp64(mode):
+    """cpn_linear_tc (the token Linears of the cost aggregation on the tcgen05 kernel) against fp64 for the layer shapes of
+    UFCLayer (aggregation.py:269-340), ragged row counts, all three activations and a missing bias."""
+    import ctypes
+    from coponerf_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for M, N, K, act, with_bias in ((256, 512, 2304, None, True), (4096, 512, 2304, None, True), (1024, 256, 256, "relu", True),
+                                    (200, 1024, 256, "gelu", True), (333, 256, 1024, None, False), (64, 128, 8, "relu", True)):
+        x = torch.randn(M, K, generator=g).cuda()
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+        b = (torch.randn(N, generator=g) * 0.1).cuda() if with_bias else None
+        packed = torch.empty(lib.cpn_linear_tc_packed_bytes(N, K), dtype=torch.uint8, device="cuda")
+        _lib.check(lib.cpn_linear_tc_pack(p(w), N, K, p(packed), st()), "pack")
+        y = torch.full((M, N), float("nan"), device="cuda")
+        _lib.check(lib.cpn_linear_tc(p(packed), N, K, p(x), K, p(b) if b is not None else None, p(y), N, M,
+                                     {None: 0, "relu": 1, "gelu": 2}[act], mode, st()), "cpn_linear_tc")
+        ref = x.double() @ w.double().t() + (b.double() if b is not None else 0)
+        ref = ref.relu() if act == "relu" else torch.nn.functional.gelu(ref) if act == "gelu" else ref
+        err = float((y.double() - ref).abs().max() / ref.abs().max())
+        print(f"linear_tc mode={mode} M={M} N={N} K={K} act={act}: rel err {err:.2e}")
+        assert err <= (2.5e-5 if mode == 4 else 6e-5), (M, N, K, act, err)   # f16x3: 8e-6 ... 1e-5 measured at K = 2304 (the tensor core's fp32 accumulation)
+    assert lib.cpn_linear_tc_packed_bytes(100, 64) == 0       # N must be a multiple of 128
