@@ -19,6 +19,7 @@ FLAG_NO_FOLD = 4
 FLAG_EARLY_V = 8
 FLAG_NO_BILINEAR = 16
 FLAG_NO_GFOLD = 32
+FLAG_FULL_H1 = 64
 TC_F16X3 = 4
 TC_CLUSTER = 8
 TC_PAIR = 16
@@ -26,6 +27,9 @@ TC_OUT_CB16 = 32
 TC_OUT_KG = 128
 TC_NO_PERSIST = 256
 TC_PPAIR = 512
+TC_A_IMAGE3 = 1024
+TC_OUT_IMAGE3 = 2048
+ACT_CHUNK3_BYTES = 12288
 TC_A_IMAGE = 1
 TC_OUT_IMAGE = 2
 ACT_CHUNK_BYTES = 16384

@@ -212,7 +212,8 @@ __global__ void attn2_kernel(cpn_render_args a, int ray0, int nr, const float* _
 template <bool F8>
 __global__ void __launch_bounds__(128) readout_image_kernel(const unsigned char* __restrict__ img,
                                                             const float* __restrict__ wts, int S2,
-                                                            float* __restrict__ hbar, int nr, int out_N, int out_ray0) {
+                                                            float* __restrict__ hbar, int nr, int out_N, int out_ray0,
+                                                            int chunk_bytes) {
   extern __shared__ float sm[];   // [2S] weights of this ray, [832] weighted sums of this branch
   float* hb = sm + S2;
   const int ray = blockIdx.x, br = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(128) readout_image_kernel(const unsigned char*
 #pragma unroll 4
     for (int r = lane; r < S2; r += 32) {
       const size_t row = row0 + r;
-      const unsigned char* p = img + (((row >> 7) * 2 + br) * KC + kc) * (size_t)ACT_CHUNK_BYTES + (row & 127) * 16;
+      const unsigned char* p = img + (((row >> 7) * 2 + br) * KC + kc) * (size_t)chunk_bytes + (row & 127) * 16;
       const uint4 hi = __ldg(reinterpret_cast<const uint4*>(p + g * 2048));
       const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w};
       float x[8];
@@ -461,7 +462,7 @@ int launch_attn2(const cpn_render_args& a, int ray0, int nr, const float* q2, co
 }
 
 int launch_readout_image(const cpn_render_args& a, int nr, const void* h1_image, const float* wts, float* hbar, int f8,
-                         cudaStream_t st, int out_N, int out_ray0) {
+                         cudaStream_t st, int out_N, int out_ray0, int chunk_bytes) {
   const int S2 = 2 * a.S;
   if (S2 % 64) {
     cpn_set_error("readout_image: S=%d unsupported (S must be a multiple of 32)", a.S);
@@ -474,10 +475,10 @@ int launch_readout_image(const cpn_render_args& a, int nr, const void* h1_image,
   const size_t smem = (S2 + CPN_FEAT_DIM) * sizeof(float);
   if (f8)
     readout_image_kernel<true><<<dim3(a.B * nr, 2), 128, smem, st>>>(reinterpret_cast<const unsigned char*>(h1_image), wts, S2,
-                                                                     hbar, nr, out_N, out_ray0);
+                                                                     hbar, nr, out_N, out_ray0, chunk_bytes);
   else
     readout_image_kernel<false><<<dim3(a.B * nr, 2), 128, smem, st>>>(reinterpret_cast<const unsigned char*>(h1_image), wts, S2,
-                                                                      hbar, nr, out_N, out_ray0);
+                                                                      hbar, nr, out_N, out_ray0, chunk_bytes);
   CPN_CHECK_LAUNCH("readout_image_kernel");
   return CPN_OK;
 }

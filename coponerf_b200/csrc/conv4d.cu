@@ -9,6 +9,7 @@
 // GroupNorm over all Co x positions of a sample is a two-phase reduction: per-CTA (sum, sum of squares) in
 // double, then a normalise + ReLU pass over the 2-8 MB output.
 #include <math.h>
+#include <stdlib.h>
 #include "cpn_common.cuh"
 
 namespace {
@@ -224,6 +225,162 @@ __global__ void __launch_bounds__(C4_THREADS) conv4d_kernel(cpn_conv4d_args a, i
   }
 }
 
+// ---- stride-1, 3 x 3 blocks (55 of the 63 Conv4d calls of a pair) ---------------------------------------------------
+// The kernel above fetches every tap from global memory per output position (2.9 TFLOP/s: tap-load latency). For k = 3,
+// stride 1 the inputs of a whole (query position, band of 256 support positions) tile are nine contiguous planes: a CTA
+// stages them in shared memory once per group of 8 input channels (8 neighbour bands + the zero-padded centre band, 76 KB)
+// and every thread then runs pure shared-memory -> FMA loops for two output positions and all Co channels
+// (one staged value feeds Co FMAs, one weight vector two positions). Sum order: ci ascending, query taps then support
+// taps, fixed -- so the result does not depend on the launch.
+constexpr int S1_THREADS = 128, S1_POS = 256, S1_CI = 8;
+
+template <int CO>
+__global__ void __launch_bounds__(S1_THREADS) conv4d_s1_kernel(cpn_conv4d_args a, double* __restrict__ partials) {
+  extern __shared__ __align__(16) float sm1[];
+  const int Ci = a.Ci, Hq = a.Hq, Hs = a.Hs;
+  const int SB = S1_POS / Hs;                  // support rows per band
+  const int nbands = Hs / SB;
+  const int PW = Hs + 2, CTR = (SB + 2) * PW;  // padded centre band
+  float* wq_s = sm1;                           // [Ci][9][CO]
+  float* ws_s = wq_s + Ci * 9 * CO;
+  float* nb = ws_s + Ci * 9 * CO;              // [8 neighbours][S1_CI][S1_POS]
+  float* ctr = nb + 8 * S1_CI * S1_POS;        // [S1_CI][CTR]
+  const int t = threadIdx.x, b = blockIdx.y;
+  const int band = blockIdx.x % nbands, q = blockIdx.x / nbands, qy = q / Hq, qx = q % Hq;
+  const int row0 = band * SB;
+  for (int j = t; j < Ci * 9 * CO; j += S1_THREADS) {   // (Co, Ci, 3, 3) -> [ci][tap][co]
+    const int tap = j % 9, ci = (j / 9) % Ci, co = j / (9 * Ci);
+    wq_s[(ci * 9 + tap) * CO + co] = a.wq[j];
+    ws_s[(ci * 9 + tap) * CO + co] = a.ws[j];
+  }
+  const size_t plane = (size_t)Hs * Hs, cplane = (size_t)Hq * Hq * plane;
+  const float* xb = a.x + (size_t)b * Ci * cplane;
+  float acc[2][CO];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int co = 0; co < CO; ++co) acc[i][co] = 0.f;
+  // this thread's two positions inside the band and their offsets in the padded centre band
+  const int p0 = t, p1 = t + S1_THREADS;
+  const int c0 = (p0 / Hs + 1) * PW + p0 % Hs + 1, c1 = (p1 / Hs + 1) * PW + p1 % Hs + 1;
+  for (int ci0 = 0; ci0 < Ci; ci0 += S1_CI) {
+    __syncthreads();   // weights staged / the previous channel group consumed
+    // 8 neighbour bands (zeros outside the query grid): float4 copies of 1 KB runs, eight loads in flight per thread (the
+    // first version issued one load per loop iteration and spent 80 % of the kernel waiting for L2)
+    constexpr int NB_V4 = 8 * S1_CI * (S1_POS / 4);
+    static_assert(NB_V4 % (S1_THREADS * 8) == 0, "neighbour bands: whole batches of 8 loads per thread");
+#pragma unroll 1
+    for (int j0 = t; j0 < NB_V4; j0 += S1_THREADS * 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u * S1_THREADS;
+        const int v4 = j % (S1_POS / 4), ci = (j / (S1_POS / 4)) % S1_CI, n = j / ((S1_POS / 4) * S1_CI);
+        const int tap = n < 4 ? n : n + 1, ny = qy + tap / 3 - 1, nx = qx + tap % 3 - 1;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ny >= 0 && ny < Hq && nx >= 0 && nx < Hq)
+          v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)(ci0 + ci) * cplane + ((size_t)ny * Hq + nx) * plane + (size_t)row0 * Hs) + v4);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) reinterpret_cast<float4*>(nb)[j0 + u * S1_THREADS] = v[u];
+    }
+    // centre band with a one-element zero halo (rows above / below the band come from the plane itself)
+    const int nctr = S1_CI * CTR;
+#pragma unroll 1
+    for (int j0 = t; j0 < nctr; j0 += S1_THREADS * 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u * S1_THREADS;
+        v[u] = 0.f;
+        if (j < nctr) {
+          const int ci = j / CTR, r = (j % CTR) / PW, c = (j % CTR) % PW;
+          const int sy = row0 + r - 1, sx = c - 1;
+          if (sy >= 0 && sy < Hs && sx >= 0 && sx < Hs)
+            v[u] = __ldg(xb + (size_t)(ci0 + ci) * cplane + ((size_t)qy * Hq + qx) * plane + (size_t)sy * Hs + sx);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (j0 + u * S1_THREADS < nctr) ctr[j0 + u * S1_THREADS] = v[u];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < S1_CI; ++ci) {
+      const float* wq_c = wq_s + (size_t)(ci0 + ci) * 9 * CO;
+      const float* ws_c = ws_s + (size_t)(ci0 + ci) * 9 * CO;
+      const float* cc = ctr + ci * CTR;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {      // query branch: the same support position in the nine neighbouring planes
+        float v0, v1;
+        if (tap == 4) {
+          v0 = cc[c0];
+          v1 = cc[c1];
+        } else {
+          const float* np = nb + ((size_t)(tap < 4 ? tap : tap - 1) * S1_CI + ci) * S1_POS;
+          v0 = np[p0];
+          v1 = np[p1];
+        }
+#pragma unroll
+        for (int co = 0; co < CO; co += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wq_c + tap * CO + co);
+          acc[0][co] = fmaf(v0, w4.x, acc[0][co]); acc[0][co + 1] = fmaf(v0, w4.y, acc[0][co + 1]);
+          acc[0][co + 2] = fmaf(v0, w4.z, acc[0][co + 2]); acc[0][co + 3] = fmaf(v0, w4.w, acc[0][co + 3]);
+          acc[1][co] = fmaf(v1, w4.x, acc[1][co]); acc[1][co + 1] = fmaf(v1, w4.y, acc[1][co + 1]);
+          acc[1][co + 2] = fmaf(v1, w4.z, acc[1][co + 2]); acc[1][co + 3] = fmaf(v1, w4.w, acc[1][co + 3]);
+        }
+      }
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {      // support branch: the 3 x 3 neighbourhood inside the centre plane
+        const int off = (tap / 3 - 1) * PW + tap % 3 - 1;
+        const float v0 = cc[c0 + off], v1 = cc[c1 + off];
+#pragma unroll
+        for (int co = 0; co < CO; co += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(ws_c + tap * CO + co);
+          acc[0][co] = fmaf(v0, w4.x, acc[0][co]); acc[0][co + 1] = fmaf(v0, w4.y, acc[0][co + 1]);
+          acc[0][co + 2] = fmaf(v0, w4.z, acc[0][co + 2]); acc[0][co + 3] = fmaf(v0, w4.w, acc[0][co + 3]);
+          acc[1][co] = fmaf(v1, w4.x, acc[1][co]); acc[1][co + 1] = fmaf(v1, w4.y, acc[1][co + 1]);
+          acc[1][co + 2] = fmaf(v1, w4.z, acc[1][co + 2]); acc[1][co + 3] = fmaf(v1, w4.w, acc[1][co + 3]);
+        }
+      }
+    }
+  }
+  // biases, store (consecutive threads -> consecutive support positions), GroupNorm partial sums in double
+  const size_t P = cplane;
+  const size_t pos_base = (size_t)q * plane + (size_t)row0 * Hs;
+  double sum = 0.0, sq = 0.0;
+#pragma unroll
+  for (int co = 0; co < CO; ++co) {
+    const float bb = a.bq[co] + a.bs[co];
+    const float v0 = acc[0][co] + bb, v1 = acc[1][co] + bb;
+    float* yo = a.y + ((size_t)b * CO + co) * P + pos_base;
+    yo[p0] = v0;
+    yo[p1] = v1;
+    sum += (double)v0 + (double)v1;
+    sq += (double)v0 * (double)v0 + (double)v1 * (double)v1;
+  }
+  __shared__ double red2[2][S1_THREADS / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if ((t & 31) == 0) {
+    red2[0][t >> 5] = sum;
+    red2[1][t >> 5] = sq;
+  }
+  __syncthreads();
+  if (t == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int i = 0; i < S1_THREADS / 32; ++i) {
+      t0 += red2[0][i];
+      t1 += red2[1][i];
+    }
+    partials[((size_t)b * gridDim.x + blockIdx.x) * 2 + 0] = t0;
+    partials[((size_t)b * gridDim.x + blockIdx.x) * 2 + 1] = t1;
+  }
+}
+
 // GroupNorm(1, Co) (biased variance, eps 1e-5, per-channel affine) + ReLU, in place.
 __global__ void __launch_bounds__(256) gn_relu_kernel(float* __restrict__ y, const double* __restrict__ partials, int nparts,
                                                       int Co, int P, const float* __restrict__ gamma,
@@ -301,13 +458,35 @@ extern "C" int cpn_conv4d(const cpn_conv4d_args* args, void* stream) {
     cpn_set_error("cpn_conv4d: workspace of %zu bytes needed, %zu given", need, a.workspace_bytes);
     return CPN_ERR_WORKSPACE;
   }
+  double* partials = reinterpret_cast<double*>(a.workspace);
+  // stride-1 3 x 3 blocks with whole 256-position bands and channel groups of 8: the shared-memory tile kernel
+  static int direct_only = -1;   // CPN_CONV4D_DIRECT=1: the per-position kernel for every geometry (A/B runs)
+  if (direct_only < 0) {
+    const char* e = getenv("CPN_CONV4D_DIRECT");
+    direct_only = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  if (!direct_only && a.k == 3 && a.stride == 1 && a.pad == 1 && a.Hq == oq && a.Hs == os && (a.Ci % S1_CI) == 0 &&
+      a.Hs <= S1_POS && (S1_POS % a.Hs) == 0 && (a.Hs % (S1_POS / a.Hs)) == 0 && (a.Hs % 4) == 0) {
+    const int nbands = a.Hs / (S1_POS / a.Hs), nblk1 = a.Hq * a.Hq * nbands;
+    const size_t smem1 = ((size_t)2 * a.Ci * 9 * a.Co + (size_t)8 * S1_CI * S1_POS +
+                          (size_t)S1_CI * (S1_POS / a.Hs + 2) * (a.Hs + 2)) * sizeof(float);
+    void (*k1)(cpn_conv4d_args, double*) = a.Co == 8 ? conv4d_s1_kernel<8> : conv4d_s1_kernel<32>;
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    k1<<<dim3(nblk1, a.B), S1_THREADS, smem1, st>>>(a, partials);
+    CPN_CHECK_LAUNCH("conv4d_s1_kernel");
+    if (a.norm_relu) {
+      dim3 g2(256, a.B);
+      gn_relu_kernel<<<g2, 256, 0, st>>>(a.y, partials, nblk1, a.Co, oq * oq * os * os, a.gamma, a.beta);
+      CPN_CHECK_LAUNCH("gn_relu_kernel");
+    }
+    return CPN_OK;
+  }
   const int P = oq * oq * os * os, nblk = (P + C4_CTA_POS - 1) / C4_CTA_POS;
   const size_t smem = ((size_t)2 * a.Ci * a.k * a.k * a.Co + (size_t)C4_WARPS * a.Co * C4_POS) * sizeof(float);
   if (smem > 96 * 1024) {
     cpn_set_error("cpn_conv4d: weights + partial sums of %zu bytes do not fit in shared memory", smem);
     return CPN_ERR_ARG;
   }
-  double* partials = reinterpret_cast<double*>(a.workspace);
   dim3 grid(nblk, a.B);
   void (*kern)(cpn_conv4d_args, int, int, double*);
   const int ks = a.k * 10 + a.stride;

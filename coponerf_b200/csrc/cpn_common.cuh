@@ -150,8 +150,9 @@ int launch_attn2(const cpn_render_args& a, int ray0, int nr, const float* q2, co
                  const float* w1 = nullptr);   // w1: wts_out = w2 + 2 w1 (combined readout weight)
 // late readout: hbar (rays, 1664) = sum over a ray's rows of w * [h_p ; h_s] read from the hidden-layer operand image
 // out_N > 0: output rows are indexed by the ray's position in the whole image (b * out_N + out_ray0 + n) instead of the chunk
+// chunk_bytes: 16384, or 12288 for a compact hidden image (CPN_TC_OUT_IMAGE3; the readout never reads the value plane)
 int launch_readout_image(const cpn_render_args& a, int nr, const void* h1_image, const float* wts, float* hbar, int f8,
-                         cudaStream_t st, int out_N = 0, int out_ray0 = 0);
+                         cudaStream_t st, int out_N = 0, int out_ray0 = 0, int chunk_bytes = 16384);
 int launch_park_r1(const cpn_render_args& a, int ray0, int nr, const float* r1, float* z_all, cudaStream_t st);
 int launch_finish_z(const cpn_render_args& a, const float* r2_all, float* z_all, cudaStream_t st);
 int launch_finish_z_bias(const cpn_render_args& a, const float* r2_all, const float* bias, float* z_all, cudaStream_t st);
@@ -163,17 +164,20 @@ int launch_ray_epilogue(const cpn_render_args& a, int ray0, int nr, const float*
 // 16 KB block [hi | lo] x [4 groups of 8 k][128 rows][8 fp16] -- exactly what the MMA reads from shared memory
 // (K-major, no swizzle), so a consumer stages it with one bulk copy. Block index = tile * (K / 32) + k-chunk.
 // Two precision schemes share the block size: "f16x3" stores [hi fp16 8 KB | lo fp16 8 KB]; the default "f8"
-// scheme stores [hi fp16 8 KB | e4m3(lo * 2^8) 4 KB | e4m3(x * 2^-6) 4 KB] with the 8-bit planes as
+// scheme stores [hi fp16 8 KB | e5m2(lo * 2^10) 4 KB | e5m2(hi) 4 KB] with the 8-bit planes as
 // [2 groups of 16 k][128 rows][16 bytes] (tc_common.cuh).
 constexpr int ACT_BK = 32;
 constexpr int ACT_CHUNK_BYTES = 2 * (ACT_BK / 8) * 128 * 16;
 constexpr int ACT_LO = 8192;      // f16x3: fp16 lo plane
-constexpr int ACT_LO8 = 8192;     // f8: e4m3 remainder plane
-constexpr int ACT_X8 = 12288;     // f8: e4m3 value plane
+constexpr int ACT_LO8 = 8192;     // f8: e5m2 remainder plane
+constexpr int ACT_X8 = 12288;     // f8: e5m2 value plane
 constexpr int CPN_TC_LAYERS = 11;
 size_t cpn_packed_fp32_floats();
 size_t cpn_tc_weights_bytes();
 int cpn_pack_tc_weights(const float* raw, const float* packed_fp32, void* dst, cudaStream_t st);
+// layer 9 fused with the 16 -> 128 ReLU layer in front of it (gemm_tc.cu)
+int launch_gemm_tc_mlp16(const void* packed, const float* x16, const float* wt, const float* bias, const float* sd1, float* s1,
+                         const float* sd2, float* s2, float* qm_cb16, int M, int mode, cudaStream_t st);
 // generic Linear on the tensor-core kernel (include/coponerf_b200.h: cpn_linear_tc); the accumulators are scaled by out_mul
 int launch_linear_tc(const void* packed, int N, int K, const float* x, int ldx, const float* bias, float* y, int ldy, int M,
                      int act, int mode, float out_mul, cudaStream_t stream);

@@ -80,8 +80,9 @@ __global__ void __launch_bounds__(256) gather_kernel(cpn_render_args a, int nr, 
 // its row (lanes along channels: every tap is a coalesced 512-byte read), splits it into fp16 hi/lo and parks it in
 // shared memory; the CTA then writes the image, where the same 8-channel group of 8 consecutive rows is 128
 // contiguous bytes (full-sector, coalesced stores).
+constexpr int GI_GROUPS = 4;   // 8-row groups per CTA
 constexpr int GI_ROWS = 8, GI_PITCH = CPN_FEAT_DIM + 24;  // halves per staged row: 1712 B = 428 words, 428 % 32 = 12 -> the 8 rows' 16-byte reads hit distinct banks
-constexpr int GI_B8 = CPN_FEAT_DIM + 16;                  // bytes per e4m3 plane of a staged row
+constexpr int GI_B8 = CPN_FEAT_DIM + 16;                  // bytes per 8-bit plane of a staged row
 
 // make_taps with out-of-range taps turned into (offset 0, weight 0): the blend needs no branches
 __device__ __forceinline__ Taps make_taps_safe(float gx, float gy, int h, int w, int C, bool border) {
@@ -124,12 +125,17 @@ template <bool F8>
 __global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, int nr, const int4* __restrict__ taps,
                                                            unsigned char* __restrict__ img) {
   // f16x3: [hi | lo][row][channel] fp16. f8: plane 0 = fp16 hi; plane 1 holds the two byte planes back to back,
-  // e4m3(lo * 2^8) in bytes [0, 832) and e4m3(x * 2^-6) in bytes [848, 1680) of each row.
+  // e5m2((x - hi) * 2^10) in bytes [0, 832) and e5m2(hi) in bytes [848, 1680) of each row (tc_common.cuh).
   __shared__ __align__(16) __half sh[2][GI_ROWS][GI_PITCH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int branch = blockIdx.y;
   const unsigned nrows = (unsigned)(a.B * nr * 2 * a.S);       // < 2^31 (checked by the launcher)
-  const unsigned row0 = blockIdx.x * GI_ROWS, row = row0 + warp;
+  // a CTA walks GI_GROUPS groups of 8 rows: the per-thread index arithmetic of the copy-out (and the level geometry) is set up
+  // once per CTA instead of once per 8 rows (a third of the kernel's instructions was integer address work, profiles/)
+#pragma unroll 1
+  for (int grp = 0; grp < GI_GROUPS; ++grp) {
+  const unsigned row0 = (blockIdx.x * GI_GROUPS + grp) * GI_ROWS, row = row0 + warp;
+  if (row0 >= nrows) break;
   if (row < nrows) {
     const unsigned S = (unsigned)a.S;
     const int v = (int)((row / S) & 1u);
@@ -217,6 +223,8 @@ __global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, in
         }
       }
     }
+  }
+  __syncthreads();   // the staged rows are free for the next group
   }
 }
 
@@ -414,7 +422,7 @@ int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowau
       CPN_CHECK_LAUNCH("gather_image_seq_kernel");
       return CPN_OK;
     }
-    dim3 grid((unsigned)((rows + GI_ROWS - 1) / GI_ROWS), 2);
+    dim3 grid((unsigned)((rows + GI_ROWS * GI_GROUPS - 1) / (GI_ROWS * GI_GROUPS)), 2);
     if (a_image == 2)
       gather_image_kernel<true><<<grid, 256, 0, st>>>(a, nr, tp, reinterpret_cast<unsigned char*>(A));
     else

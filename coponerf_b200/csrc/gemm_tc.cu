@@ -70,7 +70,7 @@ const TcLayer kLayers[CPN_TC_LAYERS] = {
     {128, 128, 128, 128, RAW_WQR2, pw::BQR2, false},  // 6 query_repeat_embed_2
     {416, 1664, 1664, 208, pw::WVF, pw::BVF, true},   // 7 latent_value o query_encode_latent_2 (both branches)
     {128, 1664, 1664, 128, pw::WKF, pw::BKF, true},   // 8 key_map o query_encode_latent_2
-    {256, 128, 128, 128, pw::WM12, pw::BM12, true},   // 9 [key_map_2 ; query_repeat_embed_2]^T query_embed_2 (bilinear logits)
+    {256, 128, 128, 256, pw::WM12, pw::BM12, true},   // 9 [key_map_2 ; query_repeat_embed_2]^T query_embed_2 (bilinear logits), one 256-column tile
     {256, 1664, 1664, 256, pw::WKF, pw::BKF, true},   // 10 [key_map ; G] o query_encode_latent_2: key hidden layer and the
                                                       //    per-row term of the round-2 query bias (cpn_common.cuh, pw::WG)
 };
@@ -83,7 +83,7 @@ size_t scheme_bytes() {
   for (int i = 0; i < CPN_TC_LAYERS; ++i) n += layer_bytes(i);
   return n;
 }
-// scheme 0: f16x3 tiles [w_hi | w_lo] fp16; scheme 1: f8 tiles [w_hi fp16 | e4m3(w_hi 2^-8) | e4m3(w_lo 2^6)];
+// scheme 0: f16x3 tiles [w_hi | w_lo] fp16; scheme 1: f8 tiles [w_hi fp16 | e4m3(w_hi 2^-10) | e4m3(w_lo)];
 // scheme 2: the f8 planes again in half tiles of NT / 2 rows (one per CTA of a cta_group::2 pair)
 size_t layer_offset(int l, int scheme) {
   size_t off = TC_HEADER_BYTES + (size_t)scheme * scheme_bytes();
@@ -110,7 +110,7 @@ __device__ __forceinline__ float layer_scale(unsigned int absmax_bits) {
 }
 
 // dst tile (nt, kc), 128 * NT bytes: f16x3 [hi | lo] x [4 k-groups][NT rows][8 halves];
-// f8 [hi as before | e4m3(hi 2^-8) | e4m3(lo 2^6)] with the byte planes as [2 k-groups of 16][NT rows][16 bytes]
+// f8 [hi as before | e4m3(hi 2^-10) | e4m3(lo)] with the byte planes as [2 k-groups of 16][NT rows][16 bytes]
 __global__ void pack_tc_kernel(const float* __restrict__ w, int out, int in, int kpad, int NT, const unsigned int* absmax,
                                __half* __restrict__ dst, unsigned char* __restrict__ dst8,
                                unsigned char* __restrict__ dstp, float* __restrict__ header, int layer) {
@@ -165,12 +165,18 @@ struct GemmArgs {
   const float* inv_scale;        // header[layer]
   int kchunks, NT;
   uint32_t idesc;
-  int f8;                        // 1: fp16 + two e4m3 correction MMAs, 0: three fp16 MMAs
+  int f8;                        // 1: fp16 + two fp8 correction MMAs (e5m2 activations x e4m3 weights), 0: three fp16 MMAs
   int out_kind;                  // fp32 output: 0 row-major, 2 column-blocked (CB16), 3 per-row dot with `dotv`,
                                  // 4 N tile 0 as kind 3 (with ReLU), the other N tiles row-major into C2 without ReLU
   float* C2;                     // out_kind 4: fp32 (M, N - NT) row-major
   unsigned long long* dbg;       // phase timestamps of the first `dbg_cap` CTAs (cpn_gemm_tc_trace), else null
   int dbg_cap;
+  // MLP16 producer (gemm_tc_kernel<false, false, 1, true>): A = relu(x16 Wt + b) computed by the producer warps
+  const float *mlp_x, *mlp_wt, *mlp_b, *mlp_sd1, *mlp_sd2;   // x (M, 16); Wt [16][128]; b [128]; sd1 / sd2: [128] vector + constant
+  float *mlp_s1, *mlp_s2;                                    // s1[row] = <A row, sd1> + sd1[128] (and s2), nullable
+  int a_chunk;                   // bytes per (tile, k-chunk) block of the A image: 16384, or 12288 for the compact form without the
+                                 // value plane (the persistent kernel derives it in shared memory)
+  int out_chunk;                 // the same for an image output
   float out_mul;                 // the accumulators are multiplied by inv_scale * out_mul before the bias (1 except the tail GEMM)
   int dbg_skip;                  // trace runs only (CPN_TC_DBG_SKIP): 1 no image stores, 2 no split / conversions, 4 no TMEM loads
   const float* dotv;             // CB16 matrix the rows are dotted with (out_kind 3); C then holds one float per row
@@ -201,7 +207,7 @@ __device__ __forceinline__ float drain_subtile(const GemmArgs& g, uint32_t tmem,
   int kbase = 0;                  // k of the next layer that column n0 of this tile maps to
   if (OUT_IMAGE) {
     int t = m0 / 128 + esub;
-    img = reinterpret_cast<unsigned char*>(g.C) + (size_t)(t / g.out_div) * g.out_kchunks * ACT_CHUNK_BYTES + rloc * 16;
+    img = reinterpret_cast<unsigned char*>(g.C) + (size_t)(t / g.out_div) * g.out_kchunks * g.out_chunk + rloc * 16;
     kbase = (t % g.out_div) * g.N + n0;
   }
   // CB16: fp32 [row tile][16-column block][128 rows][16], so that a thread's 16 columns are 64 contiguous bytes and the
@@ -236,7 +242,7 @@ __device__ __forceinline__ float drain_subtile(const GemmArgs& g, uint32_t tmem,
     if (OUT_IMAGE) {
       // 16 consecutive k of the next layer; lanes are consecutive rows -> every store instruction writes 512 B runs
       const int k = kbase + c0;
-      unsigned char* chunk = img + (size_t)(k / BK) * ACT_CHUNK_BYTES;
+      unsigned char* chunk = img + (size_t)(k / BK) * g.out_chunk;
       if (g.f8) {
         uint2 h[4];
         uint4 l8, x8;
@@ -258,7 +264,7 @@ __device__ __forceinline__ float drain_subtile(const GemmArgs& g, uint32_t tmem,
           *reinterpret_cast<uint4*>(ph) = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
           *reinterpret_cast<uint4*>(ph + A_LBO) = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
           *reinterpret_cast<uint4*>(chunk + ACT_LO8 + ((k % BK) / 16) * A_LBO) = l8;
-          *reinterpret_cast<uint4*>(chunk + ACT_X8 + ((k % BK) / 16) * A_LBO) = x8;
+          if (g.out_chunk == ACT_CHUNK_BYTES) *reinterpret_cast<uint4*>(chunk + ACT_X8 + ((k % BK) / 16) * A_LBO) = x8;
         }
       } else {
 #pragma unroll
@@ -302,9 +308,14 @@ __device__ __forceinline__ float drain_subtile(const GemmArgs& g, uint32_t tmem,
 // CLUSTER (> 1, operand-image A only): the CTAs of the N tiles of one 256-row tile form a cluster; each loads
 // 1/CLUSTER of every A stage and multicasts it to all of them, so the shared A operand is read from L2 once per
 // cluster instead of once per N tile (the GEMMs are L2 -> SM bandwidth bound, profiles/).
-template <bool A_IMAGE, bool OUT_IMAGE, int CLUSTER>
+// MLP16: the A operand is relu(x16 Wt + b) (query_embed, 16 -> 128, CoPoNeRF.py:446) computed by the producer warps from the
+// 64-byte local_coords rows, so the coordinate embedding never exists in memory (it used to be an operand image written by one
+// kernel and read back by this one: 2 x 134 MB per chunk and a launch); the scalar logit terms <q1, WS> + CS come out of it too.
+template <bool A_IMAGE, bool OUT_IMAGE, int CLUSTER, bool MLP16 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
   extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(16) float mlp_ws[MLP16 ? 16 : 1][CPN_HIDDEN];
+  __shared__ __align__(16) float mlp_v[MLP16 ? 3 : 1][CPN_HIDDEN];   // bias, sd1, sd2
   __shared__ __align__(8) uint64_t bars[3 * STAGES + 1];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -338,6 +349,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), TMEM_COLS);
+  if (MLP16) {
+    for (int i = threadIdx.x; i < 16 * CPN_HIDDEN; i += NUM_THREADS) mlp_ws[i / CPN_HIDDEN][i % CPN_HIDDEN] = g.mlp_wt[i];
+    for (int i = threadIdx.x; i < CPN_HIDDEN; i += NUM_THREADS) {
+      mlp_v[0][i] = g.mlp_b[i];
+      mlp_v[1][i] = g.mlp_sd1 ? g.mlp_sd1[i] : 0.f;
+      mlp_v[2][i] = g.mlp_sd2 ? g.mlp_sd2[i] : 0.f;
+    }
+  }
   tcgen05_fence_before();
   __syncthreads();
   if (CLUSTER > 1) cluster_sync();   // every CTA's barriers are initialised before any remote arrive / copy
@@ -402,7 +421,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
             for (int j = 0; j < BK / 16; ++j)
               mma_f16_ss(d, make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128), make_desc(b_hi + j * 2 * NT * 16, NT * 16, 128),
                          g.idesc, (i | j) != 0);
-            // e4m3 planes: K = 32 per instruction = two 16-byte core matrices along k
+            // 8-bit planes: K = 32 per instruction = two 16-byte core matrices along k
             mma_f8_ss(d, make_desc(a_hi + ACT_LO8, A_LBO, 128), make_desc(b_hi + w_half, NT * 16, 128), g.idesc | IDESC_A_E5M2, 1);
             mma_f8_ss(d, make_desc(a_hi + ACT_X8, A_LBO, 128), make_desc(b_hi + w_half + w_half / 2, NT * 16, 128),
                       g.idesc | IDESC_A_E5M2, 1);
@@ -456,7 +475,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           int r = rbase + it * 8 + r_in;
-          if (g.f8) {   // this thread's 8 k: one 16-byte fp16 group, half of a 16-byte e4m3 group in each byte plane
+          if (g.f8) {   // this thread's 8 k: one 16-byte fp16 group, half of a 16-byte 8-bit group in each byte plane
             uint2 h0, h1, l8, x8;
             split4_f8(v[it][0], h0, l8.x, x8.x);
             split4_f8(v[it][1], h1, l8.y, x8.y);
@@ -473,6 +492,62 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
         fence_proxy_async_smem();
         mbar_arrive(full_a + 8 * s);
       };
+      if (MLP16) {
+        // this thread: rows pwarp * 32 + it * 8 + r_in (it = 0..3), outputs k = 32 i + 8 c .. + 7 of every k-chunk i
+        float xin[4][16], d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = m0 + pwarp * 32 + it * 8 + r_in;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 v = row < g.M ? __ldg(reinterpret_cast<const float4*>(g.mlp_x + (size_t)row * 16 + j))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            xin[it][j] = v.x; xin[it][j + 1] = v.y; xin[it][j + 2] = v.z; xin[it][j + 3] = v.w;
+          }
+        }
+        for (int i = 0; i < g.kchunks; ++i) {
+          const int k0 = i * BK + c * 8;
+          float acc[4][8];
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[it][e] = mlp_v[0][k0 + e];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&mlp_ws[j][k0]), w1 = *reinterpret_cast<const float4*>(&mlp_ws[j][k0 + 4]);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[it][e] = fmaf(xin[it][j], wv[e], acc[it][e]);
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              acc[it][e] = fmaxf(acc[it][e], 0.f);
+              d1[it] = fmaf(acc[it][e], mlp_v[1][k0 + e], d1[it]);
+              d2[it] = fmaf(acc[it][e], mlp_v[2][k0 + e], d2[it]);
+            }
+            buf[0][it][0] = make_float4(acc[it][0], acc[it][1], acc[it][2], acc[it][3]);
+            buf[0][it][1] = make_float4(acc[it][4], acc[it][5], acc[it][6], acc[it][7]);
+          }
+          store_chunk(i, buf[0]);
+        }
+        // the four lanes that share a row (k-groups c = 0..3) add their partial dot products in a fixed order
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          d1[it] += __shfl_xor_sync(0xffffffffu, d1[it], 8);
+          d1[it] += __shfl_xor_sync(0xffffffffu, d1[it], 16);
+          d2[it] += __shfl_xor_sync(0xffffffffu, d2[it], 8);
+          d2[it] += __shfl_xor_sync(0xffffffffu, d2[it], 16);
+          const int row = m0 + pwarp * 32 + it * 8 + r_in;
+          if (c == 0 && row < g.M) {
+            if (g.mlp_s1) g.mlp_s1[row] = d1[it] + g.mlp_sd1[CPN_HIDDEN];
+            if (g.mlp_s2) g.mlp_s2[row] = d2[it] + g.mlp_sd2[CPN_HIDDEN];
+          }
+        }
+      } else {
       if (0 < g.kchunks) load_chunk(0, buf[0]);
       if (1 < g.kchunks) load_chunk(1, buf[1]);
       int i = 0;
@@ -486,6 +561,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
       }
       if (i < g.kchunks) store_chunk(i, buf[0]);
       if (i + 1 < g.kchunks) store_chunk(i + 1, buf[1]);
+      }
     }
     // ---- epilogue: warp w may touch TMEM lanes 32 * (w % 4) .. + 31; warps 2-5 drain sub-tile 0, 6-9 sub-tile 1
     const int esub = pwarp >> 2, q = warp & 3;
@@ -577,17 +653,29 @@ __device__ __forceinline__ float drain_dot2(const GemmArgs& g, uint32_t tmem, in
 // tile, profiles/r2_gemm1_trace_splitring.json): the loop is bound by L2 -> SM bandwidth, not by load latency.
 // EPI_WARPS = 8 * PARTS: 16 leaves registers for a co-resident CTA of another kernel (the gather / readout of the other chunk
 // lane: a persistent grid does not block the dispatch of later kernels the way a long CTA queue does).
-template <bool OUT_IMAGE, int P_EPI_WARPS>
+// CL = 2: the two CTAs of a cluster work on neighbouring N tiles of the SAME row tile (tiles 2p and 2p + 1); each fetches one
+// of the two 128-row activation sub-tiles of every stage and multicasts it to both, so an SM reads 42.6 KB instead of 58.6 KB
+// per k-chunk from L2. Every CTA issues its own MMAs; the only coupling is that a stage is refilled when BOTH have consumed it
+// (tcgen05.commit multicast to both `empty` barriers, count 2).
+template <bool OUT_IMAGE, int P_EPI_WARPS, int CL>
 __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_kernel(GemmArgs g, int ntiles_n, int ntiles) {
   constexpr int PARTS = P_EPI_WARPS / 8;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+  // tile list of this CTA: t = t_first, t_first + t_stride, ... (CL = 2: the cluster takes tile pairs, this CTA tile 2p + rank)
+  const int t_first = CL > 1 ? (int)(blockIdx.x / CL) * CL + (int)crank : (int)blockIdx.x, t_stride = (int)gridDim.x;
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + 2];
+  __shared__ __align__(8) uint64_t bars[3 * STAGES + 2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sdot[2][PARTS][128];     // row-dot partials of the column parts
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = smem_u32(smem);
   const uint32_t full = smem_u32(&bars[0]), empty = smem_u32(&bars[STAGES]), accum_full = smem_u32(&bars[2 * STAGES]),
                  accum_empty = smem_u32(&bars[2 * STAGES + 1]);
+  // compact A image (12 KB blocks: fp16 head + remainder plane): the value plane e5m2(head) of a stage is derived in shared
+  // memory by the epilogue warps, which are idle during the MMA loop; the MMA thread then waits on `ready` instead of `full`
+  const uint32_t ready = smem_u32(&bars[2 * STAGES + 2]);
+  const bool a3 = g.a_chunk != ACT_CHUNK_BYTES;
+  const uint32_t a_bytes = a3 ? (uint32_t)ACT_X8 : (uint32_t)A_SUB;
   const int NT = g.NT;
   const uint32_t w_half = (uint32_t)(BK / 8) * NT * 16;
   auto stamp = [&](int tile_no, int i) {   // optional phase trace, 8 x u64 per (CTA, tile) slot
@@ -603,15 +691,17 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full + 8 * s, 1);
-      mbar_init(empty + 8 * s, 1);
+      mbar_init(empty + 8 * s, CL);   // one commit from the MMA thread of every CTA that receives this stage's activations
     }
     mbar_init(accum_full, 1);
     mbar_init(accum_empty, P_EPI_WARPS);
+    for (int s = 0; s < STAGES; ++s) mbar_init(ready + 8 * s, P_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), TMEM_COLS);
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync();   // every CTA's barriers exist before a peer multicasts into them
   tcgen05_fence_after();
   const uint32_t tmem = tmem_base_s;
 
@@ -619,7 +709,7 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
     if (lane == 0) {
       const unsigned char* asrc = reinterpret_cast<const unsigned char*>(g.A);
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (int t = t_first; t < ntiles; t += t_stride) {
         const int n_tile = t % ntiles_n, m0 = (t / ntiles_n) * BM;
         const bool sub1_valid = (m0 + 128) < g.M;
         const unsigned char* wsrc = g.wtiles + (size_t)n_tile * g.kchunks * 2 * w_half;
@@ -629,11 +719,17 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
           const uint32_t u = it / STAGES;
           mbar_wait(empty + 8 * s, (u & 1) ^ 1);
           const uint32_t stage = smem0 + s * STAGE_BYTES;
-          mbar_arrive_expect_tx(full + 8 * s, 2 * w_half + (sub1_valid ? 2 : 1) * A_SUB);
+          mbar_arrive_expect_tx(full + 8 * s, 2 * w_half + (sub1_valid ? 2 : 1) * a_bytes);
           bulk_g2s(stage + 2 * A_SUB, wsrc + (size_t)i * 2 * w_half, 2 * w_half, full + 8 * s);
-          bulk_g2s(stage, asrc + (tile0 * g.kchunks + i) * ACT_CHUNK_BYTES, A_SUB, full + 8 * s);
-          if (sub1_valid)
-            bulk_g2s(stage + A_SUB, asrc + ((tile0 + 1) * g.kchunks + i) * ACT_CHUNK_BYTES, A_SUB, full + 8 * s);
+          if (CL > 1) {   // this CTA's sub-tile of the shared row tile, delivered to both CTAs (and both `full` barriers)
+            if (crank == 0 || sub1_valid)
+              bulk_g2s_multicast(stage + crank * A_SUB, asrc + ((tile0 + crank) * g.kchunks + i) * ACT_CHUNK_BYTES, A_SUB,
+                                 full + 8 * s, (uint16_t)((1u << CL) - 1));
+          } else {
+            bulk_g2s(stage, asrc + (tile0 * g.kchunks + i) * (size_t)g.a_chunk, a_bytes, full + 8 * s);
+            if (sub1_valid)
+              bulk_g2s(stage + A_SUB, asrc + ((tile0 + 1) * g.kchunks + i) * (size_t)g.a_chunk, a_bytes, full + 8 * s);
+          }
         }
       }
     }
@@ -649,7 +745,7 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
         for (int i = 0; i < g.kchunks; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t u = it / STAGES;
-          mbar_wait(full + 8 * s, u & 1);
+          mbar_wait((a3 ? ready : full) + 8 * s, u & 1);
           if (i == 0) stamp(tcount, 1);
           tcgen05_fence_after();
           const uint32_t stage = smem0 + s * STAGE_BYTES;
@@ -680,7 +776,7 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
               }
             }
           }
-          mma_commit(empty + 8 * s);
+          if (CL > 1) mma_commit_multicast(empty + 8 * s, (uint16_t)((1u << CL) - 1)); else mma_commit(empty + 8 * s);
         }
         mma_commit(accum_full);
         stamp(tcount, 2);
@@ -692,13 +788,40 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
     const int q = warp & 3, r = (warp - 2) >> 2, esub = r / PARTS, part = r % PARTS;
     const int niter = NT / 16, c_lo = (part * niter / PARTS) * 16, c_hi = ((part + 1) * niter / PARTS) * 16;
     const bool dotkind = !OUT_IMAGE && (g.out_kind == 3 || g.out_kind == 4);
-    uint32_t tcount = 0;
+    uint32_t tcount = 0, cit = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
       const int n_tile = t % ntiles_n, m0 = (t / ntiles_n) * BM;
       const bool valid = esub == 0 || (m0 + 128) < g.M;
       constexpr bool PREFETCH = !OUT_IMAGE && PARTS == 2;   // dot kinds run on the 16-warp kernel (launcher)
       DotPrefetch pf;
       if (PREFETCH && dotkind && valid) dot_prefetch(g, m0, esub, q * 32 + lane, part, pf);
+      if (a3) {
+        // value plane of every stage of this tile: thread -> (sub-tile, 16-k group, row): two 16-byte fp16 groups in, one
+        // 16-byte e5m2 group out (the same conversion, on the same fp16 values, as split4_f8 writes into a full image)
+        const int idx = (warp - 2) * 32 + lane, csub = idx >> 8, cg = (idx >> 7) & 1, cr = idx & 127;
+        const bool conv = idx < 512 && (csub == 0 || (m0 + 128) < g.M);
+        for (int i = 0; i < g.kchunks; ++i, ++cit) {
+          const int s = cit % STAGES;
+          mbar_wait(full + 8 * s, (cit / STAGES) & 1);
+          if (conv) {
+            unsigned char* st_ = smem + s * STAGE_BYTES + csub * A_SUB;
+            const uint4 h0 = *reinterpret_cast<const uint4*>(st_ + (2 * cg) * A_LBO + cr * 16);
+            const uint4 h1 = *reinterpret_cast<const uint4*>(st_ + (2 * cg + 1) * A_LBO + cr * 16);
+            const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              const uint32_t lo2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hw[2 * k2]), __NV_SATFINITE, __NV_E5M2);
+              const uint32_t hi2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hw[2 * k2 + 1]), __NV_SATFINITE, __NV_E5M2);
+              o[k2] = lo2 | (hi2 << 16);
+            }
+            *reinterpret_cast<uint4*>(st_ + ACT_X8 + cg * A_LBO + cr * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ready + 8 * s);
+        }
+      }
       mbar_wait(accum_full, tcount & 1);
       tcgen05_fence_after();
       if (threadIdx.x == 64) stamp(tcount, 3);
@@ -731,6 +854,7 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync();   // no CTA leaves while a peer may still multicast into its stages or signal its barriers
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
   if (g.dbg && threadIdx.x == 0) {
     unsigned smid;
@@ -767,7 +891,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_pair_kernel(GemmArgs g
   const uint32_t full = smem_u32(&bars[0]), peer_full = smem_u32(&bars[PSTAGES]), empty = smem_u32(&bars[2 * PSTAGES]),
                  accum = smem_u32(&bars[3 * PSTAGES]);
   const int NT = g.NT, NH = NT / 2;
-  const uint32_t wh = (uint32_t)(BK / 8) * NH * 16;          // fp16 plane of this CTA's half tile; e4m3 planes wh / 2 each
+  const uint32_t wh = (uint32_t)(BK / 8) * NH * 16;          // fp16 plane of this CTA's half tile; 8-bit planes wh / 2 each
   const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * 2 + blockIdx.x;
   unsigned long long* const dbg = (g.dbg && cta_lin < g.dbg_cap) ? g.dbg + (size_t)cta_lin * 8 : nullptr;
   auto stamp = [&](int i) {   // same slots as gemm_tc_kernel
@@ -1075,6 +1199,14 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
   g.f8 = (mode & CPN_TC_F16X3) ? 0 : 1;
   g.out_kind = (mode & CPN_TC_OUT_KG) ? 4 : ((mode & CPN_TC_OUT_ROWDOT) ? 3 : ((mode & CPN_TC_OUT_CB16) ? 2 : 0));
   g.C2 = c2;
+  g.a_chunk = (mode & CPN_TC_A_IMAGE3) ? ACT_X8 : ACT_CHUNK_BYTES;       // 12288: [fp16 head 8 KB | remainder plane 4 KB]
+  g.out_chunk = (mode & CPN_TC_OUT_IMAGE3) ? ACT_X8 : ACT_CHUNK_BYTES;
+  if ((mode & (CPN_TC_A_IMAGE3 | CPN_TC_OUT_IMAGE3)) &&
+      (!g.f8 || (mode & (CPN_TC_CLUSTER | CPN_TC_NO_PERSIST | CPN_TC_PAIR | CPN_TC_PPAIR)) || ((mode & CPN_TC_A_IMAGE3) && !a_img) ||
+       ((mode & CPN_TC_OUT_IMAGE3) && (!o_img || !a_img)))) {
+    cpn_set_error("gemm_tc: compact operand images need the fp16 + fp8 scheme and the persistent single-CTA kernel");
+    return CPN_ERR_ARG;
+  }
   g.out_mul = 1.f;
   g.dbg = g_tc_dbg;
   g.dbg_cap = g_tc_dbg_cap;
@@ -1133,7 +1265,7 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
     const char* e = getenv("CPN_TC_PPAIR");
     ppair_env = (e && atoi(e) != 0) ? 1 : 0;
   }
-  if (ppair_env) mode |= CPN_TC_PPAIR;
+  if (ppair_env && !(mode & (CPN_TC_A_IMAGE3 | CPN_TC_OUT_IMAGE3))) mode |= CPN_TC_PPAIR;
   if (a_img && g.f8 && (mode & CPN_TC_PPAIR) && (M % (2 * BM)) == 0 && (g.out_kind == 0 || g.out_kind == 2) &&
       !(mode & (CPN_TC_CLUSTER | CPN_TC_NO_PERSIST))) {
     // persistent CTA pairs: one cluster of two per SM pair walks the (512-row tile, N tile) list
@@ -1164,11 +1296,36 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
       epi_warps = (e && atoi(e) == 24) ? 24 : 16;
     }
     const bool dots = g.out_kind == 3 || g.out_kind == 4;   // their prefetching epilogue is written for two column parts
-    void (*pk)(GemmArgs, int, int) =
-        (epi_warps == 24 && !dots) ? (o_img ? gemm_tc_persist_kernel<true, 24> : gemm_tc_persist_kernel<false, 24>)
-                        : (o_img ? gemm_tc_persist_kernel<true, 16> : gemm_tc_persist_kernel<false, 16>);
-    CPN_CHECK_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    static int cl2 = -1;   // CPN_TC_CLUSTER2=1: clusters of two CTAs share the activation stages by multicast (A/B runs)
+    if (cl2 < 0) {
+      const char* e = getenv("CPN_TC_CLUSTER2");
+      cl2 = (e && atoi(e) != 0) ? 1 : 0;
+    }
     const int total = ntiles * (int)grid.y;
+    if (cl2 && !dots && (ntiles % 2) == 0 && total >= 2 && !(mode & (CPN_TC_A_IMAGE3 | CPN_TC_OUT_IMAGE3))) {
+      void (*pk2)(GemmArgs, int, int) = o_img ? gemm_tc_persist_kernel<true, 16, 2> : gemm_tc_persist_kernel<false, 16, 2>;
+      CPN_CHECK_CUDA(cudaFuncSetAttribute(pk2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      cudaLaunchConfig_t pc = {};
+      int ctas = total < n_sm ? total : n_sm;
+      ctas &= ~1;
+      pc.gridDim = dim3(ctas);
+      pc.blockDim = dim3((2 + 16) * 32);
+      pc.dynamicSmemBytes = SMEM_BYTES;
+      pc.stream = st;
+      cudaLaunchAttribute pa[1];
+      pa[0].id = cudaLaunchAttributeClusterDimension;
+      pa[0].val.clusterDim.x = 2;
+      pa[0].val.clusterDim.y = 1;
+      pa[0].val.clusterDim.z = 1;
+      pc.attrs = pa;
+      pc.numAttrs = 1;
+      CPN_CHECK_CUDA(cudaLaunchKernelEx(&pc, pk2, g, ntiles, total));
+      return CPN_OK;
+    }
+    void (*pk)(GemmArgs, int, int) =
+        (epi_warps == 24 && !dots) ? (o_img ? gemm_tc_persist_kernel<true, 24, 1> : gemm_tc_persist_kernel<false, 24, 1>)
+                        : (o_img ? gemm_tc_persist_kernel<true, 16, 1> : gemm_tc_persist_kernel<false, 16, 1>);
+    CPN_CHECK_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     pk<<<total < n_sm ? total : n_sm, (2 + ((epi_warps == 24 && !dots) ? 24 : 16)) * 32, SMEM_BYTES, st>>>(g, ntiles, total);
     CPN_CHECK_LAUNCH("gemm_tc_persist_kernel");
     return CPN_OK;
@@ -1208,9 +1365,48 @@ extern "C" int cpn_gemm_tc_rowdot(const void* packed, int layer, const void* A, 
                         (cudaStream_t)stream, dotv_cb16, div, nullptr, 0, 0);
 }
 
+// layer 9 with the 16 -> 128 ReLU layer in front of it computed by the producer warps (query_embed, CoPoNeRF.py:446):
+// Qm (CB16, 16 blocks) = [WM1 ; WM2] relu(Wq x16 + bq) + [BM1 ; BM2], s1 / s2 = <relu(.), WS> + CS
+int launch_gemm_tc_mlp16(const void* packed, const float* x16, const float* wt, const float* bias, const float* sd1, float* s1,
+                         const float* sd2, float* s2, float* qm_cb16, int M, int mode, cudaStream_t st) {
+  if (!packed || !x16 || !wt || !bias || !qm_cb16 || M < 0) {
+    cpn_set_error("gemm_tc_mlp16: bad argument");
+    return CPN_ERR_ARG;
+  }
+  if (M == 0) return CPN_OK;
+  const TcLayer& L = kLayers[9];
+  const unsigned char* tcw = reinterpret_cast<const unsigned char*>(packed) + cpn_packed_fp32_floats() * sizeof(float);
+  GemmArgs g = {};
+  g.M = M;
+  g.C = qm_cb16;
+  g.N = L.out;
+  g.out_div = g.out_kchunks = 1;
+  g.f8 = (mode & CPN_TC_F16X3) ? 0 : 1;
+  g.out_kind = 2;
+  g.wtiles = tcw + layer_offset(9, g.f8);
+  g.bias = reinterpret_cast<const float*>(packed) + L.bias;
+  g.inv_scale = reinterpret_cast<const float*>(tcw) + 9;
+  g.kchunks = L.kpad / BK;
+  g.NT = L.nt;
+  g.idesc = make_idesc_f16(128, L.nt);
+  g.dot_div = 1.f;
+  g.a_chunk = g.out_chunk = ACT_CHUNK_BYTES;
+  g.out_mul = 1.f;
+  g.mlp_x = x16; g.mlp_wt = wt; g.mlp_b = bias; g.mlp_sd1 = sd1; g.mlp_sd2 = sd2; g.mlp_s1 = s1; g.mlp_s2 = s2;
+  if ((s1 && !sd1) || (s2 && !sd2) || L.out != L.nt) {
+    cpn_set_error("gemm_tc_mlp16: inconsistent arguments");
+    return CPN_ERR_ARG;
+  }
+  void (*kern)(GemmArgs) = gemm_tc_kernel<false, false, 1, true>;
+  CPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  kern<<<dim3(1, (M + BM - 1) / BM), NUM_THREADS, SMEM_BYTES, st>>>(g);
+  CPN_CHECK_LAUNCH("gemm_tc_kernel (mlp16)");
+  return CPN_OK;
+}
+
 extern "C" int cpn_gemm_tc_kg(const void* packed, const void* h1_image, const float* dotv_cb16, int dot_blocks,
                               const float* rowadd, float div, float* logits, float* gh, int M, int mode, void* stream) {
-  return launch_gemm_tc(packed, 10, h1_image, 0, logits, 0, M, 1, (mode & CPN_TC_F16X3) | CPN_TC_A_IMAGE | CPN_TC_OUT_KG, 1, 1,
+  return launch_gemm_tc(packed, 10, h1_image, 0, logits, 0, M, 1, (mode & (CPN_TC_F16X3 | CPN_TC_A_IMAGE3 | CPN_TC_NO_PERSIST)) | CPN_TC_A_IMAGE | CPN_TC_OUT_KG, 1, 1,
                         (cudaStream_t)stream, dotv_cb16, div, rowadd, dot_blocks, 0, gh);
 }
 
@@ -1285,6 +1481,7 @@ int launch_linear_tc(const void* packed, int N, int K, const float* x, int ldx, 
   g.NT = 128;
   g.idesc = make_idesc_f16(128, 128);
   g.dot_div = 1.f;
+  g.a_chunk = g.out_chunk = ACT_CHUNK_BYTES;
   g.out_mul = out_mul;
   void (*kern)(GemmArgs) = gemm_tc_kernel<false, false, 1>;
   CPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -392,7 +392,7 @@ __global__ void sample_kernel(cpn_render_args a, int ray0, int nr, const float* 
       const float* t3 = br ? ts : tp;
       unsigned char* p = img + act_img_off((size_t)(row >> 7) * 2 + br, CPN_KA_IMG / ACT_BK, CPN_FEAT_DIM, r);
       const uint4 zero = make_uint4(0, 0, 0, 0);
-      if (a_image == 2) {   // f8 scheme: fp16 hi in group 0; the e4m3 planes have two 16-k groups
+      if (a_image == 2) {   // f8 scheme: fp16 hi in group 0; the 8-bit planes have two 16-k groups
         uint2 hi;
         uint32_t l8, x8;
         tc::split4_f8(make_float4(t3[0], t3[1], t3[2], 0.f), hi, l8, x8);

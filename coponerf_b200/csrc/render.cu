@@ -1,6 +1,7 @@
 // cpn_render_rays: the per-ray stage of CoPoNeRF.forward() (models/CoPoNeRF.py:246-566) as one
 // asynchronous sequence of kernels per chunk of rays. Also the library's error string and version.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include "cpn_common.cuh"
@@ -267,6 +268,7 @@ extern "C" int cpn_render_launch_count(const cpn_render_args* a) {
   const bool late = !unfolded && !(a->flags & CPN_FLAG_EARLY_V);
   int per_chunk = (unfolded ? 17 : (late ? 19 : 16)) + ((a->flags & CPN_FLAG_SIMT_ONLY) ? 0 : 1);   // + taps_kernel
   if (!unfolded && !(a->flags & CPN_FLAG_NO_BILINEAR)) per_chunk -= 2;   // one GEMM over the coordinate embedding instead of three 128 x 128 layers
+  if (!unfolded && !(a->flags & CPN_FLAG_NO_BILINEAR)) per_chunk -= 1;   // query_embed inside the layer-9 GEMM
   if (late && !(a->flags & (CPN_FLAG_NO_BILINEAR | CPN_FLAG_NO_GFOLD))) per_chunk -= 5;   // no round-1 readout + per-ray GEMM, encode_latent, z half of query_repeat_embed, park
   return chunks * per_chunk + (late ? 3 : 1);
 }
@@ -292,9 +294,13 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, flo
     if (use_tc(a)) {
       // per-sample encoder, CoPoNeRF.py:387-397: (835 -> 832 ReLU -> 416) for the primary and the secondary rows.
       // Activations travel between the tensor-core layers as fp16 hi/lo operand images (cpn_common.cuh).
+      // default path: the hidden image is only read by layer 10 (which derives the value plane on chip) and by the readout
+      // (which never reads it), so it is written compact: 3 bytes per element instead of 4
+      const bool h1c = gfold && a_form(a) == 2 && !(a.flags & CPN_FLAG_FULL_H1);
       {
         ProfScope prof(st);
-        CPN_TRY(launch_gemm_tc(a.weights, 0, w.A, 0, w.H1, 0, 2 * Rp, 1, CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch, 1, KC832, st));
+        CPN_TRY(launch_gemm_tc(a.weights, 0, w.A, 0, w.H1, 0, 2 * Rp, 1,
+                               CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch | (h1c ? CPN_TC_OUT_IMAGE3 : 0), 1, KC832, st));
       }
       if (a.flags & CPN_FLAG_NO_FOLD) {
         // the (tile, primary) and (tile, secondary) results land side by side: E image rows = sample rows, K = 832
@@ -315,11 +321,22 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, flo
         // 128-wide hidden vectors (cpn_common.cuh, pw::WM12): one 128 -> 256 layer on the coordinate embedding for both rounds
         // instead of one on it and one on each key / repeat-query, and the key hidden layer is dotted in the epilogue
         // of the folded key_map GEMM without ever being stored.
-        CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQT, W + pw::BQ, nullptr, 1, R, w.Q1, a_form(a) == 2, st, W + pw::WS1,
-                                   w.s1, W + pw::WS2, w.s2));
-        CPN_TRY(launch_gemm_tc(a.weights, 9, w.Q1, 0, w.Qm, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_CB16, 1, 1, st));
+        static int split_q = -1;   // CPN_SPLIT_QUERY_EMBED=1: query_embed as its own kernel writing an operand image (A/B runs)
+        if (split_q < 0) {
+          const char* e = getenv("CPN_SPLIT_QUERY_EMBED");
+          split_q = (e && atoi(e) != 0) ? 1 : 0;
+        }
+        if (split_q) {
+          CPN_TRY(launch_mlp16_image(w.local16, W + pw::WQT, W + pw::BQ, nullptr, 1, R, w.Q1, a_form(a) == 2, st, W + pw::WS1,
+                                     w.s1, W + pw::WS2, w.s2));
+          CPN_TRY(launch_gemm_tc(a.weights, 9, w.Q1, 0, w.Qm, 0, R, 0, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_CB16, 1, 1, st));
+        } else {   // query_embed computed by the producer warps of the layer-9 GEMM: the embedding never exists in memory
+          CPN_TRY(launch_gemm_tc_mlp16(a.weights, w.local16, W + pw::WQT, W + pw::BQ, W + pw::WS1, w.s1, W + pw::WS2, w.s2, w.Qm, R,
+                                       sch, st));
+        }
         if (gfold)   // w.K1 (R, 128) receives G h + g0
-          CPN_TRY(launch_gemm_tc(a.weights, 10, w.H1, 0, w.lg1, 0, R, 1, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_KG, 1, 1, st, w.Qm,
+          CPN_TRY(launch_gemm_tc(a.weights, 10, w.H1, 0, w.lg1, 0, R, 1,
+                                 CPN_TC_A_IMAGE | sch | CPN_TC_OUT_KG | (h1c ? CPN_TC_A_IMAGE3 : 0), 1, 1, st, w.Qm,
                                  11.31f, w.s1, 2 * CPN_HIDDEN / 16, 0, w.K1));
         else
           CPN_TRY(launch_gemm_tc(a.weights, 8, w.H1, 0, w.lg1, 0, R, 1, CPN_TC_A_IMAGE | sch | CPN_TC_OUT_ROWDOT, 1, 1, st, w.Qm,
@@ -379,7 +396,8 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, flo
     if (gfold) {
       // combined weight w2 + 2 w1 -> one readout into the image-level operand image; z is finished per image
       CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, nullptr, w.r1, z_all, st, w.lg2, w.wt2, w.wt1));
-      CPN_TRY(launch_readout_image(a, nr, w.H1, w.wt2, hbar_all, a_form(a) == 2, st, a.N, ray0));
+      const bool h1c = a_form(a) == 2 && !(a.flags & CPN_FLAG_FULL_H1);
+      CPN_TRY(launch_readout_image(a, nr, w.H1, w.wt2, hbar_all, a_form(a) == 2, st, a.N, ray0, h1c ? ACT_X8 : ACT_CHUNK_BYTES));
     } else if (late_v) {
       CPN_TRY(launch_attn2(a, ray0, nr, w.Kk, w.Qe, nullptr, w.r1, z_all, st, w.lg2, w.wt2));
       // the round-2 readout lands in the image-level operand image; its GEMM runs once per image (finish_image)

@@ -50,6 +50,8 @@ typedef enum {
 #define CPN_FLAG_NO_GFOLD 32  /* keep latent_value -> encode_latent -> query_repeat_embed as a per-ray chain behind a separate
                                * round-1 readout (default: folded into one 128 x 1664 map applied per sample row next to
                                * key_map, one combined readout with weights w2 + 2 w1 for z = R2 + 2 R1) */
+#define CPN_FLAG_FULL_H1 64   /* write the hidden-layer image with its value plane (4 bytes per element; default on the default
+                               * path: 3 bytes, the key GEMM derives the plane on chip). Same bits either way */
 #define CPN_FLAG_NO_FOLD 4    /* keep query_encode_latent_2, latent_value and key_map as three GEMMs (default: the
                                * activation-free query_encode_latent_2 is folded into the other two at pack time) */
 
@@ -280,7 +282,7 @@ int cpn_gemm_simt_splitk(const float* A, int lda, const float* wt, const float* 
  * 3 key_map, 4 key_map_2, 5 query_embed_2, 6 query_repeat_embed_2, 7 latent_value o query_encode_latent_2,
  * 8 key_map o query_encode_latent_2, both with K = 1664, 9 [key_map_2 ; query_repeat_embed_2]^T query_embed_2 with
  * N = 256): C[M, N_layer] = act(A[M, K_layer] * W^T + b),
- * operands split into an fp16 head plus corrections (e4m3 on the fp8 path by default, fp16 with CPN_TC_F16X3)
+ * operands split into an fp16 head plus corrections (fp8 on the tensor cores' fp8 path by default: e5m2 activation planes, e4m3 weight planes; fp16 with CPN_TC_F16X3)
  * and accumulated in fp32 on tcgen05.
  * `packed` is the blob from cpn_pack_weights. mode bit CPN_TC_A_IMAGE: A is an "operand image" (128-row tiles,
  * per 32-wide k-chunk a 16 KB block [hi|lo][4][128][8] of fp16) instead of fp32 row-major; CPN_TC_OUT_IMAGE: C is
@@ -288,11 +290,14 @@ int cpn_gemm_simt_splitk(const float* A, int lda, const float* wt, const float* 
  * k offset (t % out_div) * N_layer (how the two branches of a sample row are concatenated). */
 #define CPN_TC_A_IMAGE 1
 #define CPN_TC_OUT_IMAGE 2
-#define CPN_TC_F16X3 4   /* three fp16 MMAs per product; default is fp16 + two e4m3 correction MMAs */
+#define CPN_TC_F16X3 4   /* three fp16 MMAs per product; default is fp16 + two fp8 correction MMAs */
 #define CPN_TC_PAIR 16   /* experiment: cta_group::2 CTA pairs, each SM stages half of every weight tile (f8 scheme,
                           * M % 512 == 0); correct, but measured 20-28 % slower than independent CTAs on B200 */
 #define CPN_TC_OUT_CB16 32  /* fp32 output column-blocked: [row tile of 128][16-column block][row][16] (N = 128 layers) */
 #define CPN_TC_OUT_ROWDOT 64 /* set by cpn_gemm_tc_rowdot */
+#define CPN_TC_A_IMAGE3 1024  /* A is a COMPACT operand image: 12 KB blocks [fp16 head | remainder plane] without the value plane,
+                              * which the persistent kernel derives in shared memory (e5m2 of the fp16 head) */
+#define CPN_TC_OUT_IMAGE3 2048 /* the output image is written in that compact form (25 % fewer bytes) */
 #define CPN_TC_PPAIR 512     /* operand-image GEMMs, f8 scheme, M % 512 == 0: persistent cta_group::2 CTA pairs */
 #define CPN_TC_NO_PERSIST 256 /* operand-image GEMMs: one tile per CTA (the first kernel) instead of the persistent kernel */
 #define CPN_TC_OUT_KG 128    /* set by cpn_gemm_tc_kg */

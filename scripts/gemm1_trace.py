@@ -11,7 +11,7 @@ from cases import cuda_model
 from coponerf_b200 import _lib
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 524288       # encoder rows (layer 0); layers 8 / 10 see M / 2 sample rows
 layer = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-persist = int(sys.argv[3]) if len(sys.argv) > 3 else 1     # 1 persistent, 0 one tile per CTA, 2 cta_group::2 pairs (one tile per pair)
+persist = int(sys.argv[3]) if len(sys.argv) > 3 else 1     # 1 persistent, 0 one tile per CTA, 2 cta_group::2 pairs (one tile per pair), 3 persistent pairs
 lib = _lib.load(); eng = cuda_model().engine()
 tiles = M // 128
 kin = {0: 27, 8: 52, 10: 52}[layer]
@@ -25,7 +25,7 @@ p = lambda t: ctypes.c_void_p(t.data_ptr()); st = ctypes.c_void_p(torch.cuda.cur
 rows = M if layer == 0 else M // 2
 ntn = 4 if layer == 0 else 1
 ntiles = ntn * (rows // 256)
-extra = {1: 0, 0: _lib.TC_NO_PERSIST, 2: _lib.TC_PAIR}[persist]
+extra = {1: 0, 0: _lib.TC_NO_PERSIST, 2: _lib.TC_PAIR, 3: _lib.TC_PPAIR}[persist]
 buf = torch.zeros(ntiles * 8, dtype=torch.int64, device="cuda")
 def run():
     if layer == 0:
@@ -43,7 +43,21 @@ lib.cpn_gemm_tc_trace(None, 0)
 t = buf.cpu().numpy().reshape(ntiles, 8).astype(np.float64)
 st_ = lambda v: {"mean": float(v.mean() / 1e3), "p10": float(np.quantile(v, .1) / 1e3), "p50": float(np.median(v) / 1e3), "p90": float(np.quantile(v, .9) / 1e3)}
 out = {"layer": layer, "rows": rows, "tiles": ntiles, "persistent": bool(persist), "untraced_launch_ms": ev[0].elapsed_time(ev[1])}
-if persist == 1:
+if persist == 3:
+    nct = 148
+    per = (ntiles // 2) // 74                  # complete rounds of 512-row pair tiles per cluster
+    tt = t[:per * nct].reshape(per, nct, 8)
+    lead, peer = tt[:, 0::2], tt[:, 1::2]
+    out["kernel_span_us"] = float((t[:, 4].max() - lead[0, :, 0].min()) / 1e3)
+    out["ring_wait_at_tile_start_us"] = st_(lead[:, :, 1] - lead[:, :, 0])
+    out["mainloop_issue_us"] = st_(lead[:, :, 2] - lead[:, :, 1])
+    out["accum_ready_after_last_issue_leader_us"] = st_(lead[:, :, 3] - lead[:, :, 2])
+    out["accum_ready_after_last_issue_peer_us"] = st_(peer[:, :, 3] - lead[:, :, 2])
+    out["drain_leader_us"] = st_(lead[:, :, 4] - lead[:, :, 3])
+    out["drain_peer_us"] = st_(peer[:, :, 4] - peer[:, :, 3])
+    out["tile_period_us"] = st_(lead[1:, :, 0] - lead[:-1, :, 0])
+    out["restart_after_last_drain_us"] = st_(lead[1:, :, 0] - np.maximum(lead[:-1, :, 4], peer[:-1, :, 4]))
+elif persist == 1:
     ncta = min(148, ntiles)
     per = ntiles // ncta                      # complete rounds of tiles
     tt = t[:per * ncta].reshape(per, ncta, 8)

@@ -364,7 +364,7 @@ def test_per_ray_chain_path_matches_reference_golden(case):
     check_against(out, g, case + "/no-gfold")
 
 
-@pytest.mark.parametrize("scheme", [0, 4], ids=["f16+f8", "f16x3"])
+@pytest.mark.parametrize("scheme", [0, 4, 1024], ids=["f16+f8", "f16x3", "f16+f8/compact-image"])
 def test_gemm_tc_key_and_round2_bias_layer(scheme):
     """Layer 10 = [key_map ; G] o query_encode_latent_2 over the hidden image (cpn_gemm_tc_kg): the key tile leaves as the
     round-1 logit, the G tile as fp32 rows G h + g0, against the layer-by-layer chain of CoPoNeRF.py:393-408,463-472 in
@@ -387,14 +387,29 @@ def test_gemm_tc_key_and_round2_bias_layer(scheme):
     chunk = _lib.ACT_CHUNK_BYTES
     H1 = torch.empty(2 * Rp // 128 * 26 * chunk, dtype=torch.uint8, device="cuda")
     w = _p(eng.weights)
-    _lib.check(lib.cpn_gemm_tc(w, 0, _p(A), 848, _p(H1), 0, 2 * Rp, 1, _lib.TC_OUT_IMAGE | scheme, 1, 26, _st()), "gemm1")
+    if scheme == _lib.TC_A_IMAGE3:
+        # the compact hidden image (12 KB blocks [fp16 head | remainder plane], no value plane): layer 10 derives the value
+        # plane in shared memory. Built here by dropping the plane from the full image; cpn_render_rays writes it directly
+        # (CPN_TC_OUT_IMAGE3, covered by test_compact_hidden_image_is_bit_identical_to_the_full_one)
+        _lib.check(lib.cpn_gemm_tc(w, 0, _p(A), 848, _p(H1), 0, 2 * Rp, 1, _lib.TC_OUT_IMAGE, 1, 26, _st()), "gemm1")
+        H1c = H1.view(-1, chunk)[:, :_lib.ACT_CHUNK3_BYTES].contiguous().view(-1)      # drop the value plane of every block
+        scheme_kg = _lib.TC_A_IMAGE3
+    else:
+        _lib.check(lib.cpn_gemm_tc(w, 0, _p(A), 848, _p(H1), 0, 2 * Rp, 1, _lib.TC_OUT_IMAGE | scheme, 1, 26, _st()), "gemm1")
+        H1c, scheme_kg = H1, scheme
     # dotv: CB16 with 16 blocks per row tile (as the bilinear-logit layer writes it), blocks 0-7 used
     dv = torch.randn(Rp, 256, device="cuda")
     dv_cb = dv.view(Rp // 128, 128, 16, 16).permute(0, 2, 1, 3).contiguous()
     rowadd = torch.randn(Rp, device="cuda")
     lg = torch.full((Rp,), float("nan"), device="cuda")
     gh = torch.full((Rp, 128), float("nan"), device="cuda")
-    _lib.check(lib.cpn_gemm_tc_kg(w, _p(H1), _p(dv_cb), 16, _p(rowadd), 11.31, _p(lg), _p(gh), R, scheme, _st()), "kg")
+    _lib.check(lib.cpn_gemm_tc_kg(w, _p(H1c), _p(dv_cb), 16, _p(rowadd), 11.31, _p(lg), _p(gh), R, scheme_kg, _st()), "kg")
+    if scheme == _lib.TC_A_IMAGE3:      # bit-identical to the consumer of the full image
+        lg2 = torch.full((Rp,), float("nan"), device="cuda")
+        gh2 = torch.full((Rp, 128), float("nan"), device="cuda")
+        _lib.check(lib.cpn_gemm_tc_kg(w, _p(H1), _p(dv_cb), 16, _p(rowadd), 11.31, _p(lg2), _p(gh2), R, 0, _st()), "kg full")
+        assert torch.equal(lg[:R], lg2[:R]) and torch.equal(gh, gh2)
+        scheme = 0
     lin = torch.nn.functional.linear
     h = lin(x.double(), W1.double(), b1.double()).relu()
     e = lin(h, W2.double(), b2.double())
@@ -462,3 +477,16 @@ def test_full_image_oblique_pose_against_oracle():
     err = np.abs(a - b).max(axis=-1) / max(np.abs(b).max(), 1e-30)
     assert (err[~near] <= 1e-2).all(), float(err[~near].max())
     assert (~near).mean() > 0.1          # (points far outside the image count as 'near': the flow lookup clamps them)
+
+
+@pytest.mark.parametrize("case", CASES[:3])
+def test_compact_hidden_image_is_bit_identical_to_the_full_one(case):
+    """Default path: the hidden-layer image is written without its value plane (3 bytes per element) and layer 10 derives
+    e5m2(head) in shared memory; CPN_FLAG_FULL_H1 writes the plane. Same conversion of the same fp16 values: same bits."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, case + ".npz")))
+    H, W, n_rays, S, seed, val = [int(v) for v in g["meta"]]
+    a = run_cuda(H, W, n_rays, S, seed, val)
+    b = run_cuda(H, W, n_rays, S, seed, val, flags=64)
+    for k in EXACT_KEYS:
+        assert torch.equal(a[k], b[k]), k
+    check_against(b, g, case + "/full-h1")
