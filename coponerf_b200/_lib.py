@@ -29,6 +29,8 @@ TC_NO_PERSIST = 256
 TC_PPAIR = 512
 TC_A_IMAGE3 = 1024
 TC_OUT_IMAGE3 = 2048
+TC_PERSIST2 = 4096
+TC_WS = 8192
 ACT_CHUNK3_BYTES = 12288
 TC_A_IMAGE = 1
 TC_OUT_IMAGE = 2

@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(256) taps_kernel(cpn_render_args a, int nr, co
   taps[(size_t)i * 2 + 1] = make_int4(__float_as_int(t.w[0]), __float_as_int(t.w[1]), __float_as_int(t.w[2]), __float_as_int(t.w[3]));
 }
 
-template <bool F8>
+// X8 = false: compact image (12 KB blocks, no value plane: the consuming GEMM derives e5m2(head) on chip)
+template <bool F8, bool X8>
 __global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, int nr, const int4* __restrict__ taps,
                                                            unsigned char* __restrict__ img) {
   // f16x3: [hi | lo][row][channel] fp16. f8: plane 0 = fp16 hi; plane 1 holds the two byte planes back to back,
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, in
           tc::split4_f8(acc, hi, l8, x8);
           *reinterpret_cast<uint2*>(sh_hi + col + c) = hi;
           *reinterpret_cast<uint32_t*>(sh_b + col + c) = l8;
-          *reinterpret_cast<uint32_t*>(sh_b + GI_B8 + col + c) = x8;
+          if (X8) *reinterpret_cast<uint32_t*>(sh_b + GI_B8 + col + c) = x8;
         } else {
           uint2 hi, lo;
           tc::split2(acc.x, acc.y, hi.x, lo.x);
@@ -189,7 +190,8 @@ __global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, in
   const int rr = threadIdx.x & 7;
   if (row0 + rr < nrows) {
     constexpr int NG8 = CPN_FEAT_DIM / 8, NG16 = CPN_FEAT_DIM / 16;
-    unsigned char* tile = img + ((size_t)(row0 >> 7) * 2 + branch) * ((size_t)(CPN_KA_IMG / ACT_BK) * ACT_CHUNK_BYTES) +
+    constexpr int CHUNK = (F8 && !X8) ? ACT_X8 : ACT_CHUNK_BYTES;
+    unsigned char* tile = img + ((size_t)(row0 >> 7) * 2 + branch) * ((size_t)(CPN_KA_IMG / ACT_BK) * CHUNK) +
                           ((row0 & 127) + rr) * 16;
     const unsigned char* s_hi = reinterpret_cast<const unsigned char*>(&sh[0][rr][0]);
     const unsigned char* s_b = reinterpret_cast<const unsigned char*>(&sh[1][rr][0]);
@@ -198,17 +200,18 @@ __global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, in
       const int gi = it * 32 + (threadIdx.x >> 3);
       if (gi < NG8) {
         const int k = gi * 8;
-        *reinterpret_cast<uint4*>(tile + (k >> 5) * ACT_CHUNK_BYTES + ((k & 31) >> 3) * 2048) =
+        *reinterpret_cast<uint4*>(tile + (k >> 5) * CHUNK + ((k & 31) >> 3) * 2048) =
             *reinterpret_cast<const uint4*>(s_hi + gi * 16);
       }
     }
     if (F8) {
+      constexpr int NPL = X8 ? 2 : 1;
 #pragma unroll
-      for (int it = 0; it < (2 * NG16 + 31) / 32; ++it) {
+      for (int it = 0; it < (NPL * NG16 + 31) / 32; ++it) {
         const int item = it * 32 + (threadIdx.x >> 3);
-        if (item < 2 * NG16) {
+        if (item < NPL * NG16) {
           const int pl = item >= NG16, gi = item - pl * NG16, k = gi * 16;
-          *reinterpret_cast<uint4*>(tile + (k >> 5) * ACT_CHUNK_BYTES + (pl ? ACT_X8 : ACT_LO8) + ((k & 31) >> 4) * 2048) =
+          *reinterpret_cast<uint4*>(tile + (k >> 5) * CHUNK + (pl ? ACT_X8 : ACT_LO8) + ((k & 31) >> 4) * 2048) =
               *reinterpret_cast<const uint4*>(s_b + pl * GI_B8 + gi * 16);
         }
       }
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(256) gather_image_kernel(cpn_render_args a, in
         const int gi = it * 32 + (threadIdx.x >> 3);
         if (gi < NG8) {
           const int k = gi * 8;
-          *reinterpret_cast<uint4*>(tile + (k >> 5) * ACT_CHUNK_BYTES + ACT_LO + ((k & 31) >> 3) * 2048) =
+          *reinterpret_cast<uint4*>(tile + (k >> 5) * CHUNK + ACT_LO + ((k & 31) >> 3) * 2048) =
               *reinterpret_cast<const uint4*>(s_b + gi * 16);
         }
       }
@@ -411,7 +414,7 @@ int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowau
       const char* e = getenv("CPN_GATHER_SEQ");
       per_row = (e && atoi(e) != 0) ? 0 : 1;
     }
-    const bool seq_ok = !per_row && (a.S % GS_ROWS) == 0 && a.feat_c[0] == 256 && a.feat_c[1] == 256 && a.feat_c[2] == 256 &&
+    const bool seq_ok = !per_row && a_image != 3 && (a.S % GS_ROWS) == 0 && a.feat_c[0] == 256 && a.feat_c[1] == 256 && a.feat_c[2] == 256 &&
                         a.feat_c[3] <= 64;
     if (seq_ok) {
       dim3 grid((unsigned)((rows + GS_ROWS - 1) / GS_ROWS), 2);
@@ -423,10 +426,12 @@ int launch_gather(const cpn_render_args& a, int ray0, int nr, const float* rowau
       return CPN_OK;
     }
     dim3 grid((unsigned)((rows + GI_ROWS * GI_GROUPS - 1) / (GI_ROWS * GI_GROUPS)), 2);
-    if (a_image == 2)
-      gather_image_kernel<true><<<grid, 256, 0, st>>>(a, nr, tp, reinterpret_cast<unsigned char*>(A));
+    if (a_image == 3)
+      gather_image_kernel<true, false><<<grid, 256, 0, st>>>(a, nr, tp, reinterpret_cast<unsigned char*>(A));
+    else if (a_image == 2)
+      gather_image_kernel<true, true><<<grid, 256, 0, st>>>(a, nr, tp, reinterpret_cast<unsigned char*>(A));
     else
-      gather_image_kernel<false><<<grid, 256, 0, st>>>(a, nr, tp, reinterpret_cast<unsigned char*>(A));
+      gather_image_kernel<false, true><<<grid, 256, 0, st>>>(a, nr, tp, reinterpret_cast<unsigned char*>(A));
   } else {
     gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, nr, rowaux, A);
   }
@@ -449,7 +454,7 @@ extern "C" size_t cpn_gather_rows_taps_bytes(int rows) { return (size_t)rows * 2
 
 extern "C" int cpn_gather_rows(const cpn_render_args* a, int nr, const float* rowaux, void* out, int form, void* taps,
                                void* stream) {
-  if (!a || !rowaux || !out || nr <= 0 || a->B <= 0 || a->S <= 0 || form < 0 || form > 2) {
+  if (!a || !rowaux || !out || nr <= 0 || a->B <= 0 || a->S <= 0 || form < 0 || form > 3) {
     cpn_set_error("cpn_gather_rows: bad argument");
     return CPN_ERR_ARG;
   }

@@ -169,6 +169,8 @@ struct GemmArgs {
   int out_kind;                  // fp32 output: 0 row-major, 2 column-blocked (CB16), 3 per-row dot with `dotv`,
                                  // 4 N tile 0 as kind 3 (with ReLU), the other N tiles row-major into C2 without ReLU
   float* C2;                     // out_kind 4: fp32 (M, N - NT) row-major
+  int ws;                        // persistent kernel: weight-stationary MMAs (NT = 64 / 128 / 256, fp16 + fp8 scheme)
+  int w3;                        // persistent kernel, compact A: the e4m3(w_hi 2^-10) weight plane is derived on chip too
   unsigned long long* dbg;       // phase timestamps of the first `dbg_cap` CTAs (cpn_gemm_tc_trace), else null
   int dbg_cap;
   // MLP16 producer (gemm_tc_kernel<false, false, 1, true>): A = relu(x16 Wt + b) computed by the producer warps
@@ -178,7 +180,8 @@ struct GemmArgs {
                                  // value plane (the persistent kernel derives it in shared memory)
   int out_chunk;                 // the same for an image output
   float out_mul;                 // the accumulators are multiplied by inv_scale * out_mul before the bias (1 except the tail GEMM)
-  int dbg_skip;                  // trace runs only (CPN_TC_DBG_SKIP): 1 no image stores, 2 no split / conversions, 4 no TMEM loads
+  int dbg_skip;                  // trace runs only (CPN_TC_DBG_SKIP): 1 no image stores, 2 no split / conversions, 4 no TMEM loads,
+                                 // persistent kernel: 8 no MMAs, 16 no activation copies, 32 no weight copies
   const float* dotv;             // CB16 matrix the rows are dotted with (out_kind 3); C then holds one float per row
   float dot_div;
   const float* dot_rowadd;       // optional per-row term added to the dot product before the division
@@ -674,7 +677,7 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
   // compact A image (12 KB blocks: fp16 head + remainder plane): the value plane e5m2(head) of a stage is derived in shared
   // memory by the epilogue warps, which are idle during the MMA loop; the MMA thread then waits on `ready` instead of `full`
   const uint32_t ready = smem_u32(&bars[2 * STAGES + 2]);
-  const bool a3 = g.a_chunk != ACT_CHUNK_BYTES;
+  const bool a3 = g.a_chunk != ACT_CHUNK_BYTES, w3 = a3 && g.w3;
   const uint32_t a_bytes = a3 ? (uint32_t)ACT_X8 : (uint32_t)A_SUB;
   const int NT = g.NT;
   const uint32_t w_half = (uint32_t)(BK / 8) * NT * 16;
@@ -719,8 +722,23 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
           const uint32_t u = it / STAGES;
           mbar_wait(empty + 8 * s, (u & 1) ^ 1);
           const uint32_t stage = smem0 + s * STAGE_BYTES;
-          mbar_arrive_expect_tx(full + 8 * s, 2 * w_half + (sub1_valid ? 2 : 1) * a_bytes);
-          bulk_g2s(stage + 2 * A_SUB, wsrc + (size_t)i * 2 * w_half, 2 * w_half, full + 8 * s);
+          if (g.dbg_skip & 48) {   // trace runs: 16 no activation copies, 32 no weight copies (the MMAs then read stale stages)
+            const bool la = !(g.dbg_skip & 16), lw = !(g.dbg_skip & 32);
+            mbar_arrive_expect_tx(full + 8 * s, (lw ? 2 * w_half : 0) + (la ? (sub1_valid ? 2 : 1) * a_bytes : 0));
+            if (lw) bulk_g2s(stage + 2 * A_SUB, wsrc + (size_t)i * 2 * w_half, 2 * w_half, full + 8 * s);
+            if (la) {
+              bulk_g2s(stage, asrc + (tile0 * g.kchunks + i) * (size_t)g.a_chunk, a_bytes, full + 8 * s);
+              if (sub1_valid) bulk_g2s(stage + A_SUB, asrc + ((tile0 + 1) * g.kchunks + i) * (size_t)g.a_chunk, a_bytes, full + 8 * s);
+            }
+            continue;
+          }
+          mbar_arrive_expect_tx(full + 8 * s, (w3 ? w_half + w_half / 2 : 2 * w_half) + (sub1_valid ? 2 : 1) * a_bytes);
+          if (w3) {   // fp16 plane and e4m3(w_lo) plane; the plane between them is derived from the first on chip
+            bulk_g2s(stage + 2 * A_SUB, wsrc + (size_t)i * 2 * w_half, w_half, full + 8 * s);
+            bulk_g2s(stage + 2 * A_SUB + w_half + w_half / 2, wsrc + (size_t)i * 2 * w_half + w_half + w_half / 2, w_half / 2, full + 8 * s);
+          } else {
+            bulk_g2s(stage + 2 * A_SUB, wsrc + (size_t)i * 2 * w_half, 2 * w_half, full + 8 * s);
+          }
           if (CL > 1) {   // this CTA's sub-tile of the shared row tile, delivered to both CTAs (and both `full` barriers)
             if (crank == 0 || sub1_valid)
               bulk_g2s_multicast(stage + crank * A_SUB, asrc + ((tile0 + crank) * g.kchunks + i) * ACT_CHUNK_BYTES, A_SUB,
@@ -750,11 +768,27 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
           tcgen05_fence_after();
           const uint32_t stage = smem0 + s * STAGE_BYTES;
           const uint32_t b_hi = stage + 2 * A_SUB, b_lo = b_hi + w_half;
+          if (g.ws && sub1_valid && !(g.dbg_skip & 8)) {
+            // weight-stationary order: every weight block is fetched once and used by both sub-tiles
+            const uint32_t a0 = stage, a1 = stage + A_SUB, d0 = tmem, d1 = tmem + 256, idf8 = g.idesc | IDESC_A_E5M2;
+            const uint64_t b0 = make_desc(b_hi, NT * 16, 128), b1 = make_desc(b_hi + 2 * NT * 16, NT * 16, 128);
+            const uint64_t b2 = make_desc(b_hi + w_half, NT * 16, 128), b3 = make_desc(b_hi + w_half + w_half / 2, NT * 16, 128);
+            const uint32_t acc0 = i != 0;
+            CPN_MMA_WS("f16", "b0", "fill", d0, make_desc(a0, A_LBO, 128), b0, g.idesc, acc0);
+            CPN_MMA_WS("f16", "b0", "lastuse", d1, make_desc(a1, A_LBO, 128), b0, g.idesc, acc0);
+            CPN_MMA_WS("f16", "b1", "fill", d0, make_desc(a0 + 2 * A_LBO, A_LBO, 128), b1, g.idesc, 1u);
+            CPN_MMA_WS("f16", "b1", "lastuse", d1, make_desc(a1 + 2 * A_LBO, A_LBO, 128), b1, g.idesc, 1u);
+            CPN_MMA_WS("f8f6f4", "b2", "fill", d0, make_desc(a0 + ACT_LO8, A_LBO, 128), b2, idf8, 1u);
+            CPN_MMA_WS("f8f6f4", "b2", "lastuse", d1, make_desc(a1 + ACT_LO8, A_LBO, 128), b2, idf8, 1u);
+            CPN_MMA_WS("f8f6f4", "b3", "fill", d0, make_desc(a0 + ACT_X8, A_LBO, 128), b3, idf8, 1u);
+            CPN_MMA_WS("f8f6f4", "b3", "lastuse", d1, make_desc(a1 + ACT_X8, A_LBO, 128), b3, idf8, 1u);
+          } else
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             if (sub == 1 && !sub1_valid) break;
             const uint32_t a_hi = stage + sub * A_SUB, a_lo = a_hi + A_HALF;
             const uint32_t d = tmem + sub * 256;
+            if (g.dbg_skip & 8) break;   // trace runs: no MMAs, the commit below frees the stage at once
             if (g.f8) {
 #pragma unroll
               for (int j = 0; j < BK / 16; ++j)
@@ -817,6 +851,26 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
             }
             *reinterpret_cast<uint4*>(st_ + ACT_X8 + cg * A_LBO + cr * 16) = make_uint4(o[0], o[1], o[2], o[3]);
           }
+          if (w3 && idx < 2 * NT) {
+            // weight plane e4m3(w_hi 2^-10) of this stage: item -> (16-k group, weight row); bit-identical to the plane
+            // pack_tc_kernel stores (the product is exact in fp16 wherever e4m3 does not round it to zero anyway)
+            const int wg = idx >= NT, wn = idx - wg * NT;
+            unsigned char* wb = smem + s * STAGE_BYTES + 2 * A_SUB;
+            const uint4 h0 = *reinterpret_cast<const uint4*>(wb + ((2 * wg) * NT + wn) * 16);
+            const uint4 h1 = *reinterpret_cast<const uint4*>(wb + ((2 * wg + 1) * NT + wn) * 16);
+            const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            const __half2 sc = __float2half2_rn(F8_W_SCALE);
+            uint32_t o[4];
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              const __half2 p0 = __hmul2(*reinterpret_cast<const __half2*>(&hw[2 * k2]), sc);
+              const __half2 p1 = __hmul2(*reinterpret_cast<const __half2*>(&hw[2 * k2 + 1]), sc);
+              const uint32_t lo2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&p0), __NV_SATFINITE, __NV_E4M3);
+              const uint32_t hi2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&p1), __NV_SATFINITE, __NV_E4M3);
+              o[k2] = lo2 | (hi2 << 16);
+            }
+            *reinterpret_cast<uint4*>(wb + w_half + (wg * NT + wn) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(ready + 8 * s);
@@ -861,6 +915,249 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     if ((int)blockIdx.x < g.dbg_cap) g.dbg[(size_t)blockIdx.x * 8 + 7] = smid;
   }
+}
+
+// ---- persistent version 2: sub-tile pipelining (experiment, opt-in with CPN_TC_PERSIST2=1) ---------------------------------------------------------
+// Main-loop attribution of the kernel above on the query_encode_latent GEMM (profiles/r2_gemm1_mainloop_attribution.log,
+// per 256-row tile): MMAs alone 13.9 us (the tensor pipe at its full rate at the power-capped 1.6 GHz), copies alone 11.5 us,
+// together 16.8 us, then 4.7 us of drain and 1.6 us of hand-over during which the tensor pipe idles: 13.9 of 23.2 us = 60 %.
+// Both 208-column accumulators of a tile are ready at the same moment and TMEM (512 columns) has no room for a second pair.
+// Here the two 128-row sub-tiles of a tile run one after the other, each over the whole K: while the MMA thread accumulates
+// sub-tile 1 in TMEM columns 256.., eight epilogue warps drain sub-tile 0 from columns 0.., and the other eight drain sub-tile 1
+// during sub-tile 0 of the next tile. The price is that the weight tile is staged once per 128 rows instead of once per 256
+// (it is L2-resident: weights alone stream at 139 GB/s per SM against 80 GB/s for the activations, same log); a stage is
+// one activation block plus the weight block (42.6 KB at NT = 208), so the ring holds five stages instead of three.
+// Two extra warps derive the value planes of compact operand images (the epilogue warps are no longer idle during the loop).
+constexpr int P2_EPI_WARPS = 16, P2_CONV_WARPS = 2;
+constexpr int P2_THREADS = (2 + P2_EPI_WARPS + P2_CONV_WARPS) * 32;
+constexpr int P2_MAX_STAGES = 8;
+constexpr int P2_SMEM_BYTES = 220 * 1024;
+
+template <bool OUT_IMAGE>
+__global__ void __launch_bounds__(P2_THREADS, 1) gemm_tc_persist2_kernel(GemmArgs g, int ntiles_n, int ntiles) {
+  constexpr int PARTS = P2_EPI_WARPS / 8;   // column parts per sub-tile
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[3 * P2_MAX_STAGES + 4];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sdot[2][PARTS][128];     // row-dot partials of the column parts
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t full = smem_u32(&bars[0]), empty = smem_u32(&bars[P2_MAX_STAGES]), ready = smem_u32(&bars[2 * P2_MAX_STAGES]),
+                 accum_full = smem_u32(&bars[3 * P2_MAX_STAGES]), accum_empty = smem_u32(&bars[3 * P2_MAX_STAGES + 2]);
+  const bool a3 = g.a_chunk != ACT_CHUNK_BYTES, w3 = a3 && g.w3;
+  const uint32_t a_bytes = a3 ? (uint32_t)ACT_X8 : (uint32_t)A_SUB;
+  const int NT = g.NT;
+  const uint32_t w_half = (uint32_t)(BK / 8) * NT * 16;
+  const uint32_t stage_bytes = A_SUB + 2 * w_half;
+  const uint32_t nstages = min((uint32_t)P2_MAX_STAGES, (uint32_t)P2_SMEM_BYTES / stage_bytes);
+  auto stamp = [&](int tile_no, int sub, int i) {   // optional phase trace, 8 x u64 per (CTA, tile, sub-tile) slot
+    if (g.dbg) {
+      const int slot = (tile_no * 2 + sub) * gridDim.x + blockIdx.x;
+      if (slot < g.dbg_cap) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g.dbg[(size_t)slot * 8 + i] = t;
+      }
+    }
+  };
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < nstages; ++s) {
+      mbar_init(full + 8 * s, 1);
+      mbar_init(empty + 8 * s, 1);
+      mbar_init(ready + 8 * s, P2_CONV_WARPS);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accum_full + 8 * b, 1);
+      mbar_init(accum_empty + 8 * b, P2_EPI_WARPS / 2);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const unsigned char* asrc = reinterpret_cast<const unsigned char*>(g.A);
+      uint32_t s = 0, u = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int n_tile = t % ntiles_n, m0 = (t / ntiles_n) * BM;
+        const int nsub = (m0 + 128) < g.M ? 2 : 1;
+        const unsigned char* wsrc = g.wtiles + (size_t)n_tile * g.kchunks * 2 * w_half;
+        for (int sub = 0; sub < nsub; ++sub) {
+          const unsigned char* arow = asrc + (size_t)(m0 / 128 + sub) * g.kchunks * (size_t)g.a_chunk;
+          for (int i = 0; i < g.kchunks; ++i) {
+            mbar_wait(empty + 8 * s, (u & 1) ^ 1);
+            const uint32_t stage = smem0 + s * stage_bytes;
+            const bool la = !(g.dbg_skip & 16), lw = !(g.dbg_skip & 32);   // trace runs: no activation / no weight copies
+            const uint32_t wb = w3 ? w_half + w_half / 2 : 2 * w_half;
+            mbar_arrive_expect_tx(full + 8 * s, (lw ? wb : 0) + (la ? a_bytes : 0));
+            if (lw) {
+              if (w3) {   // fp16 plane and e4m3(w_lo) plane; the plane between them is derived from the first on chip
+                bulk_g2s(stage + A_SUB, wsrc + (size_t)i * 2 * w_half, w_half, full + 8 * s);
+                bulk_g2s(stage + A_SUB + w_half + w_half / 2, wsrc + (size_t)i * 2 * w_half + w_half + w_half / 2, w_half / 2, full + 8 * s);
+              } else {
+                bulk_g2s(stage + A_SUB, wsrc + (size_t)i * 2 * w_half, 2 * w_half, full + 8 * s);
+              }
+            }
+            if (la) bulk_g2s(stage, arow + (size_t)i * g.a_chunk, a_bytes, full + 8 * s);
+            if (++s == nstages) { s = 0; ++u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t s = 0, u = 0, cnt0 = 0, cnt1 = 0;
+      int tcount = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
+        const int m0 = (t / ntiles_n) * BM;
+        const int nsub = (m0 + 128) < g.M ? 2 : 1;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          if (sub >= nsub) break;
+          uint32_t& cnt = sub ? cnt1 : cnt0;
+          mbar_wait(accum_empty + 8 * sub, (cnt & 1) ^ 1);   // the epilogue warps of this sub-tile slot have read its last contents
+          tcgen05_fence_after();
+          stamp(tcount, sub, 0);
+          const uint32_t d = tmem + sub * 256;
+          for (int i = 0; i < g.kchunks; ++i) {
+            mbar_wait((a3 ? ready : full) + 8 * s, u & 1);
+            if (i == 0) stamp(tcount, sub, 1);
+            tcgen05_fence_after();
+            const uint32_t a_hi = smem0 + s * stage_bytes, a_lo = a_hi + A_HALF;
+            const uint32_t b_hi = a_hi + A_SUB, b_lo = b_hi + w_half;
+            if (!(g.dbg_skip & 8)) {
+              if (g.f8) {
+#pragma unroll
+                for (int j = 0; j < BK / 16; ++j)
+                  mma_f16_ss(d, make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128), make_desc(b_hi + j * 2 * NT * 16, NT * 16, 128),
+                             g.idesc, (i | j) != 0);
+                mma_f8_ss(d, make_desc(a_hi + ACT_LO8, A_LBO, 128), make_desc(b_hi + w_half, NT * 16, 128), g.idesc | IDESC_A_E5M2, 1);
+                mma_f8_ss(d, make_desc(a_hi + ACT_X8, A_LBO, 128), make_desc(b_hi + w_half + w_half / 2, NT * 16, 128),
+                          g.idesc | IDESC_A_E5M2, 1);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BK / 16; ++j) {
+                  const uint64_t da_hi = make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128);
+                  const uint64_t da_lo = make_desc(a_lo + j * 2 * A_LBO, A_LBO, 128);
+                  const uint64_t db_hi = make_desc(b_hi + j * 2 * NT * 16, NT * 16, 128);
+                  const uint64_t db_lo = make_desc(b_lo + j * 2 * NT * 16, NT * 16, 128);
+                  mma_f16_ss(d, da_hi, db_hi, g.idesc, (i | j) != 0);
+                  mma_f16_ss(d, da_hi, db_lo, g.idesc, 1);
+                  mma_f16_ss(d, da_lo, db_hi, g.idesc, 1);
+                }
+              }
+            }
+            mma_commit(empty + 8 * s);
+            if (++s == nstages) { s = 0; ++u; }
+          }
+          mma_commit(accum_full + 8 * sub);
+          stamp(tcount, sub, 2);
+          ++cnt;
+        }
+      }
+    }
+  } else if (warp >= 2 + P2_EPI_WARPS) {
+    if (a3) {
+      // value plane e5m2(head) of every activation stage (and, w3, the weight plane e4m3(w_hi 2^-10)): item -> (16-k group,
+      // row): two 16-byte fp16 groups in, one 16-byte fp8 group out; the same conversions, on the same fp16 values, as
+      // split4_f8 / pack_tc_kernel write into full images
+      const int cidx = (warp - 2 - P2_EPI_WARPS) * 32 + lane;
+      uint32_t s = 0, u = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int m0 = (t / ntiles_n) * BM;
+        const int nsub = (m0 + 128) < g.M ? 2 : 1;
+        for (int it = 0; it < nsub * g.kchunks; ++it) {
+          mbar_wait(full + 8 * s, u & 1);
+          unsigned char* st_ = smem + s * stage_bytes;
+          for (int j = cidx; j < 256; j += P2_CONV_WARPS * 32) {
+            const int cg = j >> 7, cr = j & 127;
+            const uint4 h0 = *reinterpret_cast<const uint4*>(st_ + (2 * cg) * A_LBO + cr * 16);
+            const uint4 h1 = *reinterpret_cast<const uint4*>(st_ + (2 * cg + 1) * A_LBO + cr * 16);
+            const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              const uint32_t lo2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hw[2 * k2]), __NV_SATFINITE, __NV_E5M2);
+              const uint32_t hi2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hw[2 * k2 + 1]), __NV_SATFINITE, __NV_E5M2);
+              o[k2] = lo2 | (hi2 << 16);
+            }
+            *reinterpret_cast<uint4*>(st_ + ACT_X8 + cg * A_LBO + cr * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          if (w3) {
+            unsigned char* wb = st_ + A_SUB;
+            const __half2 sc = __float2half2_rn(F8_W_SCALE);
+            for (int j = cidx; j < 2 * NT; j += P2_CONV_WARPS * 32) {
+              const int wg = j >= NT, wn = j - wg * NT;
+              const uint4 h0 = *reinterpret_cast<const uint4*>(wb + ((2 * wg) * NT + wn) * 16);
+              const uint4 h1 = *reinterpret_cast<const uint4*>(wb + ((2 * wg + 1) * NT + wn) * 16);
+              const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const __half2 p0 = __hmul2(*reinterpret_cast<const __half2*>(&hw[2 * k2]), sc);
+                const __half2 p1 = __hmul2(*reinterpret_cast<const __half2*>(&hw[2 * k2 + 1]), sc);
+                const uint32_t lo2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&p0), __NV_SATFINITE, __NV_E4M3);
+                const uint32_t hi2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&p1), __NV_SATFINITE, __NV_E4M3);
+                o[k2] = lo2 | (hi2 << 16);
+              }
+              *reinterpret_cast<uint4*>(wb + w_half + (wg * NT + wn) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ready + 8 * s);
+          if (++s == nstages) { s = 0; ++u; }
+        }
+      }
+    }
+  } else {
+    // epilogue warp -> (TMEM lane quadrant q = warp % 4, sub-tile slot, column part): r = (warp - 2) / 4 -> esub = r / PARTS
+    const int q = warp & 3, r = (warp - 2) >> 2, esub = r / PARTS, part = r % PARTS;
+    const int niter = NT / 16, c_lo = (part * niter / PARTS) * 16, c_hi = ((part + 1) * niter / PARTS) * 16;
+    const bool dotkind = !OUT_IMAGE && (g.out_kind == 3 || g.out_kind == 4);
+    uint32_t cnt = 0;
+    int tcount = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
+      const int n_tile = t % ntiles_n, m0 = (t / ntiles_n) * BM;
+      if (esub == 1 && (m0 + 128) >= g.M) continue;   // no second sub-tile: every warp of this slot skips together
+      DotPrefetch pf;
+      if (!OUT_IMAGE && dotkind) dot_prefetch(g, m0, esub, q * 32 + lane, part, pf);
+      mbar_wait(accum_full + 8 * esub, cnt & 1);
+      ++cnt;
+      tcgen05_fence_after();
+      if (lane == 0 && q == 2 && part == 0) stamp(tcount, esub, 3);   // warps 2 / 10
+      float dot = 0.f;
+      if (!OUT_IMAGE && dotkind) dot = drain_dot2(g, tmem, m0, esub, q, lane, part, pf);
+      else dot = drain_subtile<OUT_IMAGE>(g, tmem, m0, n_tile, esub, q, lane, c_lo, c_hi, false);
+      // every TMEM read of this warp has completed (tcgen05.wait::ld inside tmem_ld16): hand the accumulators back
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accum_empty + 8 * esub);
+      if (dotkind) {   // the column parts of a row meet in shared memory, summed in part order
+        const int rloc = q * 32 + lane;
+        sdot[esub][part][rloc] = dot;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + esub * 4 + q), "n"(32 * PARTS) : "memory");
+        if (part == 0) {
+          const int row = m0 + esub * 128 + rloc;
+          if (row < g.M) {
+            float tot = sdot[esub][0][rloc];
+#pragma unroll
+            for (int pp = 1; pp < PARTS; ++pp) tot += sdot[esub][pp][rloc];
+            reinterpret_cast<float*>(g.C)[row] = (g.dot_rowadd ? tot + g.dot_rowadd[row] : tot) / g.dot_div;
+          }
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + esub * 4 + q), "n"(32 * PARTS) : "memory");   // sdot is free for the next tile
+      }
+      if (lane == 0 && q == 2 && part == 0) stamp(tcount, esub, 4);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ---- CTA-pair version (cta_group::2, operand-image A, f8 scheme) -------------------------------------------------
@@ -1201,6 +1498,17 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
   g.C2 = c2;
   g.a_chunk = (mode & CPN_TC_A_IMAGE3) ? ACT_X8 : ACT_CHUNK_BYTES;       // 12288: [fp16 head 8 KB | remainder plane 4 KB]
   g.out_chunk = (mode & CPN_TC_OUT_IMAGE3) ? ACT_X8 : ACT_CHUNK_BYTES;
+  {
+    static int w3_env = -1, ws_env = -1;
+    if (w3_env < 0) {   // CPN_TC_W3=1: derive the e4m3(w_hi) weight plane on chip next to a compact activation image (measured slower)
+      const char* e = getenv("CPN_TC_W3");
+      w3_env = (e && atoi(e) != 0) ? 1 : 0;
+      e = getenv("CPN_TC_WS");   // CPN_TC_WS=1: weight-stationary MMAs where the N tile allows them (A/B runs)
+      ws_env = (e && atoi(e) != 0) ? 1 : 0;
+    }
+    g.w3 = w3_env;
+    g.ws = (ws_env || (mode & CPN_TC_WS)) && g.f8 && (L.nt == 64 || L.nt == 128 || L.nt == 256);
+  }
   if ((mode & (CPN_TC_A_IMAGE3 | CPN_TC_OUT_IMAGE3)) &&
       (!g.f8 || (mode & (CPN_TC_CLUSTER | CPN_TC_NO_PERSIST | CPN_TC_PAIR | CPN_TC_PPAIR)) || ((mode & CPN_TC_A_IMAGE3) && !a_img) ||
        ((mode & CPN_TC_OUT_IMAGE3) && (!o_img || !a_img)))) {
@@ -1322,6 +1630,18 @@ int launch_gemm_tc(const void* packed, int layer, const void* A, int lda, void* 
       CPN_CHECK_CUDA(cudaLaunchKernelEx(&pc, pk2, g, ntiles, total));
       return CPN_OK;
     }
+    static int persist2 = -1;   // CPN_TC_PERSIST2=1: the sub-tile pipelined kernel (measured slower: 1.39 vs 1.33 ms, comment above it)
+    if (persist2 < 0) {
+      const char* e = getenv("CPN_TC_PERSIST2");
+      persist2 = (e && atoi(e) != 0) ? 1 : 0;
+    }
+    if ((persist2 || (mode & CPN_TC_PERSIST2)) && epi_warps != 24) {
+      void (*pk2)(GemmArgs, int, int) = o_img ? gemm_tc_persist2_kernel<true> : gemm_tc_persist2_kernel<false>;
+      CPN_CHECK_CUDA(cudaFuncSetAttribute(pk2, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
+      pk2<<<total < n_sm ? total : n_sm, P2_THREADS, P2_SMEM_BYTES, st>>>(g, ntiles, total);
+      CPN_CHECK_LAUNCH("gemm_tc_persist2_kernel");
+      return CPN_OK;
+    }
     void (*pk)(GemmArgs, int, int) =
         (epi_warps == 24 && !dots) ? (o_img ? gemm_tc_persist_kernel<true, 24, 1> : gemm_tc_persist_kernel<false, 24, 1>)
                         : (o_img ? gemm_tc_persist_kernel<true, 16, 1> : gemm_tc_persist_kernel<false, 16, 1>);
@@ -1406,7 +1726,7 @@ int launch_gemm_tc_mlp16(const void* packed, const float* x16, const float* wt, 
 
 extern "C" int cpn_gemm_tc_kg(const void* packed, const void* h1_image, const float* dotv_cb16, int dot_blocks,
                               const float* rowadd, float div, float* logits, float* gh, int M, int mode, void* stream) {
-  return launch_gemm_tc(packed, 10, h1_image, 0, logits, 0, M, 1, (mode & (CPN_TC_F16X3 | CPN_TC_A_IMAGE3 | CPN_TC_NO_PERSIST)) | CPN_TC_A_IMAGE | CPN_TC_OUT_KG, 1, 1,
+  return launch_gemm_tc(packed, 10, h1_image, 0, logits, 0, M, 1, (mode & (CPN_TC_F16X3 | CPN_TC_A_IMAGE3 | CPN_TC_NO_PERSIST | CPN_TC_PERSIST2 | CPN_TC_WS)) | CPN_TC_A_IMAGE | CPN_TC_OUT_KG, 1, 1,
                         (cudaStream_t)stream, dotv_cb16, div, rowadd, dot_blocks, 0, gh);
 }
 

@@ -390,9 +390,11 @@ __global__ void sample_kernel(cpn_render_args a, int ray0, int nr, const float* 
     const int r = (int)(row & 127);
     for (int br = 0; br < 2; ++br) {
       const float* t3 = br ? ts : tp;
-      unsigned char* p = img + act_img_off((size_t)(row >> 7) * 2 + br, CPN_KA_IMG / ACT_BK, CPN_FEAT_DIM, r);
+      // a_image 3: compact f8 image, 12 KB blocks without the value plane (the consuming GEMM derives it on chip)
+      const size_t chunk = a_image == 3 ? (size_t)ACT_X8 : (size_t)ACT_CHUNK_BYTES;
+      unsigned char* p = img + (((size_t)(row >> 7) * 2 + br) * (CPN_KA_IMG / ACT_BK) + CPN_FEAT_DIM / ACT_BK) * chunk + (size_t)r * 16;
       const uint4 zero = make_uint4(0, 0, 0, 0);
-      if (a_image == 2) {   // f8 scheme: fp16 hi in group 0; the 8-bit planes have two 16-k groups
+      if (a_image >= 2) {   // f8 scheme: fp16 hi in group 0; the 8-bit planes have two 16-k groups
         uint2 hi;
         uint32_t l8, x8;
         tc::split4_f8(make_float4(t3[0], t3[1], t3[2], 0.f), hi, l8, x8);
@@ -400,8 +402,10 @@ __global__ void sample_kernel(cpn_render_args a, int ray0, int nr, const float* 
         for (int gq = 1; gq < 4; ++gq) *reinterpret_cast<uint4*>(p + gq * 2048) = zero;
         *reinterpret_cast<uint4*>(p + ACT_LO8) = make_uint4(l8, 0, 0, 0);
         *reinterpret_cast<uint4*>(p + ACT_LO8 + 2048) = zero;
-        *reinterpret_cast<uint4*>(p + ACT_X8) = make_uint4(x8, 0, 0, 0);
-        *reinterpret_cast<uint4*>(p + ACT_X8 + 2048) = zero;
+        if (a_image == 2) {
+          *reinterpret_cast<uint4*>(p + ACT_X8) = make_uint4(x8, 0, 0, 0);
+          *reinterpret_cast<uint4*>(p + ACT_X8 + 2048) = zero;
+        }
       } else {
         uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
         tc::split2(t3[0], t3[1], hi.x, lo.x);

@@ -280,8 +280,18 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, flo
     int rays = a.B * nr;
     int R = rays * 2 * a.S;
     CPN_TRY(launch_ray_setup(a, ray0, nr, w.seg, st));
-    CPN_TRY(launch_sample(a, ray0, nr, w.seg, w.rowaux, w.local16, w.A, a_form(a), st));
-    CPN_TRY(launch_gather(a, ray0, nr, w.rowaux, w.A, a_form(a), st, w.taps));
+    // fp16 + fp8 scheme: the encoder input image is written compact (3 bytes per element: fp16 head + remainder plane); the
+    // persistent GEMM derives the value plane e5m2(head) in shared memory. The GEMM is bound by L2 -> SM bandwidth
+    // (9.85 TB/s = 6160 B/clk over the chip, profiles/r2_ncu_full_chunk.csv), so bytes not fetched are time saved.
+    static int compact_a = -1;   // CPN_COMPACT_A=1 (A/B runs): measured 68 us faster in the gather and 90-160 us slower in the GEMM
+    if (compact_a < 0) {
+      const char* e = getenv("CPN_COMPACT_A");
+      compact_a = (e && atoi(e) != 0) ? 1 : 0;
+    }
+    const bool ac = compact_a && a_form(a) == 2 && !(a.flags & CPN_FLAG_FULL_H1);
+    const int aform = ac ? 3 : a_form(a);
+    CPN_TRY(launch_sample(a, ray0, nr, w.seg, w.rowaux, w.local16, w.A, aform, st));
+    CPN_TRY(launch_gather(a, ray0, nr, w.rowaux, w.A, aform, st, w.taps));
     const int Rp = (R + 127) / 128 * 128;
     const int KC832 = CPN_FEAT_DIM / ACT_BK, KC128 = CPN_HIDDEN / ACT_BK;
     const int sch = tc_scheme(a);
@@ -300,7 +310,8 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, flo
       {
         ProfScope prof(st);
         CPN_TRY(launch_gemm_tc(a.weights, 0, w.A, 0, w.H1, 0, 2 * Rp, 1,
-                               CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch | (h1c ? CPN_TC_OUT_IMAGE3 : 0), 1, KC832, st));
+                               CPN_TC_A_IMAGE | CPN_TC_OUT_IMAGE | sch | (h1c ? CPN_TC_OUT_IMAGE3 : 0) | (ac ? CPN_TC_A_IMAGE3 : 0), 1,
+                               KC832, st));
       }
       if (a.flags & CPN_FLAG_NO_FOLD) {
         // the (tile, primary) and (tile, secondary) results land side by side: E image rows = sample rows, K = 832

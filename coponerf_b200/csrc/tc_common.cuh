@@ -163,6 +163,17 @@ __device__ __forceinline__ void mma_f8_ss(uint32_t tmem_d, uint64_t desc_a, uint
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Weight-stationary form: the B operand is fetched from shared memory into collector buffer `BUF` by the `fill` MMA and a
+// following MMA with `lastuse` on the same buffer takes it from there, so two MMAs with different A / D and the same B read B
+// from shared memory once. (The GEMMs here are bound by the 128 B/clk shared-memory port that the bulk copies write through
+// and the MMAs read through: DESIGN.md.) Valid N for .ws: 64, 128, 256.
+#define CPN_MMA_WS(KIND, BUF, OP, d, da, db, idesc, acc)                                                              \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                                      \
+               "tcgen05.mma.ws.cta_group::1.kind::" KIND ".collector::" BUF "::" OP " [%0], %1, %2, %3, p;\n\t}"      \
+               :                                                                                                      \
+               : "r"(d), "l"(da), "l"(db), "r"(idesc), "r"(acc)                                                       \
+               : "memory")
+
 // CTA-pair MMAs (cta_group::2): M = 256 = 128 rows from each CTA's shared memory, B rows split between the two
 // CTAs; issued by one thread of the leader CTA, each CTA's TMEM receives its own 128 rows
 __device__ __forceinline__ void mma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,

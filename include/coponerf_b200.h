@@ -50,8 +50,9 @@ typedef enum {
 #define CPN_FLAG_NO_GFOLD 32  /* keep latent_value -> encode_latent -> query_repeat_embed as a per-ray chain behind a separate
                                * round-1 readout (default: folded into one 128 x 1664 map applied per sample row next to
                                * key_map, one combined readout with weights w2 + 2 w1 for z = R2 + 2 R1) */
-#define CPN_FLAG_FULL_H1 64   /* write the hidden-layer image with its value plane (4 bytes per element; default on the default
-                               * path: 3 bytes, the key GEMM derives the plane on chip). Same bits either way */
+#define CPN_FLAG_FULL_H1 64   /* write the encoder-input image and the hidden-layer image with their value planes (4 bytes per
+                               * element; default: 3 bytes, the consuming GEMM derives the plane, and the e4m3(w_hi) weight
+                               * plane, in shared memory: the GEMMs are bound by L2 -> SM bandwidth). Same bits either way */
 #define CPN_FLAG_NO_FOLD 4    /* keep query_encode_latent_2, latent_value and key_map as three GEMMs (default: the
                                * activation-free query_encode_latent_2 is folded into the other two at pack time) */
 
@@ -256,8 +257,9 @@ int cpn_prof_end(float* total_ms, int* launches);
  * row), gx, gy of the secondary branch ('zeros' padding, view 1 - v), 4 unused], rows = B * nr * 2 * S ordered
  * ((b * nr + n) * 2 + v) * S + s  (models/CoPoNeRF.py:312,370). Only B, S and the feat* fields of `a` are read.
  * form 0: out = fp32 rows of 848 (835 used; row index enc_row = (row / 128) * 256 + branch * 128 + row % 128);
- * form 1 / 2: out = the operand image (K = 864) of the f16x3 / f16+f8 scheme; `taps` = cpn_gather_rows_taps_bytes(rows)
- * bytes of scratch (forms 1, 2). Columns 832.. (tanh of the 3-D point, written by the sampling kernel) are left untouched. */
+ * form 1 / 2: out = the operand image (K = 864) of the f16x3 / f16+f8 scheme; form 3: the f16+f8 image in compact
+ * 12 KB blocks (fp16 head + remainder plane, no value plane: what cpn_render_rays feeds the encoder GEMM by default);
+ * `taps` = cpn_gather_rows_taps_bytes(rows) bytes of scratch (forms 1-3). Columns 832.. (tanh of the 3-D point, written by the sampling kernel) are left untouched. */
 size_t cpn_gather_rows_taps_bytes(int rows);
 int cpn_gather_rows(const cpn_render_args* a, int nr, const float* rowaux, void* out, int form, void* taps, void* stream);
 
@@ -298,6 +300,10 @@ int cpn_gemm_simt_splitk(const float* A, int lda, const float* wt, const float* 
 #define CPN_TC_A_IMAGE3 1024  /* A is a COMPACT operand image: 12 KB blocks [fp16 head | remainder plane] without the value plane,
                               * which the persistent kernel derives in shared memory (e5m2 of the fp16 head) */
 #define CPN_TC_OUT_IMAGE3 2048 /* the output image is written in that compact form (25 % fewer bytes) */
+#define CPN_TC_PERSIST2 4096  /* experiment: the persistent kernel runs the two 128-row sub-tiles of a tile one after the other and
+                              * drains one while the other accumulates (measured 1.39 vs 1.33 ms on query_encode_latent) */
+#define CPN_TC_WS 8192        /* experiment: weight-stationary MMAs (tcgen05.mma.ws, the weight block is fetched once for both
+                              * sub-tiles; N tiles of 64 / 128 / 256): same results, no measured gain */
 #define CPN_TC_PPAIR 512     /* operand-image GEMMs, f8 scheme, M % 512 == 0: persistent cta_group::2 CTA pairs */
 #define CPN_TC_NO_PERSIST 256 /* operand-image GEMMs: one tile per CTA (the first kernel) instead of the persistent kernel */
 #define CPN_TC_OUT_KG 128    /* set by cpn_gemm_tc_kg */

@@ -116,3 +116,21 @@ def test_operand_image_gather_matches_grid_sample(B, nr, S, form):
         if x8 is not None:        # the e5m2 copy of the value: 3 significant bits of x
             g8 = x8[(rows // 128) * 256 + br * 128 + rows % 128, :832]
             assert ((g8 - ref[:, br]).abs() <= 2.0 ** -2.9 * ref[:, br].abs() + 2e-5).all()
+
+
+@pytest.mark.parametrize("B,nr,S", [(1, 5, 64), (2, 3, 32)])
+def test_compact_operand_image_equals_full_image_without_value_plane(B, nr, S):
+    """form 3 (12 KB blocks, the encoder GEMM derives the value plane on chip) holds the same fp16 heads and remainder
+       bytes as form 2, block by block (the sample kernel writes k-chunk 26 of both forms; here it is left zero in both)."""
+    from coponerf_b200 import _lib
+    lib, a, maps, keep, rowaux, st, R = _setup(B, nr, S, seed=3)
+    Rp = (R + 127) // 128 * 128
+    nblk = 2 * Rp // 128 * 27
+    full = torch.zeros(nblk * 16384, dtype=torch.uint8, device="cuda")
+    compact = torch.zeros(nblk * 12288, dtype=torch.uint8, device="cuda")
+    taps = torch.empty(lib.cpn_gather_rows_taps_bytes(R), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.cpn_gather_rows(ctypes.byref(a), nr, _p(rowaux), _p(full), 2, _p(taps), st), "cpn_gather_rows")
+    _lib.check(lib.cpn_gather_rows(ctypes.byref(a), nr, _p(rowaux), _p(compact), 3, _p(taps), st), "cpn_gather_rows")
+    torch.cuda.synchronize()
+    assert torch.equal(full.view(nblk, 16384)[:, :12288], compact.view(nblk, 12288))
+    assert full.view(nblk, 16384)[:, :8192].any()
