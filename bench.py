@@ -81,6 +81,8 @@ def parse():
     ap.add_argument("--no-gfold", action="store_true", help="per-ray chain for the round-2 query bias + two readouts")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the one-pair ray-sharded measurement")
+    ap.add_argument("--no-pipeline", action="store_true", help="run get_z and the render of every pair back to back on one stream "
+                    "(default: get_z of the next pair overlaps the render of the current one, coponerf_b200/pipeline.py)")
     ap.add_argument("--eager-get-z", action="store_true", help="launch get_z()'s kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--stage", default="full", choices=["full", "pair", "render"],
                     help="full: get_z (encoder, cost aggregation, pose) + render per step; pair: cost aggregation "
@@ -402,6 +404,55 @@ def main():
         st = eng.prepare_pair(inp, z_d[i], rel_d[i], flow_d[i], H, W, True)
         return eng.render_rays(st, uv_d[i], S)
 
+    # ---- the default `full` step: a stream of pairs through the two-stage pipeline (coponerf_b200/pipeline.py). get_z of the
+    # next pair (about 800 short kernels, one CUDA graph) runs on a second stream while the current pair renders. A timed
+    # region starts with nothing in flight and ends with nothing in flight: `steps * ppr` get_z calls and renders inside it,
+    # the first get_z exposed, the others overlapped.
+    pipelined = full and not args.no_pipeline
+    if pipelined:
+        from coponerf_b200.pipeline import PairPipeline
+        pipe = PairPipeline(model, priority_high=os.environ.get("CPN_PIPE_PRIORITY", "1") != "0")
+    pstate = {"left": 0, "handle": None}
+
+    def pipe_begin(n_steps):
+        pstate["left"], pstate["handle"] = n_steps * ppr, None
+
+    def pipe_pair(i, src):
+        """get_z outputs of pair i (started by the previous call, or here at the start of a region); starts the next one."""
+        if pstate["handle"] is None:
+            pstate["handle"] = pipe.submit(src[i])
+        got = pipe.take(pstate["handle"])
+        pstate["left"] -= 1
+        pstate["handle"] = pipe.submit(src[(i + 1) % ppr]) if pstate["left"] > 0 else None
+        return got
+
+    def device_step_pipelined():
+        o = None
+        for i in range(ppr):
+            eng._feat_cache.clear()
+            inp, z, rel, flows = pipe_pair(i, inp_d)
+            state["z"], state["flow"], state["rel"] = z, flows, rel
+            st = eng.prepare_pair(inp, z, rel, flows, H, W, True)
+            o = eng.render_rays(st, uv_d[i], S)
+            if world > 1:
+                rgb_rank[i].copy_(o["rgb"][0])
+        if world > 1:
+            dist.gather(rgb_rank, gather_buf, dst=0)
+        state["out"] = o
+        return o
+
+    def e2e_step_pipelined():      # host buffers in (copied on the get_z stream), the reference's host-side outputs out
+        out = None
+        for i in range(ppr):
+            eng._feat_cache.clear()
+            inp, z, rel, flows = pipe_pair(i, host)
+            out = model(inp, z=z, rel_pose=rel, flow=flows, val=True)
+            rgb_rank[i].copy_(out["rgb"][0])
+        if world > 1:
+            dist.gather(rgb_rank, gather_buf, dst=0)
+        rgb_pinned.copy_(rgb_rank, non_blocking=True)
+        return out
+
     def device_step():
         o = None
         for i in range(ppr):
@@ -441,12 +492,16 @@ def main():
         if world > 1:
             dist.barrier()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, begin=None):
+        if begin and warmup:
+            begin(warmup)
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
         barrier()
         torch.cuda.synchronize()
+        if begin:
+            begin(steps)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for a, b in ev:
             flush.zero_()
@@ -469,6 +524,11 @@ def main():
         device_step()
     torch.cuda.synchronize()
     ms_dev = timed(device_step, args.steps, 0)
+    serial = None
+    if pipelined:      # the headline is the pipelined stream of pairs; the back-to-back figure stays in the line beside it
+        serial = {"value": total_pairs * N_RAYS * args.steps / (ms_dev * 1e-3), "ms_per_step": ms_dev / args.steps,
+                  "what": "get_z then render of every pair back to back on one stream (--no-pipeline)"}
+        ms_dev = timed(device_step_pipelined, args.steps, args.warmup, begin=pipe_begin)
     # roofline pass: the dominant kernel timed with CUDA events around each launch. Chunks are issued on one lane
     # here so that an event pair brackets that kernel alone (with lanes > 1 other chunks' kernels share the GPU
     # and the bracket would include their time); the step time of this pass gives the kernel's share.
@@ -494,6 +554,9 @@ def main():
         launches += args.steps * ppr * (model._ufc_ops.launches - n0)
         model.graph_get_z = not args.eager_get_z
     ms_e2e = timed(e2e_step, args.steps, 2)
+    if pipelined:
+        serial["e2e"] = {"value": total_pairs * N_RAYS * args.steps / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / args.steps}
+        ms_e2e = timed(e2e_step_pipelined, args.steps, 2, begin=pipe_begin)
 
     # ---- N > 1: ONE pair, rays sharded over the ranks (SURVEY.md 8(e) case 2). Rank 0 runs get_z, one broadcast of a
     # flat buffer carries z / rel_pose / flows to the others, every rank renders its slice, one all-gather of rgb.
@@ -578,6 +641,8 @@ def main():
                    "get_z": "eager launches" if args.eager_get_z else "CUDA graph replay",
                    "pairs_per_step": total_pairs, "pairs_per_gpu": ppr, "chunk_rays": args.chunk_rays, "lanes": args.lanes,
                    "l2": "flushed between timed steps (256 MB write)",
+                   "pipeline": ("get_z of pair k + 1 on a second stream while pair k renders (coponerf_b200/pipeline.py); every "
+                                "timed region starts and ends with nothing in flight" if pipelined else "none: get_z and render back to back"),
                    "gemm_path": "simt-fp32" if args.simt else "tcgen05: fp16 head + two fp8 correction MMAs per product (e5m2 "
                                 "activation planes, e4m3 weight planes, fp32 accumulate), persistent kernel"
                                 + ("" if args.no_fold else "; query_encode_latent_2 folded into latent_value / key_map")
@@ -604,6 +669,8 @@ def main():
                      "frac_of_parity_ceiling": None if args.simt else achieved / (peak / 2.0)},
         "clocks": clk,
     }
+    if serial is not None:
+        line["serial"] = serial
     if strong is not None:
         line["strong"] = strong
     if ufc_ms:      # cost aggregation timed on the device inside the roofline pass: an HBM-bound stage

@@ -3,6 +3,7 @@
 // Each replaces a chain of einops rearranges + F.interpolate / nn.LayerNorm / DWConv / softmax calls without
 // materialising the rearranged copies (44 % of the reference's UFC time is aten::copy_ from those rearranges).
 #include <math.h>
+#include <stdlib.h>
 #include "cpn_common.cuh"
 
 namespace {
@@ -273,9 +274,21 @@ extern "C" int cpn_cross_attention(const float* corr, const float* src_v, const 
 }
 
 // Cosine correlation of token features (aggregation.py:70-80): out[b, s, t] = <src_n[b, s], trg_n[b, t]>,
-// x_n = x / (||x|| + 1e-5). workspace: normalised src (B, L, C) + normalised, transposed trg (B, C, L).
+// x_n = x / (||x|| + 1e-5). From 2048 tokens on (the 64 x 64 level: a 4096 x 4096 x C product per pair and call, the largest
+// GEMMs of the cost aggregation) the product runs on the tcgen05 Linear kernel with the normalised target as the "weight"
+// (three fp16 MMAs per product, fp32-level: tests/test_ufc_native_gpu.py); below that on the CUDA-core GEMM.
+// workspace: normalised src (B, L, C) + normalised (tensor-core path) or normalised, transposed trg + the packed target tiles.
+static bool corr_tc(int L, int C) {
+  static int simt = -1;   // CPN_CORR_SIMT=1: CUDA-core GEMM at every size (A/B runs)
+  if (simt < 0) {
+    const char* e = getenv("CPN_CORR_SIMT");
+    simt = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return !simt && L >= 2048 && (L % 128) == 0 && (C % 8) == 0;
+}
 extern "C" size_t cpn_correlation_workspace_bytes(int B, int L, int C) {
-  return (B > 0 && L > 0 && C > 0) ? (size_t)2 * B * L * C * sizeof(float) + 512 : 0;
+  if (B <= 0 || L <= 0 || C <= 0) return 0;
+  return (size_t)2 * B * L * C * sizeof(float) + 512 + (corr_tc(L, C) ? (cpn_linear_tc_packed_bytes(L, C) + 255) / 256 * 256 : 0);
 }
 int launch_ufc_normalize(const float* in, float* out, int tokens, int C, cudaStream_t st);   // ufc_tail.cu
 extern "C" int cpn_correlation(const float* src, const float* trg, float* out, int B, int L, int C, void* workspace,
@@ -285,13 +298,26 @@ extern "C" int cpn_correlation(const float* src, const float* trg, float* out, i
   cudaStream_t st = (cudaStream_t)stream;
   float* sn = reinterpret_cast<float*>(workspace);
   float* tnT = sn + (size_t)B * L * C;
-  float* tn = out;   // the (B, L, L) output is large enough to stage the normalised target before the transpose
   if ((size_t)L < (size_t)C) {
     cpn_set_error("cpn_correlation: L < C unsupported");
     return CPN_ERR_ARG;
   }
   int rc = launch_ufc_normalize(src, sn, B * L, C, st);
   if (rc != CPN_OK) return rc;
+  if (corr_tc(L, C)) {
+    float* tn = tnT;   // (B, L, C), row-major: the (N, K) layout cpn_linear_tc_pack takes
+    unsigned char* packed = reinterpret_cast<unsigned char*>(workspace) + ((size_t)2 * B * L * C * sizeof(float) + 511) / 256 * 256;
+    rc = launch_ufc_normalize(trg, tn, B * L, C, st);
+    if (rc != CPN_OK) return rc;
+    for (int b = 0; b < B; ++b) {
+      rc = cpn_linear_tc_pack(tn + (size_t)b * L * C, L, C, packed, stream);
+      if (rc != CPN_OK) return rc;
+      rc = launch_linear_tc(packed, L, C, sn + (size_t)b * L * C, C, nullptr, out + (size_t)b * L * L, L, L, 0, CPN_TC_F16X3, 1.f, st);
+      if (rc != CPN_OK) return rc;
+    }
+    return CPN_OK;
+  }
+  float* tn = out;   // the (B, L, L) output is large enough to stage the normalised target before the transpose
   rc = launch_ufc_normalize(trg, tn, B * L, C, st);
   if (rc != CPN_OK) return rc;
   transpose_pq_kernel<<<dim3((C + 31) / 32, (L + 31) / 32, B), dim3(32, 8), 0, st>>>(tn, tnT, L, C);

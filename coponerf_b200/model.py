@@ -136,6 +136,12 @@ class CoPoNeRF(nn.Module):
         with torch.cuda.device(dev):
             return pair_stage.get_z(self, input, self._ufc_ops, use_graph=self.graph_get_z)
 
+    def render_pairs(self, inputs, val=False):
+        """forward(input, val=val) for a sequence of pairs, as a generator: get_z() of pair k + 1 runs on a second stream while
+        pair k renders (pipeline.py). Same outputs as calling forward() pair by pair."""
+        from .pipeline import render_pairs
+        return render_pairs(self, inputs, val=val)
+
     @torch.no_grad()
     def forward(self, input, z=None, rel_pose=None, val=False, flow=None, debug=False):
         """models/CoPoNeRF.py:208-576 (inference; the sm_100a path has no backward)."""

@@ -155,3 +155,29 @@ def test_graph_replay_of_get_z_is_bit_identical_to_eager(model):
     inp2["context"]["rgb"] = inp2["context"]["rgb"].flip(-2).contiguous()
     z2, p2, f2 = model.get_z(inp2)
     assert not torch.equal(z2[0], zg[0]) and torch.equal(zg[0], ze[0])
+
+
+def test_render_pairs_pipeline_is_bit_identical_to_forward_pair_by_pair(model):
+    """CoPoNeRF.render_pairs(): get_z of pair k + 1 on a second stream while pair k renders (coponerf_b200/pipeline.py).
+    Three different pairs, host tensors in: every output equals forward(input, val=True) called pair by pair."""
+    n_rays = 4096
+    inputs = []
+    for k in range(3):
+        inp = synth.make_input(CASE["H"], CASE["W"], n_rays, seed=CASE["seed"] + k, pose_set=CASE["pose_set"])
+        if k == 1:
+            inp["context"]["rgb"] = inp["context"]["rgb"].flip(-2).contiguous()
+        inputs.append(inp)
+    keys = ("rgb", "at_wt", "depth_ray", "valid_mask", "pixel_val", "rel_pose", "C2_pts_to_C1")
+    ref = []
+    for inp in inputs:
+        o = model(to_device(inp, "cuda:0"), val=True)
+        ref.append({k: o[k].detach().cpu().clone() for k in keys})
+    got = []
+    for o in model.render_pairs(inputs, val=True):
+        got.append({k: o[k].detach().cpu().clone() for k in keys})
+    assert len(got) == 3
+    for k in range(3):
+        for key in keys:
+            assert torch.equal(got[k][key], ref[k][key]), (k, key)
+    assert not torch.equal(ref[0]["rgb"], ref[1]["rgb"])
+    assert list(model.render_pairs([], val=True)) == []

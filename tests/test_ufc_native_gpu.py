@@ -42,6 +42,14 @@ def test_operators_match_torch_restatement():
     _close(cu.dwconv_gelu(xm.cuda(), wd.cuda(), bd.cuda(), 32), th.dwconv_gelu(xm, wd, bd, 32))
     s, t = r(2, 1024, 256), r(2, 1024, 256)
     _close(cu.correlation(s.cuda(), t.cuda(), 32), th.correlation(s, t, 32), tol=1e-5)
+    # the 64 x 64 level runs on the tcgen05 Linear kernel (4096 x 4096 x C per pair): against fp64, absolute on values in [-1, 1]
+    s4, t4 = r(1, 4096, 128) * torch.logspace(-2, 2, 4096)[None, :, None], r(1, 4096, 128)
+    got = cu.correlation(s4.cuda(), t4.cuda(), 64).double().cpu().reshape(4096, 4096)
+    sn = s4[0].double() / (s4[0].double().norm(dim=-1, keepdim=True) + 1e-5)
+    tn = t4[0].double() / (t4[0].double().norm(dim=-1, keepdim=True) + 1e-5)
+    err = float((got - sn @ tn.T).abs().max())
+    print(f"correlation 4096 x 4096 x 128 on tcgen05: max abs err {err:.2e}")
+    assert err < 2e-6, err
     _close(cu.upsample_tokens(s.cuda(), 64), th.upsample_tokens(s, 64))
     _close(cu.avgpool_tokens(s.cuda(), 32, 2), th.avgpool_tokens(s, 32, 2))
     small = r(2, 256, 256)
