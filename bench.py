@@ -719,10 +719,28 @@ def main():
         want = ref["rgb"][0, 0]
         per_ray_err = (got - want).abs().max(dim=-1).values / want.abs().max()
         err = float(per_ray_err.max())
+        # conditioning of the reference's own arithmetic on these rays: how far the oracle's rgb moves when the camera poses
+        # move by about one fp32 ulp (the measure tests/cases.py gates with; two seeded perturbations here)
+        import copy
+        gsens = torch.Generator().manual_seed(1234)
+        sens = torch.zeros(len(per_ray_err))
+        for _ in range(2):
+            pin = copy.deepcopy(sub)
+            for grp in ("context", "query"):
+                t = pin[grp]["cam2world"]
+                pin[grp]["cam2world"] = t * (1 + 6e-8 * torch.randn(t.shape, generator=gsens))
+            rp = rel_cpu * (1 + 6e-8 * torch.randn(rel_cpu.shape, generator=gsens))
+            alt = render_oracle.render_forward(sd, pin, z_cpu, rp, flow_cpu, H, W, S, True, chunk=512)
+            sens = torch.maximum(sens, (alt["rgb"][0, 0] - want).abs().max(dim=-1).values / want.abs().max())
+        well = sens <= 1e-6
         mse = float(((got.clamp(-1, 1) - want.clamp(-1, 1)) ** 2).mean())
         line["parity"] = {"rgb_max_rel_err_vs_oracle": err, "rgb_median_rel_err_vs_oracle": float(per_ray_err.median()),
                           "rgb_p99_rel_err_vs_oracle": float(per_ray_err.kthvalue(int(0.99 * len(per_ray_err))).values),
                           "note": "the max sits on rays where the reference itself is ill-conditioned (DESIGN.md section 2)",
+                          "oracle_one_ulp_pose_sensitivity": {"median": float(sens.median()), "max": float(sens.max()),
+                                                              "rays_at_most_1e-6": float(well.float().mean())},
+                          "rgb_max_rel_err_on_rays_with_sensitivity_at_most_1e-6":
+                              float(per_ray_err[well].max()) if bool(well.any()) else None,
                           "psnr_vs_oracle_db": (-10 * math.log10(mse)) if mse > 0 else None,   # test.py:90-91 (clamped)
                           "psnr_unclamped_db": -10 * math.log10(max(float(((got - want) ** 2).mean()), 1e-30) /
                                                                 float(want.abs().max()) ** 2),

@@ -310,7 +310,7 @@ __device__ __forceinline__ float drain_subtile(const GemmArgs& g, uint32_t tmem,
 
 // CLUSTER (> 1, operand-image A only): the CTAs of the N tiles of one 256-row tile form a cluster; each loads
 // 1/CLUSTER of every A stage and multicasts it to all of them, so the shared A operand is read from L2 once per
-// cluster instead of once per N tile (the GEMMs are L2 -> SM bandwidth bound, profiles/).
+// cluster instead of once per N tile (the hypothesis then was an L2 -> SM bandwidth bound; round 2 measured otherwise).
 // MLP16: the A operand is relu(x16 Wt + b) (query_embed, 16 -> 128, CoPoNeRF.py:446) computed by the producer warps from the
 // 64-byte local_coords rows, so the coordinate embedding never exists in memory (it used to be an operand image written by one
 // kernel and read back by this one: 2 x 134 MB per chunk and a launch); the scalar logit terms <q1, WS> + CS come out of it too.
@@ -653,7 +653,7 @@ __device__ __forceinline__ float drain_dot2(const GemmArgs& g, uint32_t tmem, in
 // a tile, and the MMA warp restarts as soon as they have read the accumulators (accum_empty).
 // A deeper operand ring does not help: with separate rings for the activation stages (4 x 32 KB) and the weight stages
 // (3 x 32 KB, a second producer warp) the query_encode_latent GEMM went from 1.33 to 1.44 ms (main loop 16.9 -> 18.1 us per
-// tile, profiles/r2_gemm1_trace_splitring.json): the loop is bound by L2 -> SM bandwidth, not by load latency.
+// tile, profiles/r2_gemm1_trace_splitring.json). What the loop is bound by: DESIGN.md section 4, main-loop attribution.
 // EPI_WARPS = 8 * PARTS: 16 leaves registers for a co-resident CTA of another kernel (the gather / readout of the other chunk
 // lane: a persistent grid does not block the dispatch of later kernels the way a long CTA queue does).
 // CL = 2: the two CTAs of a cluster work on neighbouring N tiles of the SAME row tile (tiles 2p and 2p + 1); each fetches one
@@ -1163,7 +1163,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) gemm_tc_persist2_kernel(GemmArg
 // ---- CTA-pair version (cta_group::2, operand-image A, f8 scheme) -------------------------------------------------
 // Two CTAs of a cluster own 2 x 256 rows and the same N tile. Every MMA spans both (M = 256: 128 rows from each
 // CTA's A stage) and reads half of the weight tile from each CTA's shared memory, so each SM stages only NT / 2
-// weight rows per k-chunk: 45.3 KB instead of 58.6 KB cross the L2 -> SM fabric per chunk and SM (the bound of
+// weight rows per k-chunk: 45.3 KB instead of 58.6 KB cross the L2 -> SM fabric per chunk and SM (believed to be the bound of
 // this GEMM), and the smaller stage allows a 4-deep ring. The leader CTA's MMA thread issues for the pair; the
 // peer relays "my stage has landed" to the leader with a remote mbarrier arrive; tcgen05.commit multicasts
 // "stage free" / "accumulators ready" to both CTAs.

@@ -280,10 +280,12 @@ int render_chunk(const cpn_render_args& a, const Workspace& w, float* z_all, flo
     int rays = a.B * nr;
     int R = rays * 2 * a.S;
     CPN_TRY(launch_ray_setup(a, ray0, nr, w.seg, st));
-    // fp16 + fp8 scheme: the encoder input image is written compact (3 bytes per element: fp16 head + remainder plane); the
-    // persistent GEMM derives the value plane e5m2(head) in shared memory. The GEMM is bound by L2 -> SM bandwidth
-    // (9.85 TB/s = 6160 B/clk over the chip, profiles/r2_ncu_full_chunk.csv), so bytes not fetched are time saved.
-    static int compact_a = -1;   // CPN_COMPACT_A=1 (A/B runs): measured 68 us faster in the gather and 90-160 us slower in the GEMM
+    // Experiment, off by default (CPN_COMPACT_A=1): the encoder input image written compact (3 bytes per element: fp16 head +
+    // remainder plane), the persistent GEMM derives the value plane e5m2(head) in shared memory. Measured 68 us faster in the
+    // gather and 90-160 us slower in the GEMM, whose three-stage ring then waits for a conversion pass per stage; the GEMM is
+    // not short of L2 -> SM bandwidth (copies alone run at 20 TB/s, profiles/r2_gemm1_mainloop_attribution.log). The hidden
+    // image IS written compact (h1c below): its consumer, layer 10, has the slack.
+    static int compact_a = -1;
     if (compact_a < 0) {
       const char* e = getenv("CPN_COMPACT_A");
       compact_a = (e && atoi(e) != 0) ? 1 : 0;

@@ -50,9 +50,8 @@ typedef enum {
 #define CPN_FLAG_NO_GFOLD 32  /* keep latent_value -> encode_latent -> query_repeat_embed as a per-ray chain behind a separate
                                * round-1 readout (default: folded into one 128 x 1664 map applied per sample row next to
                                * key_map, one combined readout with weights w2 + 2 w1 for z = R2 + 2 R1) */
-#define CPN_FLAG_FULL_H1 64   /* write the encoder-input image and the hidden-layer image with their value planes (4 bytes per
-                               * element; default: 3 bytes, the consuming GEMM derives the plane, and the e4m3(w_hi) weight
-                               * plane, in shared memory: the GEMMs are bound by L2 -> SM bandwidth). Same bits either way */
+#define CPN_FLAG_FULL_H1 64   /* write the hidden-layer image with its value plane (4 bytes per element; default on the default
+                               * path: 3 bytes, the key GEMM derives the plane in shared memory). Same bits either way */
 #define CPN_FLAG_NO_FOLD 4    /* keep query_encode_latent_2, latent_value and key_map as three GEMMs (default: the
                                * activation-free query_encode_latent_2 is folded into the other two at pack time) */
 
