@@ -213,9 +213,18 @@ __device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t mask
                : "memory");
 }
 
+// fp16 head of two activations, round to nearest, SATURATING (one F2FP.SATFINITE.F16.F32.PACK_AB): an activation beyond fp16's
+// range (|x| > 65504) becomes +-65504 with a large but finite remainder instead of inf - inf = NaN in every product of its row
+// (ADVICE.md r1). Same bits as __floats2half2_rn for every in-range value.
+__device__ __forceinline__ __half2 head2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // d = {upper: first source, lower: second}
+  return *reinterpret_cast<__half2*>(&r);
+}
+
 // ---- fp32 -> (fp16 hi, fp16 lo) split: x = hi + lo up to 2^-22 |x| ------------------------------------------------
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __half2 h = __floats2half2_rn(a, b);
+  __half2 h = head2(a, b);
   float2 f = __half22float2(h);
   __half2 l = __floats2half2_rn(a - f.x, b - f.y);
   hi = *reinterpret_cast<uint32_t*>(&h);
@@ -251,7 +260,7 @@ __device__ __forceinline__ uint32_t e5m2x4(float a, float b, float c, float d) {
 }
 // 4 values -> 4 fp16 hi (uint2), 4 e5m2 of the scaled remainder, 4 e5m2 of the fp16 value
 __device__ __forceinline__ void split4_f8(const float4& x, uint2& hi, uint32_t& lo8, uint32_t& x8) {
-  __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+  __half2 h0 = head2(x.x, x.y), h1 = head2(x.z, x.w);
   float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
   hi.x = *reinterpret_cast<uint32_t*>(&h0);
   hi.y = *reinterpret_cast<uint32_t*>(&h1);

@@ -458,6 +458,18 @@ def test_gemm_tc_activation_scale_robustness(scheme):
         print(f"gemm_tc scheme={scheme} {tag}: worst row rel err {worst[tag]:.2e}, median {float(err.median()):.2e}")
     for tag, e in worst.items():
         assert e < 6e-5, (tag, e, worst)      # measured / emulated: 2.5e-5 (f16+f8), 3e-5 at x1e-3 (f16x3: fp16 subnormal remainders)
+    # beyond fp16's range the head saturates (tc::head2): one activation of 1e6 costs its own row its accuracy, but nothing
+    # becomes inf - inf = NaN, and the other rows are untouched
+    A = base.clone()
+    A[7, 11] = 1e6
+    C = torch.full((M, N), float("nan"), device="cuda")
+    _lib.check(lib.cpn_gemm_tc(_p(eng.weights), 1, _p(A), K, _p(C), N, M, 0, scheme, 1, 1, _st()), "cpn_gemm_tc")
+    assert torch.isfinite(C).all()
+    ref = A.double() @ Wm.double().t() + bias.double()
+    keep = torch.ones(M, dtype=torch.bool, device="cuda")
+    keep[7] = False
+    err = (C.double() - ref)[keep].abs().amax(dim=1) / ref[keep].abs().amax(dim=1)
+    assert float(err.max()) < 6e-5, float(err.max())
 
 
 def test_full_image_oblique_pose_against_oracle():
