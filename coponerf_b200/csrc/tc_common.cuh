@@ -226,7 +226,7 @@ __device__ __forceinline__ __half2 head2(float a, float b) {
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   __half2 h = head2(a, b);
   float2 f = __half22float2(h);
-  __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  __half2 l = head2(a - f.x, b - f.y);   // saturating too: the remainder of a saturated head is out of range itself
   hi = *reinterpret_cast<uint32_t*>(&h);
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
