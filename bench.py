@@ -17,6 +17,11 @@ A "step" (default `--stage full`) is the whole drop-in call on one batch, images
 operators) followed by forward(val=True) over every ray with the estimated pose. `--stage pair` starts from the encoder's
 feature pyramid (cost aggregation + render), `--stage render` times the render half alone (z, rel_pose, flow given).
 
+The default `full` step treats the timed steps as a stream of pairs (coponerf_b200/pipeline.py, CoPoNeRF.render_pairs): get_z of
+the next pair runs on a second stream while the current pair renders. Every timed region starts and ends with nothing in flight,
+so it holds exactly `steps` x pairs get_z calls and renders. `"serial"` in the line is the same measurement with the two stages
+back to back on one stream (`--no-pipeline` makes that the headline).
+
 `value`  : inputs resident in HBM, timed on the device with CUDA events, L2 flushed between steps.
 `e2e`    : the same through the drop-in forward() with HOST inputs: pinned host -> device copies of the images / poses / uv
            and the device -> host read of rgb (+ the reference's pixel_val.cpu()) are inside the timed region.
