@@ -822,6 +822,52 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
     const int q = warp & 3, r = (warp - 2) >> 2, esub = r / PARTS, part = r % PARTS;
     const int niter = NT / 16, c_lo = (part * niter / PARTS) * 16, c_hi = ((part + 1) * niter / PARTS) * 16;
     const bool dotkind = !OUT_IMAGE && (g.out_kind == 3 || g.out_kind == 4);
+    // compact A image: derive the value plane(s) of the stage that holds global k-chunk number `c`, then release it to the MMA thread
+    const int idx = (warp - 2) * 32 + lane, csub = idx >> 8, cg = (idx >> 7) & 1, cr = idx & 127;
+    auto convert_stage = [&](uint32_t c, bool sub1) {
+      const bool conv = idx < 512 && (csub == 0 || sub1);
+      const uint32_t cit = c;
+      const int s = cit % STAGES;
+      mbar_wait(full + 8 * s, (cit / STAGES) & 1);
+      if (conv) {
+        unsigned char* st_ = smem + s * STAGE_BYTES + csub * A_SUB;
+        const uint4 h0 = *reinterpret_cast<const uint4*>(st_ + (2 * cg) * A_LBO + cr * 16);
+        const uint4 h1 = *reinterpret_cast<const uint4*>(st_ + (2 * cg + 1) * A_LBO + cr * 16);
+        const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const uint32_t lo2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hw[2 * k2]), __NV_SATFINITE, __NV_E5M2);
+          const uint32_t hi2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hw[2 * k2 + 1]), __NV_SATFINITE, __NV_E5M2);
+          o[k2] = lo2 | (hi2 << 16);
+        }
+        *reinterpret_cast<uint4*>(st_ + ACT_X8 + cg * A_LBO + cr * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      if (w3 && idx < 2 * NT) {
+        // weight plane e4m3(w_hi 2^-10) of this stage: item -> (16-k group, weight row); bit-identical to the plane
+        // pack_tc_kernel stores (the product is exact in fp16 wherever e4m3 does not round it to zero anyway)
+        const int wg = idx >= NT, wn = idx - wg * NT;
+        unsigned char* wb = smem + s * STAGE_BYTES + 2 * A_SUB;
+        const uint4 h0 = *reinterpret_cast<const uint4*>(wb + ((2 * wg) * NT + wn) * 16);
+        const uint4 h1 = *reinterpret_cast<const uint4*>(wb + ((2 * wg + 1) * NT + wn) * 16);
+        const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const __half2 sc = __float2half2_rn(F8_W_SCALE);
+        uint32_t o[4];
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const __half2 p0 = __hmul2(*reinterpret_cast<const __half2*>(&hw[2 * k2]), sc);
+          const __half2 p1 = __hmul2(*reinterpret_cast<const __half2*>(&hw[2 * k2 + 1]), sc);
+          const uint32_t lo2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&p0), __NV_SATFINITE, __NV_E4M3);
+          const uint32_t hi2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&p1), __NV_SATFINITE, __NV_E4M3);
+          o[k2] = lo2 | (hi2 << 16);
+        }
+        *reinterpret_cast<uint4*>(wb + w_half + (wg * NT + wn) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ready + 8 * s);
+    };
+    int pre = 0;
     uint32_t tcount = 0, cit = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
       const int n_tile = t % ntiles_n, m0 = (t / ntiles_n) * BM;
@@ -831,50 +877,10 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
       if (PREFETCH && dotkind && valid) dot_prefetch(g, m0, esub, q * 32 + lane, part, pf);
       if (a3) {
         // value plane of every stage of this tile: thread -> (sub-tile, 16-k group, row): two 16-byte fp16 groups in, one
-        // 16-byte e5m2 group out (the same conversion, on the same fp16 values, as split4_f8 writes into a full image)
-        const int idx = (warp - 2) * 32 + lane, csub = idx >> 8, cg = (idx >> 7) & 1, cr = idx & 127;
-        const bool conv = idx < 512 && (csub == 0 || (m0 + 128) < g.M);
-        for (int i = 0; i < g.kchunks; ++i, ++cit) {
-          const int s = cit % STAGES;
-          mbar_wait(full + 8 * s, (cit / STAGES) & 1);
-          if (conv) {
-            unsigned char* st_ = smem + s * STAGE_BYTES + csub * A_SUB;
-            const uint4 h0 = *reinterpret_cast<const uint4*>(st_ + (2 * cg) * A_LBO + cr * 16);
-            const uint4 h1 = *reinterpret_cast<const uint4*>(st_ + (2 * cg + 1) * A_LBO + cr * 16);
-            const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-            uint32_t o[4];
-#pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-              const uint32_t lo2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hw[2 * k2]), __NV_SATFINITE, __NV_E5M2);
-              const uint32_t hi2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hw[2 * k2 + 1]), __NV_SATFINITE, __NV_E5M2);
-              o[k2] = lo2 | (hi2 << 16);
-            }
-            *reinterpret_cast<uint4*>(st_ + ACT_X8 + cg * A_LBO + cr * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-          }
-          if (w3 && idx < 2 * NT) {
-            // weight plane e4m3(w_hi 2^-10) of this stage: item -> (16-k group, weight row); bit-identical to the plane
-            // pack_tc_kernel stores (the product is exact in fp16 wherever e4m3 does not round it to zero anyway)
-            const int wg = idx >= NT, wn = idx - wg * NT;
-            unsigned char* wb = smem + s * STAGE_BYTES + 2 * A_SUB;
-            const uint4 h0 = *reinterpret_cast<const uint4*>(wb + ((2 * wg) * NT + wn) * 16);
-            const uint4 h1 = *reinterpret_cast<const uint4*>(wb + ((2 * wg + 1) * NT + wn) * 16);
-            const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-            const __half2 sc = __float2half2_rn(F8_W_SCALE);
-            uint32_t o[4];
-#pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-              const __half2 p0 = __hmul2(*reinterpret_cast<const __half2*>(&hw[2 * k2]), sc);
-              const __half2 p1 = __hmul2(*reinterpret_cast<const __half2*>(&hw[2 * k2 + 1]), sc);
-              const uint32_t lo2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&p0), __NV_SATFINITE, __NV_E4M3);
-              const uint32_t hi2 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&p1), __NV_SATFINITE, __NV_E4M3);
-              o[k2] = lo2 | (hi2 << 16);
-            }
-            *reinterpret_cast<uint4*>(wb + w_half + (wg * NT + wn) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(ready + 8 * s);
-        }
+        // 16-byte e5m2 group out (the same conversion, on the same fp16 values, as split4_f8 writes into a full image).
+        // The first `pre` stages were converted at the end of the previous tile's epilogue (below).
+        for (int i = pre; i < g.kchunks; ++i, ++cit) convert_stage(cit, (m0 + 128) < g.M);
+        pre = 0;
       }
       mbar_wait(accum_full, tcount & 1);
       tcgen05_fence_after();
@@ -888,6 +894,13 @@ __global__ void __launch_bounds__((2 + P_EPI_WARPS) * 32, 1) gemm_tc_persist_ker
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(accum_empty);
+      if (a3 && t + (int)gridDim.x < ntiles) {
+        // the MMA thread may start the next tile now and its first stages landed during the drain: convert them before the rest
+        // of this epilogue (it used to wait 4 us per tile for them, profiles/r2_kg_weight_stationary.log: ring_wait_at_tile_start)
+        const int m0n = ((t + (int)gridDim.x) / ntiles_n) * BM;
+        pre = g.kchunks < STAGES ? g.kchunks : STAGES;
+        for (int i = 0; i < pre; ++i, ++cit) convert_stage(cit, (m0n + 128) < g.M);
+      }
       if (dotkind) {   // the three column parts of a row meet in shared memory, summed in part order
         const int rloc = q * 32 + lane;
         sdot[esub][part][rloc] = dot;
